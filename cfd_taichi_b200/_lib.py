@@ -1,0 +1,132 @@
+"""ctypes binding of libsph_b200.so (include/sph_b200.h).
+
+There is no CPU path: importing this module never needs a GPU (so symbol/ABI checks run anywhere),
+but `create()` fails loudly when the CUDA library or a CUDA device is missing.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_build", "libsph_b200.so")
+
+SOLVER_IDS = {"wcsph": 0, "pcisph": 1, "iisph": 2, "dfsph": 3}
+
+# enum SphField
+F_FLUID_POS, F_FLUID_VEL, F_BOUNDARY_POS, F_RIGID_POS, F_RIGID_VEL, F_RIGID_FORCE, F_FLUID_ACC = range(7)
+(F_RHO, F_ALPHA, F_RHO_DERIVATIVE, F_RHO_ADV, F_VEL_ADV, F_CELL1D, F_NEIGHBOR_COUNT,
+ F_BOUNDARY_NEIGHBOR_COUNT, F_PRESSURE, F_FORCE_A, F_FORCE_B, F_SCALAR_A, F_SCALAR_B, F_SCALAR_C,
+ F_VEC_A, F_VEC_B) = range(16, 32)
+F_CELL_START, F_SORTED_INDEX, F_BOUNDARY_CELL_START, F_BOUNDARY_SORTED_INDEX = range(64, 68)
+
+# enum SphPhase
+PH_BUILD_GRID = 0
+PH_DF_INITIALIZE, PH_DF_DIVERGENCE, PH_DF_EXT_FORCE_VEL_ADV, PH_DF_DENSITY, PH_DF_POSITION = range(10, 15)
+PH_WC_PRESSURE, PH_WC_KINEMATIC = 20, 21
+PH_PC_EXT_FORCE, PH_PC_ITERATION, PH_PC_INTEGRATION = 30, 31, 32
+PH_II_PREDICT_ADVECTION, PH_II_PRESSURE_SOLVE, PH_II_INTEGRATION = 40, 41, 42
+PH_WRITEBACK = 90
+
+
+class SphConfig(ctypes.Structure):
+    _fields_ = [
+        ("box_min", ctypes.c_double * 3),
+        ("box_max", ctypes.c_double * 3),
+        ("particle_radius", ctypes.c_double),
+        ("gravity", ctypes.c_double),
+        ("delta_time", ctypes.c_double),
+        ("boundary_handle", ctypes.c_int32),
+        ("fs_couple", ctypes.c_int32),
+        ("solver", ctypes.c_int32),
+        ("n_fluid", ctypes.c_int32),
+        ("n_boundary", ctypes.c_int32),
+        ("n_rigid", ctypes.c_int32),
+        ("active_rigid", ctypes.c_int32),
+        ("grid_num", ctypes.c_int32 * 3),
+        ("max_neighbors", ctypes.c_int32),
+        ("max_boundary_neighbors", ctypes.c_int32),
+        ("strict", ctypes.c_int32),
+        ("n_ghost_capacity", ctypes.c_int32),
+        ("rigid_rho", ctypes.c_double),
+        ("use_graph", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+class SphStats(ctypes.Structure):
+    _fields_ = [
+        ("delta_time", ctypes.c_float),
+        ("ps_delta_time", ctypes.c_float),
+        ("simulate_cnt", ctypes.c_int32),
+        ("error_flags", ctypes.c_int32),
+        ("div_iters", ctypes.c_int32),
+        ("div_first_err", ctypes.c_float),
+        ("div_err", ctypes.c_float),
+        ("den_iters", ctypes.c_int32),
+        ("den_err", ctypes.c_float),
+        ("pc_iters", ctypes.c_int32),
+        ("pc_err", ctypes.c_float),
+        ("ii_iters", ctypes.c_int32),
+        ("ii_residual", ctypes.c_float),
+        ("max_neighbors_seen", ctypes.c_int32),
+        ("max_boundary_neighbors_seen", ctypes.c_int32),
+        ("pc_delta", ctypes.c_float),
+        ("pc_max_index", ctypes.c_int32),
+        ("kernel_launches", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 3),
+    ]
+
+
+# every symbol include/sph_b200.h declares: (name, restype, argtypes)
+_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_fp = ctypes.POINTER(ctypes.c_float)
+PROTOTYPES = [
+    ("sph_create", _i, [ctypes.POINTER(SphConfig), _i, ctypes.POINTER(_vp)]),
+    ("sph_destroy", _i, [_vp]),
+    ("sph_last_error", ctypes.c_char_p, [_vp]),
+    ("sph_abi_version", _i, []),
+    ("sph_bind", _i, [_vp, _i, _vp, ctypes.c_size_t]),
+    ("sph_init_boundary", _i, [_vp, _vp]),
+    ("sph_init_rigid", _i, [_vp, _vp]),
+    ("sph_pcisph_precompute", _i, [_vp, _vp]),
+    ("sph_step", _i, [_vp, _i, _vp]),
+    ("sph_phase", _i, [_vp, _i, _vp]),
+    ("sph_rigid_reduce", _i, [_vp, _fp, _vp, _vp]),
+    ("sph_rigid_transform", _i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
+    ("sph_rigid_contacts", _i, [_vp, _fp, _fp, _fp, _fp, _vp, _vp]),
+    ("sph_set_delta_time", _i, [_vp, _f, _vp]),
+    ("sph_fetch", _i, [_vp, _i, _vp, ctypes.c_size_t, _vp]),
+    ("sph_upload_state", _i, [_vp, _vp, _vp, _vp]),
+    ("sph_download_state", _i, [_vp, _vp, _vp, _vp]),
+    ("sph_read_stats", _i, [_vp, ctypes.POINTER(SphStats)]),
+    ("sph_pack_columns", _i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    ("sph_set_counts", _i, [_vp, _i, _i]),
+]
+
+_lib = None
+
+
+class SphError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library.  No fallback: a missing build is an error."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SphError(
+                "libsph_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `python cfd_taichi_b200/build.py`. There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, res, args in PROTOTYPES:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc, handle=None):
+    if rc != 0:
+        msg = load().sph_last_error(handle)
+        raise SphError("sph_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))

@@ -1,0 +1,58 @@
+"""Builds libsph_b200.so (the C-ABI of include/sph_b200.h) in-tree with nvcc for sm_100a.
+
+The sweep translation unit is compiled twice: strict fp32 (-fmad=false, bit-exact against the
+oracle) and fast (FMA contraction + approximate reciprocals, same neighbour sets).
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libsph_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math"] + ARCH
+
+
+def _newer(src_list, target):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in src_list)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OUT, exist_ok=True)
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    hdrs.append(os.path.join(HERE, "..", "include", "sph_b200.h"))
+    units = [
+        ("sph_grid.cu", "sph_grid.o", []),
+        ("sph_api.cu", "sph_api.o", []),
+        ("sph_sweeps.cu", "sph_sweeps_strict.o", ["-DSPH_STRICT=1", "-fmad=false"]),
+        ("sph_sweeps.cu", "sph_sweeps_fast.o", ["-DSPH_STRICT=0", "-fmad=true"]),
+    ]
+    objs = []
+    procs = []
+    for src, obj, extra in units:
+        srcp, objp = os.path.join(CSRC, src), os.path.join(OUT, obj)
+        objs.append(objp)
+        if force or _newer([srcp] + hdrs, objp):
+            cmd = ["nvcc"] + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", srcp, "-o", objp]
+            procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            print(" ".join(cmd))
+            print(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    if force or _newer(objs, LIB):
+        cmd = ["nvcc", "-shared", "-o", LIB] + objs + ARCH + ["-cudart", "shared"]
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

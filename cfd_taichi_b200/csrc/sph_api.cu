@@ -1,0 +1,518 @@
+// sph_api.cu -- the C-ABI of include/sph_b200.h: handle life cycle, constant folding that mirrors the
+// reference's Python-scope arithmetic, scratch allocation, step / phase drivers and host-buffer
+// (e2e) entry points.  No torch types; one host thread per handle.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "sph_internal.h"
+
+static char g_create_error[512] = "";
+
+int sph_fail(SphHandle *h, int code, const char *fmt, ...) {
+	char *dst = h ? h->err : g_create_error;
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(dst, 512, fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+int sph_fail_cuda(SphHandle *h, cudaError_t e, const char *expr, const char *file, int line) {
+	return sph_fail(h, SPH_ECUDA, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, expr);
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+#define PI_F ((float)3.141592653589793)
+
+// Python-scope constant folding of the reference (fp64 first, then one cast to f32).
+static void fill_consts(const SphConfig &cfg, SphConsts &c) {
+	memset(&c, 0, sizeof(c));
+	double r_d = cfg.particle_radius;
+	double d_d = r_d * 2;                 // PS:81
+	double h_d = 4 * r_d;                 // PS:82 (== SB:17 kernel_h)
+	double m_d = 1000 * pow(r_d, 3) * 8;  // PS:83
+	bool wc = cfg.solver == SPH_SOLVER_WCSPH;
+	double c_s = wc ? 10 : 13;            // SB:24 / WC:18
+	double k_t = wc ? 0.2 : 0.5;          // SB:26 / WC:20
+	c.h = (float)h_d;
+	c.inv_h = 1.0f / c.h;
+	c.r = (float)r_d;
+	c.d = (float)d_d;
+	c.m = (float)m_d;
+	{
+		// largest f32 t with sqrtf(t) <= h: sqrt(r2) > h  <=>  r2 > t
+		float t = c.h * c.h;
+		while (sqrtf(t) <= c.h) t = nextafterf(t, INFINITY);
+		while (sqrtf(t) > c.h) t = nextafterf(t, -INFINITY);
+		c.cull_t = t;
+	}
+	float h3 = c.h * (c.h * c.h);
+	c.kW = 8.0f / (PI_F * h3);    // SB:79
+	c.kDW = 48.0f / (PI_F * h3);  // SB:95
+	c.kDW6 = c.kDW * 6.0f;        // SB:98
+	c.nkDW6 = (-c.kDW) * 6.0f;    // SB:100
+	c.gravity = (float)cfg.gravity;
+	c.visc_num = (float)(2 * 0.08 * h_d * c_s);   // SB:187
+	c.visc_eps_h2 = (float)(0.01 * h_d * h_d);    // SB:188
+	c.neg_m = (float)(-m_d);                      // SB:189
+	c.tension_coef = (float)(-k_t / m_d * m_d);   // SB:216
+	c.dt_cfl_c1 = (float)(0.4 * r_d * 2);         // DF:112
+	double margin = wc ? d_d : r_d;               // WC:57 vs DF:244 / PC:81 / II:197
+	for (int k = 0; k < 3; ++k) {
+		c.clamp_lo[k] = (float)(cfg.box_min[k] + margin);
+		c.clamp_hi[k] = (float)(cfg.box_max[k] - margin);
+	}
+	{
+		double dtf = (double)(float)cfg.delta_time; // f32 field read back into Python (PC:23)
+		c.pc_beta = (float)(dtf * dtf * m_d * m_d * 2 / (1000.0 * 1000.0));
+	}
+	c.gx = cfg.grid_num[0];
+	c.gy = cfg.grid_num[1];
+	c.gz = cfg.grid_num[2];
+	c.gxz = c.gx * c.gz;
+	c.G = c.gx * c.gy * c.gz;
+	c.N = cfg.n_fluid;
+	c.N_owned = cfg.n_fluid;
+	c.Nb = cfg.n_boundary;
+	c.Nr = cfg.n_rigid;
+	c.kmax = cfg.max_neighbors > 0 ? cfg.max_neighbors : 96;
+	c.kbmax = cfg.max_boundary_neighbors > 0 ? cfg.max_boundary_neighbors : 48;
+	c.krmax = 48;
+	c.boundary_handle = cfg.boundary_handle ? 1 : 0;
+	c.fs_couple = cfg.fs_couple ? 1 : 0;
+	c.solver = cfg.solver;
+	c.active_rigid = cfg.active_rigid ? 1 : 0;
+}
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n) {
+	*p = nullptr;
+	if (n == 0) n = 1;
+	return cudaMalloc((void **)p, n * sizeof(T));
+}
+
+static int alloc_grid(SphHandle *h, SphGrid &g, size_t n, size_t G) {
+	SPH_CUDA_CHECK(h, dalloc(&g.cell_of, n));
+	SPH_CUDA_CHECK(h, dalloc(&g.cell_cnt, G + 1));
+	SPH_CUDA_CHECK(h, dalloc(&g.cell_start, G + 1));
+	SPH_CUDA_CHECK(h, dalloc(&g.sorted_id, n));
+	SPH_CUDA_CHECK(h, dalloc(&g.scell, n));
+	SPH_CUDA_CHECK(h, cudaMemset(g.cell_start, 0, sizeof(int) * (G + 1)));
+	g.n = 0;
+	return SPH_OK;
+}
+
+static void free_grid(SphGrid &g) {
+	cudaFree(g.cell_of); cudaFree(g.cell_cnt); cudaFree(g.cell_start); cudaFree(g.sorted_id); cudaFree(g.scell);
+}
+
+extern "C" int sph_abi_version(void) { return 1; }
+
+extern "C" const char *sph_last_error(const SphHandle *h) { return h ? h->err : g_create_error; }
+
+extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
+	if (!cfg || !out) return sph_fail(nullptr, SPH_EINVAL, "sph_create: null argument");
+	*out = nullptr;
+	if (cfg->n_fluid < 0 || cfg->n_boundary < 0 || cfg->n_rigid < 0)
+		return sph_fail(nullptr, SPH_EINVAL, "sph_create: negative particle count");
+	if (cfg->grid_num[0] <= 0 || cfg->grid_num[1] <= 0 || cfg->grid_num[2] <= 0)
+		return sph_fail(nullptr, SPH_EINVAL, "sph_create: grid_num must be positive");
+	if ((long long)cfg->grid_num[0] * cfg->grid_num[1] * cfg->grid_num[2] > 0x7fffffffLL - 2)
+		return sph_fail(nullptr, SPH_EINVAL, "sph_create: grid too large for int32 cell ids");
+	if (cfg->solver < SPH_SOLVER_WCSPH || cfg->solver > SPH_SOLVER_DFSPH)
+		return sph_fail(nullptr, SPH_EINVAL, "sph_create: unknown solver id %d", cfg->solver);
+	if (!(cfg->particle_radius > 0)) return sph_fail(nullptr, SPH_EINVAL, "sph_create: particle_radius must be > 0");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev <= 0)
+		return sph_fail(nullptr, SPH_ECUDA, "sph_create: no CUDA device (%s); this library has no CPU path",
+		                cudaGetErrorString(e));
+	if (device < 0 || device >= ndev) return sph_fail(nullptr, SPH_EINVAL, "sph_create: bad device %d", device);
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess) return sph_fail(nullptr, SPH_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+
+	SphHandle *h = new (std::nothrow) SphHandle();
+	if (!h) return sph_fail(nullptr, SPH_ENOMEM, "sph_create: out of host memory");
+	memset(h, 0, sizeof(*h));
+	h->cfg = *cfg;
+	h->device = device;
+	fill_consts(*cfg, h->c);
+	SphConsts &c = h->c;
+	size_t ncap = (size_t)cfg->n_fluid + (size_t)(cfg->n_ghost_capacity > 0 ? cfg->n_ghost_capacity : 0);
+	size_t G = (size_t)c.G;
+	int rc;
+	if ((rc = alloc_grid(h, h->fg, ncap, G)) != SPH_OK) { *out = h; return rc; }
+	if ((rc = alloc_grid(h, h->bg, (size_t)c.Nb, G)) != SPH_OK) { *out = h; return rc; }
+	if ((rc = alloc_grid(h, h->rg, (size_t)c.Nr, c.Nr > 0 ? G : 1)) != SPH_OK) { *out = h; return rc; }
+	*out = h;
+	h->scan_sums_cap = cdiv((int)G, 2048) + 2;
+	SPH_CUDA_CHECK(h, dalloc(&h->scan_sums, (size_t)h->scan_sums_cap));
+	SPH_CUDA_CHECK(h, dalloc(&h->bspos, (size_t)c.Nb));
+	SPH_CUDA_CHECK(h, dalloc(&h->rspos, (size_t)c.Nr));
+	SPH_CUDA_CHECK(h, dalloc(&h->rsvel, (size_t)c.Nr));
+	SPH_CUDA_CHECK(h, dalloc(&h->rkin, (size_t)c.Nr * 4));
+	for (int k = 0; k < A4_COUNT; ++k) {
+		SPH_CUDA_CHECK(h, dalloc(&h->a4[k], ncap));
+		SPH_CUDA_CHECK(h, cudaMemset(h->a4[k], 0, sizeof(float4) * (ncap ? ncap : 1)));
+	}
+	for (int k = 0; k < A1_COUNT; ++k) {
+		SPH_CUDA_CHECK(h, dalloc(&h->a1[k], ncap));
+		SPH_CUDA_CHECK(h, cudaMemset(h->a1[k], 0, sizeof(float) * (ncap ? ncap : 1)));
+	}
+	size_t nwarps = (ncap + 31) / 32;
+	SPH_CUDA_CHECK(h, dalloc(&h->L.flist, nwarps * 32 * (size_t)c.kmax));
+	SPH_CUDA_CHECK(h, dalloc(&h->L.blist, nwarps * 32 * (size_t)c.kbmax));
+	SPH_CUDA_CHECK(h, dalloc(&h->L.rlist, c.Nr > 0 ? nwarps * 32 * (size_t)c.krmax : 1));
+	SPH_CUDA_CHECK(h, dalloc(&h->L.fcount, ncap));
+	SPH_CUDA_CHECK(h, dalloc(&h->L.bcount, ncap));
+	SPH_CUDA_CHECK(h, dalloc(&h->L.rcount, ncap));
+	SPH_CUDA_CHECK(h, cudaMemset(h->L.fcount, 0, sizeof(int) * (ncap ? ncap : 1)));
+	SPH_CUDA_CHECK(h, cudaMemset(h->L.bcount, 0, sizeof(int) * (ncap ? ncap : 1)));
+	SPH_CUDA_CHECK(h, cudaMemset(h->L.rcount, 0, sizeof(int) * (ncap ? ncap : 1)));
+	SPH_CUDA_CHECK(h, dalloc(&h->nbr_count, ncap));
+	SPH_CUDA_CHECK(h, dalloc(&h->ctl, 1));
+	SPH_CUDA_CHECK(h, cudaMallocHost((void **)&h->ctl_host, sizeof(SphCtl)));
+	h->n_partials = cdiv((int)(ncap ? ncap : 1), SPH_BLOCK) + 1;
+	SPH_CUDA_CHECK(h, dalloc(&h->partials, (size_t)h->n_partials));
+	memset(h->ctl_host, 0, sizeof(SphCtl));
+	h->ctl_host->dt = (float)cfg->delta_time;        // SB:16
+	{
+		double dtf = (double)h->ctl_host->dt;        // DF:20 delta_time[None] ** 2 in Python scope
+		h->ctl_host->dt2 = (float)(dtf * dtf);
+	}
+	h->ctl_host->ps_dt = 0.0f;                       // PS:37
+	SPH_CUDA_CHECK(h, cudaMemcpy(h->ctl, h->ctl_host, sizeof(SphCtl), cudaMemcpyHostToDevice));
+	snprintf(h->err, sizeof(h->err), "ok");
+	return SPH_OK;
+}
+
+extern "C" int sph_destroy(SphHandle *h) {
+	if (!h) return SPH_OK;
+	cudaSetDevice(h->device);
+	cudaDeviceSynchronize();
+	free_grid(h->fg); free_grid(h->bg); free_grid(h->rg);
+	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rsvel); cudaFree(h->rkin);
+	for (int k = 0; k < A4_COUNT; ++k) cudaFree(h->a4[k]);
+	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
+	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.rlist);
+	cudaFree(h->L.fcount); cudaFree(h->L.bcount); cudaFree(h->L.rcount);
+	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials);
+	if (h->ctl_host) cudaFreeHost(h->ctl_host);
+	delete h;
+	return SPH_OK;
+}
+
+extern "C" int sph_bind(SphHandle *h, int field, void *dev_ptr, size_t n) {
+	if (!h) return SPH_EINVAL;
+	if (!dev_ptr && n > 0) return sph_fail(h, SPH_EINVAL, "sph_bind: null pointer for field %d", field);
+	if (((uintptr_t)dev_ptr & 15u) != 0) return sph_fail(h, SPH_EINVAL, "sph_bind: field %d is not 16-byte aligned", field);
+	size_t ncap = (size_t)h->cfg.n_fluid + (size_t)(h->cfg.n_ghost_capacity > 0 ? h->cfg.n_ghost_capacity : 0);
+	switch (field) {
+	case SPH_F_FLUID_POS:
+		if (n < ncap) return sph_fail(h, SPH_EINVAL, "sph_bind: fluid pos needs %zu float4, got %zu", ncap, n);
+		h->pos = (float4 *)dev_ptr; h->n_pos = n; break;
+	case SPH_F_FLUID_VEL:
+		if (n < ncap) return sph_fail(h, SPH_EINVAL, "sph_bind: fluid vel needs %zu float4, got %zu", ncap, n);
+		h->vel = (float4 *)dev_ptr; h->n_vel = n; break;
+	case SPH_F_FLUID_ACC:
+		if (n < ncap) return sph_fail(h, SPH_EINVAL, "sph_bind: fluid acc needs %zu float4, got %zu", ncap, n);
+		h->acc = (float4 *)dev_ptr; h->n_acc = n; break;
+	case SPH_F_BOUNDARY_POS:
+		if (n < (size_t)h->c.Nb) return sph_fail(h, SPH_EINVAL, "sph_bind: boundary pos needs %d float4", h->c.Nb);
+		h->bpos = (float4 *)dev_ptr; h->n_bpos = n; h->boundary_ready = false; break;
+	case SPH_F_RIGID_POS:
+		if (n < (size_t)h->c.Nr) return sph_fail(h, SPH_EINVAL, "sph_bind: rigid pos needs %d float4", h->c.Nr);
+		h->rpos = (float4 *)dev_ptr; h->n_rpos = n; break;
+	case SPH_F_RIGID_VEL:
+		if (n < (size_t)h->c.Nr) return sph_fail(h, SPH_EINVAL, "sph_bind: rigid vel needs %d float4", h->c.Nr);
+		h->rvel = (float4 *)dev_ptr; h->n_rvel = n; break;
+	case SPH_F_RIGID_FORCE:
+		if (n < (size_t)h->c.Nr) return sph_fail(h, SPH_EINVAL, "sph_bind: rigid force needs %d float4", h->c.Nr);
+		h->rforce = (float4 *)dev_ptr; h->n_rforce = n; break;
+	default:
+		return sph_fail(h, SPH_EINVAL, "sph_bind: field %d is not bindable", field);
+	}
+	return SPH_OK;
+}
+
+static int require_state(SphHandle *h) {
+	if (!h) return SPH_EINVAL;
+	if (!h->pos || !h->vel) return sph_fail(h, SPH_ENOTBOUND, "fluid pos/vel are not bound (sph_bind)");
+	if (h->c.Nb > 0 && h->c.boundary_handle == 1 && !h->boundary_ready)
+		return sph_fail(h, SPH_ESTATE, "boundary particles are not initialised (sph_init_boundary)");
+	return SPH_OK;
+}
+
+static int check_launch(SphHandle *h, const char *what) {
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return sph_fail(h, SPH_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+	return SPH_OK;
+}
+
+extern "C" int sph_init_boundary(SphHandle *h, void *stream) {
+	if (!h) return SPH_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	if (h->c.Nb > 0) {
+		if (!h->bpos) return sph_fail(h, SPH_ENOTBOUND, "boundary pos is not bound");
+		sphg_build(h, h->bg, h->bpos, h->c.Nb, st);   // PS:322-335
+		sphg_gather_boundary(h, st);
+		if (h->cfg.strict) sph_strict::boundary_volume(h, st); // PS:309-320
+		else sph_fast::boundary_volume(h, st);
+	} else {
+		SPH_CUDA_CHECK(h, cudaMemsetAsync(h->bg.cell_start, 0, sizeof(int) * ((size_t)h->c.G + 1), st));
+	}
+	h->boundary_ready = true;
+	return check_launch(h, "sph_init_boundary");
+}
+
+extern "C" int sph_init_rigid(SphHandle *h, void *stream) {
+	(void)stream;
+	if (!h) return SPH_EINVAL;
+	return SPH_OK;
+}
+
+static int base_step(SphHandle *h, cudaStream_t st) {
+	// SB:136-143: simulate_cnt += 1 ; reset_grid ; update_grid ; reset()
+	h->simulate_cnt += 1;
+	sphg_build(h, h->fg, h->pos, h->c.N, st);
+	sphg_gather_fluid(h, st);
+	h->grid_valid = true;
+	h->lists_valid = false;
+	return SPH_OK;
+}
+
+extern "C" int sph_phase(SphHandle *h, int phase, void *stream) {
+	int rc = require_state(h);
+	if (rc != SPH_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	if (phase == SPH_PH_BUILD_GRID) {
+		base_step(h, st);
+		return check_launch(h, "sph_phase(build_grid)");
+	}
+	if (!h->grid_valid) return sph_fail(h, SPH_ESTATE, "sph_phase: grid not built (SPH_PH_BUILD_GRID first)");
+	bool strict = h->cfg.strict != 0;
+	if (phase == SPH_PH_WRITEBACK) {
+		sphg_writeback(h, h->a4[A4_POS], h->a4[A4_VEL], st);
+		return check_launch(h, "sph_phase(writeback)");
+	}
+	if (phase != SPH_PH_DF_INITIALIZE && phase != SPH_PH_WC_PRESSURE && phase != SPH_PH_PC_EXT_FORCE &&
+	    phase != SPH_PH_II_PREDICT_ADVECTION && !h->lists_valid)
+		return sph_fail(h, SPH_ESTATE, "sph_phase: neighbour lists not built (run the solver's first phase)");
+	if (phase >= SPH_PH_DF_INITIALIZE && phase <= SPH_PH_DF_POSITION) {
+		if (h->c.solver != SPH_SOLVER_DFSPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a DFSPH solver");
+		if (strict) sph_strict::df_phase(h, phase, st); else sph_fast::df_phase(h, phase, st);
+	} else if (phase >= SPH_PH_WC_PRESSURE && phase <= SPH_PH_WC_KINEMATIC) {
+		if (h->c.solver != SPH_SOLVER_WCSPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a WCSPH solver");
+		if (strict) sph_strict::wc_phase(h, phase, st); else sph_fast::wc_phase(h, phase, st);
+	} else if (phase >= SPH_PH_PC_EXT_FORCE && phase <= SPH_PH_PC_INTEGRATION) {
+		if (h->c.solver != SPH_SOLVER_PCISPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a PCISPH solver");
+		if (strict) sph_strict::pc_phase(h, phase, st); else sph_fast::pc_phase(h, phase, st);
+	} else if (phase >= SPH_PH_II_PREDICT_ADVECTION && phase <= SPH_PH_II_INTEGRATION) {
+		if (h->c.solver != SPH_SOLVER_IISPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not an IISPH solver");
+		if (strict) sph_strict::ii_phase(h, phase, st); else sph_fast::ii_phase(h, phase, st);
+	} else {
+		return sph_fail(h, SPH_EINVAL, "sph_phase: unknown phase %d", phase);
+	}
+	return check_launch(h, "sph_phase");
+}
+
+extern "C" int sph_step(SphHandle *h, int n_substeps, void *stream) {
+	int rc = require_state(h);
+	if (rc != SPH_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	bool strict = h->cfg.strict != 0;
+	for (int k = 0; k < n_substeps; ++k) {
+		base_step(h, st);
+		switch (h->c.solver) {
+		case SPH_SOLVER_DFSPH:
+			if (strict) sph_strict::df_step(h, st); else sph_fast::df_step(h, st);
+			break;
+		case SPH_SOLVER_WCSPH:
+			for (int p = SPH_PH_WC_PRESSURE; p <= SPH_PH_WC_KINEMATIC; ++p)
+				if (strict) sph_strict::wc_phase(h, p, st); else sph_fast::wc_phase(h, p, st);
+			break;
+		case SPH_SOLVER_PCISPH:
+			for (int p = SPH_PH_PC_EXT_FORCE; p <= SPH_PH_PC_INTEGRATION; ++p)
+				if (strict) sph_strict::pc_phase(h, p, st); else sph_fast::pc_phase(h, p, st);
+			break;
+		case SPH_SOLVER_IISPH:
+			for (int p = SPH_PH_II_PREDICT_ADVECTION; p <= SPH_PH_II_INTEGRATION; ++p)
+				if (strict) sph_strict::ii_phase(h, p, st); else sph_fast::ii_phase(h, p, st);
+			break;
+		default: break;
+		}
+		h->grid_valid = false; // positions moved: sorted buffers describe the previous state
+		h->lists_valid = false;
+	}
+	return check_launch(h, "sph_step");
+}
+
+extern "C" int sph_pcisph_precompute(SphHandle *h, void *stream) {
+	int rc = require_state(h);
+	if (rc != SPH_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	sphg_build(h, h->fg, h->pos, h->c.N, st); // PC:29-31
+	sphg_gather_fluid(h, st);
+	h->grid_valid = true;
+	if (h->cfg.strict) sph_strict::pc_precompute(h, st); else sph_fast::pc_precompute(h, st);
+	return check_launch(h, "sph_pcisph_precompute");
+}
+
+__global__ void k_set_dt(SphCtl *ctl, float dt) {
+	ctl->dt = dt;
+	ctl->dt2 = dt * dt;
+}
+
+extern "C" int sph_set_delta_time(SphHandle *h, float dt, void *stream) {
+	if (!h) return SPH_EINVAL;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	k_set_dt<<<1, 1, 0, (cudaStream_t)stream>>>(h->ctl, dt);
+	h->launches++;
+	return check_launch(h, "sph_set_delta_time");
+}
+
+extern "C" int sph_fetch(SphHandle *h, int field, void *dev_out, size_t n, void *stream) {
+	if (!h || !dev_out) return SPH_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	const SphConsts &c = h->c;
+	size_t N = (size_t)c.N;
+	auto f1 = [&](const float *src) -> int {
+		if (n < N) return sph_fail(h, SPH_EINVAL, "sph_fetch: output too small (%zu < %zu)", n, N);
+		sphg_unsort_f1(h, h->fg, src, (float *)dev_out, c.N, st);
+		return SPH_OK;
+	};
+	auto f4 = [&](const float4 *src) -> int {
+		if (n < N) return sph_fail(h, SPH_EINVAL, "sph_fetch: output too small (%zu < %zu)", n, N);
+		sphg_unsort_f4(h, h->fg, src, (float4 *)dev_out, c.N, st);
+		return SPH_OK;
+	};
+	auto i1 = [&](const int *src) -> int {
+		if (n < N) return sph_fail(h, SPH_EINVAL, "sph_fetch: output too small (%zu < %zu)", n, N);
+		sphg_unsort_i1(h, h->fg, src, (int *)dev_out, c.N, st);
+		return SPH_OK;
+	};
+	auto raw = [&](const void *src, size_t cnt, size_t esz) -> int {
+		if (n < cnt) return sph_fail(h, SPH_EINVAL, "sph_fetch: output too small (%zu < %zu)", n, cnt);
+		SPH_CUDA_CHECK(h, cudaMemcpyAsync(dev_out, src, cnt * esz, cudaMemcpyDeviceToDevice, st));
+		return SPH_OK;
+	};
+	int rc;
+	switch (field) {
+	case SPH_F_RHO: rc = f1(h->a1[A1_RHO]); break;
+	case SPH_F_ALPHA: rc = f1(h->a1[A1_ALPHA]); break;
+	case SPH_F_RHO_DERIVATIVE: rc = f1(h->a1[A1_DRHO]); break;
+	case SPH_F_RHO_ADV: rc = f1(h->a1[A1_RHOADV]); break;
+	case SPH_F_PRESSURE: rc = f1(h->a1[A1_P]); break;
+	case SPH_F_SCALAR_A: rc = f1(h->a1[A1_SA]); break;
+	case SPH_F_SCALAR_B: rc = f1(h->a1[A1_SB]); break;
+	case SPH_F_SCALAR_C: rc = f1(h->a1[A1_SC]); break;
+	case SPH_F_VEL_ADV: rc = f4(h->a4[A4_VADV]); break;
+	case SPH_F_FORCE_A: rc = f4(h->a4[A4_FA]); break;
+	case SPH_F_FORCE_B: rc = f4(h->a4[A4_FB]); break;
+	case SPH_F_VEC_A: rc = f4(h->a4[A4_FC]); break;
+	case SPH_F_VEC_B: rc = f4(h->a4[A4_FD]); break;
+	case SPH_F_FLUID_VEL: rc = f4(h->a4[A4_VEL]); break;   // in-step (sorted) velocity, original order
+	case SPH_F_FLUID_POS: rc = f4(h->a4[A4_POS]); break;
+	case SPH_F_CELL1D: rc = raw(h->fg.cell_of, N, sizeof(int)); break;
+	case SPH_F_NEIGHBOR_COUNT: rc = i1(h->nbr_count); break;
+	case SPH_F_BOUNDARY_NEIGHBOR_COUNT: rc = i1(h->L.bcount); break;
+	case SPH_F_CELL_START: rc = raw(h->fg.cell_start, (size_t)c.G + 1, sizeof(int)); break;
+	case SPH_F_SORTED_INDEX: rc = raw(h->fg.sorted_id, N, sizeof(int)); break;
+	case SPH_F_BOUNDARY_CELL_START: rc = raw(h->bg.cell_start, (size_t)c.G + 1, sizeof(int)); break;
+	case SPH_F_BOUNDARY_SORTED_INDEX: rc = raw(h->bg.sorted_id, (size_t)c.Nb, sizeof(int)); break;
+	default: return sph_fail(h, SPH_EINVAL, "sph_fetch: field %d cannot be fetched", field);
+	}
+	if (rc != SPH_OK) return rc;
+	return check_launch(h, "sph_fetch");
+}
+
+extern "C" int sph_upload_state(SphHandle *h, const float *host_pos4, const float *host_vel4, void *stream) {
+	if (!h || !h->pos || !h->vel) return h ? sph_fail(h, SPH_ENOTBOUND, "sph_upload_state: state not bound") : SPH_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	size_t bytes = sizeof(float4) * (size_t)h->c.N_owned;
+	if (host_pos4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(h->pos, host_pos4, bytes, cudaMemcpyHostToDevice, st));
+	if (host_vel4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(h->vel, host_vel4, bytes, cudaMemcpyHostToDevice, st));
+	return SPH_OK;
+}
+
+extern "C" int sph_download_state(SphHandle *h, float *host_pos4, float *host_vel4, void *stream) {
+	if (!h || !h->pos || !h->vel) return h ? sph_fail(h, SPH_ENOTBOUND, "sph_download_state: state not bound") : SPH_EINVAL;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	size_t bytes = sizeof(float4) * (size_t)h->c.N_owned;
+	if (host_pos4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_pos4, h->pos, bytes, cudaMemcpyDeviceToHost, st));
+	if (host_vel4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_vel4, h->vel, bytes, cudaMemcpyDeviceToHost, st));
+	SPH_CUDA_CHECK(h, cudaStreamSynchronize(st));
+	return SPH_OK;
+}
+
+extern "C" int sph_read_stats(SphHandle *h, SphStats *out) {
+	if (!h || !out) return SPH_EINVAL;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	int sim = h->simulate_cnt;
+	SPH_CUDA_CHECK(h, cudaDeviceSynchronize());
+	SPH_CUDA_CHECK(h, cudaMemcpy(h->ctl_host, h->ctl, sizeof(SphCtl), cudaMemcpyDeviceToHost));
+	const SphCtl &k = *h->ctl_host;
+	memset(out, 0, sizeof(*out));
+	out->delta_time = k.dt;
+	out->ps_delta_time = k.ps_dt;
+	out->simulate_cnt = sim;
+	out->error_flags = k.error_flags;
+	out->div_iters = k.div_iters;
+	out->div_first_err = k.div_first;
+	out->div_err = k.div_err;
+	out->den_iters = k.den_iters;
+	out->den_err = (float)((double)k.den_avg - 1000.0);
+	out->pc_iters = k.pc_iters;
+	out->pc_err = k.pc_err;
+	out->pc_delta = k.pc_delta;
+	out->pc_max_index = k.pc_max_index;
+	out->ii_iters = k.ii_iters;
+	out->ii_residual = k.ii_residual;
+	out->max_neighbors_seen = k.max_nbr;
+	out->max_boundary_neighbors_seen = k.max_bnbr;
+	out->kernel_launches = h->launches;
+	return SPH_OK;
+}
+
+// ---- entry points completed in later sections of the build (rigid coupling, multi-GPU) ----------
+extern "C" int sph_rigid_reduce(SphHandle *h, const float centroid[3], float *dev_out6, void *stream) {
+	(void)centroid; (void)dev_out6; (void)stream;
+	return sph_fail(h, SPH_ESTATE, "sph_rigid_reduce: no rigid body in this handle");
+}
+extern "C" int sph_rigid_transform(SphHandle *h, const float centroid[3], const float R[9], const float disp[3],
+                                   const float vel[3], const float omega[3], const float alpha[3],
+                                   const float acc[3], void *stream) {
+	(void)centroid; (void)R; (void)disp; (void)vel; (void)omega; (void)alpha; (void)acc; (void)stream;
+	return sph_fail(h, SPH_ESTATE, "sph_rigid_transform: no rigid body in this handle");
+}
+extern "C" int sph_rigid_contacts(SphHandle *h, const float vel[3], const float omega[3], const float centroid[3],
+                                  const float disp[3], float *dev_out16, void *stream) {
+	(void)vel; (void)omega; (void)centroid; (void)disp; (void)dev_out16; (void)stream;
+	return sph_fail(h, SPH_ESTATE, "sph_rigid_contacts: no rigid body in this handle");
+}
+extern "C" int sph_pack_columns(SphHandle *h, int col_lo, int col_hi, float *dev_pos4, float *dev_vel4,
+                                int32_t *dev_count, int capacity, void *stream) {
+	(void)col_lo; (void)col_hi; (void)dev_pos4; (void)dev_vel4; (void)dev_count; (void)capacity; (void)stream;
+	return sph_fail(h, SPH_ESTATE, "sph_pack_columns: not available");
+}
+extern "C" int sph_set_counts(SphHandle *h, int n_owned, int n_ghost) {
+	if (!h) return SPH_EINVAL;
+	size_t ncap = (size_t)h->cfg.n_fluid + (size_t)(h->cfg.n_ghost_capacity > 0 ? h->cfg.n_ghost_capacity : 0);
+	if (n_owned < 0 || n_ghost < 0 || (size_t)n_owned + (size_t)n_ghost > ncap)
+		return sph_fail(h, SPH_EINVAL, "sph_set_counts: %d owned + %d ghost exceeds capacity %zu", n_owned, n_ghost, ncap);
+	h->c.N_owned = n_owned;
+	h->c.N = n_owned + n_ghost;
+	return SPH_OK;
+}

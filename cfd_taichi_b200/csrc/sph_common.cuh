@@ -1,0 +1,96 @@
+// sph_common.cuh -- shared declarations of the B200 SPH hot path (internal; the public C-ABI is
+// include/sph_b200.h).  Compiled for sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sph_b200.h"
+
+#define SPH_BLOCK 128            // threads per sweep block (one sorted particle per thread)
+#define SPH_RHO0 1000.0f         // solver_base.rho_0 (SB:19)
+
+// error flag bits latched on the device (SphStats.error_flags)
+#define SPH_ERR_OUT_OF_GRID 1
+#define SPH_ERR_LIST_OVERFLOW 2
+#define SPH_ERR_BLIST_OVERFLOW 4
+#define SPH_ERR_DENSITY_CAP 8
+#define SPH_ERR_NONFINITE 16
+
+// Constants the reference evaluates in Python scope (fp64) and then casts to f32 where they meet
+// an f32 expression.  Filled once on the host in sph_api.cu.
+struct SphConsts {
+	float h;            // support_radius = 4 r (PS:82)
+	float inv_h;        // fast mode only
+	float cull_t;       // largest f32 t with sqrtf(t) <= h  (sqrt-free form of PS:466)
+	float r, d;         // particle_radius, particle_diameter
+	float m;            // particle_m (PS:83)
+	float kW;           // 8 / (pi h^3)   (SB:79)
+	float kDW;          // 48 / (pi h^3)  (SB:95)
+	float kDW6, nkDW6;  // (k*6) and ((-k)*6) of SB:98,100
+	float gravity;
+	float visc_num;     // 2 * alpha * h * c_s  (SB:187)
+	float visc_eps_h2;  // eps * h * h          (SB:188)
+	float neg_m;        // -particle_m          (SB:189)
+	float tension_coef; // -k_t / m * m         (SB:216)
+	float dt_cfl_c1;    // 0.4 * r * 2          (DF:112)
+	float clamp_lo[3], clamp_hi[3]; // box_min + margin, box_max - margin (clamp boundary mode)
+	float pc_beta;      // PC:23
+	int gx, gy, gz;     // grid_num (PS:101)
+	int gxz;            // gx * gz = y stride (PS:102)
+	int G;              // number of cells
+	int N;              // fluid particles handled by this handle (owned + ghost)
+	int N_owned;        // owned fluid particles (== N on one GPU)
+	int Nb, Nr;
+	int kmax, kbmax, krmax; // neighbour-list capacities
+	int boundary_handle, fs_couple, solver;
+	int active_rigid;
+};
+
+// Device-resident solver control block: time step, loop state, reduction results.
+// Written by single-thread controller kernels, read by every sweep (no host round trip).
+struct SphCtl {
+	float dt, dt2, ps_dt;
+	int error_flags;
+	int simulate_cnt;
+	// DFSPH divergence loop (DF:393-416)
+	int div_active, div_iters;
+	float div_err, div_past, div_first;
+	// DFSPH density loop (DF:221-233)
+	int den_active, den_iters;
+	float den_avg;
+	// PCISPH (PC:47-70)
+	int pc_active, pc_iters;
+	float pc_err, pc_delta;
+	int pc_max_index;
+	// IISPH (II:78-100)
+	int ii_active, ii_iters, ii_have_last;
+	float ii_residual, ii_last;
+	int max_nbr, max_bnbr;
+	float max_vel;
+	int graph_cond; // scratch for conditional graph nodes
+};
+
+struct SphPartial {
+	double sum;
+	int cnt;
+	float maxv;
+};
+
+// Per-step neighbour lists, warp-interleaved: entry k of sorted particle s lives at
+// list[((s >> 5) * cap + k) * 32 + (s & 31)], so that lane l of a warp reads consecutive words.
+struct SphLists {
+	uint32_t *flist; int *fcount;   // fluid neighbours (indices into the sorted fluid arrays)
+	uint32_t *blist; int *bcount;   // boundary neighbours (indices into the sorted boundary arrays)
+	uint32_t *rlist; int *rcount;   // rigid neighbours (indices into the sorted rigid arrays)
+};
+
+__host__ __device__ inline size_t sph_list_base(int s, int cap) {
+	return ((size_t)(s >> 5) * (size_t)cap) * 32u + (size_t)(s & 31);
+}
+
+#define SPH_CUDA_CHECK(h, expr)                                                         \
+	do {                                                                                \
+		cudaError_t e_ = (expr);                                                        \
+		if (e_ != cudaSuccess) return sph_fail_cuda((h), e_, #expr, __FILE__, __LINE__); \
+	} while (0)

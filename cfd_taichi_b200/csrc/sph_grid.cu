@@ -1,0 +1,284 @@
+// sph_grid.cu -- uniform-grid neighbour search for sm_100a:
+//   warp-aggregated cell hash + count  ->  block-scan exclusive prefix sum  ->  counting-sort
+//   scatter  ->  per-cell index fix-up (stable order)  ->  reorder into cell-contiguous float4 SoA.
+//
+// Replaces ParticleSystem.reset_grid / update_grid_fluid_particles / update_grid_rigid_particles /
+// update_boundary_grids (PS:322-335, 368-407): the reference's per-cell dynamic lists become a CSR
+// (cell_start[G+1] + sorted_id[N]) whose order inside a cell is ascending original index, i.e. the
+// arrival order of ti.cpu with one thread.  Cell ids are bit-exact: floor(pos / h) with an IEEE
+// f32 division (PS:490-494, box_min ignored), 1-D id = x + gx*gz*y + gx*z (PS:102, 486-488).
+#include "sph_internal.h"
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+// ---------------------------------------------------------------------------------------------
+// K0: cell hash + warp-aggregated count
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_hash_count(const float4 *__restrict__ pos, int n, SphConsts c,
+                                                     int *__restrict__ cell_of, int *__restrict__ cell_cnt,
+                                                     SphCtl *ctl) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	int idx = -1;
+	if (i < n) {
+		float4 p = pos[i];
+		// PS:494 ti.floor(pos / support_radius, ti.i32): true division, then floor
+		int cx = (int)floorf(__fdiv_rn(p.x, c.h));
+		int cy = (int)floorf(__fdiv_rn(p.y, c.h));
+		int cz = (int)floorf(__fdiv_rn(p.z, c.h));
+		bool bad = cx < 0 || cy < 0 || cz < 0 || cx >= c.gx || cy >= c.gy || cz >= c.gz ||
+		           !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z));
+		if (bad) {
+			// the reference only prints (PS:393-395, 492-493); latch a flag and keep the particle
+			// addressable by clamping it into the grid
+			atomicOr(&ctl->error_flags, SPH_ERR_OUT_OF_GRID);
+			cx = min(max(cx, 0), c.gx - 1);
+			cy = min(max(cy, 0), c.gy - 1);
+			cz = min(max(cz, 0), c.gz - 1);
+		}
+		idx = cx + cy * c.gxz + cz * c.gx;
+		cell_of[i] = idx;
+	}
+	// warp-aggregated increment: lanes that hit the same cell elect one leader
+	unsigned peers = __match_any_sync(0xffffffffu, idx);
+	if (idx >= 0) {
+		int leader = __ffs(peers) - 1;
+		if ((threadIdx.x & 31) == leader) atomicAdd(&cell_cnt[idx], __popc(peers));
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: exclusive prefix sum over the cell counts (three launches, block scan with warp shuffles)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v) {
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, v, o);
+		if ((threadIdx.x & 31) >= o) v += t;
+	}
+	return v;
+}
+
+// inclusive scan of one value per thread across the block; returns inclusive value, total in *total
+__device__ __forceinline__ int block_incl_scan(int v, int *total) {
+	__shared__ int wsum[32];
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	int inc = warp_incl_scan(v);
+	if (lane == 31) wsum[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		int nw = (blockDim.x + 31) >> 5;
+		int x = lane < nw ? wsum[lane] : 0;
+		x = warp_incl_scan(x);
+		wsum[lane] = x;
+	}
+	__syncthreads();
+	int base = w > 0 ? wsum[w - 1] : 0;
+	*total = wsum[((blockDim.x + 31) >> 5) - 1];
+	__syncthreads();
+	return inc + base;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int *__restrict__ cnt, int G,
+                                                               int *__restrict__ sums) {
+	int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	int s = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) {
+		int g = base + k;
+		if (g < G) s += cnt[g];
+	}
+	int total;
+	block_incl_scan(s, &total);
+	if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(int *sums, int nb) {
+	__shared__ int carry_s;
+	if (threadIdx.x == 0) carry_s = 0;
+	__syncthreads();
+	for (int base = 0; base < nb; base += 1024) {
+		int i = base + threadIdx.x;
+		int v = i < nb ? sums[i] : 0;
+		int total;
+		int inc = block_incl_scan(v, &total);
+		int carry = carry_s;
+		if (i < nb) sums[i] = carry + inc - v;
+		__syncthreads();
+		if (threadIdx.x == 0) carry_s = carry + total;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) sums[nb] = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(int *__restrict__ cnt, int G,
+                                                              const int *__restrict__ sums, int nb,
+                                                              int *__restrict__ start) {
+	int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+	int v[SCAN_ITEMS];
+	int s = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) {
+		int g = base + k;
+		v[k] = g < G ? cnt[g] : 0;
+		s += v[k];
+	}
+	int total;
+	int inc = block_incl_scan(s, &total);
+	int run = sums[blockIdx.x] + inc - s;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) {
+		int g = base + k;
+		if (g < G) {
+			start[g] = run;
+			cnt[g] = 0; // becomes the fill cursor of the scatter
+		}
+		run += v[k];
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) start[G] = sums[nb];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: counting-sort scatter (arrival order inside a cell is arbitrary here ...)
+// K3: ... and is made canonical (ascending original index) by a per-cell insertion sort
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(const int *__restrict__ cell_of, int n,
+                                                  const int *__restrict__ start, int *__restrict__ fill,
+                                                  int *__restrict__ sorted_id) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	int c = cell_of[i];
+	int slot = start[c] + atomicAdd(&fill[c], 1);
+	sorted_id[slot] = i;
+}
+
+__global__ void __launch_bounds__(256) k_cell_fix(const int *__restrict__ start, int G,
+                                                   int *__restrict__ sorted_id) {
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= G) return;
+	int a = start[c], b = start[c + 1];
+	for (int i = a + 1; i < b; ++i) {
+		int key = sorted_id[i];
+		int j = i - 1;
+		while (j >= a) {
+			int t = sorted_id[j];
+			if (t <= key) break;
+			sorted_id[j + 1] = t;
+			--j;
+		}
+		sorted_id[j + 1] = key;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: reorder into cell-contiguous float4 SoA
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_fluid(const int *__restrict__ sorted_id,
+                                                       const int *__restrict__ cell_of, int n,
+                                                       const float4 *__restrict__ pos,
+                                                       const float4 *__restrict__ vel,
+                                                       float4 *__restrict__ spos, float4 *__restrict__ svel,
+                                                       int *__restrict__ scell) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	int i = sorted_id[s];
+	float4 p = pos[i];
+	p.w = 0.0f;
+	spos[s] = p;
+	svel[s] = vel[i];
+	scell[s] = cell_of[i];
+}
+
+__global__ void __launch_bounds__(256) k_gather_pos(const int *__restrict__ sorted_id,
+                                                     const int *__restrict__ cell_of, int n,
+                                                     const float4 *__restrict__ pos,
+                                                     float4 *__restrict__ spos, int *__restrict__ scell) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	int i = sorted_id[s];
+	spos[s] = pos[i];
+	scell[s] = cell_of[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_unsort(const int *__restrict__ sorted_id, int n,
+                                                 const T *__restrict__ in, T *__restrict__ out) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	out[sorted_id[s]] = in[s];
+}
+
+__global__ void __launch_bounds__(256) k_writeback(const int *__restrict__ sorted_id, int n, int n_owned,
+                                                    const float4 *__restrict__ spos,
+                                                    const float4 *__restrict__ svel,
+                                                    float4 *__restrict__ pos, float4 *__restrict__ vel) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	int i = sorted_id[s];
+	if (i >= n_owned) return; // ghost particles (multi-GPU) are read-only copies
+	float4 p = spos[s];
+	p.w = 0.0f;
+	pos[i] = p;
+	vel[i] = svel[s];
+}
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+void sphg_build(SphHandle *h, SphGrid &g, const float4 *pos, int n, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	g.n = n;
+	cudaMemsetAsync(g.cell_cnt, 0, sizeof(int) * (size_t)c.G, st);
+	if (n > 0) {
+		k_hash_count<<<cdiv(n, 256), 256, 0, st>>>(pos, n, c, g.cell_of, g.cell_cnt, h->ctl);
+		h->launches++;
+	}
+	int nb = cdiv(c.G, SCAN_TILE);
+	k_scan_reduce<<<nb, SCAN_THREADS, 0, st>>>(g.cell_cnt, c.G, h->scan_sums);
+	k_scan_sums<<<1, 1024, 0, st>>>(h->scan_sums, nb);
+	k_scan_apply<<<nb, SCAN_THREADS, 0, st>>>(g.cell_cnt, c.G, h->scan_sums, nb, g.cell_start);
+	h->launches += 3;
+	if (n > 0) {
+		k_scatter<<<cdiv(n, 256), 256, 0, st>>>(g.cell_of, n, g.cell_start, g.cell_cnt, g.sorted_id);
+		k_cell_fix<<<cdiv(c.G, 256), 256, 0, st>>>(g.cell_start, c.G, g.sorted_id);
+		h->launches += 2;
+	}
+}
+
+void sphg_gather_fluid(SphHandle *h, cudaStream_t st) {
+	int n = h->fg.n;
+	if (n <= 0) return;
+	k_gather_fluid<<<cdiv(n, 256), 256, 0, st>>>(h->fg.sorted_id, h->fg.cell_of, n, h->pos, h->vel,
+	                                              h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell);
+	h->launches++;
+}
+
+void sphg_gather_boundary(SphHandle *h, cudaStream_t st) {
+	int n = h->bg.n;
+	if (n <= 0) return;
+	k_gather_pos<<<cdiv(n, 256), 256, 0, st>>>(h->bg.sorted_id, h->bg.cell_of, n, h->bpos, h->bspos,
+	                                            h->bg.scell);
+	h->launches++;
+}
+
+void sphg_unsort_f1(SphHandle *h, const SphGrid &g, const float *in, float *out, int n, cudaStream_t st) {
+	if (n <= 0) return;
+	k_unsort<float><<<cdiv(n, 256), 256, 0, st>>>(g.sorted_id, n, in, out);
+	h->launches++;
+}
+void sphg_unsort_i1(SphHandle *h, const SphGrid &g, const int *in, int *out, int n, cudaStream_t st) {
+	if (n <= 0) return;
+	k_unsort<int><<<cdiv(n, 256), 256, 0, st>>>(g.sorted_id, n, in, out);
+	h->launches++;
+}
+void sphg_unsort_f4(SphHandle *h, const SphGrid &g, const float4 *in, float4 *out, int n, cudaStream_t st) {
+	if (n <= 0) return;
+	k_unsort<float4><<<cdiv(n, 256), 256, 0, st>>>(g.sorted_id, n, in, out);
+	h->launches++;
+}
+void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaStream_t st) {
+	int n = h->c.N;
+	if (n <= 0) return;
+	k_writeback<<<cdiv(n, 256), 256, 0, st>>>(h->fg.sorted_id, n, h->c.N_owned, spos, svel, h->pos, h->vel);
+	h->launches++;
+}

@@ -1,0 +1,93 @@
+// sph_internal.h -- handle layout and internal launcher prototypes (not part of the C-ABI).
+#pragma once
+#include "sph_common.cuh"
+
+// float4 work arrays in SORTED (cell-contiguous) order; roles per solver are listed in DESIGN.md.
+enum {
+	A4_POS = 0, // xyz = position, w = 0
+	A4_VEL,     // xyz = velocity, w = solver-persistent scalar (warm_start_k / p_past)
+	A4_T1,      // xyz = position, w = neighbour payload #1 (e.g. (k/dt)/rho for the warm start)
+	A4_T2,      // xyz = position, w = neighbour payload #2
+	A4_T3,      // xyz = position, w = neighbour payload #3
+	A4_PR,      // xyz = position, w = rho
+	A4_VADV,    // xyz = advected / predicted velocity
+	A4_FA,      // generic vec (force_ext, press_force, d_ii ...)
+	A4_FB,      // generic vec
+	A4_FC,      // generic vec
+	A4_FD,      // generic vec
+	A4_COUNT
+};
+enum {
+	A1_RHO = 0, A1_ALPHA, A1_DRHO, A1_RHOADV, A1_P, A1_SA, A1_SB, A1_SC, A1_SD, A1_COUNT
+};
+
+struct SphGrid {
+	int *cell_of;      // per particle (original order): 1-D cell id
+	int *cell_cnt;     // per cell: counter / fill cursor
+	int *cell_start;   // G + 1 exclusive prefix sums
+	int *sorted_id;    // per sorted slot: original index
+	int *scell;        // per sorted slot: 1-D cell id
+	int n;
+};
+
+struct SphHandle {
+	SphConfig cfg;
+	SphConsts c;
+	int device;
+	char err[512];
+	int launches;
+	int simulate_cnt; // SB:137
+	// caller-owned state
+	float4 *pos, *vel, *bpos, *rpos, *rvel, *rforce, *acc;
+	size_t n_pos, n_vel, n_bpos, n_rpos, n_rvel, n_rforce, n_acc;
+	// grids
+	SphGrid fg, bg, rg;
+	int *scan_sums;
+	int scan_sums_cap;
+	// sorted static boundary / rigid
+	float4 *bspos;  // xyz, w = volume
+	float4 *rspos;  // xyz, w = volume * rho0-free volume
+	float4 *rsvel;  // predicted rigid particle velocity used by the coupling terms
+	float4 *rkin;   // per rigid particle: vel, omega, alpha, acc (4 x float4), original order
+	// sorted work arrays
+	float4 *a4[A4_COUNT];
+	float *a1[A1_COUNT];
+	SphLists L;
+	int *nbr_count; // get_neighbour_count (PS:424-445), sorted order
+	SphCtl *ctl;        // device
+	SphCtl *ctl_host;   // pinned mirror
+	SphPartial *partials;
+	int n_partials;
+	bool grid_valid, boundary_ready, lists_valid;
+	int sweep_blocks;
+	// CUDA graph state
+	void *graph_exec;
+	int last_den_chunk;
+};
+
+int sph_fail(SphHandle *h, int code, const char *fmt, ...);
+int sph_fail_cuda(SphHandle *h, cudaError_t e, const char *expr, const char *file, int line);
+
+// ---- sph_grid.cu (mode independent) -------------------------------------------------------
+void sphg_build(SphHandle *h, SphGrid &g, const float4 *pos, int n, cudaStream_t st);
+void sphg_gather_fluid(SphHandle *h, cudaStream_t st);
+void sphg_gather_boundary(SphHandle *h, cudaStream_t st);
+void sphg_unsort_f1(SphHandle *h, const SphGrid &g, const float *in, float *out, int n, cudaStream_t st);
+void sphg_unsort_i1(SphHandle *h, const SphGrid &g, const int *in, int *out, int n, cudaStream_t st);
+void sphg_unsort_f4(SphHandle *h, const SphGrid &g, const float4 *in, float4 *out, int n, cudaStream_t st);
+void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaStream_t st);
+
+// ---- sph_sweeps.cu, compiled twice (namespace sph_strict with -fmad=false, sph_fast) -------
+#define SPH_SWEEP_API(NS)                                                                   \
+	namespace NS {                                                                          \
+	void boundary_volume(SphHandle *h, cudaStream_t st);                                    \
+	void build_lists(SphHandle *h, cudaStream_t st);                                        \
+	void df_step(SphHandle *h, cudaStream_t st);                                            \
+	void df_phase(SphHandle *h, int phase, cudaStream_t st);                                \
+	void wc_phase(SphHandle *h, int phase, cudaStream_t st);                                \
+	void pc_phase(SphHandle *h, int phase, cudaStream_t st);                                \
+	void pc_precompute(SphHandle *h, cudaStream_t st);                                      \
+	void ii_phase(SphHandle *h, int phase, cudaStream_t st);                                \
+	}
+SPH_SWEEP_API(sph_strict)
+SPH_SWEEP_API(sph_fast)

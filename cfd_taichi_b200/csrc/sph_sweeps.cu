@@ -1,0 +1,629 @@
+// sph_sweeps.cu -- neighbour-list construction and the for_all_neighbor sweeps of every solver.
+// Compiled twice (see sph_math.cuh): namespace sph_strict (-fmad=false) and sph_fast.
+//
+// Design: positions are frozen inside a solver step (they change only in the
+// final integrate kernel: DF:238, PC:206, II:191, WC:52), so the 27-cell traversal with its exact
+// distance cull (PS:447-469, 337-366) is done ONCE per step by k_build_lists, which emits compact
+// per-particle neighbour lists in the reference's canonical visiting order.  Every later sweep
+// walks those lists: one coalesced index load and one float4 gather per neighbour.  Quantities a
+// neighbour contributes as a single scalar (k_j/rho_j, p_j/rho_j^2 ...) are pre-divided by their
+// producer kernel and ride in the .w lane of a position copy, so one 16-byte gather per pair
+// brings everything.  No per-pair atomics anywhere; reductions are warp-shuffle + one smem hop.
+#include "sph_math.cuh"
+#include "sph_internal.h"
+
+namespace SPH_NS {
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// decode the 1-D cell id (PS:102) back into (x, y, z)
+__device__ __forceinline__ void cell_xyz(int cid, const SphConsts &c, int &cx, int &cy, int &cz) {
+	cy = cid / c.gxz;
+	int rem = cid - cy * c.gxz;
+	cz = rem / c.gx;
+	cx = rem - cz * c.gx;
+}
+
+// Iterate the 27 cells around (cx,cy,cz) in the reference's order: ndrange((-1,2),(-1,2),(-1,2)),
+// dx outermost, dz innermost (PS:452), skipping out-of-range cells (PS:453-456).
+#define SPH_FOR_27(c, cx, cy, cz, C1)                                                   \
+	for (int dx_ = -1; dx_ <= 1; ++dx_)                                                 \
+		for (int dy_ = -1; dy_ <= 1; ++dy_)                                             \
+			for (int dz_ = -1; dz_ <= 1; ++dz_)                                         \
+				if ((unsigned)((cx) + dx_) < (unsigned)(c).gx && (unsigned)((cy) + dy_) < (unsigned)(c).gy && \
+				    (unsigned)((cz) + dz_) < (unsigned)(c).gz)                          \
+					for (int C1 = ((cx) + dx_) + ((cy) + dy_) * (c).gxz + ((cz) + dz_) * (c).gx, once_ = 1; once_; once_ = 0)
+
+// ---------------------------------------------------------------------------------------------
+// Akinci boundary volumes, once at start-up (PS:309-320): V_b = 1 / sum_{b' != b} W
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SPH_BLOCK) k_boundary_volume(SphConsts c, float4 *__restrict__ bspos,
+                                                                const int *__restrict__ bscell,
+                                                                const int *__restrict__ bstart,
+                                                                const int *__restrict__ bsorted_id,
+                                                                float4 *__restrict__ bpos_user) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.Nb) return;
+	float4 pi = bspos[s];
+	int cx, cy, cz;
+	cell_xyz(bscell[s], c, cx, cy, cz);
+	float volume = 0.0f;
+	SPH_FOR_27(c, cx, cy, cz, c1) {
+		int a = bstart[c1], b = bstart[c1 + 1];
+		for (int e = a; e < b; ++e) {
+			if (e == s) continue; // PS:362 (same material: skip self)
+			float4 pj = bspos[e];
+			Pair p = make_pair(pi, pj);
+			if (culled(p, c)) continue;
+			volume += cubic_w(p, c);
+		}
+	}
+	float v = 1.0f / volume;
+	// .w of neighbours is not read in this kernel, so the in-place update is race free
+	bspos[s].w = v;
+	bpos_user[bsorted_id[s]].w = v;
+}
+
+void boundary_volume(SphHandle *h, cudaStream_t st) {
+	if (h->c.Nb <= 0) return;
+	k_boundary_volume<<<cdiv(h->c.Nb, SPH_BLOCK), SPH_BLOCK, 0, st>>>(h->c, h->bspos, h->bg.scell, h->bg.cell_start,
+	                                                                   h->bg.sorted_id, h->bpos);
+	h->launches++;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_build_lists: the only 27-cell traversal of a step.  Emits the fluid and boundary neighbour
+// lists (canonical order), the neighbour count of get_neighbour_count (PS:424-445), rho
+// (SB:41-72) and, for DFSPH, alpha (DF:32-89) -- all of which depend on positions only.
+// ---------------------------------------------------------------------------------------------
+template <bool ALPHA>
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__restrict__ svel,
+              const int *__restrict__ scell, const int *__restrict__ cstart,
+              const float4 *__restrict__ bspos, const int *__restrict__ bstart, SphLists L,
+              int *__restrict__ nbr_count, float *__restrict__ rho, float *__restrict__ alpha,
+              float4 *__restrict__ posR, float4 *__restrict__ posT1, SphCtl *ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	int nf = 0, nb = 0;
+	if (s < c.N) {
+		float4 pi = spos[s];
+		int cx, cy, cz;
+		cell_xyz(scell[s], c, cx, cy, cz);
+		uint32_t *fl = L.flist + sph_list_base(s, c.kmax);
+		float rho_f = 0.001f; // SB:44
+		f3 ss = F3(0.0f, 0.0f, 0.0f);
+		float sq = 0.0f;
+		SPH_FOR_27(c, cx, cy, cz, c1) {
+			int a = cstart[c1], b = cstart[c1 + 1];
+			for (int e = a; e < b; ++e) {
+				if (e == s) continue; // PS:461
+				float4 pj = spos[e];
+				Pair p = make_pair(pi, pj);
+				if (culled(p, c)) continue; // PS:466
+				if (nf < c.kmax) fl[(size_t)nf * 32] = (uint32_t)e;
+				nf++;
+				rho_f += c.m * cubic_w(p, c); // SB:62
+				if (ALPHA) {
+					f3 g = c.m * cubic_dw(p, c); // DF:58, 70
+					ss = ss + g;
+					sq += dot(g, g);
+				}
+			}
+		}
+		float rho_i = rho_f;
+		float den = dot(ss, ss) + sq;
+		if (c.boundary_handle == 1) {
+			uint32_t *bl = L.blist + sph_list_base(s, c.kbmax);
+			float rho_b = 0.0f;
+			f3 ssb = F3(0.0f, 0.0f, 0.0f);
+			float sqb = 0.0f;
+			SPH_FOR_27(c, cx, cy, cz, c1) {
+				int a = bstart[c1], b = bstart[c1 + 1];
+				for (int e = a; e < b; ++e) {
+					float4 pj = bspos[e];
+					Pair p = make_pair(pi, pj);
+					if (culled(p, c)) continue; // PS:364
+					if (nb < c.kbmax) bl[(size_t)nb * 32] = (uint32_t)e;
+					nb++;
+					rho_b += pj.w * cubic_w(p, c); // SB:71
+					if (ALPHA) {
+						f3 g = (pj.w * SPH_RHO0) * cubic_dw(p, c); // DF:82, 88
+						ssb = ssb + g;
+						sqb += dot(g, g);
+					}
+				}
+			}
+			rho_i = rho_f + rho_b * SPH_RHO0; // SB:49
+			den = ((dot(ss, ss) + sq) + sqb) + dot(ssb, ssb); // DF:45
+		}
+		L.fcount[s] = min(nf, c.kmax);
+		L.bcount[s] = min(nb, c.kbmax);
+		nbr_count[s] = nf;
+		rho[s] = rho_i;
+		posR[s] = make_float4(pi.x, pi.y, pi.z, rho_i);
+		if (ALPHA) {
+			float al = fabsf(den) < 1e-6f ? 0.0f : rho_i / den; // DF:48-51
+			alpha[s] = al;
+			// payload of the warm start (DF:333-337): (k / dt) / rho
+			float k = svel[s].w;
+			posT1[s] = make_float4(pi.x, pi.y, pi.z, (k / ctl->dt) / rho_i);
+		}
+	}
+	int mf = warp_max_i(nf), mb = warp_max_i(nb);
+	if ((threadIdx.x & 31) == 0) {
+		if (mf > c.kmax) atomicOr(&ctl->error_flags, SPH_ERR_LIST_OVERFLOW);
+		if (mb > c.kbmax) atomicOr(&ctl->error_flags, SPH_ERR_BLIST_OVERFLOW);
+		if (mf > ctl->max_nbr) atomicMax(&ctl->max_nbr, mf);
+		if (mb > ctl->max_bnbr) atomicMax(&ctl->max_bnbr, mb);
+	}
+}
+
+void build_lists(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	if (c.N <= 0) return;
+	int nb = cdiv(c.N, SPH_BLOCK);
+	if (c.solver == SPH_SOLVER_DFSPH)
+		k_build_lists<true><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,
+		                                              h->bspos, h->bg.cell_start, h->L, h->nbr_count, h->a1[A1_RHO],
+		                                              h->a1[A1_ALPHA], h->a4[A4_PR], h->a4[A4_T1], h->ctl);
+	else
+		k_build_lists<false><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,
+		                                               h->bspos, h->bg.cell_start, h->L, h->nbr_count, h->a1[A1_RHO],
+		                                               h->a1[A1_ALPHA], h->a4[A4_PR], h->a4[A4_T1], h->ctl);
+	h->launches++;
+	h->lists_valid = true;
+}
+
+// list walkers ---------------------------------------------------------------------------------
+#define SPH_FOR_FLUID(L, c, s, J)                                               \
+	for (int k_ = 0, n_ = (L).fcount[s]; k_ < n_; ++k_)                         \
+		for (uint32_t J = (L).flist[sph_list_base(s, (c).kmax) + (size_t)k_ * 32], once_ = 1; once_; once_ = 0)
+#define SPH_FOR_BOUNDARY(L, c, s, J)                                            \
+	for (int k_ = 0, n_ = (L).bcount[s]; k_ < n_; ++k_)                         \
+		for (uint32_t J = (L).blist[sph_list_base(s, (c).kbmax) + (size_t)k_ * 32], once_ = 1; once_; once_ = 0)
+
+// =============================================================================================
+// DFSPH (dfsph_solver.py)
+// =============================================================================================
+
+// DF:314-355 divergence_warm_start.  Reads neighbour payload t1 = (k/dt)/rho from posT1.w.
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_df_warm_start(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float4 *__restrict__ bspos,
+                const float *__restrict__ rho, float4 *__restrict__ svel, const SphCtl *__restrict__ ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N_owned) return;
+	float dt = ctl->dt;
+	float4 pi = posT1[s];
+	float4 vi = svel[s];
+	f3 va = F3(0.0f, 0.0f, 0.0f);
+	SPH_FOR_FLUID(L, c, s, j) {
+		float4 pj = __ldg(&posT1[j]);
+		Pair p = make_pair(pi, pj);
+		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:337
+	}
+	f3 v = xyz(vi);
+	if (c.boundary_handle == 1) {
+		float k_i = vi.w / dt; // DF:353
+		float rho_i = rho[s];
+		f3 vb = F3(0.0f, 0.0f, 0.0f);
+		SPH_FOR_BOUNDARY(L, c, s, j) {
+			float4 pj = __ldg(&bspos[j]);
+			Pair p = make_pair(pi, pj);
+			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:354
+		}
+		v = v - (va + vb * SPH_RHO0) * dt; // DF:322
+	} else {
+		v = v - va * dt; // DF:324
+	}
+	svel[s] = F4(v, 0.0f); // DF:325 warm_start_k.fill(0)
+}
+
+// DF:252-300 derivative_iter_all_rho.  Writes drho and the payload t2 = ((drho*alpha)/dt)/rho of
+// the following divergence iteration (DF:363-367); block partials feed the device-side average.
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_df_drho(SphConsts c, SphLists L, const float4 *__restrict__ spos, const float4 *__restrict__ svel,
+          const float4 *__restrict__ bspos, const int *__restrict__ nbr_count, const float *__restrict__ rho,
+          const float *__restrict__ alpha, float *__restrict__ drho, float4 *__restrict__ posT2,
+          const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
+	if (gated && !ctl->div_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	double psum = 0.0;
+	int pcnt = 0;
+	if (s < c.N_owned) {
+		float4 pi = spos[s];
+		float out = 0.0f;
+		if (nbr_count[s] >= 20) { // DF:258-261
+			f3 vi = xyz(svel[s]);
+			float rd = 0.0f;
+			SPH_FOR_FLUID(L, c, s, j) {
+				float4 pj = __ldg(&spos[j]);
+				f3 vj = xyz(__ldg(&svel[j]));
+				Pair p = make_pair(pi, pj);
+				rd += c.m * dot(vi - vj, cubic_dw(p, c)); // DF:287
+			}
+			if (c.boundary_handle == 1) {
+				float rdb = 0.0f;
+				SPH_FOR_BOUNDARY(L, c, s, j) {
+					float4 pj = __ldg(&bspos[j]);
+					Pair p = make_pair(pi, pj);
+					rdb += pj.w * dot(vi, cubic_dw(p, c)); // DF:300
+				}
+				out = fmaxf(rd + rdb * SPH_RHO0, 0.0f); // DF:267
+			} else {
+				out = fmaxf(rd, 0.0f);
+			}
+		}
+		drho[s] = out;
+		posT2[s] = make_float4(pi.x, pi.y, pi.z, ((out * alpha[s]) / ctl->dt) / rho[s]);
+		if (out > 0.0f) { psum = (double)out; pcnt = 1; } // DF:275-277
+	}
+	block_partial(psum, pcnt, 0.0f, partials);
+}
+
+// DF:302-312, 357-391 divergence_iter_all_vel_adv fused with DF:381-384 sum_up_stiff
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_df_div_iter(SphConsts c, SphLists L, const float4 *__restrict__ posT2, const float4 *__restrict__ bspos,
+              const float *__restrict__ rho, const float *__restrict__ alpha, const float *__restrict__ drho,
+              float4 *__restrict__ svel, const SphCtl *__restrict__ ctl) {
+	if (!ctl->div_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N_owned) return;
+	float dt = ctl->dt;
+	float4 pi = posT2[s];
+	float4 vi = svel[s];
+	f3 va = F3(0.0f, 0.0f, 0.0f);
+	SPH_FOR_FLUID(L, c, s, j) {
+		float4 pj = __ldg(&posT2[j]);
+		Pair p = make_pair(pi, pj);
+		float f = pi.w + pj.w;
+		f3 dw = cubic_dw(p, c);
+		if (f > 1e-5f) va = va + (c.m * f) * dw; // DF:367-369
+	}
+	float da = drho[s] * alpha[s];
+	f3 v = xyz(vi);
+	if (c.boundary_handle == 1) {
+		float k_i = da / dt; // DF:388
+		float rho_i = rho[s];
+		f3 vb = F3(0.0f, 0.0f, 0.0f);
+		SPH_FOR_BOUNDARY(L, c, s, j) {
+			float4 pj = __ldg(&bspos[j]);
+			Pair p = make_pair(pi, pj);
+			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:390
+		}
+		v = v - (va + vb * SPH_RHO0) * dt; // DF:310
+	} else {
+		v = v - va * dt;
+	}
+	svel[s] = F4(v, vi.w + da); // DF:384
+}
+
+// DF:91-122: tension (SB:204-217) + viscosity (SB:170-202) + f_ext + v* = v + dt f / m, and the
+// block maxima of |v*| for the adaptive time step.
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_df_ext_force(SphConsts c, SphLists L, const float4 *__restrict__ posR, const float4 *__restrict__ svel,
+               float4 *__restrict__ svadv, float4 *__restrict__ fext, const SphCtl *__restrict__ ctl,
+               SphPartial *__restrict__ partials) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	float vmax = -INFINITY;
+	if (s < c.N_owned) {
+		float dt = ctl->dt;
+		float4 pi = posR[s];
+		f3 vi = xyz(svel[s]);
+		f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
+		SPH_FOR_FLUID(L, c, s, j) {
+			float4 pj = __ldg(&posR[j]);
+			f3 vj = xyz(__ldg(&svel[j]));
+			Pair p = make_pair(pi, pj);
+			ten = ten + (c.tension_coef * cubic_w(p, c)) * p.r; // SB:216
+			f3 v_ij = vi - vj;
+			float shear = dot(v_ij, p.r); // SB:183
+			if (shear < 0.0f) {
+#if SPH_STRICT
+				float q = sqrtf(p.r2);
+				float q2 = q * q;
+#else
+				float q2 = p.r2;
+#endif
+				float nu = c.visc_num / (pi.w + pj.w);                 // SB:187
+				float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);  // SB:188
+				visc = visc + (c.neg_m * pi_ij) * cubic_dw(p, c);      // SB:189
+			}
+		}
+		f3 tension = ten * c.m;  // SB:209
+		f3 viscosity = visc * c.m; // SB:175
+		f3 g = F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
+		f3 f = (g + tension) + viscosity; // DF:96
+		f3 va = vi + (dt * f) / c.m;       // DF:102
+		fext[s] = F4(f, 0.0f);
+		svadv[s] = F4(va, 0.0f);
+		vmax = sqrtf(dot(va, va)); // DF:103
+	}
+	block_partial(0.0, 0, vmax, partials);
+}
+
+// DF:124-176 compute_all_rho_adv.  Writes rho_adv and the payload t3 = (((rho_adv-rho0)*alpha)/dt2)/rho
+// of iter_all_vel_adv (DF:199-203).
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_df_rho_adv(SphConsts c, SphLists L, const float4 *__restrict__ spos, const float4 *__restrict__ svadv,
+             const float4 *__restrict__ bspos, const float *__restrict__ rho, const float *__restrict__ alpha,
+             float *__restrict__ rho_adv, float4 *__restrict__ posT3, const SphCtl *__restrict__ ctl,
+             SphPartial *__restrict__ partials, int gated) {
+	if (gated && !ctl->den_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	double psum = 0.0;
+	int pcnt = 0;
+	if (s < c.N_owned) {
+		float dt = ctl->dt, dt2 = ctl->dt2;
+		float4 pi = spos[s];
+		f3 vi = xyz(svadv[s]);
+		float delta = 0.0f;
+		SPH_FOR_FLUID(L, c, s, j) {
+			float4 pj = __ldg(&spos[j]);
+			f3 vj = xyz(__ldg(&svadv[j]));
+			Pair p = make_pair(pi, pj);
+			delta += c.m * dot(vi - vj, cubic_dw(p, c)); // DF:162
+		}
+		float rho_i = rho[s];
+		float ra;
+		if (c.boundary_handle == 1) {
+			float db = 0.0f;
+			SPH_FOR_BOUNDARY(L, c, s, j) {
+				float4 pj = __ldg(&bspos[j]);
+				Pair p = make_pair(pi, pj);
+				db += pj.w * dot(vi, cubic_dw(p, c)); // DF:176
+			}
+			ra = fmaxf(rho_i + dt * (delta + db * SPH_RHO0), SPH_RHO0); // DF:135
+		} else {
+			ra = fmaxf(rho_i + dt * delta, SPH_RHO0); // DF:137
+		}
+		rho_adv[s] = ra;
+		posT3[s] = make_float4(pi.x, pi.y, pi.z, (((ra - SPH_RHO0) * alpha[s]) / dt2) / rho_i);
+		if (!(ra == SPH_RHO0)) { psum = (double)ra; pcnt = 1; } // DF:139-141
+	}
+	block_partial(psum, pcnt, 0.0f, partials);
+}
+
+// DF:178-219 iter_all_vel_adv (fluid + boundary part; the rigid force gather is k_rigid_force)
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_df_vel_adv_iter(SphConsts c, SphLists L, const float4 *__restrict__ posT3, const float4 *__restrict__ bspos,
+                  const float *__restrict__ rho, const float *__restrict__ alpha,
+                  const float *__restrict__ rho_adv, float4 *__restrict__ svadv,
+                  const SphCtl *__restrict__ ctl, int gated) {
+	if (gated && !ctl->den_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N_owned) return;
+	float dt = ctl->dt, dt2 = ctl->dt2;
+	float4 pi = posT3[s];
+	f3 va = F3(0.0f, 0.0f, 0.0f);
+	SPH_FOR_FLUID(L, c, s, j) {
+		float4 pj = __ldg(&posT3[j]);
+		Pair p = make_pair(pi, pj);
+		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:203
+	}
+	f3 delta = va;
+	if (c.boundary_handle == 1) {
+		float rho_i = rho[s];
+		float k_i = ((rho_adv[s] - SPH_RHO0) * alpha[s]) / dt2; // DF:217
+		f3 vb = F3(0.0f, 0.0f, 0.0f);
+		SPH_FOR_BOUNDARY(L, c, s, j) {
+			float4 pj = __ldg(&bspos[j]);
+			Pair p = make_pair(pi, pj);
+			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:219
+		}
+		delta = va + vb * SPH_RHO0; // DF:187
+	}
+	float4 v = svadv[s];
+	svadv[s] = F4(xyz(v) - delta * dt, 0.0f); // DF:191
+}
+
+// DF:235-250 compute_all_position, fused with the write-back into the caller's original-order state
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_df_position(SphConsts c, const int *__restrict__ sorted_id, const float4 *__restrict__ spos,
+              const float4 *__restrict__ svel, const float4 *__restrict__ svadv, float4 *__restrict__ pos,
+              float4 *__restrict__ vel, const SphCtl *__restrict__ ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N) return;
+	int i = sorted_id[s];
+	if (i >= c.N_owned) return;
+	float dt = ctl->dt;
+	f3 va = xyz(svadv[s]);
+	f3 x = xyz(spos[s]) + (dt * va) * 0.9999f; // DF:238
+	f3 v = va * 0.9999f;                       // DF:239
+	if (c.boundary_handle == 0) {              // DF:241-250
+		float *xp = &x.x, *vp = &v.x;
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			if (xp[k] <= c.clamp_lo[k]) { xp[k] = c.clamp_lo[k]; vp[k] *= -0.5f; }
+			if (xp[k] >= c.clamp_hi[k]) { xp[k] = c.clamp_hi[k]; vp[k] *= -0.5f; }
+		}
+	}
+	pos[i] = F4(x, 0.0f);
+	vel[i] = F4(v, svel[s].w);
+}
+
+// ---- controller kernels: one block; deterministic reduction of the block partials, then the
+// ---- reference's host-side loop logic evaluated on the device ---------------------------------
+__device__ __forceinline__ void reduce_partials(const SphPartial *p, int n, double &sum, int &cnt, float &mx) {
+	__shared__ double ss[256];
+	__shared__ int sc[256];
+	__shared__ float sm[256];
+	double a = 0.0;
+	int b = 0;
+	float m = -INFINITY;
+	for (int i = threadIdx.x; i < n; i += 256) { a += p[i].sum; b += p[i].cnt; m = fmaxf(m, p[i].maxv); }
+	ss[threadIdx.x] = a; sc[threadIdx.x] = b; sm[threadIdx.x] = m;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if (threadIdx.x < o) {
+			ss[threadIdx.x] += ss[threadIdx.x + o];
+			sc[threadIdx.x] += sc[threadIdx.x + o];
+			sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + o]);
+		}
+		__syncthreads();
+	}
+	sum = ss[0]; cnt = sc[0]; mx = sm[0];
+}
+
+// mode 0: first evaluation (DF:398-399); mode 1: after an iteration (DF:406-414)
+__global__ void __launch_bounds__(256) k_df_ctl_div(SphCtl *ctl, const SphPartial *partials, int n, int mode) {
+	if (mode == 1 && !ctl->div_active) return;
+	double sum; int cnt; float mx;
+	reduce_partials(partials, n, sum, cnt, mx);
+	if (threadIdx.x != 0) return;
+	float avg = cnt > 0 ? (float)(sum / (double)cnt) : 0.0f; // DF:278-279
+	if (mode == 0) {
+		ctl->div_first = avg;
+		ctl->div_err = avg;
+		ctl->div_past = 0.0f;
+		ctl->div_iters = 0;
+		ctl->div_active = 1; // iter_cnt < min_iteration_density_divergence
+	} else {
+		ctl->div_past = ctl->div_err;
+		ctl->div_err = avg;
+		if (fabs((double)avg - (double)ctl->div_past) < 1e-5) { // DF:410-412: break before iter_cnt += 1
+			ctl->div_active = 0;
+		} else {
+			int it = ctl->div_iters + 1;
+			ctl->div_iters = it;
+			ctl->div_active = ((it < 1 || avg > 10.0f) && it < 15) ? 1 : 0; // DF:400
+		}
+	}
+}
+
+// DF:100-119: max |v*| (+ rigid surface speed) -> adaptive dt on the device
+__global__ void __launch_bounds__(256) k_df_ctl_dt(SphCtl *ctl, const SphPartial *partials, int n, SphConsts c,
+                                                    float max_rigid_vel) {
+	double sum; int cnt; float mx;
+	reduce_partials(partials, n, sum, cnt, mx);
+	if (threadIdx.x != 0) return;
+	float max_vel = mx + max_rigid_vel;              // DF:111
+	float max_dt = (c.dt_cfl_c1 / max_vel) * 0.2f;   // DF:112
+	float dt;
+	if (max_dt > 1e-3f) dt = 1e-3f;                  // DF:114-115
+	else dt = fmaxf(max_dt, 1e-5f);                  // DF:117
+	ctl->max_vel = max_vel;
+	ctl->dt = dt;
+	ctl->dt2 = dt * dt;                              // DF:118
+	ctl->ps_dt = dt;                                 // DF:119
+	ctl->den_active = 1;
+	ctl->den_iters = 0;
+	ctl->den_avg = INFINITY;
+}
+
+// DF:221-233: evaluated after compute_all_rho_adv of iteration `den_iters`; den_active then tells
+// whether the NEXT iteration runs.  The iter_all_vel_adv of the current iteration always runs, so it
+// is gated on the value den_active had when this iteration started (kept in graph_cond).
+__global__ void __launch_bounds__(256) k_df_ctl_den(SphCtl *ctl, const SphPartial *partials, int n) {
+	if (!ctl->den_active) { if (threadIdx.x == 0) ctl->graph_cond = 0; return; }
+	double sum; int cnt; float mx;
+	reduce_partials(partials, n, sum, cnt, mx);
+	if (threadIdx.x != 0) return;
+	float avg = cnt > 0 ? (float)(sum / (double)cnt) : 1000.0f; // DF:128, 148-149
+	ctl->den_avg = avg;
+	ctl->graph_cond = 1;
+}
+__global__ void k_df_ctl_den_next(SphCtl *ctl) {
+	if (!ctl->graph_cond) return;
+	int it = ctl->den_iters + 1;
+	ctl->den_iters = it;
+	ctl->den_active = (it < 2 || (double)ctl->den_avg - 1000.0 > 0.1 * 1000 * 0.01) ? 1 : 0; // DF:225
+	if (it >= 1000) { ctl->den_active = 0; atomicOr(&ctl->error_flags, SPH_ERR_DENSITY_CAP); }
+}
+
+// ---- DFSPH drivers -----------------------------------------------------------------------------
+static void df_divergence(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	k_df_warm_start<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl);
+	k_df_drho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
+	                                    h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 0);
+	k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0);
+	h->launches += 3;
+	for (int it = 0; it < 15; ++it) { // max_iteration_density_divergence (DF:24); gated on ctl->div_active
+		k_df_div_iter<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
+		                                        h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
+		k_df_drho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
+		                                    h->a1[A1_RHO], h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl,
+		                                    h->partials, 1);
+		k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1);
+		h->launches += 3;
+	}
+}
+
+static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	k_df_ext_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_PR], h->a4[A4_VEL], h->a4[A4_VADV], h->a4[A4_FA], h->ctl,
+	                                         h->partials);
+	k_df_ctl_dt<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, c, 0.0f);
+	h->launches += 2;
+}
+
+static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	for (int it = first; it < first + count; ++it) {
+		int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
+		k_df_rho_adv<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
+		                                       h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials,
+		                                       gated);
+		k_df_ctl_den<<<1, 256, 0, st>>>(h->ctl, h->partials, nb);
+		k_df_vel_adv_iter<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
+		                                            h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
+		k_df_ctl_den_next<<<1, 1, 0, st>>>(h->ctl);
+		h->launches += 4;
+	}
+}
+
+static int df_density(SphHandle *h, cudaStream_t st) {
+	// The reference loop has no iteration cap (DF:225).  Iterations are enqueued in chunks gated by the
+	// device flag; the host looks at the flag once per chunk (not per iteration).
+	int chunk = h->last_den_chunk > 0 ? h->last_den_chunk : 3;
+	int done = 0;
+	for (;;) {
+		df_density_iters(h, done, chunk, st);
+		done += chunk;
+		cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SphCtl), cudaMemcpyDeviceToHost, st);
+		cudaStreamSynchronize(st);
+		if (!h->ctl_host->den_active) break;
+		chunk = 2;
+	}
+	h->last_den_chunk = h->ctl_host->den_iters + 1;
+	return 0;
+}
+
+static void df_position(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	k_df_position<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VEL],
+	                                                          h->a4[A4_VADV], h->pos, h->vel, h->ctl);
+	h->launches++;
+}
+
+void df_phase(SphHandle *h, int phase, cudaStream_t st) {
+	switch (phase) {
+	case SPH_PH_DF_INITIALIZE: build_lists(h, st); break;
+	case SPH_PH_DF_DIVERGENCE: df_divergence(h, st); break;
+	case SPH_PH_DF_EXT_FORCE_VEL_ADV: df_ext_force_vel_adv(h, st); break;
+	case SPH_PH_DF_DENSITY: df_density(h, st); break;
+	case SPH_PH_DF_POSITION: df_position(h, st); break;
+	default: break;
+	}
+}
+
+void df_step(SphHandle *h, cudaStream_t st) {
+	build_lists(h, st);
+	df_divergence(h, st);
+	df_ext_force_vel_adv(h, st);
+	df_density(h, st);
+	df_position(h, st);
+}
+
+// placeholders filled in by the other solver sections below
+void wc_phase(SphHandle *h, int phase, cudaStream_t st);
+void pc_phase(SphHandle *h, int phase, cudaStream_t st);
+void pc_precompute(SphHandle *h, cudaStream_t st);
+void ii_phase(SphHandle *h, int phase, cudaStream_t st);
+
+} // namespace SPH_NS
+
+#include "sph_sweeps_other.cuh"

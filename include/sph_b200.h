@@ -1,0 +1,201 @@
+/*
+ * sph_b200.h -- C-ABI of the B200-native SPH hot path (drop-in for CFD_Taichi's
+ * ParticleSystem / *_solver kernels).  Plain pointers and sizes only; no torch types.
+ *
+ * The reference has no FFI: its "operator API" is the set of @ti.kernel methods that main.py
+ * reaches through ParticleSystem / solver_base / <name>_solver.step().  Each entry point below
+ * cites the reference method(s) it replaces (file:line in the upstream repository).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SPH_E* code on failure; the message is
+ *     available from sph_last_error().  No exceptions cross the boundary.
+ *   - all work is asynchronous on the `stream` argument (a cudaStream_t passed as void*);
+ *     only sph_read_stats, sph_upload_* / sph_download_* with host buffers, and sph_create /
+ *     sph_destroy synchronise.
+ *   - one host thread per handle (as in the reference: one Python thread drives main.py:95-206).
+ *   - the caller (Python/torch) owns the particle state buffers bound with sph_bind; the
+ *     library owns scratch only (cell arrays, neighbour lists, sorted work buffers).
+ */
+#ifndef SPH_B200_H
+#define SPH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH_OK 0
+#define SPH_EINVAL (-1)
+#define SPH_ECUDA (-2)
+#define SPH_ENOMEM (-3)
+#define SPH_ESTATE (-4)
+#define SPH_ENOTBOUND (-5)
+
+/* solver ids (main.py:65-68 resolves "<name>_solver") */
+#define SPH_SOLVER_WCSPH 0
+#define SPH_SOLVER_PCISPH 1
+#define SPH_SOLVER_IISPH 2
+#define SPH_SOLVER_DFSPH 3
+
+/* Mirrors the JSON blocks read by ParticleSystem.__init__ (PS:31-127), solver_base.__init__
+ * (SB:7-39) and rigid_solver.__init__ (RS:6-31).  Host-side derived numbers (particle counts,
+ * grid_num) are computed by the Python mirror with the reference's own fp64 formulas and
+ * passed in, exactly as ParticleSystem does before it allocates its fields. */
+typedef struct SphConfig {
+	double box_min[3];
+	double box_max[3];
+	double particle_radius;   /* scene.particle_radius */
+	double gravity;           /* scene.gravity */
+	double delta_time;        /* solver.delta_time */
+	int32_t boundary_handle;  /* solver.boundary_handle (1 = Akinci particles, 0 = box clamp) */
+	int32_t fs_couple;        /* solver.fs_couple */
+	int32_t solver;           /* SPH_SOLVER_* */
+	int32_t n_fluid;          /* PS:85-86 particle_num */
+	int32_t n_boundary;       /* PS:129-137 */
+	int32_t n_rigid;          /* voxel points of solid.mesh (0 = no rigid body) */
+	int32_t active_rigid;     /* solid.active */
+	int32_t grid_num[3];      /* PS:100-101 */
+	int32_t max_neighbors;          /* capacity of the per-step fluid neighbour list (0 = default) */
+	int32_t max_boundary_neighbors; /* capacity of the boundary neighbour list (0 = default) */
+	int32_t strict;           /* 1 = strict-fp32 kernels (no FMA, IEEE div/sqrt, reference operation
+	                             order: bit-exact against the oracle); 0 = fast kernels (same
+	                             neighbour sets, results within 1e-5) */
+	int32_t n_ghost_capacity; /* multi-GPU: room for ghost fluid particles after the owned ones */
+	double rigid_rho;         /* solid.rho_0 */
+	int32_t use_graph;        /* 1 = run the solver loops as CUDA-graph WHILE nodes (no host sync) */
+	int32_t reserved;
+} SphConfig;
+
+/* Fields that can be bound (caller-owned device memory) or fetched (library scratch copied
+ * into caller memory in ORIGINAL particle order). */
+enum SphField {
+	/* bindable state, float4 per particle */
+	SPH_F_FLUID_POS = 0,   /* xyz = fluid_particles.pos (PS:6-20), w unused */
+	SPH_F_FLUID_VEL = 1,   /* xyz = fluid_particles.vel, w = solver-persistent scalar
+	                          (DFSPH warm_start_k DF:17, IISPH p_past II:21) */
+	SPH_F_BOUNDARY_POS = 2,/* xyz = boundary_particles.pos, w = boundary_particles.volume */
+	SPH_F_RIGID_POS = 3,   /* xyz = rigid_particles.pos, w = rigid_particles.volume */
+	SPH_F_RIGID_VEL = 4,   /* xyz = rigid_particles.vel, w = rigid_particles.mass */
+	SPH_F_RIGID_FORCE = 5, /* xyz = rigid_particles.force */
+	SPH_F_FLUID_ACC = 6,   /* xyz = fluid_particles.acc (WCSPH only) */
+	/* fetchable per-fluid-particle results (float unless noted), original order */
+	SPH_F_RHO = 16, SPH_F_ALPHA, SPH_F_RHO_DERIVATIVE, SPH_F_RHO_ADV, SPH_F_VEL_ADV /*float4*/,
+	SPH_F_CELL1D /*int32*/, SPH_F_NEIGHBOR_COUNT /*int32*/, SPH_F_BOUNDARY_NEIGHBOR_COUNT /*int32*/,
+	SPH_F_PRESSURE, SPH_F_FORCE_A /*float4 generic force/acc buffer*/, SPH_F_FORCE_B /*float4*/,
+	SPH_F_SCALAR_A, SPH_F_SCALAR_B, SPH_F_SCALAR_C, SPH_F_VEC_A /*float4*/, SPH_F_VEC_B /*float4*/,
+	/* grid arrays (int32), fetched verbatim */
+	SPH_F_CELL_START = 64,   /* G+1 exclusive prefix sums == per-cell list offsets */
+	SPH_F_SORTED_INDEX,      /* N: original index of the particle in sorted slot s */
+	SPH_F_BOUNDARY_CELL_START,
+	SPH_F_BOUNDARY_SORTED_INDEX
+};
+
+/* Phases, for callers that drive a solver piecewise like the reference's public methods. */
+enum SphPhase {
+	SPH_PH_BUILD_GRID = 0,        /* PS:368-407 reset_grid + update_grid (+ reorder + lists) */
+	/* DFSPH */
+	SPH_PH_DF_INITIALIZE = 10,    /* DF:423-426 */
+	SPH_PH_DF_DIVERGENCE,         /* DF:393-416 correct_divergence_error */
+	SPH_PH_DF_EXT_FORCE_VEL_ADV,  /* DF:91-122 compute_all_ext_force + compute_all_vel_adv */
+	SPH_PH_DF_DENSITY,            /* DF:221-233 correct_density_error */
+	SPH_PH_DF_POSITION,           /* DF:235-250 compute_all_position */
+	/* WCSPH */
+	SPH_PH_WC_PRESSURE = 20,      /* WC:32-38 */
+	SPH_PH_WC_KINEMATIC,          /* WC:40-63 */
+	/* PCISPH */
+	SPH_PH_PC_EXT_FORCE = 30,     /* PC:220-226 */
+	SPH_PH_PC_ITERATION,          /* PC:47-70 */
+	SPH_PH_PC_INTEGRATION,        /* PC:200-218 */
+	/* IISPH */
+	SPH_PH_II_PREDICT_ADVECTION = 40, /* II:35-75 */
+	SPH_PH_II_PRESSURE_SOLVE,         /* II:78-100 */
+	SPH_PH_II_INTEGRATION,            /* II:184-206 */
+	/* commit the sorted work buffers back into the bound original-order state */
+	SPH_PH_WRITEBACK = 90
+};
+
+/* Read by sph_read_stats (the only synchronising query; replaces the kernel return values
+ * DF:125,253 PC:122 II:103 and the prints DF:233,416 PC:70 II:96). */
+typedef struct SphStats {
+	float delta_time;          /* solver.delta_time[None] after the step (DFSPH: adaptive, DF:112-119) */
+	float ps_delta_time;       /* ps.delta_time[None] (DF:119) */
+	int32_t simulate_cnt;      /* SB:137 */
+	int32_t error_flags;       /* bit0 particle outside grid (PS:393-395), bit1 neighbour list overflow,
+	                              bit2 boundary list overflow, bit3 density loop hit the safety cap,
+	                              bit4 non-finite value */
+	int32_t div_iters;         /* DF:416 */
+	float div_first_err, div_err;
+	int32_t den_iters;         /* DF:233 */
+	float den_err;
+	int32_t pc_iters;          /* PC:70 */
+	float pc_err;
+	int32_t ii_iters;          /* II:96 */
+	float ii_residual;
+	int32_t max_neighbors_seen, max_boundary_neighbors_seen;
+	float pc_delta;            /* PC:45 */
+	int32_t pc_max_index;      /* PS:409-422 */
+	int32_t kernel_launches;   /* launches issued by the library since creation */
+	int32_t reserved[3];
+} SphStats;
+
+typedef struct SphHandle SphHandle;
+
+int sph_create(const SphConfig *cfg, int device, SphHandle **out);
+int sph_destroy(SphHandle *h);
+const char *sph_last_error(const SphHandle *h); /* h may be NULL: message of the failed sph_create */
+int sph_abi_version(void);
+
+/* Borrow caller-owned device memory for a state field (float4 * n). */
+int sph_bind(SphHandle *h, int field, void *dev_ptr, size_t n);
+
+/* One-time static boundary set-up: boundary grid (PS:322-335) and Akinci volumes (PS:309-320).
+ * Writes the volume into SPH_F_BOUNDARY_POS.w. */
+int sph_init_boundary(SphHandle *h, void *stream);
+/* One-time rigid set-up: volumes/masses (PS:249-263).  Mass properties (PS:265-291) are O(1)
+ * host algebra on the fetched arrays and stay in the Python mirror. */
+int sph_init_rigid(SphHandle *h, void *stream);
+
+/* PCISPH pre_compute (PC:28-45): delta from the "max neighbour" particle. */
+int sph_pcisph_precompute(SphHandle *h, void *stream);
+
+/* One full solver.step() (SB:136-143 + <name>_solver.step), n_substeps times. */
+int sph_step(SphHandle *h, int n_substeps, void *stream);
+/* One phase (see enum SphPhase). */
+int sph_phase(SphHandle *h, int phase, void *stream);
+
+/* Rigid body: force/torque reduction over rigid particles (RS:35-38, 121-123); writes
+ * out6[0..2] = sum of forces, out6[3..5] = torque about `centroid`, then zeroes the forces. */
+int sph_rigid_reduce(SphHandle *h, const float centroid[3], float *dev_out6, void *stream);
+/* Rigid body: rotate about centroid with R (row-major 3x3) then translate (RS:135-136, 98-99)
+ * and refresh the per-particle vel/omega/alpha/acc used by the coupling terms. */
+int sph_rigid_transform(SphHandle *h, const float centroid[3], const float R[9], const float disp[3],
+                        const float vel[3], const float omega[3], const float alpha[3],
+                        const float acc[3], void *stream);
+/* Rigid wall contact scan (RS:53-76): per-axis displacement clamp and contact accumulation. */
+int sph_rigid_contacts(SphHandle *h, const float vel[3], const float omega[3], const float centroid[3],
+                       const float disp[3], float *dev_out16, void *stream);
+
+int sph_set_delta_time(SphHandle *h, float dt, void *stream);
+
+/* Copy a result field into caller device memory, original particle order. */
+int sph_fetch(SphHandle *h, int field, void *dev_out, size_t n, void *stream);
+
+/* Host-buffer entry points (the e2e path): pinned or pageable host memory, float4 * n. */
+int sph_upload_state(SphHandle *h, const float *host_pos4, const float *host_vel4, void *stream);
+int sph_download_state(SphHandle *h, float *host_pos4, float *host_vel4, void *stream);
+
+int sph_read_stats(SphHandle *h, SphStats *out);
+
+/* Multi-GPU slab support (no collectives inside the library; NCCL plumbing is the caller's):
+ * pack the owned particles whose x-cell column lies in [col_lo, col_hi) into a contiguous
+ * float4 buffer pair, and append received ghost particles behind the owned ones. */
+int sph_pack_columns(SphHandle *h, int col_lo, int col_hi, float *dev_pos4, float *dev_vel4,
+                     int32_t *dev_count, int capacity, void *stream);
+int sph_set_counts(SphHandle *h, int n_owned, int n_ghost);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
