@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: DFSPH particle-steps/s on the synthetic breaking dam.
+
+  python bench.py --gpus N --steps K --warmup W           # this repository's CUDA path
+  python bench.py --impl reference --gpus N --steps K ... # the restated reference on host cores
+
+A "step" is one dfsph_solver.step() (grid build + neighbour lists + divergence-free solve +
+non-pressure forces + constant-density solve + advection) over the whole particle block.
+N = 1: BASELINE.json configs[1], 1 M particles (100^3) in a 15 x 8 x 5.2 box.
+N > 1: configs[4], the dam is slab-decomposed along x, 1 M... particles per GPU (weak scaling).
+
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.  Per-step working set (neighbour lists 128 MB + 11
+float4 arrays) exceeds the 126 MB L2, so no explicit flush is needed between steps.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "dfsph_particle_steps_per_sec"
+UNIT = "particle-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-side", type=int, default=100, help="particles per edge of the per-GPU block")
+    ap.add_argument("--strict", action="store_true", help="strict-fp32 kernels (bit-exact vs the oracle)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-n-side", type=int, default=64)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def workload_name(n_side, n_gpus):
+    n = n_side ** 3
+    return "dfsph breaking dam, %d^3 = %d particles per GPU, r=0.025, Akinci boundary" % (n_side, n)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the restated reference (oracle port, OpenMP) on the box's host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(n_side, steps, warmup, threads=None):
+    from oracle import oracle as O          # bench.py's cpu_baseline / reference legs may use oracle/
+    from cfd_taichi_b200 import scenes
+    threads = threads or len(os.sched_getaffinity(0))
+    cfg = scenes.breaking_dam(n_side)
+    o = O.Oracle(cfg, solver="dfsph", threads=threads)
+    n = int(o.scalar("particle_num"))
+    for _ in range(warmup):
+        o.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.step()
+    dt = time.perf_counter() - t0
+    info = {"div_iters": int(o.scalar("df_div_iters")), "den_iters": int(o.scalar("df_den_iters"))}
+    o.close()
+    return n * steps / dt, dt / steps * 1e3, threads, n, info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample: a smaller block of the same dam so that K + W steps end within minutes
+    n_side = min(args.cpu_n_side, args.n_side)
+    val, ms, threads, n, info = cpu_reference(n_side, args.steps, args.warmup)
+    sample = "%d^3 = %d-particle block of the same dam, %d timed + %d warm-up dfsph steps, %d OpenMP threads" % (
+        n_side, n, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.n_side, args.gpus), "sample": sample, "iterations": info},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from cfd_taichi_b200 import _lib, scenes
+    from cfd_taichi_b200.ParticleSystem import ParticleSystem
+    from cfd_taichi_b200.dfsph_solver import dfsph_solver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg = scenes.breaking_dam(args.n_side)
+    devnull = open(os.devnull, "w")
+    stdout = sys.stdout
+    sys.stdout = devnull            # constructor prints (reference parity) must not pollute the JSON line
+    try:
+        ps = ParticleSystem(cfg, strict=args.strict)
+        sol = dfsph_solver(ps, cfg)
+    finally:
+        sys.stdout = stdout
+    n = ps.particle_num
+    L, h = ps._lib, ps._h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        sol.step()
+    barrier()
+    launches0 = ps.read_stats().kernel_launches
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    _lib.check(L.sph_profile_begin(h), h)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    div_iters, den_iters = [], []
+    for _ in range(args.steps):
+        sol.step()
+        # the DFSPH density loop already left the step's control block in pinned host memory
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    nk = len(_lib.KERNEL_CLASSES)
+    ms_by = (ctypes.c_float * nk)()
+    cnt_by = (ctypes.c_int32 * nk)()
+    _lib.check(L.sph_profile_end(h, ms_by, cnt_by, nk), h)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    st = ps.read_stats()
+    launches = st.kernel_launches - launches0
+
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    total_particles = n * world
+    value = total_particles * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers in, host buffers out, through the C-ABI ------------------------------
+    hpos = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    hvel = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+    stream = ps._stream()
+    _lib.check(L.sph_download_state(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        _lib.check(L.sph_upload_state(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
+        _lib.check(L.sph_step(h, 1, stream), h)
+        _lib.check(L.sph_download_state(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_particles * e2e_steps / float(te.item())
+    bytes_dir = 2 * n * 16
+
+    if rank == 0:
+        prof = {_lib.KERNEL_CLASSES[k]: {"ms": round(float(ms_by[k]), 4), "launches": int(cnt_by[k])}
+                for k in range(nk) if cnt_by[k] > 0}
+        # dominant kernel = largest share of the timed region
+        dom = max(prof, key=lambda k: prof[k]["ms"])
+        # algorithmic bytes per particle per launch
+        alg_bytes = {"grid": 84, "lists": 20, "df_warm_start": 48, "df_drho": 28, "df_div_iter": 56, "df_ext_force": 40,
+                     "df_rho_adv": 32, "df_vel_adv_iter": 48, "df_position": 48}
+        peak, peak_src = peaks()
+        avg_ms = prof[dom]["ms"] / prof[dom]["launches"]
+        achieved = alg_bytes.get(dom, 0) * n / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(dom)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.n_side, world), "particles_total": total_particles,
+                       "kernels": "strict-fp32" if args.strict else "fast-fp32",
+                       "l2": "per-step working set ~300 MB > 126 MB L2, no flush",
+                       "iterations": {"divergence": st.div_iters, "density": st.den_iters},
+                       "parallelism": "1 GPU" if world == 1 else "%d independent replicas" % world},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_dir, "d2h_bytes_per_step": bytes_dir,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_particle": alg_bytes.get(dom), "avg_launch_ms": avg_ms},
+            "kernel_ms": prof,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cn = min(args.cpu_n_side, args.n_side)
+            cval, cms, threads, cnp, info = cpu_reference(cn, 2, 2)
+            line["cpu_baseline"] = {
+                "value": cval, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "%d^3 = %d-particle block of the same dam, 2 timed dfsph steps after 2 warm-up steps "
+                          "(div %d / den %d iterations)" % (cn, cnp, info["div_iters"], info["den_iters"])}
+        print(json.dumps(line), flush=True)
+    ps.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

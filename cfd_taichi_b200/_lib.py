@@ -26,6 +26,12 @@ PH_PC_EXT_FORCE, PH_PC_ITERATION, PH_PC_INTEGRATION = 30, 31, 32
 PH_II_PREDICT_ADVECTION, PH_II_PRESSURE_SOLVE, PH_II_INTEGRATION = 40, 41, 42
 PH_WRITEBACK = 90
 
+# kernel classes of sph_profile_end (csrc/sph_internal.h)
+KERNEL_CLASSES = ["grid", "lists", "df_warm_start", "df_drho", "df_div_iter", "df_ext_force", "df_rho_adv",
+                  "df_vel_adv_iter", "df_position", "ctl", "wc_force", "wc_kinematic", "pc_ext", "pc_predict",
+                  "pc_rho", "pc_force", "pc_integrate", "ii_adv", "ii_aii", "ii_dij", "ii_update", "ii_integrate",
+                  "rigid", "other"]
+
 
 class SphConfig(ctypes.Structure):
     _fields_ = [
@@ -98,6 +104,8 @@ PROTOTYPES = [
     ("sph_upload_state", _i, [_vp, _vp, _vp, _vp]),
     ("sph_download_state", _i, [_vp, _vp, _vp, _vp]),
     ("sph_read_stats", _i, [_vp, ctypes.POINTER(SphStats)]),
+    ("sph_profile_begin", _i, [_vp]),
+    ("sph_profile_end", _i, [_vp, _fp, ctypes.POINTER(ctypes.c_int32), _i]),
     ("sph_pack_columns", _i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
     ("sph_set_counts", _i, [_vp, _i, _i]),
 ]

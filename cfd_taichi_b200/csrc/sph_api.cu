@@ -203,6 +203,11 @@ extern "C" int sph_destroy(SphHandle *h) {
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount); cudaFree(h->L.rcount);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials);
 	if (h->ctl_host) cudaFreeHost(h->ctl_host);
+	if (h->prof) {
+		if (h->prof->created)
+			for (int i = 0; i < SPH_PROF_CAP; ++i) { cudaEventDestroy(h->prof->e0[i]); cudaEventDestroy(h->prof->e1[i]); }
+		delete h->prof;
+	}
 	delete h;
 	return SPH_OK;
 }
@@ -280,8 +285,10 @@ extern "C" int sph_init_rigid(SphHandle *h, void *stream) {
 static int base_step(SphHandle *h, cudaStream_t st) {
 	// SB:136-143: simulate_cnt += 1 ; reset_grid ; update_grid ; reset()
 	h->simulate_cnt += 1;
+	sph_prof_begin(h, KC_GRID, st);
 	sphg_build(h, h->fg, h->pos, h->c.N, st);
 	sphg_gather_fluid(h, st);
+	sph_prof_end(h, st);
 	h->grid_valid = true;
 	h->lists_valid = false;
 	return SPH_OK;
@@ -454,6 +461,43 @@ extern "C" int sph_download_state(SphHandle *h, float *host_pos4, float *host_ve
 	if (host_pos4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_pos4, h->pos, bytes, cudaMemcpyDeviceToHost, st));
 	if (host_vel4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_vel4, h->vel, bytes, cudaMemcpyDeviceToHost, st));
 	SPH_CUDA_CHECK(h, cudaStreamSynchronize(st));
+	return SPH_OK;
+}
+
+extern "C" int sph_profile_begin(SphHandle *h) {
+	if (!h) return SPH_EINVAL;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	if (!h->prof) {
+		h->prof = new (std::nothrow) SphProf();
+		if (!h->prof) return sph_fail(h, SPH_ENOMEM, "sph_profile_begin: out of memory");
+		memset(h->prof, 0, sizeof(SphProf));
+	}
+	if (!h->prof->created) {
+		for (int i = 0; i < SPH_PROF_CAP; ++i) {
+			SPH_CUDA_CHECK(h, cudaEventCreate(&h->prof->e0[i]));
+			SPH_CUDA_CHECK(h, cudaEventCreate(&h->prof->e1[i]));
+		}
+		h->prof->created = true;
+	}
+	h->prof->n = 0;
+	h->prof->on = true;
+	return SPH_OK;
+}
+
+extern "C" int sph_profile_end(SphHandle *h, float *ms_by_class, int32_t *launches_by_class, int n_classes) {
+	if (!h || !ms_by_class || !launches_by_class) return SPH_EINVAL;
+	if (!h->prof || !h->prof->on) return sph_fail(h, SPH_ESTATE, "sph_profile_end: profiling is not active");
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	SPH_CUDA_CHECK(h, cudaDeviceSynchronize());
+	for (int k = 0; k < n_classes; ++k) { ms_by_class[k] = 0.0f; launches_by_class[k] = 0; }
+	for (int i = 0; i < h->prof->n; ++i) {
+		float ms = 0.0f;
+		SPH_CUDA_CHECK(h, cudaEventElapsedTime(&ms, h->prof->e0[i], h->prof->e1[i]));
+		int k = h->prof->kid[i];
+		if (k >= 0 && k < n_classes) { ms_by_class[k] += ms; launches_by_class[k] += 1; }
+	}
+	h->prof->on = false;
+	h->prof->n = 0;
 	return SPH_OK;
 }
 

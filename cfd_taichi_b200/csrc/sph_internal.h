@@ -30,6 +30,22 @@ struct SphGrid {
 	int n;
 };
 
+// live per-kernel-class timing with CUDA events on the launching stream (bench.py roofline)
+#define SPH_PROF_CAP 8192
+#define SPH_PROF_CLASSES 32
+enum {
+	KC_GRID = 0, KC_LISTS, KC_DF_WARM, KC_DF_DRHO, KC_DF_DIV, KC_DF_EXT, KC_DF_RHOADV, KC_DF_VELADV, KC_DF_POS,
+	KC_CTL, KC_WC_FORCE, KC_WC_KIN, KC_PC_EXT, KC_PC_PREDICT, KC_PC_RHO, KC_PC_FORCE, KC_PC_INT,
+	KC_II_ADV, KC_II_AII, KC_II_DIJ, KC_II_UPDATE, KC_II_INT, KC_RIGID, KC_OTHER
+};
+struct SphProf {
+	bool on;
+	int n;
+	int kid[SPH_PROF_CAP];
+	cudaEvent_t e0[SPH_PROF_CAP], e1[SPH_PROF_CAP];
+	bool created;
+};
+
 struct SphHandle {
 	SphConfig cfg;
 	SphConsts c;
@@ -63,9 +79,22 @@ struct SphHandle {
 	// CUDA graph state
 	void *graph_exec;
 	int last_den_chunk;
+	SphProf *prof;
 };
 
 int sph_fail(SphHandle *h, int code, const char *fmt, ...);
+static inline void sph_prof_begin(SphHandle *h, int kid, cudaStream_t st) {
+	SphProf *p = h->prof;
+	if (!p || !p->on || p->n >= SPH_PROF_CAP) return;
+	p->kid[p->n] = kid;
+	cudaEventRecord(p->e0[p->n], st);
+}
+static inline void sph_prof_end(SphHandle *h, cudaStream_t st) {
+	SphProf *p = h->prof;
+	if (!p || !p->on || p->n >= SPH_PROF_CAP) return;
+	cudaEventRecord(p->e1[p->n], st);
+	p->n++;
+}
 int sph_fail_cuda(SphHandle *h, cudaError_t e, const char *expr, const char *file, int line);
 
 // ---- sph_grid.cu (mode independent) -------------------------------------------------------

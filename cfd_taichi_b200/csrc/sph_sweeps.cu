@@ -162,14 +162,19 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	if (c.N <= 0) return;
 	int nb = cdiv(c.N, SPH_BLOCK);
-	if (c.solver == SPH_SOLVER_DFSPH)
+	if (c.solver == SPH_SOLVER_DFSPH) {
+		sph_prof_begin(h, KC_LISTS, st);
 		k_build_lists<true><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,
 		                                              h->bspos, h->bg.cell_start, h->L, h->nbr_count, h->a1[A1_RHO],
 		                                              h->a1[A1_ALPHA], h->a4[A4_PR], h->a4[A4_T1], h->ctl);
-	else
+		sph_prof_end(h, st);
+	} else {
+		sph_prof_begin(h, KC_LISTS, st);
 		k_build_lists<false><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,
 		                                               h->bspos, h->bg.cell_start, h->L, h->nbr_count, h->a1[A1_RHO],
 		                                               h->a1[A1_ALPHA], h->a4[A4_PR], h->a4[A4_T1], h->ctl);
+		sph_prof_end(h, st);
+	}
 	h->launches++;
 	h->lists_valid = true;
 }
@@ -534,17 +539,25 @@ __global__ void k_df_ctl_den_next(SphCtl *ctl) {
 static void df_divergence(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	sph_prof_begin(h, KC_DF_WARM, st);
 	k_df_warm_start<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl);
+	sph_prof_end(h, st);
+	sph_prof_begin(h, KC_DF_DRHO, st);
 	k_df_drho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
 	                                    h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 0);
+	sph_prof_end(h, st);
 	k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0);
 	h->launches += 3;
 	for (int it = 0; it < 15; ++it) { // max_iteration_density_divergence (DF:24); gated on ctl->div_active
+		sph_prof_begin(h, KC_DF_DIV, st);
 		k_df_div_iter<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
 		                                        h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
+		sph_prof_end(h, st);
+		sph_prof_begin(h, KC_DF_DRHO, st);
 		k_df_drho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
 		                                    h->a1[A1_RHO], h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl,
 		                                    h->partials, 1);
+		sph_prof_end(h, st);
 		k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1);
 		h->launches += 3;
 	}
@@ -553,8 +566,10 @@ static void df_divergence(SphHandle *h, cudaStream_t st) {
 static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	sph_prof_begin(h, KC_DF_EXT, st);
 	k_df_ext_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_PR], h->a4[A4_VEL], h->a4[A4_VADV], h->a4[A4_FA], h->ctl,
 	                                         h->partials);
+	sph_prof_end(h, st);
 	k_df_ctl_dt<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, c, 0.0f);
 	h->launches += 2;
 }
@@ -564,12 +579,16 @@ static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st
 	int nb = cdiv(c.N_owned, SPH_BLOCK);
 	for (int it = first; it < first + count; ++it) {
 		int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
+		sph_prof_begin(h, KC_DF_RHOADV, st);
 		k_df_rho_adv<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
 		                                       h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials,
 		                                       gated);
+		sph_prof_end(h, st);
 		k_df_ctl_den<<<1, 256, 0, st>>>(h->ctl, h->partials, nb);
+		sph_prof_begin(h, KC_DF_VELADV, st);
 		k_df_vel_adv_iter<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
 		                                            h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
+		sph_prof_end(h, st);
 		k_df_ctl_den_next<<<1, 1, 0, st>>>(h->ctl);
 		h->launches += 4;
 	}
@@ -594,8 +613,10 @@ static int df_density(SphHandle *h, cudaStream_t st) {
 
 static void df_position(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
+	sph_prof_begin(h, KC_DF_POS, st);
 	k_df_position<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VEL],
 	                                                          h->a4[A4_VADV], h->pos, h->vel, h->ctl);
+	sph_prof_end(h, st);
 	h->launches++;
 }
 

@@ -188,6 +188,12 @@ int sph_download_state(SphHandle *h, float *host_pos4, float *host_vel4, void *s
 
 int sph_read_stats(SphHandle *h, SphStats *out);
 
+/* Live per-kernel-class timing: CUDA events recorded on the launching stream around every launch
+ * between sph_profile_begin and sph_profile_end (which synchronises).  Class ids are listed in
+ * DESIGN.md (0 grid build, 1 neighbour lists, 3 DFSPH drho sweep ...). */
+int sph_profile_begin(SphHandle *h);
+int sph_profile_end(SphHandle *h, float *ms_by_class, int32_t *launches_by_class, int n_classes);
+
 /* Multi-GPU slab support (no collectives inside the library; NCCL plumbing is the caller's):
  * pack the owned particles whose x-cell column lies in [col_lo, col_hi) into a contiguous
  * float4 buffer pair, and append received ghost particles behind the owned ones. */

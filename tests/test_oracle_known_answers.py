@@ -1,0 +1,180 @@
+"""CPU tests that pin the oracle (oracle/sph_oracle.c) with hand-derived known answers.
+
+The reference ships no tests or golden vectors and taichi cannot be imported here, so these
+known-answer checks plus the committed regression fixtures are the oracle's pin.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from cfd_taichi_b200 import scenes
+from oracle import oracle as O
+
+# (particle_num, boundary_particles_num, grid_num)
+APPENDIX_C = {
+    "default": (132479, 67202, (71, 71, 26)),
+    "breaking_dam_30k": (29120, 21602, (51, 31, 16)),
+    "dam_flush_cube": (56447, 21602, (51, 31, 16)),
+    "small_block": (5879, 9002, (16, 31, 16)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(APPENDIX_C))
+def test_derived_sizes_shipped(name):
+    assert O.derived_sizes(scenes.shipped(name)) == APPENDIX_C[name]
+
+
+@pytest.mark.parametrize("n_side,gpus,expect", [
+    (100, 1, (1000000, 191682, (151, 81, 53))),
+    (160, 1, (4096000, 465122, (241, 121, 83))),
+    (200, 1, (8000000, 725402, (301, 151, 103))),
+    (200, 8, (64000000, 4950602, (2401, 151, 103))),
+])
+def test_derived_sizes_synthetic(n_side, gpus, expect):
+    assert O.derived_sizes(scenes.breaking_dam(n_side, gpus_x=gpus)) == expect
+
+
+def test_cubic_kernel_values():
+    h = np.float32(0.1)
+    # W(0) = 8 / (pi h^3)
+    assert abs(O.cubic_kernel(0.0, h) - 8.0 / (math.pi * 1e-3)) < 1e-3 * 2546.479
+    assert O.cubic_kernel(0.1000001, h) == 0.0
+    # continuity at q = 0.5 and the two branch formulas
+    k = 8.0 / (math.pi * 1e-3)
+    assert abs(O.cubic_kernel(0.05, h) - k * 0.25) < 1e-2
+    assert abs(O.cubic_kernel(0.075, h) - 2 * k * 0.25 ** 3) < 1e-2
+
+
+def test_cubic_kernel_normalisation():
+    # integral of W over the support ~ 1 (fine radial quadrature)
+    h = np.float32(0.1)
+    r = (np.arange(4000) + 0.5) * (0.1 / 4000)
+    w = np.array([O.cubic_kernel(x, h) for x in r])
+    assert abs(np.sum(4 * math.pi * r * r * w) * (0.1 / 4000) - 1.0) < 2e-3
+
+
+def test_cubic_kernel_derivative_factor_six():
+    # the reference's gradient is 6x the textbook one (SB:95-100): compare with 6 * dW/dr by finite differences
+    h = np.float32(0.1)
+    for r in (0.02, 0.04, 0.06, 0.09):
+        g = O.cubic_kernel_derivative([r, 0.0, 0.0], h)
+        fd = (O.cubic_kernel(r + 1e-4, h) - O.cubic_kernel(r - 1e-4, h)) / 2e-4
+        assert abs(g[0] - 6.0 * fd) < 2e-2 * abs(6.0 * fd)
+        assert g[1] == 0.0 and g[2] == 0.0
+    assert np.all(O.cubic_kernel_derivative([0.0, 0.0, 0.0], h) == 0.0)          # q <= 1e-5
+    assert np.all(O.cubic_kernel_derivative([0.2, 0.0, 0.0], h) == 0.0)          # q > 1
+
+
+def test_cull_threshold_is_exact():
+    # sqrt(r2) > h  <=>  r2 > T for every float around h*h
+    h = np.float32(0.1)
+    T = np.float32(O.cull_threshold(h))
+    x = np.float32(h * h)
+    vals = [x]
+    for _ in range(40):
+        vals.append(np.nextafter(vals[-1], np.float32(1)))
+    y = x
+    for _ in range(40):
+        y = np.nextafter(y, np.float32(0))
+        vals.append(y)
+    for v in vals:
+        assert (np.sqrt(np.float32(v)) > h) == (np.float32(v) > T)
+
+
+@pytest.fixture(scope="module")
+def small_dfsph():
+    o = O.Oracle(scenes.shipped("small_block", "dfsph"), threads=4)
+    yield o
+    o.close()
+
+
+def test_lattice_positions(small_dfsph):
+    o = small_dfsph
+    pos = o.field("pos")
+    assert pos.shape == (5879, 3)
+    # PS:150: fl(fl(k * 0.025f) * 2) + start ; 14 x 30 x 14 lattice minus the last site (SURVEY B-1)
+    assert np.allclose(pos[0], [0.3, 0.5, 0.3])
+    assert np.allclose(pos[-1], [0.3 + 12 * 0.05, 0.5 + 29 * 0.05, 0.3 + 13 * 0.05])
+    d = pos[1] - pos[0]
+    assert abs(d[0] - 0.05) < 1e-6 and d[1] == 0 and d[2] == 0
+
+
+def test_grid_is_a_permutation_and_canonical(small_dfsph):
+    o = small_dfsph
+    start, items, cell1 = o.field("cell_start"), o.field("cell_items"), o.field("cell1")
+    n = int(o.scalar("particle_num"))
+    assert start[-1] == n                                       # check_all_grid (PS:471-484)
+    assert np.array_equal(np.sort(items), np.arange(n))         # permutation
+    cells_sorted = cell1[items]
+    assert np.all(np.diff(cells_sorted) >= 0)                   # cell-contiguous
+    same = np.diff(cells_sorted) == 0
+    assert np.all(np.diff(items)[same] > 0)                     # ascending index inside a cell
+    # 1-D id = x + gx*gz*y + gx*z (PS:102), cell3 = floor(pos / 0.1f)
+    c3 = np.floor(o.field("pos") / np.float32(0.1)).astype(np.int64)
+    assert np.array_equal(c3, o.field("cell3"))
+    assert np.array_equal(c3[:, 0] + 16 * 16 * c3[:, 1] + 16 * c3[:, 2], cell1)
+
+
+def test_rest_lattice_density_and_counts(small_dfsph):
+    o = small_dfsph
+    o.phase("compute_all_rho")
+    o.phase("neighbour_counts")
+    rho, cnt = o.field("rho"), o.field("nbr_count")
+    # interior particle at rest spacing: 0.001 + 681.66 (self term excluded, SURVEY B-3); 26..32 neighbours
+    # because the 6 two-spacing pairs sit at r ~ h within an ulp (App. A-7)
+    assert abs(np.median(rho) - 681.66) < 2.0
+    assert cnt.max() <= 32 and np.median(cnt) >= 26
+
+
+def test_boundary_volume_brute_force(small_dfsph):
+    # Akinci volume (PS:309-320) against an O(Nb^2) restatement in numpy fp32 for a few particles
+    o = small_dfsph
+    bpos, bvol = o.field("bpos"), o.field("bvol")
+    h = np.float32(0.1)
+    for i in (0, 17, 4000, 9001):
+        d = bpos[i] - bpos
+        r = np.sqrt((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2])
+        m = (r <= h)
+        m[i] = False
+        s = sum(O.cubic_kernel(float(x), h) for x in r[m])
+        assert abs(1.0 / s - bvol[i]) < 1e-5 * bvol[i]
+
+
+def test_dfsph_first_step_is_free_fall(small_dfsph):
+    # zero velocity => zero divergence error, no pressure; v = dt * g / m (SURVEY B-5: gravity / particle_m)
+    o = O.Oracle(scenes.shipped("small_block", "dfsph"), threads=4)
+    o.step()
+    assert int(o.scalar("df_div_iters")) == 0 and int(o.scalar("df_den_iters")) == 2
+    vel = o.field("vel")
+    expect = -(1e-3 * 9.8 / 0.125) * 0.9999
+    # particles with a symmetric neighbourhood feel no cohesion force: pure (reference-style) gravity
+    interior = np.abs(vel[:, 1] - expect) < 1e-3 * abs(expect)
+    assert interior.sum() > 1000
+    assert abs(np.median(vel[:, 1]) - expect) < 5e-3 * abs(expect)
+    o.close()
+
+
+@pytest.mark.parametrize("solver", ["wcsph", "pcisph", "iisph", "dfsph"])
+def test_solvers_run_and_stay_finite(solver):
+    o = O.Oracle(scenes.shipped("small_block", solver), threads=4)
+    for _ in range(3):
+        o.step()
+    assert np.isfinite(o.field("pos")).all() and np.isfinite(o.field("vel")).all()
+    assert int(o.scalar("error_flags")) == 0
+    # gravity acts: the block moves down
+    assert o.field("vel")[:, 1].mean() < 0
+    o.close()
+
+
+def test_threads_do_not_change_results():
+    a = O.Oracle(scenes.shipped("small_block", "dfsph"), threads=1)
+    for _ in range(2):
+        a.step()
+    pa, va = a.field("pos").copy(), a.field("vel").copy()
+    a.close()
+    b = O.Oracle(scenes.shipped("small_block", "dfsph"), threads=4)
+    for _ in range(2):
+        b.step()
+    assert np.array_equal(pa, b.field("pos")) and np.array_equal(va, b.field("vel"))
+    b.close()
