@@ -15,7 +15,7 @@ SOLVER_IDS = {"wcsph": 0, "pcisph": 1, "iisph": 2, "dfsph": 3}
 F_FLUID_POS, F_FLUID_VEL, F_BOUNDARY_POS, F_RIGID_POS, F_RIGID_VEL, F_RIGID_FORCE, F_FLUID_ACC = range(7)
 (F_RHO, F_ALPHA, F_RHO_DERIVATIVE, F_RHO_ADV, F_VEL_ADV, F_CELL1D, F_NEIGHBOR_COUNT,
  F_BOUNDARY_NEIGHBOR_COUNT, F_PRESSURE, F_FORCE_A, F_FORCE_B, F_SCALAR_A, F_SCALAR_B, F_SCALAR_C,
- F_VEC_A, F_VEC_B) = range(16, 32)
+ F_VEC_A, F_VEC_B, F_VEC_C) = range(16, 33)
 F_CELL_START, F_SORTED_INDEX, F_BOUNDARY_CELL_START, F_BOUNDARY_SORTED_INDEX = range(64, 68)
 
 # enum SphPhase
@@ -94,6 +94,7 @@ PROTOTYPES = [
     ("sph_init_boundary", _i, [_vp, _vp]),
     ("sph_init_rigid", _i, [_vp, _vp]),
     ("sph_pcisph_precompute", _i, [_vp, _vp]),
+    ("sph_pcisph_delta", _i, [_vp, _i, _vp]),
     ("sph_step", _i, [_vp, _i, _vp]),
     ("sph_phase", _i, [_vp, _i, _vp]),
     ("sph_rigid_reduce", _i, [_vp, _fp, _vp, _vp]),

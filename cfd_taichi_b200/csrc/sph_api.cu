@@ -374,6 +374,18 @@ extern "C" int sph_pcisph_precompute(SphHandle *h, void *stream) {
 	return check_launch(h, "sph_pcisph_precompute");
 }
 
+extern "C" int sph_pcisph_delta(SphHandle *h, int particle_index, void *stream) {
+	int rc = require_state(h);
+	if (rc != SPH_OK) return rc;
+	if (!h->lists_valid) return sph_fail(h, SPH_ESTATE, "sph_pcisph_delta: call sph_pcisph_precompute first");
+	if (particle_index < 0 || particle_index >= h->c.N_owned)
+		return sph_fail(h, SPH_EINVAL, "sph_pcisph_delta: particle index %d out of range", particle_index);
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	if (h->cfg.strict) sph_strict::pc_set_delta(h, particle_index, st); else sph_fast::pc_set_delta(h, particle_index, st);
+	return check_launch(h, "sph_pcisph_delta");
+}
+
 __global__ void k_set_dt(SphCtl *ctl, float dt) {
 	ctl->dt = dt;
 	ctl->dt2 = dt * dt;
@@ -428,6 +440,7 @@ extern "C" int sph_fetch(SphHandle *h, int field, void *dev_out, size_t n, void 
 	case SPH_F_FORCE_B: rc = f4(h->a4[A4_FB]); break;
 	case SPH_F_VEC_A: rc = f4(h->a4[A4_FC]); break;
 	case SPH_F_VEC_B: rc = f4(h->a4[A4_FD]); break;
+	case SPH_F_VEC_C: rc = f4(h->a4[A4_T2]); break;
 	case SPH_F_FLUID_VEL: rc = f4(h->a4[A4_VEL]); break;   // in-step (sorted) velocity, original order
 	case SPH_F_FLUID_POS: rc = f4(h->a4[A4_POS]); break;
 	case SPH_F_CELL1D: rc = raw(h->fg.cell_of, N, sizeof(int)); break;

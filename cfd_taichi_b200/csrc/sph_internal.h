@@ -116,6 +116,7 @@ void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaSt
 	void wc_phase(SphHandle *h, int phase, cudaStream_t st);                                \
 	void pc_phase(SphHandle *h, int phase, cudaStream_t st);                                \
 	void pc_precompute(SphHandle *h, cudaStream_t st);                                      \
+	void pc_set_delta(SphHandle *h, int target, cudaStream_t st);                           \
 	void ii_phase(SphHandle *h, int phase, cudaStream_t st);                                \
 	}
 SPH_SWEEP_API(sph_strict)

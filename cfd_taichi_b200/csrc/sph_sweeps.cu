@@ -643,6 +643,7 @@ void df_step(SphHandle *h, cudaStream_t st) {
 void wc_phase(SphHandle *h, int phase, cudaStream_t st);
 void pc_phase(SphHandle *h, int phase, cudaStream_t st);
 void pc_precompute(SphHandle *h, cudaStream_t st);
+void pc_set_delta(SphHandle *h, int target, cudaStream_t st);
 void ii_phase(SphHandle *h, int phase, cudaStream_t st);
 
 } // namespace SPH_NS

@@ -1,11 +1,704 @@
 // sph_sweeps_other.cuh -- WCSPH / PCISPH / IISPH sweeps (included by sph_sweeps.cu, both modes).
+// Same structure as the DFSPH section: neighbour lists built once per step by k_build_lists,
+// list-walking sweeps with one float4 gather per neighbour and per-neighbour scalars riding in .w.
 #pragma once
 
 namespace SPH_NS {
 
-void wc_phase(SphHandle *h, int phase, cudaStream_t st) { (void)h; (void)phase; (void)st; }
-void pc_phase(SphHandle *h, int phase, cudaStream_t st) { (void)h; (void)phase; (void)st; }
-void pc_precompute(SphHandle *h, cudaStream_t st) { (void)h; (void)st; }
-void ii_phase(SphHandle *h, int phase, cudaStream_t st) { (void)h; (void)phase; (void)st; }
+// shared non-pressure force pass: tension (SB:204-217) + viscosity (SB:170-202) for fluid neighbours.
+// posR.w = rho (written by k_build_lists).
+__device__ __forceinline__ void tension_viscosity(const SphConsts &c, const SphLists &L, int s,
+                                                  const float4 *__restrict__ posR, const float4 *__restrict__ svel,
+                                                  const float4 &pi, const f3 &vi, f3 &tension, f3 &viscosity) {
+	f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
+	SPH_FOR_FLUID(L, c, s, j) {
+		float4 pj = __ldg(&posR[j]);
+		f3 vj = xyz(__ldg(&svel[j]));
+		Pair p = make_pair(pi, pj);
+		ten = ten + (c.tension_coef * cubic_w(p, c)) * p.r; // SB:216
+		f3 v_ij = vi - vj;
+		float shear = dot(v_ij, p.r); // SB:183
+		if (shear < 0.0f) {
+#if SPH_STRICT
+			float q = sqrtf(p.r2);
+			float q2 = q * q;
+#else
+			float q2 = p.r2;
+#endif
+			float nu = c.visc_num / (pi.w + pj.w);                // SB:187
+			float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2); // SB:188
+			visc = visc + (c.neg_m * pi_ij) * cubic_dw(p, c);     // SB:189
+		}
+	}
+	tension = ten * c.m;    // SB:209
+	viscosity = visc * c.m; // SB:175
+}
+
+__device__ __forceinline__ void clamp_box(const SphConsts &c, f3 &x, f3 &v) {
+	float *xp = &x.x, *vp = &v.x;
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		if (xp[k] <= c.clamp_lo[k]) { xp[k] = c.clamp_lo[k]; vp[k] *= -0.5f; }
+		if (xp[k] >= c.clamp_hi[k]) { xp[k] = c.clamp_hi[k]; vp[k] *= -0.5f; }
+	}
+}
+
+// =============================================================================================
+// WCSPH (wcsph_solver.py)
+// =============================================================================================
+
+// WC:65-68, 86-90 solve_p, and the payloads of the force pass: posT1.w = p / rho^2, velR.w = rho
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_wc_pressure(SphConsts c, const float4 *__restrict__ posR, const float4 *__restrict__ svel,
+              float *__restrict__ pressure, float4 *__restrict__ posT1, float4 *__restrict__ velR) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N) return;
+	float4 pr = posR[s];
+	float rho = pr.w;
+	float rho_i = fmaxf(rho, SPH_RHO0);
+	float a = rho_i / SPH_RHO0;
+	float a2 = a * a, a3 = a * a2, a4 = a2 * a2; // ** 7 by squaring
+	float p = 70000.0f * (a3 * a4 - 1.0f);       // WC:89
+	pressure[s] = p;
+	posT1[s] = make_float4(pr.x, pr.y, pr.z, p / (rho * rho));
+	float4 v = svel[s];
+	velR[s] = make_float4(v.x, v.y, v.z, rho);
+}
+
+// WC:70-84 + 92-129 pressure gradient / boundary pressure, fused with viscosity and tension
+// (separate accumulators, so each sum keeps the reference's order).
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_wc_force(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float4 *__restrict__ velR,
+           const float4 *__restrict__ bspos, const float *__restrict__ pressure,
+           float4 *__restrict__ pgrad, float4 *__restrict__ visc_out, float4 *__restrict__ ten_out,
+           float4 *__restrict__ bacc_out) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N_owned) return;
+	float4 pi = posT1[s];
+	float4 vr = velR[s];
+	f3 vi = xyz(vr);
+	float rho_i = vr.w;
+	f3 acc = F3(0.0f, 0.0f, 0.0f), ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
+	SPH_FOR_FLUID(L, c, s, j) {
+		float4 pj = __ldg(&posT1[j]);
+		float4 vj4 = __ldg(&velR[j]);
+		Pair p = make_pair(pi, pj);
+		f3 dw = cubic_dw(p, c);
+		acc = acc - (c.m * (pi.w + pj.w)) * dw;              // WC:116
+		ten = ten + (c.tension_coef * cubic_w(p, c)) * p.r;  // SB:216
+		f3 v_ij = vi - xyz(vj4);
+		float shear = dot(v_ij, p.r);
+		if (shear < 0.0f) {
+#if SPH_STRICT
+			float q = sqrtf(p.r2);
+			float q2 = q * q;
+#else
+			float q2 = p.r2;
+#endif
+			float nu = c.visc_num / (rho_i + vj4.w);
+			float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);
+			visc = visc + (c.neg_m * pi_ij) * dw;
+		}
+	}
+	f3 bacc = F3(0.0f, 0.0f, 0.0f);
+	if (c.boundary_handle == 1) {
+		float p_i = pressure[s];
+		float rho_i_2 = rho_i * rho_i;
+		SPH_FOR_BOUNDARY(L, c, s, j) {
+			float4 pj = __ldg(&bspos[j]);
+			Pair p = make_pair(pi, pj);
+			bacc = bacc - ((pj.w * p_i) / rho_i_2) * cubic_dw(p, c); // WC:99
+		}
+		bacc = bacc * SPH_RHO0; // WC:83
+	}
+	pgrad[s] = F4(acc, 0.0f);
+	visc_out[s] = F4(visc * c.m, 0.0f);
+	ten_out[s] = F4(ten * c.m, 0.0f);
+	bacc_out[s] = F4(bacc, 0.0f);
+}
+
+// WC:40-63 kinematic_phase (+ SB:131-134 reset: acc = gravity) and write-back to original order
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_wc_kinematic(SphConsts c, const int *__restrict__ sorted_id, const float4 *__restrict__ spos,
+               const float4 *__restrict__ svel, const float4 *__restrict__ pgrad, const float4 *__restrict__ visc,
+               const float4 *__restrict__ ten, const float4 *__restrict__ bacc, float4 *__restrict__ pos,
+               float4 *__restrict__ vel, float4 *__restrict__ acc_out, const SphCtl *__restrict__ ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N) return;
+	int i = sorted_id[s];
+	if (i >= c.N_owned) return;
+	float dt = ctl->dt;
+	f3 a = F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
+	f3 add = (xyz(pgrad[s]) + xyz(visc[s])) + xyz(ten[s]);
+	if (c.boundary_handle == 1) add = add + xyz(bacc[s]);
+	a = a + add;                          // WC:44-47
+	float4 v4 = svel[s];
+	f3 v = xyz(v4) + a * dt;              // WC:50
+	v = v * 0.9998f;                      // WC:51
+	f3 x = xyz(spos[s]) + v * dt;         // WC:52
+	if (c.boundary_handle == 0) clamp_box(c, x, v); // WC:54-63 (margin = particle_diameter)
+	pos[i] = F4(x, 0.0f);
+	vel[i] = F4(v, v4.w);
+	if (acc_out) acc_out[i] = F4(a, 0.0f);
+}
+
+void wc_phase(SphHandle *h, int phase, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N_owned, SPH_BLOCK), nba = cdiv(c.N, SPH_BLOCK);
+	if (phase == SPH_PH_WC_PRESSURE) {
+		build_lists(h, st);
+		sph_prof_begin(h, KC_WC_FORCE, st);
+		k_wc_pressure<<<nba, SPH_BLOCK, 0, st>>>(c, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_P], h->a4[A4_T1], h->a4[A4_VADV]);
+		k_wc_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a4[A4_VADV], h->bspos, h->a1[A1_P], h->a4[A4_FA],
+		                                     h->a4[A4_FB], h->a4[A4_FC], h->a4[A4_FD]);
+		sph_prof_end(h, st);
+		h->launches += 2;
+	} else if (phase == SPH_PH_WC_KINEMATIC) {
+		sph_prof_begin(h, KC_WC_KIN, st);
+		k_wc_kinematic<<<nba, SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA],
+		                                          h->a4[A4_FB], h->a4[A4_FC], h->a4[A4_FD], h->pos, h->vel, h->acc, h->ctl);
+		sph_prof_end(h, st);
+		h->launches += 1;
+	}
+}
+
+// =============================================================================================
+// PCISPH (pcisph_solver.py)
+// =============================================================================================
+
+// PC:220-226 compute_ext_force (rho comes from k_build_lists) + PC:228-231 reset + first
+// PC:72-87 predict_vel_pos (press_force = 0)
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_pc_ext_force(SphConsts c, SphLists L, const float4 *__restrict__ posR, const float4 *__restrict__ svel,
+               float4 *__restrict__ ext_force, float4 *__restrict__ press_force, float *__restrict__ press,
+               float4 *__restrict__ posT1) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N) return;
+	float4 pi = posR[s];
+	press[s] = 0.0f;                                 // PC:230
+	press_force[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); // PC:231
+	posT1[s] = make_float4(pi.x, pi.y, pi.z, 0.0f);  // payload of the force pass: press_iter
+	if (s >= c.N_owned) return;
+	f3 vi = xyz(svel[s]);
+	f3 tension, viscosity;
+	tension_viscosity(c, L, s, posR, svel, pi, vi, tension, viscosity);
+	f3 g = F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
+	ext_force[s] = F4((g + tension) + viscosity, 0.0f); // PC:226
+}
+
+// PC:72-87 predict_vel_pos
+__device__ __forceinline__ void pc_predict(const SphConsts &c, float dt, f3 x, f3 v, f3 ext, f3 press,
+                                           float4 *pos_predict, float4 *vel_predict, int s) {
+	f3 vp = v + (dt * (ext + press)) / c.m; // PC:75
+	f3 xp = x + dt * vp;                    // PC:76
+	if (c.boundary_handle == 0) clamp_box(c, xp, vp); // PC:78-87
+	vel_predict[s] = F4(vp, 0.0f);
+	pos_predict[s] = F4(xp, 0.0f);
+}
+
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_pc_predict(SphConsts c, const float4 *__restrict__ spos, const float4 *__restrict__ svel,
+             const float4 *__restrict__ ext_force, const float4 *__restrict__ press_force,
+             float4 *__restrict__ pos_predict, float4 *__restrict__ vel_predict, const SphCtl *__restrict__ ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N_owned) return;
+	pc_predict(c, ctl->dt, xyz(spos[s]), xyz(svel[s]), xyz(ext_force[s]), xyz(press_force[s]), pos_predict,
+	           vel_predict, s);
+}
+
+// PC:89-101 predict_rho (+ PC:121-133 residual partials, + speculative PC:103-107 iter_press into
+// p_next: it is committed by the next force pass only if the loop continues)
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_pc_predict_rho(SphConsts c, SphLists L, const float4 *__restrict__ pos_predict, const float4 *__restrict__ bspos,
+                 float *__restrict__ rho_predict, float *__restrict__ rho_err, const float *__restrict__ press,
+                 float *__restrict__ p_next, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials,
+                 int gated) {
+	if (gated && !ctl->pc_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	double psum = 0.0;
+	int pcnt = 0;
+	if (s < c.N_owned) {
+		float4 pi = pos_predict[s];
+		float rp = 0.0f;
+		SPH_FOR_FLUID(L, c, s, j) {
+			float4 pj = __ldg(&pos_predict[j]);
+			f3 d = xyz(pi) - xyz(pj);
+			float q = sqrtf(dot(d, d));          // PC:141
+			rp += cubic_w_r(q, c) * c.m;         // PC:142
+		}
+		float out = rp;
+		if (c.boundary_handle == 1) {
+			float rb = 0.0f;
+			SPH_FOR_BOUNDARY(L, c, s, j) {
+				float4 pj = __ldg(&bspos[j]);
+				f3 d = xyz(pi) - xyz(pj);
+				float q = sqrtf(dot(d, d));      // PC:152
+				rb += cubic_w_r(q, c) * pj.w;    // PC:153
+			}
+			out = rp + rb * SPH_RHO0;            // PC:98
+		}
+		float err = out - SPH_RHO0;              // PC:101
+		rho_predict[s] = out;
+		rho_err[s] = err;
+		p_next[s] = fmaxf(0.0f, press[s] + err * ctl->pc_delta); // PC:106-107
+		float e = fmaxf(err, 0.0f);
+		if (e > 0.0f) { psum = (double)e; pcnt = 1; }
+	}
+	block_partial(psum, pcnt, 0.0f, partials);
+}
+
+// commits iter_press (PC:103-107) for every particle and publishes it as the .w payload
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_pc_commit_press(SphConsts c, const float *__restrict__ p_next, float *__restrict__ press,
+                  float4 *__restrict__ posT1, const SphCtl *__restrict__ ctl) {
+	if (!ctl->pc_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N) return;
+	float p = p_next[s];
+	press[s] = p;
+	posT1[s].w = p;
+}
+
+// PC:109-119 update_press_force fused with the following PC:72-87 predict_vel_pos
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_pc_press_force(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float4 *__restrict__ bspos,
+                 const float *__restrict__ rho, const float4 *__restrict__ svel, const float4 *__restrict__ ext_force,
+                 float4 *__restrict__ press_force, float4 *__restrict__ pos_predict, float4 *__restrict__ vel_predict,
+                 const SphCtl *__restrict__ ctl) {
+	if (!ctl->pc_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N_owned) return;
+	float4 pi = posT1[s];
+	f3 pf = F3(0.0f, 0.0f, 0.0f);
+	SPH_FOR_FLUID(L, c, s, j) {
+		float4 pj = __ldg(&posT1[j]);
+		Pair p = make_pair(pi, pj);
+		pf = pf + ((((pi.w + pj.w) * cubic_dw(p, c)) / 1000000.0f) * c.m) * c.m; // PC:177
+	}
+	f3 out = neg(pf);
+	if (c.boundary_handle == 1) {
+		float rho_i = rho[s];
+		float rho_i_2 = rho_i * rho_i;
+		f3 bacc = F3(0.0f, 0.0f, 0.0f);
+		SPH_FOR_BOUNDARY(L, c, s, j) {
+			float4 pj = __ldg(&bspos[j]);
+			Pair p = make_pair(pi, pj);
+			bacc = bacc - ((pj.w * pi.w) / rho_i_2) * cubic_dw(p, c); // PC:197
+		}
+		out = neg(pf) + (bacc * SPH_RHO0) * c.m; // PC:117
+	}
+	press_force[s] = F4(out, 0.0f);
+	pc_predict(c, ctl->dt, xyz(pi), xyz(svel[s]), xyz(ext_force[s]), out, pos_predict, vel_predict, s);
+}
+
+// mode 0: first evaluation (PC:54); mode 1: end of a loop body (PC:68-69)
+__global__ void __launch_bounds__(256) k_pc_ctl(SphCtl *ctl, const SphPartial *partials, int n, int mode) {
+	if (mode == 1 && !ctl->pc_active) return;
+	double sum; int cnt; float mx;
+	reduce_partials(partials, n, sum, cnt, mx);
+	if (threadIdx.x != 0) return;
+	float avg = cnt > 0 ? (float)(sum / (double)cnt) : 0.0f; // PC:131-132
+	int it = mode == 0 ? 0 : ctl->pc_iters + 1;
+	ctl->pc_iters = it;
+	ctl->pc_err = avg;
+	ctl->pc_active = (((double)avg > 1000 * .1 * 0.01 || it < 1) && it < 80) ? 1 : 0; // PC:56
+}
+
+// PC:200-218 integration + write-back
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_pc_integration(SphConsts c, const int *__restrict__ sorted_id, const float4 *__restrict__ spos,
+                 const float4 *__restrict__ svel, const float4 *__restrict__ ext_force,
+                 const float4 *__restrict__ press_force, float4 *__restrict__ pos, float4 *__restrict__ vel,
+                 const SphCtl *__restrict__ ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N) return;
+	int i = sorted_id[s];
+	if (i >= c.N_owned) return;
+	float dt = ctl->dt;
+	float4 v4 = svel[s];
+	f3 v = xyz(v4) + (dt * (xyz(ext_force[s]) + xyz(press_force[s]))) / c.m; // PC:203-204
+	v = v * 0.9999f;                                                          // PC:205
+	f3 x = xyz(spos[s]) + dt * v;                                             // PC:206
+	if (c.boundary_handle == 0) clamp_box(c, x, v);
+	pos[i] = F4(x, 0.0f);
+	vel[i] = F4(v, v4.w);
+}
+
+// PC:39-45 pre_compute_delta for the particle with original index `target` (un-weighted sums, PC:156-167)
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_pc_delta(SphConsts c, SphLists L, const float4 *__restrict__ spos, const int *__restrict__ sorted_id, int target,
+           SphCtl *ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N || sorted_id[s] != target) return;
+	float4 pi = spos[s];
+	f3 sum = F3(0.0f, 0.0f, 0.0f);
+	float sq = 0.0f;
+	SPH_FOR_FLUID(L, c, s, j) {
+		Pair p = make_pair(pi, spos[j]);
+		f3 dw = cubic_dw(p, c);
+		sum = sum + dw;
+		sq += dot(dw, dw);
+	}
+	ctl->pc_delta = 1.0f / ((dot(sum, sum) + sq) * c.pc_beta); // PC:45
+	ctl->pc_max_index = target;
+}
+
+void pc_precompute(SphHandle *h, cudaStream_t st) {
+	// PC:28-37: grid (done by the caller), neighbour counts; the arg-max (PS:409-422) is evaluated by the
+	// Python mirror from the fetched counts and passed back through h->cfg.reserved.
+	build_lists(h, st);
+}
+
+void pc_set_delta(SphHandle *h, int target, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	k_pc_delta<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->fg.sorted_id, target, h->ctl);
+	h->launches++;
+}
+
+static void pc_iteration(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N_owned, SPH_BLOCK), nba = cdiv(c.N, SPH_BLOCK);
+	float4 *pos_predict = h->a4[A4_T2], *vel_predict = h->a4[A4_VADV];
+	sph_prof_begin(h, KC_PC_PREDICT, st);
+	k_pc_predict<<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA], h->a4[A4_FB], pos_predict,
+	                                       vel_predict, h->ctl);
+	sph_prof_end(h, st);
+	sph_prof_begin(h, KC_PC_RHO, st);
+	k_pc_predict_rho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB], h->a1[A1_P],
+	                                           h->a1[A1_SC], h->ctl, h->partials, 0);
+	sph_prof_end(h, st);
+	k_pc_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0);
+	h->launches += 3;
+	int done = 0;
+	int chunk = h->last_den_chunk > 0 ? h->last_den_chunk : 4;
+	for (;;) {
+		for (int it = 0; it < chunk && done < 80; ++it, ++done) { // max_iteration (PC:21); gated on ctl->pc_active
+			k_pc_commit_press<<<nba, SPH_BLOCK, 0, st>>>(c, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+			sph_prof_begin(h, KC_PC_FORCE, st);
+			k_pc_press_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
+			                                           h->a4[A4_FA], h->a4[A4_FB], pos_predict, vel_predict, h->ctl);
+			sph_prof_end(h, st);
+			sph_prof_begin(h, KC_PC_RHO, st);
+			k_pc_predict_rho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB],
+			                                           h->a1[A1_P], h->a1[A1_SC], h->ctl, h->partials, 1);
+			sph_prof_end(h, st);
+			k_pc_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1);
+			h->launches += 4;
+		}
+		if (done >= 80) break;
+		// one look at the device flag per chunk (not per iteration)
+		cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SphCtl), cudaMemcpyDeviceToHost, st);
+		cudaStreamSynchronize(st);
+		if (!h->ctl_host->pc_active) break;
+		chunk = 4;
+	}
+	if (done < 80) h->last_den_chunk = h->ctl_host->pc_iters + 1;
+	else h->last_den_chunk = 80;
+}
+
+void pc_phase(SphHandle *h, int phase, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nba = cdiv(c.N, SPH_BLOCK);
+	if (phase == SPH_PH_PC_EXT_FORCE) {
+		build_lists(h, st);
+		sph_prof_begin(h, KC_PC_EXT, st);
+		k_pc_ext_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_PR], h->a4[A4_VEL], h->a4[A4_FA], h->a4[A4_FB],
+		                                          h->a1[A1_P], h->a4[A4_T1]);
+		sph_prof_end(h, st);
+		h->launches++;
+	} else if (phase == SPH_PH_PC_ITERATION) {
+		pc_iteration(h, st);
+	} else if (phase == SPH_PH_PC_INTEGRATION) {
+		sph_prof_begin(h, KC_PC_INT, st);
+		k_pc_integration<<<nba, SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA],
+		                                            h->a4[A4_FB], h->pos, h->vel, h->ctl);
+		sph_prof_end(h, st);
+		h->launches++;
+	}
+}
+
+// =============================================================================================
+// IISPH (iisph_solver.py)
+// =============================================================================================
+
+// the recurring factor  - dt * dt * m / (rho_i * rho_i)  (II:244-245, 283-284, 291-292, 301-302)
+__device__ __forceinline__ float ii_dji_coef(const SphConsts &c, float dt, float rho_i) {
+	return (((-dt) * dt) * c.m) / (rho_i * rho_i);
+}
+
+// II:42-55: tension, viscosity, f_adv, v_adv and d_ii in one pass over the lists
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_ii_advect(SphConsts c, SphLists L, const float4 *__restrict__ posR, const float4 *__restrict__ svel,
+            const float4 *__restrict__ bspos, float4 *__restrict__ f_adv, float4 *__restrict__ v_adv,
+            float4 *__restrict__ d_ii, const SphCtl *__restrict__ ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N_owned) return;
+	float dt = ctl->dt;
+	float4 pi = posR[s];
+	float rho_i = pi.w;
+	f3 vi = xyz(svel[s]);
+	f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f), dii = F3(0.0f, 0.0f, 0.0f);
+	float cf = (-c.m) / (rho_i * rho_i); // II:261
+	SPH_FOR_FLUID(L, c, s, j) {
+		float4 pj = __ldg(&posR[j]);
+		f3 vj = xyz(__ldg(&svel[j]));
+		Pair p = make_pair(pi, pj);
+		f3 dw = cubic_dw(p, c);
+		ten = ten + (c.tension_coef * cubic_w(p, c)) * p.r;
+		f3 v_ij = vi - vj;
+		float shear = dot(v_ij, p.r);
+		if (shear < 0.0f) {
+#if SPH_STRICT
+			float q = sqrtf(p.r2);
+			float q2 = q * q;
+#else
+			float q2 = p.r2;
+#endif
+			float nu = c.visc_num / (rho_i + pj.w);
+			float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);
+			visc = visc + (c.neg_m * pi_ij) * dw;
+		}
+		dii = dii + cf * dw;
+	}
+	f3 g = F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
+	f3 f = (g + ten * c.m) + visc * c.m;      // II:45
+	f_adv[s] = F4(f, 0.0f);
+	v_adv[s] = F4(vi + (dt * f) / c.m, 0.0f); // II:47
+	if (c.boundary_handle == 1) {
+		f3 db = F3(0.0f, 0.0f, 0.0f);
+		SPH_FOR_BOUNDARY(L, c, s, j) {
+			float4 pj = __ldg(&bspos[j]);
+			Pair p = make_pair(pi, pj);
+			db = db + ((-pj.w) / (rho_i * rho_i)) * cubic_dw(p, c); // II:273
+		}
+		d_ii[s] = F4(((dii + db * SPH_RHO0) * dt) * dt, 0.0f); // II:53
+	} else {
+		d_ii[s] = F4((dii * dt) * dt, 0.0f);
+	}
+}
+
+// II:57-75: rho_adv, p_iter = 0.5 p_past, a_ii
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_ii_rho_adv_aii(SphConsts c, SphLists L, const float4 *__restrict__ posR, const float4 *__restrict__ v_adv,
+                 const float4 *__restrict__ bspos, const float4 *__restrict__ d_ii, const float4 *__restrict__ svel,
+                 float *__restrict__ rho_adv, float *__restrict__ a_ii, float *__restrict__ press,
+                 float4 *__restrict__ posT1, const SphCtl *__restrict__ ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N) return;
+	float4 pi = posR[s];
+	float p0 = 0.5f * svel[s].w; // II:67
+	press[s] = p0;
+	posT1[s] = make_float4(pi.x, pi.y, pi.z, p0);
+	if (s >= c.N_owned) return;
+	float dt = ctl->dt;
+	float rho_i = pi.w;
+	f3 va = xyz(v_adv[s]);
+	f3 dii = xyz(d_ii[s]);
+	float coef = ii_dji_coef(c, dt, rho_i);
+	float ra = 0.0f, aii = 0.0f;
+	SPH_FOR_FLUID(L, c, s, j) {
+		float4 pj = __ldg(&posR[j]);
+		f3 vj = xyz(__ldg(&v_adv[j]));
+		Pair p = make_pair(pi, pj);
+		f3 dw = cubic_dw(p, c);
+		ra += c.m * dot(va - vj, dw);           // II:324
+		f3 d_ji = coef * neg(dw);               // II:283-284: kernel derivative of -q is the negated vector
+		aii += c.m * dot(dii - d_ji, dw);       // II:285
+	}
+	if (c.boundary_handle == 1) {
+		float rab = 0.0f, ab = 0.0f;
+		SPH_FOR_BOUNDARY(L, c, s, j) {
+			float4 pj = __ldg(&bspos[j]);
+			Pair p = make_pair(pi, pj);
+			f3 dw = cubic_dw(p, c);
+			rab += pj.w * dot(va, dw);          // II:340
+			f3 d_ji = coef * neg(dw);
+			ab += pj.w * dot(dii - d_ji, dw);   // II:303
+		}
+		rho_adv[s] = (ra + rab * SPH_RHO0) * dt + rho_i; // II:63
+		a_ii[s] = aii + ab * SPH_RHO0;                    // II:73
+	} else {
+		rho_adv[s] = ra * dt + rho_i;
+		a_ii[s] = aii;
+	}
+}
+
+// II:121-126, 305-314 compute_all_d_ij.  posT1.w = p_iter of the neighbour.
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_ii_dij(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float *__restrict__ rho,
+         float4 *__restrict__ d_ij, const SphCtl *__restrict__ ctl) {
+	if (!ctl->ii_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N_owned) return;
+	float dt = ctl->dt;
+	float4 pi = posT1[s];
+	f3 dij = F3(0.0f, 0.0f, 0.0f);
+	SPH_FOR_FLUID(L, c, s, j) {
+		float4 pj = __ldg(&posT1[j]);
+		float rho_j = __ldg(&rho[j]);
+		Pair p = make_pair(pi, pj);
+		dij = dij + (((-c.m) * pj.w) * cubic_dw(p, c)) / (rho_j * rho_j); // II:313
+	}
+	d_ij[s] = F4((dij * dt) * dt, 0.0f); // II:126
+}
+
+// II:128-147 update_p (sum_factor II:228-253) + residual partials (II:102-113); p_next is committed
+// by k_ii_commit so that neighbours keep reading the current iterate.
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_ii_update_p(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float4 *__restrict__ bspos,
+              const float *__restrict__ rho, const float4 *__restrict__ d_ij, const float4 *__restrict__ d_ii,
+              const float *__restrict__ a_ii, const float *__restrict__ rho_adv, float *__restrict__ r_sum,
+              float *__restrict__ p_next, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials) {
+	if (!ctl->ii_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	double psum = 0.0;
+	int pcnt = 0;
+	if (s < c.N_owned) {
+		float dt = ctl->dt;
+		float4 pi = posT1[s];
+		float rho_i = rho[s];
+		f3 dij_i = xyz(d_ij[s]);
+		float coef = ii_dji_coef(c, dt, rho_i);
+		float sum = 0.0f;
+		SPH_FOR_FLUID(L, c, s, j) {
+			float4 pj = __ldg(&posT1[j]);
+			f3 dij_j = xyz(__ldg(&d_ij[j]));
+			f3 dii_j = xyz(__ldg(&d_ii[j]));
+			Pair p = make_pair(pi, pj);
+			f3 w_ij = cubic_dw(p, c);
+			f3 d_ji = (coef * neg(w_ij)) * pi.w;                       // II:244-245
+			f3 t = (dij_i - dii_j * pj.w) - (dij_j - d_ji);            // II:246
+			sum += c.m * dot(t, w_ij);
+		}
+		float rs = sum;
+		if (c.boundary_handle == 1) {
+			float bsum = 0.0f;
+			SPH_FOR_BOUNDARY(L, c, s, j) {
+				float4 pj = __ldg(&bspos[j]);
+				Pair p = make_pair(pi, pj);
+				bsum += (dot(dij_i, cubic_dw(p, c)) * pj.w) * SPH_RHO0; // II:232
+			}
+			rs = sum + bsum; // II:136
+		}
+		r_sum[s] = rs;
+		float a = a_ii[s], ra = rho_adv[s];
+		float pn;
+		if (fabsf(a) > 1e-7f) pn = 0.5f * pi.w + (0.5f * ((SPH_RHO0 - ra) - rs)) / a; // II:140-142
+		else pn = 0.0f;
+		pn = fmaxf(pn, 0.0f); // II:147
+		p_next[s] = pn;
+		if (pn > 0.0f) { psum = (double)(((a * pn + rs) + ra) - 1000.0f); pcnt = 1; } // II:108-110
+	}
+	block_partial(psum, pcnt, 0.0f, partials);
+}
+
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_ii_commit(SphConsts c, const float *__restrict__ p_next, float *__restrict__ press, float4 *__restrict__ posT1,
+            const SphCtl *__restrict__ ctl) {
+	if (!ctl->ii_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N_owned) return;
+	float p = p_next[s];
+	press[s] = p;
+	posT1[s].w = p;
+}
+
+// II:78-100 loop control.  mode 0 = before the loop, mode 1 = after an iteration.
+__global__ void __launch_bounds__(256) k_ii_ctl(SphCtl *ctl, const SphPartial *partials, int n, int mode) {
+	if (mode == 0) {
+		if (threadIdx.x == 0) { ctl->ii_active = 1; ctl->ii_iters = 0; ctl->ii_have_last = 0; ctl->ii_residual = INFINITY; }
+		return;
+	}
+	if (!ctl->ii_active) return;
+	double sum; int cnt; float mx;
+	reduce_partials(partials, n, sum, cnt, mx);
+	if (threadIdx.x != 0) return;
+	float res = cnt > 0 ? (float)(sum / (double)cnt) : 0.0f; // II:111-112
+	int l = ctl->ii_iters + 1;                                // II:88
+	ctl->ii_iters = l;
+	ctl->ii_residual = res;
+	if (ctl->ii_have_last && (double)res - (double)ctl->ii_last > 0) { ctl->ii_active = 0; return; } // II:91-93
+	ctl->ii_last = res;
+	ctl->ii_have_last = 1;
+	ctl->ii_active = (((double)res > .1 * 1000 * 0.01 || l < 1) && l < 180) ? 1 : 0; // II:83
+}
+
+// II:184-206 intergation (sic) + write-back
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_ii_integration(SphConsts c, const int *__restrict__ sorted_id, const float4 *__restrict__ spos,
+                 const float4 *__restrict__ v_adv, const float4 *__restrict__ d_ij, const float4 *__restrict__ d_ii,
+                 const float *__restrict__ press, float4 *__restrict__ f_press, float4 *__restrict__ pos,
+                 float4 *__restrict__ vel, const SphCtl *__restrict__ ctl) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.N) return;
+	int i = sorted_id[s];
+	if (i >= c.N_owned) return;
+	float dt = ctl->dt;
+	float p = press[s];
+	f3 f = ((xyz(d_ij[s]) + xyz(d_ii[s]) * p) * c.m) / (dt * dt); // II:167
+	f_press[s] = F4(f, 0.0f);
+	f3 v = xyz(v_adv[s]) + (dt * f) / c.m; // II:189
+	v = v * 0.9999f;                       // II:190
+	f3 x = xyz(spos[s]) + dt * v;          // II:191
+	if (c.boundary_handle == 0) clamp_box(c, x, v);
+	pos[i] = F4(x, 0.0f);
+	vel[i] = F4(v, p);                     // II:206 p_past = p_iter
+}
+
+static void ii_pressure_solve(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0);
+	h->launches++;
+	int done = 0;
+	int chunk = h->last_den_chunk > 0 ? h->last_den_chunk : 4;
+	for (;;) {
+		for (int it = 0; it < chunk && done < 180; ++it, ++done) { // max_iter_cnt (II:27); gated on ctl->ii_active
+			sph_prof_begin(h, KC_II_DIJ, st);
+			k_ii_dij<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->ctl);
+			sph_prof_end(h, st);
+			sph_prof_begin(h, KC_II_UPDATE, st);
+			k_ii_update_p<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
+			                                        h->a4[A4_FC], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
+			                                        h->a1[A1_SC], h->ctl, h->partials);
+			sph_prof_end(h, st);
+			k_ii_commit<<<nb, SPH_BLOCK, 0, st>>>(c, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+			k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1);
+			h->launches += 4;
+		}
+		if (done >= 180) break;
+		cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SphCtl), cudaMemcpyDeviceToHost, st);
+		cudaStreamSynchronize(st);
+		if (!h->ctl_host->ii_active) break;
+		chunk = 4;
+	}
+	h->last_den_chunk = done < 180 ? h->ctl_host->ii_iters + 1 : 180;
+}
+
+void ii_phase(SphHandle *h, int phase, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N_owned, SPH_BLOCK), nba = cdiv(c.N, SPH_BLOCK);
+	if (phase == SPH_PH_II_PREDICT_ADVECTION) {
+		build_lists(h, st);
+		sph_prof_begin(h, KC_II_ADV, st);
+		k_ii_advect<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_PR], h->a4[A4_VEL], h->bspos, h->a4[A4_FA], h->a4[A4_VADV],
+		                                      h->a4[A4_FC], h->ctl);
+		sph_prof_end(h, st);
+		sph_prof_begin(h, KC_II_AII, st);
+		k_ii_rho_adv_aii<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_PR], h->a4[A4_VADV], h->bspos, h->a4[A4_FC],
+		                                            h->a4[A4_VEL], h->a1[A1_RHOADV], h->a1[A1_SA], h->a1[A1_P],
+		                                            h->a4[A4_T1], h->ctl);
+		sph_prof_end(h, st);
+		h->launches += 2;
+	} else if (phase == SPH_PH_II_PRESSURE_SOLVE) {
+		ii_pressure_solve(h, st);
+	} else if (phase == SPH_PH_II_INTEGRATION) {
+		sph_prof_begin(h, KC_II_INT, st);
+		k_ii_integration<<<nba, SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VADV], h->a4[A4_FB],
+		                                            h->a4[A4_FC], h->a1[A1_P], h->a4[A4_FD], h->pos, h->vel, h->ctl);
+		sph_prof_end(h, st);
+		h->launches++;
+	}
+}
 
 } // namespace SPH_NS

@@ -85,6 +85,7 @@ enum SphField {
 	SPH_F_CELL1D /*int32*/, SPH_F_NEIGHBOR_COUNT /*int32*/, SPH_F_BOUNDARY_NEIGHBOR_COUNT /*int32*/,
 	SPH_F_PRESSURE, SPH_F_FORCE_A /*float4 generic force/acc buffer*/, SPH_F_FORCE_B /*float4*/,
 	SPH_F_SCALAR_A, SPH_F_SCALAR_B, SPH_F_SCALAR_C, SPH_F_VEC_A /*float4*/, SPH_F_VEC_B /*float4*/,
+	SPH_F_VEC_C /*float4*/,
 	/* grid arrays (int32), fetched verbatim */
 	SPH_F_CELL_START = 64,   /* G+1 exclusive prefix sums == per-cell list offsets */
 	SPH_F_SORTED_INDEX,      /* N: original index of the particle in sorted slot s */
@@ -157,8 +158,11 @@ int sph_init_boundary(SphHandle *h, void *stream);
  * host algebra on the fetched arrays and stay in the Python mirror. */
 int sph_init_rigid(SphHandle *h, void *stream);
 
-/* PCISPH pre_compute (PC:28-45): delta from the "max neighbour" particle. */
+/* PCISPH pre_compute (PC:28-37): grid + neighbour lists/counts of the initial state.  The arg-max of
+ * get_max_neighbor_particle_index (PS:409-422) is O(N) host logic on the fetched counts; its result is
+ * handed to sph_pcisph_delta, which evaluates pre_compute_delta (PC:39-45) for that particle. */
 int sph_pcisph_precompute(SphHandle *h, void *stream);
+int sph_pcisph_delta(SphHandle *h, int particle_index, void *stream);
 
 /* One full solver.step() (SB:136-143 + <name>_solver.step), n_substeps times. */
 int sph_step(SphHandle *h, int n_substeps, void *stream);
