@@ -82,7 +82,9 @@ class ParticleSystem:
             self.rigid_rho = solid_config.get('rho_0')
             self.rigid_vertex_count = verts.shape[0]
             self.rigid_particles_num = pts.shape[0]
-            self._rigid_vertices = torch.from_numpy(verts.astype(np.float32)).to(dev)
+            self._rverts4 = torch.zeros((max(verts.shape[0], 1), 4), dtype=torch.float32, device=dev)
+            self._rverts4[:verts.shape[0], :3] = torch.from_numpy(verts.astype(np.float32)).to(dev)
+            self._rigid_vertices = self._rverts4[:verts.shape[0], :3]
             self.rigid_vertices = TensorField(self._rigid_vertices)
             self.rigid_inertia_tensor = TensorField(torch.zeros((3, 3), dtype=torch.float32, device=dev))
             self.rigid_inertia_tensor_inv = TensorField(torch.zeros((3, 3), dtype=torch.float32, device=dev))
@@ -181,6 +183,7 @@ class ParticleSystem:
             _lib.check(L.sph_bind(h, _lib.F_RIGID_POS, self._rpos4.data_ptr(), self._rpos4.shape[0]), h)
             _lib.check(L.sph_bind(h, _lib.F_RIGID_VEL, self._rvel4.data_ptr(), self._rvel4.shape[0]), h)
             _lib.check(L.sph_bind(h, _lib.F_RIGID_FORCE, self._rforce4.data_ptr(), self._rforce4.shape[0]), h)
+            _lib.check(L.sph_bind(h, _lib.F_RIGID_VERTICES, self._rverts4.data_ptr(), self.rigid_vertex_count), h)
 
     def _ensure_solver(self, solver_name):
         """Solvers are located by name (main.py:65-68); a solver class built on a ParticleSystem whose
@@ -188,6 +191,8 @@ class ParticleSystem:
         if solver_name != self._solver_name:
             self._create_handle(solver_name)
             _lib.check(self._lib.sph_init_boundary(self._h, self._stream()), self._h)
+            if self.exist_rigid[None]:
+                _lib.check(self._lib.sph_init_rigid(self._h, self._stream()), self._h)
 
     def close(self):
         if getattr(self, '_h', None) is not None:
@@ -235,7 +240,7 @@ class ParticleSystem:
         nr = self.rigid_particles_num
         p = torch.from_numpy(self._rigid_points).to(self._device)
         self._rpos4[:nr, :3] = _rot_rows(R, p) + off
-        self._rigid_vertices.copy_(_rot_rows(R, self._rigid_vertices) + off)
+        self._rverts4[:self.rigid_vertex_count, :3] = _rot_rows(R, self._rigid_vertices.clone()) + off
 
     def init_particles_data(self):                                                  # PS:225-247
         self.reset_boundary_grids()
@@ -258,7 +263,22 @@ class ParticleSystem:
         self._boundary_dirty = False
 
     def init_rigid_particles_data(self):                                            # PS:249-295
-        raise _lib.SphError("rigid-body coupling is not built yet in this round")
+        _lib.check(self._lib.sph_init_rigid(self._h, self._stream()), self._h)
+        info = self.rigid_state()
+        dev = self._device
+        self.rigid_centriod.tensor.copy_(torch.tensor(list(info.centroid), dtype=torch.float32, device=dev))
+        self.rigid_inertia_tensor.tensor.copy_(torch.tensor(list(info.inertia), dtype=torch.float32, device=dev).reshape(3, 3))
+        self.rigid_inertia_tensor_inv.tensor.copy_(
+            torch.tensor(list(info.inertia_inv), dtype=torch.float32, device=dev).reshape(3, 3))
+        self._rrgb[:self.rigid_particles_num] = torch.tensor([1.0, 0.0, 0.0], device=dev)            # PS:295
+        print("Centroid: {}".format(list(info.centroid)))
+        print("Intertia tensor: {}".format([list(info.inertia)[k * 3:k * 3 + 3] for k in range(3)]))
+
+    def rigid_state(self):
+        """Device-resident rigid-body state (centroid, inertia, velocities ...); synchronises."""
+        info = _lib.SphRigidInfo()
+        _lib.check(self._lib.sph_rigid_state(self._h, ctypes.byref(info)), self._h)
+        return info
 
     def reset_grid(self):                                                           # PS:368-373
         pass  # cell counters are cleared inside the grid build (sph_phase BUILD_GRID)

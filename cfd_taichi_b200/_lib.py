@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "_build", "libsph_b200.so")
 SOLVER_IDS = {"wcsph": 0, "pcisph": 1, "iisph": 2, "dfsph": 3}
 
 # enum SphField
-F_FLUID_POS, F_FLUID_VEL, F_BOUNDARY_POS, F_RIGID_POS, F_RIGID_VEL, F_RIGID_FORCE, F_FLUID_ACC = range(7)
+F_FLUID_POS, F_FLUID_VEL, F_BOUNDARY_POS, F_RIGID_POS, F_RIGID_VEL, F_RIGID_FORCE, F_FLUID_ACC, F_RIGID_VERTICES = range(8)
 (F_RHO, F_ALPHA, F_RHO_DERIVATIVE, F_RHO_ADV, F_VEL_ADV, F_CELL1D, F_NEIGHBOR_COUNT,
  F_BOUNDARY_NEIGHBOR_COUNT, F_PRESSURE, F_FORCE_A, F_FORCE_B, F_SCALAR_A, F_SCALAR_B, F_SCALAR_C,
  F_VEC_A, F_VEC_B, F_VEC_C) = range(16, 33)
@@ -82,6 +82,14 @@ class SphStats(ctypes.Structure):
     ]
 
 
+class SphRigidInfo(ctypes.Structure):
+    _fields_ = [("centroid", ctypes.c_float * 3), ("inertia", ctypes.c_float * 9), ("inertia_inv", ctypes.c_float * 9),
+                ("vel", ctypes.c_float * 3), ("omega", ctypes.c_float * 3), ("alpha", ctypes.c_float * 3),
+                ("acc", ctypes.c_float * 3), ("attitude", ctypes.c_float * 3), ("force_sum", ctypes.c_float * 3),
+                ("torque", ctypes.c_float * 3), ("mass", ctypes.c_float), ("delta_time", ctypes.c_float),
+                ("collision_cnt", ctypes.c_int32), ("simulate_cnt", ctypes.c_int32)]
+
+
 # every symbol include/sph_b200.h declares: (name, restype, argtypes)
 _vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 _fp = ctypes.POINTER(ctypes.c_float)
@@ -97,9 +105,8 @@ PROTOTYPES = [
     ("sph_pcisph_delta", _i, [_vp, _i, _vp]),
     ("sph_step", _i, [_vp, _i, _vp]),
     ("sph_phase", _i, [_vp, _i, _vp]),
-    ("sph_rigid_reduce", _i, [_vp, _fp, _vp, _vp]),
-    ("sph_rigid_transform", _i, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
-    ("sph_rigid_contacts", _i, [_vp, _fp, _fp, _fp, _fp, _vp, _vp]),
+    ("sph_rigid_step", _i, [_vp, _vp]),
+    ("sph_rigid_state", _i, [_vp, _vp]),
     ("sph_set_delta_time", _i, [_vp, _f, _vp]),
     ("sph_fetch", _i, [_vp, _i, _vp, ctypes.c_size_t, _vp]),
     ("sph_upload_state", _i, [_vp, _vp, _vp, _vp]),

@@ -102,13 +102,14 @@ static int alloc_grid(SphHandle *h, SphGrid &g, size_t n, size_t G) {
 	SPH_CUDA_CHECK(h, dalloc(&g.cell_start, G + 1));
 	SPH_CUDA_CHECK(h, dalloc(&g.sorted_id, n));
 	SPH_CUDA_CHECK(h, dalloc(&g.scell, n));
+	SPH_CUDA_CHECK(h, dalloc(&g.slot_of, n));
 	SPH_CUDA_CHECK(h, cudaMemset(g.cell_start, 0, sizeof(int) * (G + 1)));
 	g.n = 0;
 	return SPH_OK;
 }
 
 static void free_grid(SphGrid &g) {
-	cudaFree(g.cell_of); cudaFree(g.cell_cnt); cudaFree(g.cell_start); cudaFree(g.sorted_id); cudaFree(g.scell);
+	cudaFree(g.cell_of); cudaFree(g.cell_cnt); cudaFree(g.cell_start); cudaFree(g.sorted_id); cudaFree(g.scell); cudaFree(g.slot_of);
 }
 
 extern "C" int sph_abi_version(void) { return 1; }
@@ -155,7 +156,12 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	SPH_CUDA_CHECK(h, dalloc(&h->bspos, (size_t)c.Nb));
 	SPH_CUDA_CHECK(h, dalloc(&h->rspos, (size_t)c.Nr));
 	SPH_CUDA_CHECK(h, dalloc(&h->rsvel, (size_t)c.Nr));
-	SPH_CUDA_CHECK(h, dalloc(&h->rkin, (size_t)c.Nr * 4));
+	SPH_CUDA_CHECK(h, dalloc(&h->rkin, (size_t)1));
+	SPH_CUDA_CHECK(h, dalloc(&h->rstate, 1));
+	SPH_CUDA_CHECK(h, cudaMemset(h->rstate, 0, sizeof(SphRigidState)));
+	h->rl_cap = 96;
+	SPH_CUDA_CHECK(h, dalloc(&h->rl_list, (size_t)((c.Nr + 31) / 32) * 32 * (size_t)h->rl_cap));
+	SPH_CUDA_CHECK(h, dalloc(&h->rl_count, (size_t)c.Nr));
 	for (int k = 0; k < A4_COUNT; ++k) {
 		SPH_CUDA_CHECK(h, dalloc(&h->a4[k], ncap));
 		SPH_CUDA_CHECK(h, cudaMemset(h->a4[k], 0, sizeof(float4) * (ncap ? ncap : 1)));
@@ -187,6 +193,13 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	}
 	h->ctl_host->ps_dt = 0.0f;                       // PS:37
 	SPH_CUDA_CHECK(h, cudaMemcpy(h->ctl, h->ctl_host, sizeof(SphCtl), cudaMemcpyHostToDevice));
+	{
+		SphRigidState rs;
+		memset(&rs, 0, sizeof(rs));
+		rs.rs_dt = (float)cfg->delta_time; // RS:13
+		rs.active = c.active_rigid;
+		SPH_CUDA_CHECK(h, cudaMemcpy(h->rstate, &rs, sizeof(rs), cudaMemcpyHostToDevice));
+	}
 	snprintf(h->err, sizeof(h->err), "ok");
 	return SPH_OK;
 }
@@ -196,7 +209,7 @@ extern "C" int sph_destroy(SphHandle *h) {
 	cudaSetDevice(h->device);
 	cudaDeviceSynchronize();
 	free_grid(h->fg); free_grid(h->bg); free_grid(h->rg);
-	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rsvel); cudaFree(h->rkin);
+	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rsvel); cudaFree(h->rkin); cudaFree(h->rstate); cudaFree(h->rl_list); cudaFree(h->rl_count);
 	for (int k = 0; k < A4_COUNT; ++k) cudaFree(h->a4[k]);
 	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
 	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.rlist);
@@ -239,6 +252,8 @@ extern "C" int sph_bind(SphHandle *h, int field, void *dev_ptr, size_t n) {
 	case SPH_F_RIGID_FORCE:
 		if (n < (size_t)h->c.Nr) return sph_fail(h, SPH_EINVAL, "sph_bind: rigid force needs %d float4", h->c.Nr);
 		h->rforce = (float4 *)dev_ptr; h->n_rforce = n; break;
+	case SPH_F_RIGID_VERTICES:
+		h->rverts = (float4 *)dev_ptr; h->n_rverts = n; break;
 	default:
 		return sph_fail(h, SPH_EINVAL, "sph_bind: field %d is not bindable", field);
 	}
@@ -250,6 +265,8 @@ static int require_state(SphHandle *h) {
 	if (!h->pos || !h->vel) return sph_fail(h, SPH_ENOTBOUND, "fluid pos/vel are not bound (sph_bind)");
 	if (h->c.Nb > 0 && h->c.boundary_handle == 1 && !h->boundary_ready)
 		return sph_fail(h, SPH_ESTATE, "boundary particles are not initialised (sph_init_boundary)");
+	if (h->c.Nr > 0 && h->c.active_rigid && h->c.solver != SPH_SOLVER_DFSPH)
+		return sph_fail(h, SPH_ESTATE, "rigid-fluid coupling is built for the DFSPH solver only in this round");
 	return SPH_OK;
 }
 
@@ -276,9 +293,57 @@ extern "C" int sph_init_boundary(SphHandle *h, void *stream) {
 	return check_launch(h, "sph_init_boundary");
 }
 
-extern "C" int sph_init_rigid(SphHandle *h, void *stream) {
-	(void)stream;
+static int require_rigid(SphHandle *h) {
 	if (!h) return SPH_EINVAL;
+	if (h->c.Nr <= 0) return sph_fail(h, SPH_ESTATE, "no rigid body in this handle");
+	if (!h->rpos || !h->rvel || !h->rforce) return sph_fail(h, SPH_ENOTBOUND, "rigid pos/vel/force are not bound");
+	return SPH_OK;
+}
+
+extern "C" int sph_init_rigid(SphHandle *h, void *stream) {
+	int rc = require_rigid(h);
+	if (rc != SPH_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	// PS:249-295: needs the rigid particles in the grid (only when active, SURVEY B-R2)
+	sphg_build(h, h->rg, h->rpos, h->c.Nr, st);
+	sphg_gather_rigid(h, st);
+	if (h->cfg.strict) sph_strict::rigid_init(h, st); else sph_fast::rigid_init(h, st);
+	h->rigid_ready = true;
+	return check_launch(h, "sph_init_rigid");
+}
+
+extern "C" int sph_rigid_step(SphHandle *h, void *stream) {
+	int rc = require_rigid(h);
+	if (rc != SPH_OK) return rc;
+	if (!h->rigid_ready) return sph_fail(h, SPH_ESTATE, "sph_rigid_step: call sph_init_rigid first");
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	if (h->cfg.strict) sph_strict::rigid_step(h, st); else sph_fast::rigid_step(h, st);
+	return check_launch(h, "sph_rigid_step");
+}
+
+extern "C" int sph_rigid_state(SphHandle *h, SphRigidInfo *out) {
+	if (!h || !out) return SPH_EINVAL;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	SphRigidState s;
+	SPH_CUDA_CHECK(h, cudaDeviceSynchronize());
+	SPH_CUDA_CHECK(h, cudaMemcpy(&s, h->rstate, sizeof(s), cudaMemcpyDeviceToHost));
+	memset(out, 0, sizeof(*out));
+	memcpy(out->centroid, s.centroid, sizeof(s.centroid));
+	memcpy(out->inertia, s.inertia, sizeof(s.inertia));
+	memcpy(out->inertia_inv, s.inertia_inv, sizeof(s.inertia_inv));
+	memcpy(out->vel, s.vel, sizeof(s.vel));
+	memcpy(out->omega, s.omega, sizeof(s.omega));
+	memcpy(out->alpha, s.alpha, sizeof(s.alpha));
+	memcpy(out->acc, s.acc, sizeof(s.acc));
+	memcpy(out->attitude, s.attitude, sizeof(s.attitude));
+	memcpy(out->force_sum, s.force_sum, sizeof(s.force_sum));
+	memcpy(out->torque, s.torque, sizeof(s.torque));
+	out->mass = s.mass;
+	out->delta_time = s.rs_dt;
+	out->collision_cnt = s.collision_cnt;
+	out->simulate_cnt = s.simulate_cnt;
 	return SPH_OK;
 }
 
@@ -288,6 +353,10 @@ static int base_step(SphHandle *h, cudaStream_t st) {
 	sph_prof_begin(h, KC_GRID, st);
 	sphg_build(h, h->fg, h->pos, h->c.N, st);
 	sphg_gather_fluid(h, st);
+	if (h->c.Nr > 0 && h->c.active_rigid) { // PS:385-386, 399-407
+		sphg_build(h, h->rg, h->rpos, h->c.Nr, st);
+		sphg_gather_rigid(h, st);
+	}
 	sph_prof_end(h, st);
 	h->grid_valid = true;
 	h->lists_valid = false;
@@ -543,22 +612,7 @@ extern "C" int sph_read_stats(SphHandle *h, SphStats *out) {
 	return SPH_OK;
 }
 
-// ---- entry points completed in later sections of the build (rigid coupling, multi-GPU) ----------
-extern "C" int sph_rigid_reduce(SphHandle *h, const float centroid[3], float *dev_out6, void *stream) {
-	(void)centroid; (void)dev_out6; (void)stream;
-	return sph_fail(h, SPH_ESTATE, "sph_rigid_reduce: no rigid body in this handle");
-}
-extern "C" int sph_rigid_transform(SphHandle *h, const float centroid[3], const float R[9], const float disp[3],
-                                   const float vel[3], const float omega[3], const float alpha[3],
-                                   const float acc[3], void *stream) {
-	(void)centroid; (void)R; (void)disp; (void)vel; (void)omega; (void)alpha; (void)acc; (void)stream;
-	return sph_fail(h, SPH_ESTATE, "sph_rigid_transform: no rigid body in this handle");
-}
-extern "C" int sph_rigid_contacts(SphHandle *h, const float vel[3], const float omega[3], const float centroid[3],
-                                  const float disp[3], float *dev_out16, void *stream) {
-	(void)vel; (void)omega; (void)centroid; (void)disp; (void)dev_out16; (void)stream;
-	return sph_fail(h, SPH_ESTATE, "sph_rigid_contacts: no rigid body in this handle");
-}
+// ---- multi-GPU slab support ------------------------------------------------------------------------
 extern "C" int sph_pack_columns(SphHandle *h, int col_lo, int col_hi, float *dev_pos4, float *dev_vel4,
                                 int32_t *dev_count, int capacity, void *stream) {
 	(void)col_lo; (void)col_hi; (void)dev_pos4; (void)dev_vel4; (void)dev_count; (void)capacity; (void)stream;

@@ -71,6 +71,36 @@ struct SphCtl {
 	int graph_cond; // scratch for conditional graph nodes
 };
 
+// Device-resident rigid-body state (rigid_solver.py:12-31 + the uniform per-particle fields the
+// reference fills with .fill(): vel RS:97, omega RS:96, alpha RS:128, acc RS:41).
+struct SphRigidState {
+	float centroid[3];      // ps.rigid_centriod (PS:271)
+	float inertia[9];       // PS:290
+	float inertia_inv[9];   // PS:291, rotated every step (RS:141)
+	float vel[3], omega[3], alpha[3], acc[3];
+	float attitude[3];      // RS:127
+	float mass;             // RS:161
+	float rs_dt;            // rigid_solver.delta_time (RS:13, 223-224)
+	float max_surface_vel;  // DF:104-110
+	float force_sum[3], torque[3];
+	int collision_cnt;
+	int simulate_cnt;
+	int active;
+};
+
+#define SPH_RIGID_BIT 0x80000000u
+
+// what the sweeps need to evaluate a rigid neighbour
+struct SphRigidArgs {
+	const float4 *rspos;        // sorted rigid particles: xyz, w = volume
+	const int *rstart;          // rigid grid CSR
+	const int *rsorted_id;      // sorted rigid slot -> rigid-local index
+	const SphRigidState *st;
+	const float4 *pos_orig;     // fluid positions in ORIGINAL order (neighbour-count quirk, PS:440-442)
+	const int *slot_of;         // fluid original index -> sorted slot (viscosity quirk, SB:199)
+	int active;
+};
+
 struct SphPartial {
 	double sum;
 	int cnt;

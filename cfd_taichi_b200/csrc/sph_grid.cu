@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) k_gather_fluid(const int *__restrict__ so
                                                        const float4 *__restrict__ pos,
                                                        const float4 *__restrict__ vel,
                                                        float4 *__restrict__ spos, float4 *__restrict__ svel,
-                                                       int *__restrict__ scell) {
+                                                       int *__restrict__ scell, int *__restrict__ slot_of) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= n) return;
 	int i = sorted_id[s];
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(256) k_gather_fluid(const int *__restrict__ so
 	spos[s] = p;
 	svel[s] = vel[i];
 	scell[s] = cell_of[i];
+	slot_of[i] = s;
 }
 
 __global__ void __launch_bounds__(256) k_gather_pos(const int *__restrict__ sorted_id,
@@ -249,7 +250,7 @@ void sphg_gather_fluid(SphHandle *h, cudaStream_t st) {
 	int n = h->fg.n;
 	if (n <= 0) return;
 	k_gather_fluid<<<cdiv(n, 256), 256, 0, st>>>(h->fg.sorted_id, h->fg.cell_of, n, h->pos, h->vel,
-	                                              h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell);
+	                                              h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.slot_of);
 	h->launches++;
 }
 
@@ -258,6 +259,13 @@ void sphg_gather_boundary(SphHandle *h, cudaStream_t st) {
 	if (n <= 0) return;
 	k_gather_pos<<<cdiv(n, 256), 256, 0, st>>>(h->bg.sorted_id, h->bg.cell_of, n, h->bpos, h->bspos,
 	                                            h->bg.scell);
+	h->launches++;
+}
+
+void sphg_gather_rigid(SphHandle *h, cudaStream_t st) {
+	int n = h->rg.n;
+	if (n <= 0) return;
+	k_gather_pos<<<cdiv(n, 256), 256, 0, st>>>(h->rg.sorted_id, h->rg.cell_of, n, h->rpos, h->rspos, h->rg.scell);
 	h->launches++;
 }
 

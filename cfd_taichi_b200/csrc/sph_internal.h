@@ -27,6 +27,7 @@ struct SphGrid {
 	int *cell_start;   // G + 1 exclusive prefix sums
 	int *sorted_id;    // per sorted slot: original index
 	int *scell;        // per sorted slot: 1-D cell id
+	int *slot_of;      // per particle (original order): sorted slot
 	int n;
 };
 
@@ -64,7 +65,11 @@ struct SphHandle {
 	float4 *bspos;  // xyz, w = volume
 	float4 *rspos;  // xyz, w = volume * rho0-free volume
 	float4 *rsvel;  // predicted rigid particle velocity used by the coupling terms
-	float4 *rkin;   // per rigid particle: vel, omega, alpha, acc (4 x float4), original order
+	float4 *rkin;   // unused
+	SphRigidState *rstate;      // device
+	float4 *rverts; size_t n_rverts; // caller-owned mesh vertices (float4)
+	uint32_t *rl_list; int *rl_count; int rl_cap; // rigid-centric fluid neighbour lists (force gather)
+	bool rigid_ready;
 	// sorted work arrays
 	float4 *a4[A4_COUNT];
 	float *a1[A1_COUNT];
@@ -101,6 +106,7 @@ int sph_fail_cuda(SphHandle *h, cudaError_t e, const char *expr, const char *fil
 void sphg_build(SphHandle *h, SphGrid &g, const float4 *pos, int n, cudaStream_t st);
 void sphg_gather_fluid(SphHandle *h, cudaStream_t st);
 void sphg_gather_boundary(SphHandle *h, cudaStream_t st);
+void sphg_gather_rigid(SphHandle *h, cudaStream_t st);
 void sphg_unsort_f1(SphHandle *h, const SphGrid &g, const float *in, float *out, int n, cudaStream_t st);
 void sphg_unsort_i1(SphHandle *h, const SphGrid &g, const int *in, int *out, int n, cudaStream_t st);
 void sphg_unsort_f4(SphHandle *h, const SphGrid &g, const float4 *in, float4 *out, int n, cudaStream_t st);
@@ -118,6 +124,8 @@ void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaSt
 	void pc_precompute(SphHandle *h, cudaStream_t st);                                      \
 	void pc_set_delta(SphHandle *h, int target, cudaStream_t st);                           \
 	void ii_phase(SphHandle *h, int phase, cudaStream_t st);                                \
+	void rigid_init(SphHandle *h, cudaStream_t st);                                         \
+	void rigid_step(SphHandle *h, cudaStream_t st);                                         \
 	}
 SPH_SWEEP_API(sph_strict)
 SPH_SWEEP_API(sph_fast)

@@ -24,6 +24,29 @@ __device__ __forceinline__ void cell_xyz(int cid, const SphConsts &c, int &cx, i
 	cx = rem - cz * c.gx;
 }
 
+__device__ __forceinline__ f3 ld3(const float *p) { return F3(p[0], p[1], p[2]); }
+
+// velocity of a rigid particle as seen by the coupling terms (DF:168-169, 292-293; II:328-330):
+// v_j = (vel + acc*dt) + cross(omega [+ alpha*dt], pos_j - centroid)
+__device__ __forceinline__ f3 rigid_velocity(const SphRigidState *st, f3 pos_j, float dt, bool with_alpha) {
+	f3 om = ld3(st->omega);
+	if (with_alpha) om = om + ld3(st->alpha) * dt;
+	f3 v_omega = cross(om, pos_j - ld3(st->centroid));
+	return (ld3(st->vel) + ld3(st->acc) * dt) + v_omega;
+}
+
+static inline SphRigidArgs rigid_args(const SphHandle *h) {
+	SphRigidArgs a;
+	a.rspos = h->rspos;
+	a.rstart = h->rg.cell_start;
+	a.rsorted_id = h->rg.sorted_id;
+	a.st = h->rstate;
+	a.pos_orig = h->pos;
+	a.slot_of = h->fg.slot_of;
+	a.active = (h->c.Nr > 0 && h->c.active_rigid && h->rigid_ready) ? 1 : 0;
+	return a;
+}
+
 // Iterate the 27 cells around (cx,cy,cz) in the reference's order: ndrange((-1,2),(-1,2),(-1,2)),
 // dx outermost, dz innermost (PS:452), skipping out-of-range cells (PS:453-456).
 #define SPH_FOR_27(c, cx, cy, cz, C1)                                                   \
@@ -76,11 +99,11 @@ void boundary_volume(SphHandle *h, cudaStream_t st) {
 // lists (canonical order), the neighbour count of get_neighbour_count (PS:424-445), rho
 // (SB:41-72) and, for DFSPH, alpha (DF:32-89) -- all of which depend on positions only.
 // ---------------------------------------------------------------------------------------------
-template <bool ALPHA>
+template <bool ALPHA, bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK)
 k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__restrict__ svel,
-              const int *__restrict__ scell, const int *__restrict__ cstart,
-              const float4 *__restrict__ bspos, const int *__restrict__ bstart, SphLists L,
+              const int *__restrict__ scell, const int *__restrict__ cstart, const int *__restrict__ sorted_id,
+              const float4 *__restrict__ bspos, const int *__restrict__ bstart, SphLists L, SphRigidArgs rg,
               int *__restrict__ nbr_count, float *__restrict__ rho, float *__restrict__ alpha,
               float4 *__restrict__ posR, float4 *__restrict__ posT1, SphCtl *ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,6 +116,8 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		float rho_f = 0.001f; // SB:44
 		f3 ss = F3(0.0f, 0.0f, 0.0f);
 		float sq = 0.0f;
+		int ncount = 0; // get_neighbour_count (PS:424-445)
+		int i_orig = RIGID ? sorted_id[s] : 0;
 		SPH_FOR_27(c, cx, cy, cz, c1) {
 			int a = cstart[c1], b = cstart[c1 + 1];
 			for (int e = a; e < b; ++e) {
@@ -102,11 +127,38 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 				if (culled(p, c)) continue; // PS:466
 				if (nf < c.kmax) fl[(size_t)nf * 32] = (uint32_t)e;
 				nf++;
+				ncount++;
 				rho_f += c.m * cubic_w(p, c); // SB:62
 				if (ALPHA) {
 					f3 g = c.m * cubic_dw(p, c); // DF:58, 70
 					ss = ss + g;
 					sq += dot(g, g);
+				}
+			}
+			if (RIGID) {
+				// rigid particles follow the fluid ones inside a cell (second append kernel, PS:385-386)
+				int ra = rg.rstart[c1], rb = rg.rstart[c1 + 1];
+				for (int e = ra; e < rb; ++e) {
+					// PS:440-442 quirk: the count compares the rigid-LOCAL index with i and measures the
+					// distance to the FLUID particle with that index (SURVEY B-7)
+					int k = rg.rsorted_id[e];
+					if (k != i_orig) {
+						float4 pq = rg.pos_orig[min(k, c.N_owned - 1)];
+						Pair q = make_pair(pi, pq);
+						if (!culled(q, c)) ncount++;
+					}
+					float4 pj = rg.rspos[e];
+					Pair p = make_pair(pi, pj);
+					if (culled(p, c)) continue;
+					if (c.fs_couple != 1) continue; // SB:64: the tasks return 0
+					if (nf < c.kmax) fl[(size_t)nf * 32] = (uint32_t)e | SPH_RIGID_BIT;
+					nf++;
+					rho_f += (pj.w * cubic_w(p, c)) * SPH_RHO0; // SB:65
+					if (ALPHA) {
+						f3 g = (pj.w * SPH_RHO0) * cubic_dw(p, c); // DF:62, 75
+						ss = ss + g;
+						sq += dot(g, g);
+					}
 				}
 			}
 		}
@@ -138,7 +190,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		}
 		L.fcount[s] = min(nf, c.kmax);
 		L.bcount[s] = min(nb, c.kbmax);
-		nbr_count[s] = nf;
+		nbr_count[s] = ncount;
 		rho[s] = rho_i;
 		posR[s] = make_float4(pi.x, pi.y, pi.z, rho_i);
 		if (ALPHA) {
@@ -162,19 +214,20 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	if (c.N <= 0) return;
 	int nb = cdiv(c.N, SPH_BLOCK);
-	if (c.solver == SPH_SOLVER_DFSPH) {
-		sph_prof_begin(h, KC_LISTS, st);
-		k_build_lists<true><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,
-		                                              h->bspos, h->bg.cell_start, h->L, h->nbr_count, h->a1[A1_RHO],
-		                                              h->a1[A1_ALPHA], h->a4[A4_PR], h->a4[A4_T1], h->ctl);
-		sph_prof_end(h, st);
-	} else {
-		sph_prof_begin(h, KC_LISTS, st);
-		k_build_lists<false><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,
-		                                               h->bspos, h->bg.cell_start, h->L, h->nbr_count, h->a1[A1_RHO],
-		                                               h->a1[A1_ALPHA], h->a4[A4_PR], h->a4[A4_T1], h->ctl);
-		sph_prof_end(h, st);
-	}
+	SphRigidArgs rg = rigid_args(h);
+	bool al = c.solver == SPH_SOLVER_DFSPH;
+	sph_prof_begin(h, KC_LISTS, st);
+#define SPH_BL(A, R)                                                                                              \
+	k_build_lists<A, R><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,  \
+	                                              h->fg.sorted_id, h->bspos, h->bg.cell_start, h->L, rg,           \
+	                                              h->nbr_count, h->a1[A1_RHO], h->a1[A1_ALPHA], h->a4[A4_PR],      \
+	                                              h->a4[A4_T1], h->ctl)
+	if (al && rg.active) SPH_BL(true, true);
+	else if (al) SPH_BL(true, false);
+	else if (rg.active) SPH_BL(false, true);
+	else SPH_BL(false, false);
+#undef SPH_BL
+	sph_prof_end(h, st);
 	h->launches++;
 	h->lists_valid = true;
 }
@@ -191,25 +244,37 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 // DFSPH (dfsph_solver.py)
 // =============================================================================================
 
+// A rigid neighbour entry of the fluid list: sorted rigid slot with SPH_RIGID_BIT set.
+#define SPH_IS_RIGID(j) (RIGID && ((j) & SPH_RIGID_BIT))
+#define SPH_RIGID_SLOT(j) ((j) & ~SPH_RIGID_BIT)
+
 // DF:314-355 divergence_warm_start.  Reads neighbour payload t1 = (k/dt)/rho from posT1.w.
+template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_df_warm_start(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float4 *__restrict__ bspos,
-                const float *__restrict__ rho, float4 *__restrict__ svel, const SphCtl *__restrict__ ctl) {
+k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT1,
+                const float4 *__restrict__ bspos, const float *__restrict__ rho, float4 *__restrict__ svel,
+                const SphCtl *__restrict__ ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N_owned) return;
 	float dt = ctl->dt;
 	float4 pi = posT1[s];
 	float4 vi = svel[s];
+	float k_i = vi.w / dt; // DF:333, 342, 353
+	float rho_i = rho[s];
 	f3 va = F3(0.0f, 0.0f, 0.0f);
 	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			Pair p = make_pair(pi, pj);
+			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * cubic_dw(p, c); // DF:345
+			continue;
+		}
 		float4 pj = __ldg(&posT1[j]);
 		Pair p = make_pair(pi, pj);
 		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:337
 	}
 	f3 v = xyz(vi);
 	if (c.boundary_handle == 1) {
-		float k_i = vi.w / dt; // DF:353
-		float rho_i = rho[s];
 		f3 vb = F3(0.0f, 0.0f, 0.0f);
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
@@ -225,11 +290,12 @@ k_df_warm_start(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const
 
 // DF:252-300 derivative_iter_all_rho.  Writes drho and the payload t2 = ((drho*alpha)/dt)/rho of
 // the following divergence iteration (DF:363-367); block partials feed the device-side average.
+template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_df_drho(SphConsts c, SphLists L, const float4 *__restrict__ spos, const float4 *__restrict__ svel,
-          const float4 *__restrict__ bspos, const int *__restrict__ nbr_count, const float *__restrict__ rho,
-          const float *__restrict__ alpha, float *__restrict__ drho, float4 *__restrict__ posT2,
-          const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
+k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ spos,
+          const float4 *__restrict__ svel, const float4 *__restrict__ bspos, const int *__restrict__ nbr_count,
+          const float *__restrict__ rho, const float *__restrict__ alpha, float *__restrict__ drho,
+          float4 *__restrict__ posT2, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
 	if (gated && !ctl->div_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	double psum = 0.0;
@@ -237,10 +303,18 @@ k_df_drho(SphConsts c, SphLists L, const float4 *__restrict__ spos, const float4
 	if (s < c.N_owned) {
 		float4 pi = spos[s];
 		float out = 0.0f;
+		float dt = ctl->dt;
 		if (nbr_count[s] >= 20) { // DF:258-261
 			f3 vi = xyz(svel[s]);
 			float rd = 0.0f;
 			SPH_FOR_FLUID(L, c, s, j) {
+				if (SPH_IS_RIGID(j)) {
+					float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+					Pair p = make_pair(pi, pj);
+					f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, false);             // DF:292-293
+					rd += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));        // DF:294
+					continue;
+				}
 				float4 pj = __ldg(&spos[j]);
 				f3 vj = xyz(__ldg(&svel[j]));
 				Pair p = make_pair(pi, pj);
@@ -259,36 +333,43 @@ k_df_drho(SphConsts c, SphLists L, const float4 *__restrict__ spos, const float4
 			}
 		}
 		drho[s] = out;
-		posT2[s] = make_float4(pi.x, pi.y, pi.z, ((out * alpha[s]) / ctl->dt) / rho[s]);
+		posT2[s] = make_float4(pi.x, pi.y, pi.z, ((out * alpha[s]) / dt) / rho[s]);
 		if (out > 0.0f) { psum = (double)out; pcnt = 1; } // DF:275-277
 	}
 	block_partial(psum, pcnt, 0.0f, partials);
 }
 
 // DF:302-312, 357-391 divergence_iter_all_vel_adv fused with DF:381-384 sum_up_stiff
+template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_df_div_iter(SphConsts c, SphLists L, const float4 *__restrict__ posT2, const float4 *__restrict__ bspos,
-              const float *__restrict__ rho, const float *__restrict__ alpha, const float *__restrict__ drho,
-              float4 *__restrict__ svel, const SphCtl *__restrict__ ctl) {
+k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT2,
+              const float4 *__restrict__ bspos, const float *__restrict__ rho, const float *__restrict__ alpha,
+              const float *__restrict__ drho, float4 *__restrict__ svel, const SphCtl *__restrict__ ctl) {
 	if (!ctl->div_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N_owned) return;
 	float dt = ctl->dt;
 	float4 pi = posT2[s];
 	float4 vi = svel[s];
+	float da = drho[s] * alpha[s];
+	float k_i = da / dt; // DF:363, 374, 388
+	float rho_i = rho[s];
 	f3 va = F3(0.0f, 0.0f, 0.0f);
 	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			Pair p = make_pair(pi, pj);
+			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * cubic_dw(p, c); // DF:377
+			continue;
+		}
 		float4 pj = __ldg(&posT2[j]);
 		Pair p = make_pair(pi, pj);
 		float f = pi.w + pj.w;
 		f3 dw = cubic_dw(p, c);
 		if (f > 1e-5f) va = va + (c.m * f) * dw; // DF:367-369
 	}
-	float da = drho[s] * alpha[s];
 	f3 v = xyz(vi);
 	if (c.boundary_handle == 1) {
-		float k_i = da / dt; // DF:388
-		float rho_i = rho[s];
 		f3 vb = F3(0.0f, 0.0f, 0.0f);
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
@@ -302,12 +383,33 @@ k_df_div_iter(SphConsts c, SphLists L, const float4 *__restrict__ posT2, const f
 	svel[s] = F4(v, vi.w + da); // DF:384
 }
 
+// SB:190-201: viscosity contribution of a rigid neighbour (uses rho[particle_j.index], SURVEY B-6)
+template <bool RIGID>
+__device__ __forceinline__ void rigid_viscosity(const SphConsts &c, const SphRigidArgs &rg, uint32_t j,
+                                                const float4 &pi, const f3 &vi, float rho_i,
+                                                const float *__restrict__ rho, f3 &visc) {
+	uint32_t r = SPH_RIGID_SLOT(j);
+	float4 pj = __ldg(&rg.rspos[r]);
+	Pair p = make_pair(pi, pj);
+	f3 v_ij = vi - ld3(rg.st->vel);
+	float shear = dot(v_ij, p.r);
+	if (shear < 0.0f) {
+		float q = sqrtf(p.r2);
+		float q2 = q * q;
+		int jr = min(rg.rsorted_id[r], c.N_owned - 1);
+		float nu = c.visc_num / (rho_i + rho[rg.slot_of[jr]]);
+		float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);
+		visc = visc + ((-SPH_RHO0 * pj.w) * pi_ij) * cubic_dw(p, c); // SB:201
+	}
+}
+
 // DF:91-122: tension (SB:204-217) + viscosity (SB:170-202) + f_ext + v* = v + dt f / m, and the
 // block maxima of |v*| for the adaptive time step.
+template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_df_ext_force(SphConsts c, SphLists L, const float4 *__restrict__ posR, const float4 *__restrict__ svel,
-               float4 *__restrict__ svadv, float4 *__restrict__ fext, const SphCtl *__restrict__ ctl,
-               SphPartial *__restrict__ partials) {
+k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posR,
+               const float4 *__restrict__ svel, const float *__restrict__ rho, float4 *__restrict__ svadv,
+               float4 *__restrict__ fext, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	float vmax = -INFINITY;
 	if (s < c.N_owned) {
@@ -316,6 +418,10 @@ k_df_ext_force(SphConsts c, SphLists L, const float4 *__restrict__ posR, const f
 		f3 vi = xyz(svel[s]);
 		f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
 		SPH_FOR_FLUID(L, c, s, j) {
+			if (SPH_IS_RIGID(j)) {
+				rigid_viscosity<RIGID>(c, rg, j, pi, vi, pi.w, rho, visc);
+				continue;
+			}
 			float4 pj = __ldg(&posR[j]);
 			f3 vj = xyz(__ldg(&svel[j]));
 			Pair p = make_pair(pi, pj);
@@ -348,11 +454,12 @@ k_df_ext_force(SphConsts c, SphLists L, const float4 *__restrict__ posR, const f
 
 // DF:124-176 compute_all_rho_adv.  Writes rho_adv and the payload t3 = (((rho_adv-rho0)*alpha)/dt2)/rho
 // of iter_all_vel_adv (DF:199-203).
+template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_df_rho_adv(SphConsts c, SphLists L, const float4 *__restrict__ spos, const float4 *__restrict__ svadv,
-             const float4 *__restrict__ bspos, const float *__restrict__ rho, const float *__restrict__ alpha,
-             float *__restrict__ rho_adv, float4 *__restrict__ posT3, const SphCtl *__restrict__ ctl,
-             SphPartial *__restrict__ partials, int gated) {
+k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ spos,
+             const float4 *__restrict__ svadv, const float4 *__restrict__ bspos, const float *__restrict__ rho,
+             const float *__restrict__ alpha, float *__restrict__ rho_adv, float4 *__restrict__ posT3,
+             const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
 	if (gated && !ctl->den_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	double psum = 0.0;
@@ -363,6 +470,13 @@ k_df_rho_adv(SphConsts c, SphLists L, const float4 *__restrict__ spos, const flo
 		f3 vi = xyz(svadv[s]);
 		float delta = 0.0f;
 		SPH_FOR_FLUID(L, c, s, j) {
+			if (SPH_IS_RIGID(j)) {
+				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+				Pair p = make_pair(pi, pj);
+				f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, true);                  // DF:168-169
+				delta += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));         // DF:170
+				continue;
+			}
 			float4 pj = __ldg(&spos[j]);
 			f3 vj = xyz(__ldg(&svadv[j]));
 			Pair p = make_pair(pi, pj);
@@ -388,27 +502,35 @@ k_df_rho_adv(SphConsts c, SphLists L, const float4 *__restrict__ spos, const flo
 	block_partial(psum, pcnt, 0.0f, partials);
 }
 
-// DF:178-219 iter_all_vel_adv (fluid + boundary part; the rigid force gather is k_rigid_force)
+// DF:178-219 iter_all_vel_adv (fluid + boundary part; the rigid force scatter DF:212 is the gather
+// kernel k_rigid_force_df in sph_rigid.cuh)
+template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_df_vel_adv_iter(SphConsts c, SphLists L, const float4 *__restrict__ posT3, const float4 *__restrict__ bspos,
-                  const float *__restrict__ rho, const float *__restrict__ alpha,
-                  const float *__restrict__ rho_adv, float4 *__restrict__ svadv,
-                  const SphCtl *__restrict__ ctl, int gated) {
+k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT3,
+                  const float4 *__restrict__ bspos, const float *__restrict__ rho, const float *__restrict__ alpha,
+                  const float *__restrict__ rho_adv, float4 *__restrict__ svadv, const SphCtl *__restrict__ ctl,
+                  int gated) {
 	if (gated && !ctl->den_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N_owned) return;
 	float dt = ctl->dt, dt2 = ctl->dt2;
 	float4 pi = posT3[s];
+	float rho_i = rho[s];
+	float k_i = ((rho_adv[s] - SPH_RHO0) * alpha[s]) / dt2; // DF:199, 208, 217
 	f3 va = F3(0.0f, 0.0f, 0.0f);
 	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			Pair p = make_pair(pi, pj);
+			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * cubic_dw(p, c); // DF:211
+			continue;
+		}
 		float4 pj = __ldg(&posT3[j]);
 		Pair p = make_pair(pi, pj);
 		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:203
 	}
 	f3 delta = va;
 	if (c.boundary_handle == 1) {
-		float rho_i = rho[s];
-		float k_i = ((rho_adv[s] - SPH_RHO0) * alpha[s]) / dt2; // DF:217
 		f3 vb = F3(0.0f, 0.0f, 0.0f);
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
@@ -497,10 +619,11 @@ __global__ void __launch_bounds__(256) k_df_ctl_div(SphCtl *ctl, const SphPartia
 
 // DF:100-119: max |v*| (+ rigid surface speed) -> adaptive dt on the device
 __global__ void __launch_bounds__(256) k_df_ctl_dt(SphCtl *ctl, const SphPartial *partials, int n, SphConsts c,
-                                                    float max_rigid_vel) {
+                                                    const SphRigidState *rs, int rigid_exists) {
 	double sum; int cnt; float mx;
 	reduce_partials(partials, n, sum, cnt, mx);
 	if (threadIdx.x != 0) return;
+	float max_rigid_vel = rigid_exists ? rs->max_surface_vel : 0.0f; // DF:104-110 (loops over ALL rigid particles)
 	float max_vel = mx + max_rigid_vel;              // DF:111
 	float max_dt = (c.dt_cfl_c1 / max_vel) * 0.2f;   // DF:112
 	float dt;
@@ -536,27 +659,37 @@ __global__ void k_df_ctl_den_next(SphCtl *ctl) {
 }
 
 // ---- DFSPH drivers -----------------------------------------------------------------------------
+// launch a kernel templated on RIGID with the instantiation the scene needs
+#define SPH_LAUNCH_R(K, GRID, ...)                                                        \
+	do {                                                                                  \
+		if (rg.active) K<true><<<GRID, SPH_BLOCK, 0, st>>>(__VA_ARGS__);                  \
+		else K<false><<<GRID, SPH_BLOCK, 0, st>>>(__VA_ARGS__);                           \
+	} while (0)
+
+void rigid_lists(SphHandle *h, cudaStream_t st);
+void rigid_force_df(SphHandle *h, int gated, cudaStream_t st);
+
 static void df_divergence(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_WARM, st);
-	k_df_warm_start<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl);
+	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl);
 	sph_prof_end(h, st);
 	sph_prof_begin(h, KC_DF_DRHO, st);
-	k_df_drho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
-	                                    h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 0);
+	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
+	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 0);
 	sph_prof_end(h, st);
 	k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0);
 	h->launches += 3;
 	for (int it = 0; it < 15; ++it) { // max_iteration_density_divergence (DF:24); gated on ctl->div_active
 		sph_prof_begin(h, KC_DF_DIV, st);
-		k_df_div_iter<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-		                                        h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
+		SPH_LAUNCH_R(k_df_div_iter, nb, c, h->L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
+		             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
 		sph_prof_end(h, st);
 		sph_prof_begin(h, KC_DF_DRHO, st);
-		k_df_drho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
-		                                    h->a1[A1_RHO], h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl,
-		                                    h->partials, 1);
+		SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
+		             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 1);
 		sph_prof_end(h, st);
 		k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1);
 		h->launches += 3;
@@ -566,29 +699,32 @@ static void df_divergence(SphHandle *h, cudaStream_t st) {
 static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_EXT, st);
-	k_df_ext_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_PR], h->a4[A4_VEL], h->a4[A4_VADV], h->a4[A4_FA], h->ctl,
-	                                         h->partials);
+	SPH_LAUNCH_R(k_df_ext_force, nb, c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->a4[A4_VADV],
+	             h->a4[A4_FA], h->ctl, h->partials);
 	sph_prof_end(h, st);
-	k_df_ctl_dt<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, c, 0.0f);
+	// DF:105-110 loops over all rigid particles whenever a rigid body exists, active or not
+	k_df_ctl_dt<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, c, h->rstate, (c.Nr > 0 && h->rigid_ready) ? 1 : 0);
 	h->launches += 2;
 }
 
 static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	SphRigidArgs rg = rigid_args(h);
 	for (int it = first; it < first + count; ++it) {
 		int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
 		sph_prof_begin(h, KC_DF_RHOADV, st);
-		k_df_rho_adv<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
-		                                       h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials,
-		                                       gated);
+		SPH_LAUNCH_R(k_df_rho_adv, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
+		             h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated);
 		sph_prof_end(h, st);
 		k_df_ctl_den<<<1, 256, 0, st>>>(h->ctl, h->partials, nb);
 		sph_prof_begin(h, KC_DF_VELADV, st);
-		k_df_vel_adv_iter<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-		                                            h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
+		SPH_LAUNCH_R(k_df_vel_adv_iter, nb, c, h->L, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
+		             h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
 		sph_prof_end(h, st);
+		if (rg.active) rigid_force_df(h, gated, st); // DF:212, gather form
 		k_df_ctl_den_next<<<1, 1, 0, st>>>(h->ctl);
 		h->launches += 4;
 	}
@@ -599,6 +735,7 @@ static int df_density(SphHandle *h, cudaStream_t st) {
 	// device flag; the host looks at the flag once per chunk (not per iteration).
 	int chunk = h->last_den_chunk > 0 ? h->last_den_chunk : 3;
 	int done = 0;
+	if (rigid_args(h).active) rigid_lists(h, st);
 	for (;;) {
 		df_density_iters(h, done, chunk, st);
 		done += chunk;
@@ -648,4 +785,5 @@ void ii_phase(SphHandle *h, int phase, cudaStream_t st);
 
 } // namespace SPH_NS
 
+#include "sph_rigid.cuh"
 #include "sph_sweeps_other.cuh"

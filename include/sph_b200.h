@@ -80,6 +80,7 @@ enum SphField {
 	SPH_F_RIGID_VEL = 4,   /* xyz = rigid_particles.vel, w = rigid_particles.mass */
 	SPH_F_RIGID_FORCE = 5, /* xyz = rigid_particles.force */
 	SPH_F_FLUID_ACC = 6,   /* xyz = fluid_particles.acc (WCSPH only) */
+	SPH_F_RIGID_VERTICES = 7, /* xyz = ps.rigid_vertices (mesh vertices moved with the body, RS:101-102, 138-139) */
 	/* fetchable per-fluid-particle results (float unless noted), original order */
 	SPH_F_RHO = 16, SPH_F_ALPHA, SPH_F_RHO_DERIVATIVE, SPH_F_RHO_ADV, SPH_F_VEL_ADV /*float4*/,
 	SPH_F_CELL1D /*int32*/, SPH_F_NEIGHBOR_COUNT /*int32*/, SPH_F_BOUNDARY_NEIGHBOR_COUNT /*int32*/,
@@ -154,8 +155,8 @@ int sph_bind(SphHandle *h, int field, void *dev_ptr, size_t n);
 /* One-time static boundary set-up: boundary grid (PS:322-335) and Akinci volumes (PS:309-320).
  * Writes the volume into SPH_F_BOUNDARY_POS.w. */
 int sph_init_boundary(SphHandle *h, void *stream);
-/* One-time rigid set-up: volumes/masses (PS:249-263).  Mass properties (PS:265-291) are O(1)
- * host algebra on the fetched arrays and stay in the Python mirror. */
+/* One-time rigid set-up (PS:249-295): Akinci volumes and masses of the rigid particles (written to
+ * SPH_F_RIGID_POS.w / SPH_F_RIGID_VEL.w), centroid, inertia tensor and its inverse (device state). */
 int sph_init_rigid(SphHandle *h, void *stream);
 
 /* PCISPH pre_compute (PC:28-37): grid + neighbour lists/counts of the initial state.  The arg-max of
@@ -169,17 +170,19 @@ int sph_step(SphHandle *h, int n_substeps, void *stream);
 /* One phase (see enum SphPhase). */
 int sph_phase(SphHandle *h, int phase, void *stream);
 
-/* Rigid body: force/torque reduction over rigid particles (RS:35-38, 121-123); writes
- * out6[0..2] = sum of forces, out6[3..5] = torque about `centroid`, then zeroes the forces. */
-int sph_rigid_reduce(SphHandle *h, const float centroid[3], float *dev_out6, void *stream);
-/* Rigid body: rotate about centroid with R (row-major 3x3) then translate (RS:135-136, 98-99)
- * and refresh the per-particle vel/omega/alpha/acc used by the coupling terms. */
-int sph_rigid_transform(SphHandle *h, const float centroid[3], const float R[9], const float disp[3],
-                        const float vel[3], const float omega[3], const float alpha[3],
-                        const float acc[3], void *stream);
-/* Rigid wall contact scan (RS:53-76): per-axis displacement clamp and contact accumulation. */
-int sph_rigid_contacts(SphHandle *h, const float vel[3], const float omega[3], const float centroid[3],
-                       const float disp[3], float *dev_out16, void *stream);
+/* One rigid_solver.step() (RS:216-234), entirely on the device: torque and force reductions over the
+ * rigid particles (RS:121-123, 35-38; hierarchical warp/block reductions in the fast kernels, serial
+ * reference order in the strict kernels), attitude / rotation (RS:118-141), wall contact scan and
+ * impulse (RS:53-94), particle, vertex and centroid update (RS:96-104).  Fluid->rigid forces are
+ * GATHERED per rigid particle inside the fluid solver step (no per-pair atomics; replaces DF:212). */
+int sph_rigid_step(SphHandle *h, void *stream);
+typedef struct SphRigidInfo {
+	float centroid[3], inertia[9], inertia_inv[9];
+	float vel[3], omega[3], alpha[3], acc[3], attitude[3], force_sum[3], torque[3];
+	float mass, delta_time;
+	int32_t collision_cnt, simulate_cnt;
+} SphRigidInfo;
+int sph_rigid_state(SphHandle *h, SphRigidInfo *out); /* synchronises */
 
 int sph_set_delta_time(SphHandle *h, float dt, void *stream);
 
