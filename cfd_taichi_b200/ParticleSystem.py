@@ -11,7 +11,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib, scene
+from . import _lib, scene, slab as slab_plan
 from .fields import DeviceScalar, FetchedField, HostScalar, ParticleFields, TensorField
 
 
@@ -21,7 +21,9 @@ class ParticleSystem:
     material_solid = 2
 
     def __init__(self, config, device=None, strict=None, solver_name=None, ghost_capacity=0,
-                 max_neighbors=None, base_dir=None):
+                 max_neighbors=None, base_dir=None, slab=None):
+        """`slab=(rank, nranks)`: this process holds one x-slab of the domain (multi-GPU, SURVEY 8(e));
+        torch.distributed must be initialised (it carries the NCCL id; the exchange itself is in the library)."""
         if not torch.cuda.is_available():
             raise _lib.SphError("ParticleSystem needs a CUDA device: the B200 SPH path has no CPU fallback")
         self._lib = _lib.load()
@@ -55,14 +57,32 @@ class ParticleSystem:
         self._3d_to_1d_tran = [1, self.grid_num[0] * self.grid_num[2], self.grid_num[0]]
         print('Boundary particle count: {}k'.format(self.boundary_particles_num / 1000))
 
+        self._slab = None
+        self._owned_ids = None
+        self._n_owned_cap = self.particle_num
+        if slab is not None and slab[1] > 1:
+            rank, nranks = int(slab[0]), int(slab[1])
+            hist, _ = slab_plan.column_histogram(config)
+            cuts = slab_plan.plan_cuts(hist, nranks)
+            ids, _, _ = slab_plan.owned_lattice_ids(config, cuts[rank], cuts[rank + 1])
+            owned0, owned_cap, ghost_cap = slab_plan.capacities(config, cuts, rank)
+            assert owned0 == len(ids)
+            self._slab = dict(rank=rank, nranks=nranks, cuts=cuts, col_lo=cuts[rank], col_hi=cuts[rank + 1])
+            self._owned_ids = ids
+            self._n_owned_cap = owned_cap
+            self._ghost_capacity = ghost_cap
+            if self.exist_rigid[None] == 1:
+                raise _lib.SphError("multi-GPU slabs do not carry a rigid body in this round")
+
         dev = self._device
-        n, nb = self.particle_num, self.boundary_particles_num
+        n, nb = self._n_owned_cap, self.boundary_particles_num
         ncap = n + self._ghost_capacity
         # caller-owned state, float4 SoA (see include/sph_b200.h enum SphField)
         self._pos4 = torch.zeros((ncap, 4), dtype=torch.float32, device=dev)
         self._vel4 = torch.zeros((ncap, 4), dtype=torch.float32, device=dev)
         self._acc4 = torch.zeros((ncap, 4), dtype=torch.float32, device=dev)
         self._bpos4 = torch.zeros((max(nb, 1), 4), dtype=torch.float32, device=dev)
+        self._gid = torch.zeros((ncap,), dtype=torch.int32, device=dev) if self._slab else None
         self._rgb = torch.zeros((n, 3), dtype=torch.float32, device=dev)
         self.rgba = TensorField(torch.tensor([0.0, 0.26, 0.68, 1.0], device=dev).repeat(n, 1))   # PS:113,152
         self.rgb = TensorField(torch.tensor([0.0, 0.28, 1.0], device=dev).repeat(n, 1))          # PS:116-117
@@ -151,7 +171,7 @@ class ParticleSystem:
         cfg.boundary_handle = 1 if solver_config.get('boundary_handle', True) else 0   # SB:31
         cfg.fs_couple = 1 if solver_config.get('fs_couple', True) else 0               # SB:32
         cfg.solver = _lib.SOLVER_IDS[solver_name]
-        cfg.n_fluid = self.particle_num
+        cfg.n_fluid = self._n_owned_cap
         cfg.n_boundary = self.boundary_particles_num
         cfg.n_rigid = self.rigid_particles_num
         cfg.active_rigid = int(self.active_rigid[None])
@@ -171,6 +191,8 @@ class ParticleSystem:
         self._h = h
         self._solver_name = solver_name
         self._bind_all()
+        if self._slab:
+            self._join_slab()
 
     def _bind_all(self):
         L, h = self._lib, self._h
@@ -184,6 +206,41 @@ class ParticleSystem:
             _lib.check(L.sph_bind(h, _lib.F_RIGID_VEL, self._rvel4.data_ptr(), self._rvel4.shape[0]), h)
             _lib.check(L.sph_bind(h, _lib.F_RIGID_FORCE, self._rforce4.data_ptr(), self._rforce4.shape[0]), h)
             _lib.check(L.sph_bind(h, _lib.F_RIGID_VERTICES, self._rverts4.data_ptr(), self.rigid_vertex_count), h)
+
+    def _join_slab(self):
+        """Bind the global ids, set the owned count and join the NCCL communicator (sph_comm_init)."""
+        import torch.distributed as dist
+        L, h, sl = self._lib, self._h, self._slab
+        n0 = len(self._owned_ids)
+        self._gid[:n0] = torch.from_numpy(self._owned_ids.astype(np.int32)).to(self._device)
+        _lib.check(L.sph_bind(h, _lib.F_FLUID_GID, self._gid.data_ptr(), self._gid.shape[0]), h)
+        _lib.check(L.sph_set_counts(h, n0, 0), h)
+        buf = ctypes.create_string_buffer(128)
+        if sl['rank'] == 0:
+            _lib.check(L.sph_comm_unique_id(buf))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=self._device)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+        _lib.check(L.sph_comm_init(h, raw, sl['rank'], sl['nranks'], sl['col_lo'], sl['col_hi']), h)
+
+    def comm_info(self):
+        out = (ctypes.c_int32 * 8)()
+        _lib.check(self._lib.sph_comm_info(self._h, out), self._h)
+        return dict(owned=out[0], ghosts=out[1], sent=(out[2], out[3]), received=(out[4], out[5]), rank=out[6],
+                    nranks=out[7])
+
+    def local_count(self):
+        """Particles this handle currently sorts (owned + ghosts); == particle_num on one GPU."""
+        if not self._slab:
+            return self.particle_num
+        i = self.comm_info()
+        return i['owned'] + i['ghosts']
+
+    def owned_state(self):
+        """(gid, pos, vel) of the particles this rank owns, as numpy arrays (tests / output writers)."""
+        n = self.comm_info()['owned'] if self._slab else self.particle_num
+        gid = self._gid[:n].cpu().numpy() if self._slab else np.arange(n, dtype=np.int32)
+        return gid, self._pos4[:n, :3].cpu().numpy(), self._vel4[:n].cpu().numpy()
 
     def _ensure_solver(self, solver_name):
         """Solvers are located by name (main.py:65-68); a solver class built on a ParticleSystem whose
@@ -206,7 +263,7 @@ class ParticleSystem:
             pass
 
     def _fetch(self, field_id, width, dtype, count=None):
-        n = self.particle_num if count is None else count
+        n = self.local_count() if count is None else count
         out = torch.empty((n, width), dtype=dtype, device=self._device)
         _lib.check(self._lib.sph_fetch(self._h, field_id, out.data_ptr(), n, self._stream()), self._h)
         return out
@@ -227,8 +284,8 @@ class ParticleSystem:
 
     def init_particle_pos(self):                                                    # PS:139-195
         n, nb = self.particle_num, self.boundary_particles_num
-        fp = scene.init_fluid_positions(self.config, n)
-        self._pos4[:n, :3].copy_(torch.from_numpy(fp).to(self._device))
+        fp = scene.init_fluid_positions(self.config, n, self._owned_ids)
+        self._pos4[:fp.shape[0], :3].copy_(torch.from_numpy(fp).to(self._device))
         if nb > 0:
             bp = scene.init_boundary_positions(self.config, nb)
             self._bpos4[:nb, :3].copy_(torch.from_numpy(bp).to(self._device))
@@ -311,13 +368,13 @@ class ParticleSystem:
 
     def cell_indices_1d(self):
         """1-D cell id per fluid particle, original order (PS:486-494)."""
-        return self._fetch_raw(_lib.F_CELL1D, self.particle_num)
+        return self._fetch_raw(_lib.F_CELL1D, self.local_count())
 
     def cell_start(self):
         return self._fetch_raw(_lib.F_CELL_START, self.grid_count + 1)
 
     def sorted_index(self):
-        return self._fetch_raw(_lib.F_SORTED_INDEX, self.particle_num)
+        return self._fetch_raw(_lib.F_SORTED_INDEX, self.local_count())
 
     def neighbour_counts(self):
         """get_neighbour_count(i) for every fluid particle (PS:424-445); needs the step's lists."""

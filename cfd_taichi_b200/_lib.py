@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "_build", "libsph_b200.so")
 SOLVER_IDS = {"wcsph": 0, "pcisph": 1, "iisph": 2, "dfsph": 3}
 
 # enum SphField
-F_FLUID_POS, F_FLUID_VEL, F_BOUNDARY_POS, F_RIGID_POS, F_RIGID_VEL, F_RIGID_FORCE, F_FLUID_ACC, F_RIGID_VERTICES = range(8)
+F_FLUID_POS, F_FLUID_VEL, F_BOUNDARY_POS, F_RIGID_POS, F_RIGID_VEL, F_RIGID_FORCE, F_FLUID_ACC, F_RIGID_VERTICES, F_FLUID_GID = range(9)
 (F_RHO, F_ALPHA, F_RHO_DERIVATIVE, F_RHO_ADV, F_VEL_ADV, F_CELL1D, F_NEIGHBOR_COUNT,
  F_BOUNDARY_NEIGHBOR_COUNT, F_PRESSURE, F_FORCE_A, F_FORCE_B, F_SCALAR_A, F_SCALAR_B, F_SCALAR_C,
  F_VEC_A, F_VEC_B, F_VEC_C) = range(16, 33)
@@ -114,7 +114,9 @@ PROTOTYPES = [
     ("sph_read_stats", _i, [_vp, ctypes.POINTER(SphStats)]),
     ("sph_profile_begin", _i, [_vp]),
     ("sph_profile_end", _i, [_vp, _fp, ctypes.POINTER(ctypes.c_int32), _i]),
-    ("sph_pack_columns", _i, [_vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    ("sph_comm_unique_id", _i, [ctypes.c_char_p]),
+    ("sph_comm_init", _i, [_vp, ctypes.c_char_p, _i, _i, _i, _i]),
+    ("sph_comm_info", _i, [_vp, ctypes.POINTER(ctypes.c_int32)]),
     ("sph_set_counts", _i, [_vp, _i, _i]),
 ]
 

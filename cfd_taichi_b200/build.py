@@ -12,6 +12,22 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libsph_b200.so")
 
+def _nccl_include():
+    # the torch-bundled NCCL (the library the process maps at run time); fall back to the system header
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            p = os.path.join(list(spec.submodule_search_locations)[0], "include")
+            if os.path.exists(os.path.join(p, "nccl.h")):
+                return p
+    except Exception:
+        pass
+    return "/usr/include"
+
+
+NCCL_INC = _nccl_include()
+
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math"] + ARCH
 
@@ -30,6 +46,7 @@ def build(force=False, verbose=False):
     units = [
         ("sph_grid.cu", "sph_grid.o", []),
         ("sph_api.cu", "sph_api.o", []),
+        ("sph_multigpu.cu", "sph_multigpu.o", ["-I", NCCL_INC]),
         ("sph_sweeps.cu", "sph_sweeps_strict.o", ["-DSPH_STRICT=1", "-fmad=false"]),
         ("sph_sweeps.cu", "sph_sweeps_fast.o", ["-DSPH_STRICT=0", "-fmad=true"]),
     ]
@@ -49,7 +66,7 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if force or _newer(objs, LIB):
-        cmd = ["nvcc", "-shared", "-o", LIB] + objs + ARCH + ["-cudart", "shared"]
+        cmd = ["nvcc", "-shared", "-o", LIB] + objs + ARCH + ["-cudart", "shared", "-ldl"]
         subprocess.run(cmd, check=True)
     return LIB
 

@@ -185,6 +185,7 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	SPH_CUDA_CHECK(h, cudaMallocHost((void **)&h->ctl_host, sizeof(SphCtl)));
 	h->n_partials = cdiv((int)(ncap ? ncap : 1), SPH_BLOCK) + 1;
 	SPH_CUDA_CHECK(h, dalloc(&h->partials, (size_t)h->n_partials));
+	SPH_CUDA_CHECK(h, dalloc(&h->red, 4));
 	memset(h->ctl_host, 0, sizeof(SphCtl));
 	h->ctl_host->dt = (float)cfg->delta_time;        // SB:16
 	{
@@ -214,7 +215,8 @@ extern "C" int sph_destroy(SphHandle *h) {
 	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
 	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.rlist);
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount); cudaFree(h->L.rcount);
-	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials);
+	mg_destroy(h);
+	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);
 	if (h->ctl_host) cudaFreeHost(h->ctl_host);
 	if (h->prof) {
 		if (h->prof->created)
@@ -228,7 +230,7 @@ extern "C" int sph_destroy(SphHandle *h) {
 extern "C" int sph_bind(SphHandle *h, int field, void *dev_ptr, size_t n) {
 	if (!h) return SPH_EINVAL;
 	if (!dev_ptr && n > 0) return sph_fail(h, SPH_EINVAL, "sph_bind: null pointer for field %d", field);
-	if (((uintptr_t)dev_ptr & 15u) != 0) return sph_fail(h, SPH_EINVAL, "sph_bind: field %d is not 16-byte aligned", field);
+	if (((uintptr_t)dev_ptr & 15u) != 0 && field != SPH_F_FLUID_GID) return sph_fail(h, SPH_EINVAL, "sph_bind: field %d is not 16-byte aligned", field);
 	size_t ncap = (size_t)h->cfg.n_fluid + (size_t)(h->cfg.n_ghost_capacity > 0 ? h->cfg.n_ghost_capacity : 0);
 	switch (field) {
 	case SPH_F_FLUID_POS:
@@ -254,6 +256,9 @@ extern "C" int sph_bind(SphHandle *h, int field, void *dev_ptr, size_t n) {
 		h->rforce = (float4 *)dev_ptr; h->n_rforce = n; break;
 	case SPH_F_RIGID_VERTICES:
 		h->rverts = (float4 *)dev_ptr; h->n_rverts = n; break;
+	case SPH_F_FLUID_GID:
+		if (n < ncap) return sph_fail(h, SPH_EINVAL, "sph_bind: fluid gid needs %zu int32, got %zu", ncap, n);
+		h->gid = (int *)dev_ptr; h->n_gid = n; break;
 	default:
 		return sph_fail(h, SPH_EINVAL, "sph_bind: field %d is not bindable", field);
 	}
@@ -351,7 +356,7 @@ static int base_step(SphHandle *h, cudaStream_t st) {
 	// SB:136-143: simulate_cnt += 1 ; reset_grid ; update_grid ; reset()
 	h->simulate_cnt += 1;
 	sph_prof_begin(h, KC_GRID, st);
-	sphg_build(h, h->fg, h->pos, h->c.N, st);
+	sphg_build(h, h->fg, h->pos, h->c.N, st, h->comm ? h->gid : nullptr);
 	sphg_gather_fluid(h, st);
 	if (h->c.Nr > 0 && h->c.active_rigid) { // PS:385-386, 399-407
 		sphg_build(h, h->rg, h->rpos, h->c.Nr, st);
@@ -369,6 +374,10 @@ extern "C" int sph_phase(SphHandle *h, int phase, void *stream) {
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
 	if (phase == SPH_PH_BUILD_GRID) {
+		if (h->comm) {
+			rc = mg_begin_step(h, st);
+			if (rc != SPH_OK) return rc;
+		}
 		base_step(h, st);
 		return check_launch(h, "sph_phase(build_grid)");
 	}
@@ -406,6 +415,10 @@ extern "C" int sph_step(SphHandle *h, int n_substeps, void *stream) {
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
 	bool strict = h->cfg.strict != 0;
 	for (int k = 0; k < n_substeps; ++k) {
+		if (h->comm) { // multi-GPU slab: migration + ghost particles first (positions moved last step)
+			rc = mg_begin_step(h, st);
+			if (rc != SPH_OK) return rc;
+		}
 		base_step(h, st);
 		switch (h->c.solver) {
 		case SPH_SOLVER_DFSPH:
@@ -613,11 +626,6 @@ extern "C" int sph_read_stats(SphHandle *h, SphStats *out) {
 }
 
 // ---- multi-GPU slab support ------------------------------------------------------------------------
-extern "C" int sph_pack_columns(SphHandle *h, int col_lo, int col_hi, float *dev_pos4, float *dev_vel4,
-                                int32_t *dev_count, int capacity, void *stream) {
-	(void)col_lo; (void)col_hi; (void)dev_pos4; (void)dev_vel4; (void)dev_count; (void)capacity; (void)stream;
-	return sph_fail(h, SPH_ESTATE, "sph_pack_columns: not available");
-}
 extern "C" int sph_set_counts(SphHandle *h, int n_owned, int n_ghost) {
 	if (!h) return SPH_EINVAL;
 	size_t ncap = (size_t)h->cfg.n_fluid + (size_t)(h->cfg.n_ghost_capacity > 0 ? h->cfg.n_ghost_capacity : 0);

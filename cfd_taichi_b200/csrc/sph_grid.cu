@@ -153,17 +153,21 @@ __global__ void __launch_bounds__(256) k_scatter(const int *__restrict__ cell_of
 	sorted_id[slot] = i;
 }
 
+// gid (optional): global particle id used as the tie-break when the handle holds one slab of a
+// multi-GPU domain, so that the order inside a cell equals the single-domain order.
 __global__ void __launch_bounds__(256) k_cell_fix(const int *__restrict__ start, int G,
-                                                   int *__restrict__ sorted_id) {
+                                                   int *__restrict__ sorted_id, const int *__restrict__ gid) {
 	int c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= G) return;
 	int a = start[c], b = start[c + 1];
 	for (int i = a + 1; i < b; ++i) {
 		int key = sorted_id[i];
+		int kk = gid ? gid[key] : key;
 		int j = i - 1;
 		while (j >= a) {
 			int t = sorted_id[j];
-			if (t <= key) break;
+			int tk = gid ? gid[t] : t;
+			if (tk <= kk) break;
 			sorted_id[j + 1] = t;
 			--j;
 		}
@@ -226,7 +230,7 @@ __global__ void __launch_bounds__(256) k_writeback(const int *__restrict__ sorte
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
-void sphg_build(SphHandle *h, SphGrid &g, const float4 *pos, int n, cudaStream_t st) {
+void sphg_build(SphHandle *h, SphGrid &g, const float4 *pos, int n, cudaStream_t st, const int *gid) {
 	const SphConsts &c = h->c;
 	g.n = n;
 	cudaMemsetAsync(g.cell_cnt, 0, sizeof(int) * (size_t)c.G, st);
@@ -241,7 +245,7 @@ void sphg_build(SphHandle *h, SphGrid &g, const float4 *pos, int n, cudaStream_t
 	h->launches += 3;
 	if (n > 0) {
 		k_scatter<<<cdiv(n, 256), 256, 0, st>>>(g.cell_of, n, g.cell_start, g.cell_cnt, g.sorted_id);
-		k_cell_fix<<<cdiv(c.G, 256), 256, 0, st>>>(g.cell_start, c.G, g.sorted_id);
+		k_cell_fix<<<cdiv(c.G, 256), 256, 0, st>>>(g.cell_start, c.G, g.sorted_id, gid);
 		h->launches += 2;
 	}
 }

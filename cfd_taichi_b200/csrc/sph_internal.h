@@ -79,12 +79,16 @@ struct SphHandle {
 	SphCtl *ctl_host;   // pinned mirror
 	SphPartial *partials;
 	int n_partials;
+	double *red; // device: {sum, cnt, max} of the last reduction (all ranks)
 	bool grid_valid, boundary_ready, lists_valid;
 	int sweep_blocks;
 	// CUDA graph state
 	void *graph_exec;
 	int last_den_chunk;
 	SphProf *prof;
+	struct SphComm *comm; // multi-GPU slab state (sph_multigpu.cu); null on one GPU
+	int *gid;             // caller-owned global particle ids (multi-GPU)
+	size_t n_gid;
 };
 
 int sph_fail(SphHandle *h, int code, const char *fmt, ...);
@@ -103,7 +107,7 @@ static inline void sph_prof_end(SphHandle *h, cudaStream_t st) {
 int sph_fail_cuda(SphHandle *h, cudaError_t e, const char *expr, const char *file, int line);
 
 // ---- sph_grid.cu (mode independent) -------------------------------------------------------
-void sphg_build(SphHandle *h, SphGrid &g, const float4 *pos, int n, cudaStream_t st);
+void sphg_build(SphHandle *h, SphGrid &g, const float4 *pos, int n, cudaStream_t st, const int *gid = nullptr);
 void sphg_gather_fluid(SphHandle *h, cudaStream_t st);
 void sphg_gather_boundary(SphHandle *h, cudaStream_t st);
 void sphg_gather_rigid(SphHandle *h, cudaStream_t st);
@@ -111,6 +115,15 @@ void sphg_unsort_f1(SphHandle *h, const SphGrid &g, const float *in, float *out,
 void sphg_unsort_i1(SphHandle *h, const SphGrid &g, const int *in, int *out, int n, cudaStream_t st);
 void sphg_unsort_f4(SphHandle *h, const SphGrid &g, const float4 *in, float4 *out, int n, cudaStream_t st);
 void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaStream_t st);
+
+// ---- sph_multigpu.cu: slab decomposition along x, NCCL halo exchange / migration / allreduce -------
+// Every call is a no-op (returns immediately) when h->comm is null.
+enum { MG_F4_T1R = 0 /* posT1.w + posR.w */, MG_F4_VEL, MG_F4_T2, MG_F4_VADV, MG_F4_T3 };
+void mg_exchange(SphHandle *h, int what, cudaStream_t st);       // ghost values of one field, both neighbours
+void mg_allreduce(SphHandle *h, int n_blocks, cudaStream_t st);  // partials -> h->red (sum, cnt, max) over ranks
+int mg_begin_step(SphHandle *h, cudaStream_t st);                // migration + ghost exchange + counts
+void mg_after_grid(SphHandle *h, cudaStream_t st);               // sorted slots of the send / recv lists
+void mg_destroy(SphHandle *h);
 
 // ---- sph_sweeps.cu, compiled twice (namespace sph_strict with -fmad=false, sph_fast) -------
 #define SPH_SWEEP_API(NS)                                                                   \

@@ -108,7 +108,16 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
               float4 *__restrict__ posR, float4 *__restrict__ posT1, SphCtl *ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	int nf = 0, nb = 0;
-	if (s < c.N) {
+	if (s < c.N && c.N != c.N_owned && sorted_id[s] >= c.N_owned) {
+		// ghost copy of a neighbour rank's particle (multi-GPU): never a centre particle; its rho / alpha /
+		// payloads arrive through the halo exchange.  fcount < 0 is the ownership flag every sweep tests.
+		float4 pi = spos[s];
+		L.fcount[s] = -1;
+		L.bcount[s] = 0;
+		nbr_count[s] = 0;
+		posR[s] = make_float4(pi.x, pi.y, pi.z, 0.0f);
+		if (ALPHA) posT1[s] = make_float4(pi.x, pi.y, pi.z, 0.0f);
+	} else if (s < c.N) {
 		float4 pi = spos[s];
 		int cx, cy, cz;
 		cell_xyz(scell[s], c, cx, cy, cz);
@@ -255,7 +264,7 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
                 const float4 *__restrict__ bspos, const float *__restrict__ rho, float4 *__restrict__ svel,
                 const SphCtl *__restrict__ ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N_owned) return;
+	if (s >= c.N || L.fcount[s] < 0) return;
 	float dt = ctl->dt;
 	float4 pi = posT1[s];
 	float4 vi = svel[s];
@@ -300,7 +309,7 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	double psum = 0.0;
 	int pcnt = 0;
-	if (s < c.N_owned) {
+	if (s < c.N && L.fcount[s] >= 0) {
 		float4 pi = spos[s];
 		float out = 0.0f;
 		float dt = ctl->dt;
@@ -347,7 +356,7 @@ k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
               const float *__restrict__ drho, float4 *__restrict__ svel, const SphCtl *__restrict__ ctl) {
 	if (!ctl->div_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N_owned) return;
+	if (s >= c.N || L.fcount[s] < 0) return;
 	float dt = ctl->dt;
 	float4 pi = posT2[s];
 	float4 vi = svel[s];
@@ -412,7 +421,7 @@ k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restric
                float4 *__restrict__ fext, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	float vmax = -INFINITY;
-	if (s < c.N_owned) {
+	if (s < c.N && L.fcount[s] >= 0) {
 		float dt = ctl->dt;
 		float4 pi = posR[s];
 		f3 vi = xyz(svel[s]);
@@ -464,7 +473,7 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	double psum = 0.0;
 	int pcnt = 0;
-	if (s < c.N_owned) {
+	if (s < c.N && L.fcount[s] >= 0) {
 		float dt = ctl->dt, dt2 = ctl->dt2;
 		float4 pi = spos[s];
 		f3 vi = xyz(svadv[s]);
@@ -512,7 +521,7 @@ k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__rest
                   int gated) {
 	if (gated && !ctl->den_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N_owned) return;
+	if (s >= c.N || L.fcount[s] < 0) return;
 	float dt = ctl->dt, dt2 = ctl->dt2;
 	float4 pi = posT3[s];
 	float rho_i = rho[s];
@@ -570,6 +579,14 @@ k_df_position(SphConsts c, const int *__restrict__ sorted_id, const float4 *__re
 
 // ---- controller kernels: one block; deterministic reduction of the block partials, then the
 // ---- reference's host-side loop logic evaluated on the device ---------------------------------
+// multi-GPU: partials are reduced by k_reduce_partials, all-reduced with NCCL and handed to the
+// controller kernels through `red` = {sum, count, max}; on one GPU the controller reduces them itself.
+__device__ __forceinline__ void reduce_partials(const SphPartial *p, int n, double &sum, int &cnt, float &mx);
+__device__ __forceinline__ void reduced_or_partials(const double *red, const SphPartial *p, int n, double &sum,
+                                                    int &cnt, float &mx) {
+	if (red) { sum = red[0]; cnt = (int)red[1]; mx = (float)red[2]; __syncthreads(); }
+	else reduce_partials(p, n, sum, cnt, mx);
+}
 __device__ __forceinline__ void reduce_partials(const SphPartial *p, int n, double &sum, int &cnt, float &mx) {
 	__shared__ double ss[256];
 	__shared__ int sc[256];
@@ -591,11 +608,18 @@ __device__ __forceinline__ void reduce_partials(const SphPartial *p, int n, doub
 	sum = ss[0]; cnt = sc[0]; mx = sm[0];
 }
 
-// mode 0: first evaluation (DF:398-399); mode 1: after an iteration (DF:406-414)
-__global__ void __launch_bounds__(256) k_df_ctl_div(SphCtl *ctl, const SphPartial *partials, int n, int mode) {
-	if (mode == 1 && !ctl->div_active) return;
+__global__ void __launch_bounds__(256) k_reduce_partials(const SphPartial *partials, int n, double *red) {
 	double sum; int cnt; float mx;
 	reduce_partials(partials, n, sum, cnt, mx);
+	if (threadIdx.x == 0) { red[0] = sum; red[1] = (double)cnt; red[2] = (double)mx; }
+}
+
+// mode 0: first evaluation (DF:398-399); mode 1: after an iteration (DF:406-414)
+__global__ void __launch_bounds__(256) k_df_ctl_div(SphCtl *ctl, const SphPartial *partials, int n, int mode,
+                                                     const double *red) {
+	if (mode == 1 && !ctl->div_active) return;
+	double sum; int cnt; float mx;
+	reduced_or_partials(red, partials, n, sum, cnt, mx);
 	if (threadIdx.x != 0) return;
 	float avg = cnt > 0 ? (float)(sum / (double)cnt) : 0.0f; // DF:278-279
 	if (mode == 0) {
@@ -619,9 +643,9 @@ __global__ void __launch_bounds__(256) k_df_ctl_div(SphCtl *ctl, const SphPartia
 
 // DF:100-119: max |v*| (+ rigid surface speed) -> adaptive dt on the device
 __global__ void __launch_bounds__(256) k_df_ctl_dt(SphCtl *ctl, const SphPartial *partials, int n, SphConsts c,
-                                                    const SphRigidState *rs, int rigid_exists) {
+                                                    const SphRigidState *rs, int rigid_exists, const double *red) {
 	double sum; int cnt; float mx;
-	reduce_partials(partials, n, sum, cnt, mx);
+	reduced_or_partials(red, partials, n, sum, cnt, mx);
 	if (threadIdx.x != 0) return;
 	float max_rigid_vel = rigid_exists ? rs->max_surface_vel : 0.0f; // DF:104-110 (loops over ALL rigid particles)
 	float max_vel = mx + max_rigid_vel;              // DF:111
@@ -641,10 +665,11 @@ __global__ void __launch_bounds__(256) k_df_ctl_dt(SphCtl *ctl, const SphPartial
 // DF:221-233: evaluated after compute_all_rho_adv of iteration `den_iters`; den_active then tells
 // whether the NEXT iteration runs.  The iter_all_vel_adv of the current iteration always runs, so it
 // is gated on the value den_active had when this iteration started (kept in graph_cond).
-__global__ void __launch_bounds__(256) k_df_ctl_den(SphCtl *ctl, const SphPartial *partials, int n) {
+__global__ void __launch_bounds__(256) k_df_ctl_den(SphCtl *ctl, const SphPartial *partials, int n,
+                                                     const double *red) {
 	if (!ctl->den_active) { if (threadIdx.x == 0) ctl->graph_cond = 0; return; }
 	double sum; int cnt; float mx;
-	reduce_partials(partials, n, sum, cnt, mx);
+	reduced_or_partials(red, partials, n, sum, cnt, mx);
 	if (threadIdx.x != 0) return;
 	float avg = cnt > 0 ? (float)(sum / (double)cnt) : 1000.0f; // DF:128, 148-149
 	ctl->den_avg = avg;
@@ -671,47 +696,56 @@ void rigid_force_df(SphHandle *h, int gated, cudaStream_t st);
 
 static void df_divergence(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_WARM, st);
 	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl);
 	sph_prof_end(h, st);
+	mg_exchange(h, MG_F4_VEL, st);
 	sph_prof_begin(h, KC_DF_DRHO, st);
 	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
 	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 0);
 	sph_prof_end(h, st);
-	k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0);
+	mg_exchange(h, MG_F4_T2, st);
+	mg_allreduce(h, nb, st);
+	k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0, h->comm ? h->red : nullptr);
 	h->launches += 3;
 	for (int it = 0; it < 15; ++it) { // max_iteration_density_divergence (DF:24); gated on ctl->div_active
 		sph_prof_begin(h, KC_DF_DIV, st);
 		SPH_LAUNCH_R(k_df_div_iter, nb, c, h->L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
 		             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
 		sph_prof_end(h, st);
+		mg_exchange(h, MG_F4_VEL, st);
 		sph_prof_begin(h, KC_DF_DRHO, st);
 		SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
 		             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 1);
 		sph_prof_end(h, st);
-		k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1);
+		mg_exchange(h, MG_F4_T2, st);
+		mg_allreduce(h, nb, st);
+		k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1, h->comm ? h->red : nullptr);
 		h->launches += 3;
 	}
 }
 
 static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_EXT, st);
 	SPH_LAUNCH_R(k_df_ext_force, nb, c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->a4[A4_VADV],
 	             h->a4[A4_FA], h->ctl, h->partials);
 	sph_prof_end(h, st);
 	// DF:105-110 loops over all rigid particles whenever a rigid body exists, active or not
-	k_df_ctl_dt<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, c, h->rstate, (c.Nr > 0 && h->rigid_ready) ? 1 : 0);
+	mg_allreduce(h, nb, st);
+	k_df_ctl_dt<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, c, h->rstate, (c.Nr > 0 && h->rigid_ready) ? 1 : 0,
+	                               h->comm ? h->red : nullptr);
+	mg_exchange(h, MG_F4_VADV, st);
 	h->launches += 2;
 }
 
 static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N_owned, SPH_BLOCK);
+	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	for (int it = first; it < first + count; ++it) {
 		int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
@@ -719,11 +753,14 @@ static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st
 		SPH_LAUNCH_R(k_df_rho_adv, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
 		             h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated);
 		sph_prof_end(h, st);
-		k_df_ctl_den<<<1, 256, 0, st>>>(h->ctl, h->partials, nb);
+		mg_allreduce(h, nb, st);
+		k_df_ctl_den<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, h->comm ? h->red : nullptr);
+		mg_exchange(h, MG_F4_T3, st);
 		sph_prof_begin(h, KC_DF_VELADV, st);
 		SPH_LAUNCH_R(k_df_vel_adv_iter, nb, c, h->L, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
 		             h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
 		sph_prof_end(h, st);
+		mg_exchange(h, MG_F4_VADV, st);
 		if (rg.active) rigid_force_df(h, gated, st); // DF:212, gather form
 		k_df_ctl_den_next<<<1, 1, 0, st>>>(h->ctl);
 		h->launches += 4;
@@ -759,7 +796,7 @@ static void df_position(SphHandle *h, cudaStream_t st) {
 
 void df_phase(SphHandle *h, int phase, cudaStream_t st) {
 	switch (phase) {
-	case SPH_PH_DF_INITIALIZE: build_lists(h, st); break;
+	case SPH_PH_DF_INITIALIZE: build_lists(h, st); mg_exchange(h, MG_F4_T1R, st); break;
 	case SPH_PH_DF_DIVERGENCE: df_divergence(h, st); break;
 	case SPH_PH_DF_EXT_FORCE_VEL_ADV: df_ext_force_vel_adv(h, st); break;
 	case SPH_PH_DF_DENSITY: df_density(h, st); break;
@@ -770,6 +807,7 @@ void df_phase(SphHandle *h, int phase, cudaStream_t st) {
 
 void df_step(SphHandle *h, cudaStream_t st) {
 	build_lists(h, st);
+	mg_exchange(h, MG_F4_T1R, st);
 	df_divergence(h, st);
 	df_ext_force_vel_adv(h, st);
 	df_density(h, st);
@@ -787,3 +825,11 @@ void ii_phase(SphHandle *h, int phase, cudaStream_t st);
 
 #include "sph_rigid.cuh"
 #include "sph_sweeps_other.cuh"
+
+#if SPH_STRICT
+// mode independent (pure fp64 / int reduction); defined once, in the strict translation unit
+void sph_reduce_partials_launch(SphHandle *h, int n_blocks, cudaStream_t st) {
+	sph_strict::k_reduce_partials<<<1, 256, 0, st>>>(h->partials, n_blocks, h->red);
+	h->launches++;
+}
+#endif

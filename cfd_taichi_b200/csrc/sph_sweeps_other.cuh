@@ -529,7 +529,7 @@ k_ii_dij(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float 
          float4 *__restrict__ d_ij, const SphCtl *__restrict__ ctl) {
 	if (!ctl->ii_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N_owned) return;
+	if (s >= c.N || L.fcount[s] < 0) return;
 	float dt = ctl->dt;
 	float4 pi = posT1[s];
 	f3 dij = F3(0.0f, 0.0f, 0.0f);

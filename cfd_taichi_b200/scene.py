@@ -33,8 +33,9 @@ def derive_sizes(config):
     return particle_num, boundary_num, grid_num
 
 
-def init_fluid_positions(config, particle_num):
-    """Fluid lattice of init_particle_pos (PS:142-151).  Returns (N, 3) float32."""
+def init_fluid_positions(config, particle_num, ids=None):
+    """Fluid lattice of init_particle_pos (PS:142-151).  Returns (N, 3) float32.  `ids` (optional)
+    restricts the result to a subset of the global lattice indices (multi-GPU slabs)."""
     scene, fluid = config["scene"], config["fluid"]
     r = scene["particle_radius"]
     d = r * 2
@@ -44,7 +45,7 @@ def init_fluid_positions(config, particle_num):
     xz_num_d = x_num_d * z_num_d
     n = particle_num
     if n < (1 << 24):
-        fi = np.arange(n, dtype=np.int32).astype(F32)
+        fi = (np.arange(n, dtype=np.int32) if ids is None else np.asarray(ids, dtype=np.int32)).astype(F32)
         x_num, z_num, xz_num = F32(x_num_d), F32(z_num_d), F32(xz_num_d)
         x = fi - x_num * np.floor(fi / x_num)                      # PS:147  i % x_num (float mod)
         t = np.floor(fi / x_num)
@@ -52,13 +53,13 @@ def init_fluid_positions(config, particle_num):
         y = (fi / xz_num).astype(np.int32).astype(F32)             # PS:149  int(i / xz_num)
     else:
         # the reference's f32 index arithmetic is inexact beyond 2^24: integer lattice
-        i = np.arange(n, dtype=np.int64)
+        i = np.arange(n, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
         xi, zi = int(round(x_num_d)), int(round(z_num_d))
         x = (i % xi).astype(F32)
         z = ((i // xi) % zi).astype(F32)
         y = (i // (xi * zi)).astype(F32)
     rad = F32(r)
-    pos = np.empty((n, 3), dtype=F32)
+    pos = np.empty((x.shape[0], 3), dtype=F32)
     pos[:, 0] = (x * rad) * F32(2.0) + F32(sp[0])                  # PS:150
     pos[:, 1] = (y * rad) * F32(2.0) + F32(sp[1])
     pos[:, 2] = (z * rad) * F32(2.0) + F32(sp[2])

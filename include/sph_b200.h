@@ -80,6 +80,7 @@ enum SphField {
 	SPH_F_RIGID_VEL = 4,   /* xyz = rigid_particles.vel, w = rigid_particles.mass */
 	SPH_F_RIGID_FORCE = 5, /* xyz = rigid_particles.force */
 	SPH_F_FLUID_ACC = 6,   /* xyz = fluid_particles.acc (WCSPH only) */
+	SPH_F_FLUID_GID = 8,   /* int32 global particle id per fluid particle (multi-GPU slabs) */
 	SPH_F_RIGID_VERTICES = 7, /* xyz = ps.rigid_vertices (mesh vertices moved with the body, RS:101-102, 138-139) */
 	/* fetchable per-fluid-particle results (float unless noted), original order */
 	SPH_F_RHO = 16, SPH_F_ALPHA, SPH_F_RHO_DERIVATIVE, SPH_F_RHO_ADV, SPH_F_VEL_ADV /*float4*/,
@@ -201,11 +202,17 @@ int sph_read_stats(SphHandle *h, SphStats *out);
 int sph_profile_begin(SphHandle *h);
 int sph_profile_end(SphHandle *h, float *ms_by_class, int32_t *launches_by_class, int n_classes);
 
-/* Multi-GPU slab support (no collectives inside the library; NCCL plumbing is the caller's):
- * pack the owned particles whose x-cell column lies in [col_lo, col_hi) into a contiguous
- * float4 buffer pair, and append received ghost particles behind the owned ones. */
-int sph_pack_columns(SphHandle *h, int col_lo, int col_hi, float *dev_pos4, float *dev_vel4,
-                     int32_t *dev_count, int capacity, void *stream);
+/* Multi-GPU: one handle per GPU holds one x-slab [col_lo, col_hi) of the global grid.
+ * The caller creates the handle with n_fluid = owned-particle capacity and n_ghost_capacity > 0, binds
+ * SPH_F_FLUID_GID (int32 global particle ids, the sort tie-break that keeps the single-domain order),
+ * sets the initial owned count with sph_set_counts and joins the NCCL communicator:
+ *   rank 0: sph_comm_unique_id(id) -> broadcast the 128 bytes (torch.distributed plumbing) -> every
+ *   rank: sph_comm_init(h, id, rank, nranks, col_lo, col_hi).
+ * sph_step then performs, per step: particle migration, one-column ghost exchange, per-sweep ghost
+ * value exchange and the loop-decision all-reduces, all over NCCL on the caller's stream. */
+int sph_comm_unique_id(char *out128);
+int sph_comm_init(SphHandle *h, const char *id128, int rank, int nranks, int col_lo, int col_hi);
+int sph_comm_info(SphHandle *h, int32_t *out8); /* owned, ghosts, sent L/R, received L/R, rank, nranks */
 int sph_set_counts(SphHandle *h, int n_owned, int n_ghost);
 
 #ifdef __cplusplus
