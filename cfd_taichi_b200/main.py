@@ -1,0 +1,120 @@
+# coding=utf-8
+"""main -- headless mirror of the reference entry point (main.py:13-211).
+
+    python main.py --config <scene.json> [--steps N] [--output-dir DIR]
+
+Same contract for everything on the hot path: the config schema (utils.read_config), the solver lookup
+by name (module `<name>_solver`, class `<name>_solver`, main.py:65-68), one ParticleSystem, `iter_cnt`
+solver steps then `iter_cnt` rigid steps per frame (main.py:166-171), simulated time advanced by
+`iter_cnt * solver.delta_time[None]` (main.py:173), stop at t > 4.0 or 100 000 frames (main.py:98, 205),
+PLY / OBJ export every 1 / output_fps of simulated time (main.py:189-200).  The GGUI window, camera and
+keyboard handling (main.py:51-62, 108-161) need a display and are out of scope: this driver is headless
+and defaults the camera keys the reference requires (SURVEY B-15).
+"""
+import argparse
+import importlib
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+if HERE not in sys.path:          # lets importlib resolve "<name>_solver" as a top-level module name
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+
+from cfd_taichi_b200 import utils  # noqa: E402
+from cfd_taichi_b200.ParticleSystem import ParticleSystem  # noqa: E402
+from cfd_taichi_b200.rigid_solver import rigid_solver  # noqa: E402
+
+
+def write_ply(path, pos, rgba):
+    """ASCII PLY with the vertex layout of ti.tools.PLYWriter (x y z red green blue alpha)."""
+    n = pos.shape[0]
+    with open(path, 'w') as f:
+        f.write('ply\nformat ascii 1.0\nelement vertex %d\n' % n)
+        for name in ('x', 'y', 'z', 'red', 'green', 'blue', 'alpha'):
+            f.write('property float %s\n' % name)
+        f.write('end_header\n')
+        np.savetxt(f, np.concatenate([pos, rgba], axis=1), fmt='%.6f')
+
+
+def write_obj(path, vertices, faces):
+    with open(path, 'w') as f:
+        for v in vertices:
+            f.write('v %.6f %.6f %.6f\n' % tuple(v))
+        if faces is not None:
+            for t in faces:
+                f.write('f %d %d %d\n' % (t[0] + 1, t[1] + 1, t[2] + 1))
+
+
+def save_state(path, ps, solver, rs=None):
+    """Restartable dump: everything a step depends on."""
+    n = ps.particle_num
+    data = dict(pos4=ps._pos4[:n].cpu().numpy(), vel4=ps._vel4[:n].cpu().numpy(), delta_time=solver.delta_time[None])
+    if ps.exist_rigid[None]:
+        info = ps.rigid_state()
+        data.update(rpos4=ps._rpos4.cpu().numpy(), rvel4=ps._rvel4.cpu().numpy(), rforce4=ps._rforce4.cpu().numpy(),
+                    centroid=np.array(list(info.centroid)), omega=np.array(list(info.omega)))
+    np.savez(path, **data)
+
+
+def run(config, max_frames=None, output_dir='./output', quiet=False):
+    scene_config = config.get('scene')
+    solver_config = config.get('solver')
+    print("Simulation Start!")
+    start_time = time.time()
+    ps = ParticleSystem(config)
+    solver_name = solver_config.get('name')
+    module = importlib.import_module('cfd_taichi_b200.' + solver_name + '_solver')     # main.py:65-68
+    solver = getattr(module, solver_name + '_solver')(ps, config)
+    rs = rigid_solver(ps, config) if config.get('solid', {}) else None                 # main.py:70-71
+
+    frame_cnt = 0
+    iter_cnt = solver_config.get('iter_cnt')
+    np_rgba = np.reshape(ps.rgba.to_numpy(), (ps.particle_num, 4))
+    is_output_ply = scene_config.get('is_output_ply', False)
+    output_fps = scene_config.get('output_fps', 60)
+    frame_time = 1.0 / output_fps
+    ply_cnt = 0
+    t = 0.0
+    if is_output_ply:
+        os.makedirs(output_dir, exist_ok=True)
+    while True:
+        if frame_cnt > 100000 or (max_frames is not None and frame_cnt >= max_frames):
+            break
+        for _ in range(iter_cnt):
+            solver.step()
+        for _ in range(iter_cnt):
+            if rs and ps.active_rigid[None] == 1:
+                rs.step()
+        frame_cnt += 1
+        t += iter_cnt * solver.delta_time[None]
+        if not quiet and frame_cnt % 50 == 0:
+            print("time: {:.4f}  frame_cnt: {}  delta time: {:.5f}".format(t, frame_cnt, solver.delta_time[None]))
+        if is_output_ply and (t / frame_time) > ply_cnt:
+            np_pos = np.reshape(ps.fluid_particles.pos.to_numpy(), (ps.particle_num, 3))
+            write_ply(os.path.join(output_dir, 'output_%06d.ply' % ply_cnt), np_pos, np_rgba)
+            if ps.exist_rigid[None] == 1:
+                ps.update_mesh_vextics()
+                write_obj(os.path.join(output_dir, 'obj_%06d.obj' % ply_cnt), ps.mesh_vertices, ps._rigid_faces)
+            ply_cnt += 1
+        if t > 4.0:
+            break
+    print("Simulation time: {}".format(time.time() - start_time))
+    return ps, solver, rs, t
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description='SPH on B200 (headless)')
+    parser.add_argument('--config', help="Please input a scene config json file.", type=str, default='default.json')
+    parser.add_argument('--steps', help="stop after this many frames (default: run to t > 4.0)", type=int, default=None)
+    parser.add_argument('--output-dir', type=str, default='./output')
+    args = parser.parse_args(argv)
+    config = utils.read_config(args.config)
+    run(config, args.steps, args.output_dir)
+
+
+if __name__ == "__main__":
+    main()

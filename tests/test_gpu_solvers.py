@@ -134,3 +134,23 @@ def test_piecewise_phase_api_matches_full_step(built):
     o.step()
     assert np.array_equal(ps.fluid_particles.pos.to_numpy(), o.field("pos"))
     ps.close(); o.close()
+
+
+def test_headless_main_runs_and_exports(built, tmp_path):
+    """main.py contract: config file in, solver found by name, PLY frames out."""
+    import json
+    from cfd_taichi_b200 import main as app
+    cfg = scenes.shipped("small_block", "wcsph")
+    cfg["scene"]["is_output_ply"] = True
+    cfg["scene"]["output_fps"] = 1000
+    p = tmp_path / "scene.json"
+    p.write_text(json.dumps(cfg))
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        ps, solver, rs, t = app.run(app.utils.read_config(str(p)), max_frames=5, output_dir=str(tmp_path / "out"), quiet=True)
+    assert abs(t - 5 * 5e-4) < 1e-9 and rs is None
+    files = sorted((tmp_path / "out").glob("output_*.ply"))
+    assert len(files) >= 2
+    head = files[0].read_text().splitlines()
+    assert head[0] == "ply" and head[2] == "element vertex 5879"
+    ps.close()
