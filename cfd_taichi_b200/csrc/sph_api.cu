@@ -56,6 +56,8 @@ static void fill_consts(const SphConfig &cfg, SphConsts &c) {
 	c.kDW = 48.0f / (PI_F * h3);  // SB:95
 	c.kDW6 = c.kDW * 6.0f;        // SB:98
 	c.nkDW6 = (-c.kDW) * 6.0f;    // SB:100
+	c.dwA = (float)((double)c.kDW6 / (h_d * h_d));
+	c.dwB = (float)((double)c.nkDW6 / h_d);
 	c.gravity = (float)cfg.gravity;
 	c.visc_num = (float)(2 * 0.08 * h_d * c_s);   // SB:187
 	c.visc_eps_h2 = (float)(0.01 * h_d * h_d);    // SB:188
@@ -87,6 +89,10 @@ static void fill_consts(const SphConfig &cfg, SphConsts &c) {
 	c.fs_couple = cfg.fs_couple ? 1 : 0;
 	c.solver = cfg.solver;
 	c.active_rigid = cfg.active_rigid ? 1 : 0;
+	{
+		const char *e = getenv("SPH_TILES");
+		c.use_tiles = e ? atoi(e) : 0;
+	}
 }
 
 template <typename T>
@@ -172,6 +178,7 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	}
 	size_t nwarps = (ncap + 31) / 32;
 	SPH_CUDA_CHECK(h, dalloc(&h->L.flist, nwarps * 32 * (size_t)c.kmax));
+	SPH_CUDA_CHECK(h, dalloc(&h->L.flist16, nwarps * 32 * (size_t)c.kmax));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.blist, nwarps * 32 * (size_t)c.kbmax));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.rlist, c.Nr > 0 ? nwarps * 32 * (size_t)c.krmax : 1));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.fcount, ncap));
@@ -213,7 +220,7 @@ extern "C" int sph_destroy(SphHandle *h) {
 	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rsvel); cudaFree(h->rkin); cudaFree(h->rstate); cudaFree(h->rl_list); cudaFree(h->rl_count);
 	for (int k = 0; k < A4_COUNT; ++k) cudaFree(h->a4[k]);
 	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
-	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.rlist);
+	cudaFree(h->L.flist); cudaFree(h->L.flist16); cudaFree(h->L.blist); cudaFree(h->L.rlist);
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount); cudaFree(h->L.rcount);
 	mg_destroy(h);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);

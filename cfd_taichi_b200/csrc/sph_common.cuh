@@ -28,6 +28,7 @@ struct SphConsts {
 	float kW;           // 8 / (pi h^3)   (SB:79)
 	float kDW;          // 48 / (pi h^3)  (SB:95)
 	float kDW6, nkDW6;  // (k*6) and ((-k)*6) of SB:98,100
+	float dwA, dwB;     // fast kernels: kDW6 / h^2 and nkDW6 / h
 	float gravity;
 	float visc_num;     // 2 * alpha * h * c_s  (SB:187)
 	float visc_eps_h2;  // eps * h * h          (SB:188)
@@ -45,6 +46,7 @@ struct SphConsts {
 	int kmax, kbmax, krmax; // neighbour-list capacities
 	int boundary_handle, fs_couple, solver;
 	int active_rigid;
+	int use_tiles;      // stage neighbour runs in shared memory (SphTile); 0 = gather from global memory
 };
 
 // Device-resident solver control block: time step, loop state, reduction results.
@@ -111,6 +113,7 @@ struct SphPartial {
 // list[((s >> 5) * cap + k) * 32 + (s & 31)], so that lane l of a warp reads consecutive words.
 struct SphLists {
 	uint32_t *flist; int *fcount;   // fluid neighbours (indices into the sorted fluid arrays)
+	uint16_t *flist16;              // the same neighbours as tile-local indices (see SphTile)
 	uint32_t *blist; int *bcount;   // boundary neighbours (indices into the sorted boundary arrays)
 	uint32_t *rlist; int *rcount;   // rigid neighbours (indices into the sorted rigid arrays)
 };

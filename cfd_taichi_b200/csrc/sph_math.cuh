@@ -57,6 +57,21 @@ __device__ __forceinline__ Pair make_pair(const float4 &pi, const float4 &pj) {
 }
 __device__ __forceinline__ bool culled(const Pair &p, const SphConsts &c) { return p.r2 > c.cull_t; }
 
+// Pair geometry inside the list-walking sweeps.  The neighbour set is already fixed by the lists, so
+// the fast kernels may contract r2 into FMAs; the strict kernels keep the reference arithmetic.
+__device__ __forceinline__ Pair sweep_pair(const float4 &pi, const float4 &pj) {
+#if SPH_STRICT
+	return make_pair(pi, pj);
+#else
+	Pair p;
+	p.r.x = pi.x - pj.x;
+	p.r.y = pi.y - pj.y;
+	p.r.z = pi.z - pj.z;
+	p.r2 = fmaf(p.r.z, p.r.z, fmaf(p.r.y, p.r.y, p.r.x * p.r.x));
+	return p;
+#endif
+}
+
 // SB:74-88 cubic_kernel(|r|, h)
 __device__ __forceinline__ float cubic_w(const Pair &p, const SphConsts &c) {
 #if SPH_STRICT
@@ -115,14 +130,14 @@ __device__ __forceinline__ f3 cubic_dw(const Pair &p, const SphConsts &c) {
 	}
 	return ret;
 #else
+	// grad W = g * r with g = coef(q) / (h |r|).  For q <= 1/2: kDW6 q (3q - 2) / (h |r|) = (kDW6 / h^2)(3q - 2)
+	// (finite at r = 0, where r itself vanishes); for 1/2 < q <= 1: nkDW6 (1 - q)^2 / (h |r|).
 	float rinv = rsqrtf(fmaxf(p.r2, 1e-30f));
 	float q = (p.r2 * rinv) * c.inv_h;
 	float t = 1.0f - q;
-	float a = c.kDW6 * q * (3.0f * q - 2.0f);
-	float b = c.nkDW6 * (t * t);
-	float co = q <= 0.5f ? a : (q <= 1.0f ? b : 0.0f);
-	co = q > 1e-5f ? co : 0.0f;
-	float g = co * (rinv * c.inv_h);
+	float ga = fmaf(3.0f * c.dwA, q, -2.0f * c.dwA);
+	float gb = (c.dwB * (t * t)) * rinv;
+	float g = q <= 0.5f ? ga : (q <= 1.0f ? gb : 0.0f);
 	return g * p.r;
 #endif
 }
