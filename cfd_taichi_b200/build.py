@@ -43,12 +43,13 @@ def build(force=False, verbose=False):
     os.makedirs(OUT, exist_ok=True)
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     hdrs.append(os.path.join(HERE, "..", "include", "sph_b200.h"))
+    extra = os.environ.get("SPH_EXTRA_NVCC", "").split()
     units = [
         ("sph_grid.cu", "sph_grid.o", []),
         ("sph_api.cu", "sph_api.o", []),
         ("sph_multigpu.cu", "sph_multigpu.o", ["-I", NCCL_INC]),
-        ("sph_sweeps.cu", "sph_sweeps_strict.o", ["-DSPH_STRICT=1", "-fmad=false"]),
-        ("sph_sweeps.cu", "sph_sweeps_fast.o", ["-DSPH_STRICT=0", "-fmad=true"]),
+        ("sph_sweeps.cu", "sph_sweeps_strict.o", ["-DSPH_STRICT=1", "-fmad=false"] + extra),
+        ("sph_sweeps.cu", "sph_sweeps_fast.o", ["-DSPH_STRICT=0", "-fmad=true"] + extra),
     ]
     objs = []
     procs = []

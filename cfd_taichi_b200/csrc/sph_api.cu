@@ -89,10 +89,6 @@ static void fill_consts(const SphConfig &cfg, SphConsts &c) {
 	c.fs_couple = cfg.fs_couple ? 1 : 0;
 	c.solver = cfg.solver;
 	c.active_rigid = cfg.active_rigid ? 1 : 0;
-	{
-		const char *e = getenv("SPH_TILES");
-		c.use_tiles = e ? atoi(e) : 0;
-	}
 }
 
 template <typename T>
@@ -172,13 +168,14 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 		SPH_CUDA_CHECK(h, dalloc(&h->a4[k], ncap));
 		SPH_CUDA_CHECK(h, cudaMemset(h->a4[k], 0, sizeof(float4) * (ncap ? ncap : 1)));
 	}
+	SPH_CUDA_CHECK(h, dalloc(&h->pv, 2 * ncap));
+	SPH_CUDA_CHECK(h, cudaMemset(h->pv, 0, sizeof(float4) * 2 * (ncap ? ncap : 1)));
 	for (int k = 0; k < A1_COUNT; ++k) {
 		SPH_CUDA_CHECK(h, dalloc(&h->a1[k], ncap));
 		SPH_CUDA_CHECK(h, cudaMemset(h->a1[k], 0, sizeof(float) * (ncap ? ncap : 1)));
 	}
 	size_t nwarps = (ncap + 31) / 32;
 	SPH_CUDA_CHECK(h, dalloc(&h->L.flist, nwarps * 32 * (size_t)c.kmax));
-	SPH_CUDA_CHECK(h, dalloc(&h->L.flist16, nwarps * 32 * (size_t)c.kmax));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.blist, nwarps * 32 * (size_t)c.kbmax));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.rlist, c.Nr > 0 ? nwarps * 32 * (size_t)c.krmax : 1));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.fcount, ncap));
@@ -219,8 +216,9 @@ extern "C" int sph_destroy(SphHandle *h) {
 	free_grid(h->fg); free_grid(h->bg); free_grid(h->rg);
 	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rsvel); cudaFree(h->rkin); cudaFree(h->rstate); cudaFree(h->rl_list); cudaFree(h->rl_count);
 	for (int k = 0; k < A4_COUNT; ++k) cudaFree(h->a4[k]);
+	cudaFree(h->pv);
 	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
-	cudaFree(h->L.flist); cudaFree(h->L.flist16); cudaFree(h->L.blist); cudaFree(h->L.rlist);
+	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.rlist);
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount); cudaFree(h->L.rcount);
 	mg_destroy(h);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);

@@ -46,7 +46,6 @@ struct SphConsts {
 	int kmax, kbmax, krmax; // neighbour-list capacities
 	int boundary_handle, fs_couple, solver;
 	int active_rigid;
-	int use_tiles;      // stage neighbour runs in shared memory (SphTile); 0 = gather from global memory
 };
 
 // Device-resident solver control block: time step, loop state, reduction results.
@@ -113,7 +112,6 @@ struct SphPartial {
 // list[((s >> 5) * cap + k) * 32 + (s & 31)], so that lane l of a warp reads consecutive words.
 struct SphLists {
 	uint32_t *flist; int *fcount;   // fluid neighbours (indices into the sorted fluid arrays)
-	uint16_t *flist16;              // the same neighbours as tile-local indices (see SphTile)
 	uint32_t *blist; int *bcount;   // boundary neighbours (indices into the sorted boundary arrays)
 	uint32_t *rlist; int *rcount;   // rigid neighbours (indices into the sorted rigid arrays)
 };

@@ -72,6 +72,7 @@ struct SphHandle {
 	bool rigid_ready;
 	// sorted work arrays
 	float4 *a4[A4_COUNT];
+	float4 *pv;     // interleaved (pos, vel) records, 32 B per sorted particle (256-bit gathers)
 	float *a1[A1_COUNT];
 	SphLists L;
 	int *nbr_count; // get_neighbour_count (PS:424-445), sorted order
@@ -121,6 +122,7 @@ void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaSt
 enum { MG_F4_T1R = 0 /* posT1.w + posR.w */, MG_F4_VEL, MG_F4_T2, MG_F4_VADV, MG_F4_T3 };
 void mg_exchange(SphHandle *h, int what, cudaStream_t st);       // ghost values of one field, both neighbours
 void mg_allreduce(SphHandle *h, int n_blocks, cudaStream_t st);  // partials -> h->red (sum, cnt, max) over ranks
+void mg_exchange_reduce(SphHandle *h, int what, int n_blocks, cudaStream_t st); // both in one NCCL group
 int mg_begin_step(SphHandle *h, cudaStream_t st);                // migration + ghost exchange + counts
 void mg_after_grid(SphHandle *h, cudaStream_t st);               // sorted slots of the send / recv lists
 void mg_destroy(SphHandle *h);

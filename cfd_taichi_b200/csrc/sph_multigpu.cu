@@ -199,30 +199,38 @@ k_mg_unpack_halo(const char *rl, const char *rr, int has_left, int has_right, in
 	}
 }
 
-// per-sweep ghost values: pack one float4 per sent particle from the sorted work arrays
+// per-sweep ghost values: one float4 per sent particle, both neighbours in one launch
 __global__ void __launch_bounds__(256)
-k_mg_pack_values(int what, const int *__restrict__ send_orig, const int *__restrict__ slot_of, int n,
-                 const float4 *__restrict__ a, const float4 *__restrict__ b, float4 *__restrict__ out) {
+k_mg_pack_values(int what, const int *__restrict__ send_orig_l, const int *__restrict__ send_orig_r,
+                 const int *__restrict__ slot_of, int nl, int nr, const float4 *__restrict__ a,
+                 const float4 *__restrict__ b, float4 *__restrict__ out_l, float4 *__restrict__ out_r) {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= n) return;
-	int s = slot_of[send_orig[k]];
+	if (k >= nl + nr) return;
+	bool left = k < nl;
+	int kk = left ? k : k - nl;
+	int s = slot_of[(left ? send_orig_l : send_orig_r)[kk]];
 	float4 v;
 	if (what == MG_F4_T1R) v = make_float4(a[s].w, b[s].w, 0.0f, 0.0f); // posT1.w, posR.w
 	else if (what == MG_F4_T2 || what == MG_F4_T3) v = make_float4(a[s].w, 0.0f, 0.0f, 0.0f);
 	else v = a[s];
-	out[k] = v;
+	(left ? out_l : out_r)[kk] = v;
 }
 __global__ void __launch_bounds__(256)
-k_mg_unpack_values(int what, const int *__restrict__ slot_of, int first_orig, int n, const float4 *__restrict__ in,
-                   const float4 *__restrict__ spos, float4 *__restrict__ a, float4 *__restrict__ b) {
+k_mg_unpack_values(int what, const int *__restrict__ slot_of, int first_orig, int nl, int nr,
+                   const float4 *__restrict__ in_l, const float4 *__restrict__ in_r,
+                   const float4 *__restrict__ spos, float4 *__restrict__ a, float4 *__restrict__ b,
+                   float4 *__restrict__ pv) {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k >= n) return;
-	int s = slot_of[first_orig + k];
-	float4 v = in[k];
+	if (k >= nl + nr) return;
+	int s = slot_of[first_orig + k]; // ghosts are stored left block first, then right block
+	float4 v = k < nl ? in_l[k] : in_r[k - nl];
 	float4 p = spos[s]; // the payload buffers carry a position copy; ghosts get theirs here
 	if (what == MG_F4_T1R) { a[s] = make_float4(p.x, p.y, p.z, v.x); b[s] = make_float4(p.x, p.y, p.z, v.y); }
 	else if (what == MG_F4_T2 || what == MG_F4_T3) a[s] = make_float4(p.x, p.y, p.z, v.x);
-	else a[s] = v;
+	else {
+		a[s] = v;
+		if (what == MG_F4_VEL) pv[2 * (size_t)s + 1] = v; // the 256-bit (pos, vel) records of k_df_drho
+	}
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -350,7 +358,12 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 
 void mg_after_grid(SphHandle *h, cudaStream_t st) { (void)h; (void)st; }
 
-void mg_exchange(SphHandle *h, int what, cudaStream_t st) {
+void sph_reduce_partials_launch(SphHandle *h, int n_blocks, cudaStream_t st); // sph_sweeps.cu
+
+// Ghost values of one field to / from both neighbours; when reduce_blocks > 0 the loop-decision
+// all-reduce of the same sweep's block partials rides in the same NCCL group (one launch of the
+// communication kernel instead of two).
+static void mg_exchange_impl(SphHandle *h, int what, int reduce_blocks, cudaStream_t st) {
 	SphComm *m = h->comm;
 	if (!m) return;
 	const float4 *a = nullptr, *b = nullptr;
@@ -361,47 +374,40 @@ void mg_exchange(SphHandle *h, int what, cudaStream_t st) {
 	case MG_F4_T2: a = wa = h->a4[A4_T2]; break;
 	case MG_F4_VADV: a = wa = h->a4[A4_VADV]; break;
 	case MG_F4_T3: a = wa = h->a4[A4_T3]; break;
-	default: return;
+	default: break;
 	}
-	for (int d = 0; d < 2; ++d)
-		if (m->n_send[d] > 0) {
-			k_mg_pack_values<<<cdiv(m->n_send[d], 256), 256, 0, st>>>(what, m->send_orig[d], h->fg.slot_of, m->n_send[d], a, b,
-			                                                          m->xsend[d]);
-			h->launches++;
-		}
+	int ns = m->n_send[0] + m->n_send[1], nr = m->n_recv[0] + m->n_recv[1];
+	if (a && ns > 0) {
+		k_mg_pack_values<<<cdiv(ns, 256), 256, 0, st>>>(what, m->send_orig[0], m->send_orig[1], h->fg.slot_of, m->n_send[0],
+		                                                m->n_send[1], a, b, m->xsend[0], m->xsend[1]);
+		h->launches++;
+	}
+	if (reduce_blocks > 0) sph_reduce_partials_launch(h, reduce_blocks, st);
 	int left = m->rank - 1, right = m->rank + 1;
 	g_nccl.GroupStart();
-	if (left >= 0) {
+	if (a && left >= 0) {
 		if (m->n_send[0] > 0) g_nccl.Send(m->xsend[0], (size_t)m->n_send[0] * 4, ncclFloat, left, m->comm, st);
 		if (m->n_recv[0] > 0) g_nccl.Recv(m->xrecv[0], (size_t)m->n_recv[0] * 4, ncclFloat, left, m->comm, st);
 	}
-	if (right < m->nranks) {
+	if (a && right < m->nranks) {
 		if (m->n_send[1] > 0) g_nccl.Send(m->xsend[1], (size_t)m->n_send[1] * 4, ncclFloat, right, m->comm, st);
 		if (m->n_recv[1] > 0) g_nccl.Recv(m->xrecv[1], (size_t)m->n_recv[1] * 4, ncclFloat, right, m->comm, st);
 	}
+	if (reduce_blocks > 0) {
+		g_nccl.AllReduce(h->red, h->red, 2, ncclDouble, ncclSum, m->comm, st);
+		g_nccl.AllReduce(h->red + 2, h->red + 2, 1, ncclDouble, ncclMax, m->comm, st);
+	}
 	g_nccl.GroupEnd();
-	int first = h->c.N_owned;
-	for (int d = 0; d < 2; ++d) {
-		if (m->n_recv[d] > 0) {
-			k_mg_unpack_values<<<cdiv(m->n_recv[d], 256), 256, 0, st>>>(what, h->fg.slot_of, first, m->n_recv[d], m->xrecv[d],
-			                                                            h->a4[A4_POS], wa, wb);
-			h->launches++;
-		}
-		first += m->n_recv[d];
+	if (a && nr > 0) {
+		k_mg_unpack_values<<<cdiv(nr, 256), 256, 0, st>>>(what, h->fg.slot_of, h->c.N_owned, m->n_recv[0], m->n_recv[1],
+		                                                  m->xrecv[0], m->xrecv[1], h->a4[A4_POS], wa, wb, h->pv);
+		h->launches++;
 	}
 }
 
-void sph_reduce_partials_launch(SphHandle *h, int n_blocks, cudaStream_t st); // sph_sweeps.cu
-
-void mg_allreduce(SphHandle *h, int n_blocks, cudaStream_t st) {
-	SphComm *m = h->comm;
-	if (!m) return;
-	sph_reduce_partials_launch(h, n_blocks, st);
-	g_nccl.GroupStart();
-	g_nccl.AllReduce(h->red, h->red, 2, ncclDouble, ncclSum, m->comm, st);
-	g_nccl.AllReduce(h->red + 2, h->red + 2, 1, ncclDouble, ncclMax, m->comm, st);
-	g_nccl.GroupEnd();
-}
+void mg_exchange(SphHandle *h, int what, cudaStream_t st) { mg_exchange_impl(h, what, 0, st); }
+void mg_allreduce(SphHandle *h, int n_blocks, cudaStream_t st) { mg_exchange_impl(h, -1, n_blocks, st); }
+void mg_exchange_reduce(SphHandle *h, int what, int n_blocks, cudaStream_t st) { mg_exchange_impl(h, what, n_blocks, st); }
 
 extern "C" int sph_comm_info(SphHandle *h, int32_t *out8) {
 	if (!h || !out8) return SPH_EINVAL;

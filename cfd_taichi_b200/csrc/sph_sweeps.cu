@@ -12,6 +12,10 @@
 #include "sph_math.cuh"
 #include "sph_internal.h"
 
+#ifndef SPH_MINB
+#define SPH_MINB 1 // minimum resident blocks per SM requested from ptxas for the list-walking sweeps
+#endif
+
 namespace SPH_NS {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -25,6 +29,20 @@ __device__ __forceinline__ void cell_xyz(int cid, const SphConsts &c, int &cx, i
 }
 
 __device__ __forceinline__ f3 ld3(const float *p) { return F3(p[0], p[1], p[2]); }
+
+// One 32-byte record per sorted particle: position (+ payload) and velocity side by side, so that the
+// sweeps that need both fetch them with ONE 256-bit load (LDG.E.256 on sm_100a) from one 32-byte sector
+// instead of two 128-bit gathers from two arrays.
+struct __align__(32) SphPV {
+	float4 p, v;
+};
+__device__ __forceinline__ SphPV ldg256(const SphPV *ptr) {
+	SphPV r;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(r.p.x), "=f"(r.p.y), "=f"(r.p.z), "=f"(r.p.w), "=f"(r.v.x), "=f"(r.v.y), "=f"(r.v.z), "=f"(r.v.w)
+	             : "l"(ptr));
+	return r;
+}
 
 // velocity of a rigid particle as seen by the coupling terms (DF:168-169, 292-293; II:328-330):
 // v_j = (vel + acc*dt) + cross(omega [+ alpha*dt], pos_j - centroid)
@@ -56,62 +74,6 @@ static inline SphRigidArgs rigid_args(const SphHandle *h) {
 				if ((unsigned)((cx) + dx_) < (unsigned)(c).gx && (unsigned)((cy) + dy_) < (unsigned)(c).gy && \
 				    (unsigned)((cz) + dz_) < (unsigned)(c).gz)                          \
 					for (int C1 = ((cx) + dx_) + ((cy) + dy_) * (c).gxz + ((cz) + dz_) * (c).gx, once_ = 1; once_; once_ = 0)
-
-// ---------------------------------------------------------------------------------------------
-// Shared-memory tiles.  A block owns SPH_BLOCK consecutive sorted particles, i.e. a contiguous range
-// of 1-D cell ids [c_first, c_last].  Every neighbour lives in one of nine shifted cell-id ranges
-// [c_first + off - 1, c_last + off + 1], off = dy*gx*gz + dz*gx, each of which is one CONTIGUOUS run
-// of the sorted particle arrays.  The sweeps stage those nine runs of a float4 array in shared
-// memory (one coalesced copy per run) and walk 16-bit tile-local neighbour indices that
-// k_build_lists emitted with the same rule: a gather is then one LDS.128 instead of an L1/L2 access.
-// Blocks whose nine runs exceed SPH_TILE_CAP particles (sparse spray over a dense layer) fall back
-// to the 32-bit global lists; both lists are built every step.
-// ---------------------------------------------------------------------------------------------
-#define SPH_TILE_CAP 1536
-struct SphTile {
-	int start[9]; // first sorted slot of run r
-	int off[10];  // tile-local offset of run r; off[9] = total
-	int ok;       // fits in SPH_TILE_CAP
-};
-
-// all threads of the block call this; ends with a barrier
-__device__ __forceinline__ void tile_setup(const SphConsts &c, const int *__restrict__ scell,
-                                           const int *__restrict__ cstart, SphTile *t) {
-	int tid = threadIdx.x;
-	int s0 = blockIdx.x * SPH_BLOCK;
-	if (!c.use_tiles) { // block-uniform: gather from global memory, no staging
-		if (tid == 0) t->ok = 0;
-		__syncthreads();
-		return;
-	}
-	if (tid < 9) {
-		int s1 = min(s0 + SPH_BLOCK, c.N) - 1;
-		int cf = scell[s0], cl = scell[s1];
-		int offc = (tid / 3 - 1) * c.gxz + (tid % 3 - 1) * c.gx;
-		int lo = max(cf + offc - 1, 0), hi = min(cl + offc + 1, c.G - 1);
-		int a = 0, b = 0;
-		if (hi >= lo) { a = cstart[lo]; b = cstart[hi + 1]; }
-		t->start[tid] = a;
-		t->off[tid + 1] = b - a;
-	}
-	__syncthreads();
-	if (tid == 0) {
-		t->off[0] = 0;
-		for (int r = 0; r < 9; ++r) t->off[r + 1] += t->off[r];
-		t->ok = (c.use_tiles && t->off[9] <= SPH_TILE_CAP && c.Nr < 32768) ? 1 : 0;
-	}
-	__syncthreads();
-}
-
-__device__ __forceinline__ void tile_load(const SphTile *t, const float4 *__restrict__ arr, float4 *tile) {
-#pragma unroll 1
-	for (int r = 0; r < 9; ++r) {
-		int len = t->off[r + 1] - t->off[r];
-		const float4 *src = arr + t->start[r];
-		float4 *dst = tile + t->off[r];
-		for (int k = threadIdx.x; k < len; k += SPH_BLOCK) dst[k] = src[k];
-	}
-}
 
 // ---------------------------------------------------------------------------------------------
 // Akinci boundary volumes, once at start-up (PS:309-320): V_b = 1 / sum_{b' != b} W
@@ -161,11 +123,10 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
               const int *__restrict__ scell, const int *__restrict__ cstart, const int *__restrict__ sorted_id,
               const float4 *__restrict__ bspos, const int *__restrict__ bstart, SphLists L, SphRigidArgs rg,
               int *__restrict__ nbr_count, float *__restrict__ rho, float *__restrict__ alpha,
-              float4 *__restrict__ posR, float4 *__restrict__ posT1, SphCtl *ctl) {
-	__shared__ SphTile tile;
-	tile_setup(c, scell, cstart, &tile);
+              float4 *__restrict__ posR, float4 *__restrict__ posT1, float4 *__restrict__ pv, SphCtl *ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	int nf = 0, nb = 0;
+	if (s < c.N && ALPHA) { pv[2 * (size_t)s] = spos[s]; pv[2 * (size_t)s + 1] = svel[s]; }
 	if (s < c.N && c.N != c.N_owned && sorted_id[s] >= c.N_owned) {
 		// ghost copy of a neighbour rank's particle (multi-GPU): never a centre particle; its rho / alpha /
 		// payloads arrive through the halo exchange.  fcount < 0 is the ownership flag every sweep tests.
@@ -180,35 +141,20 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		int cx, cy, cz;
 		cell_xyz(scell[s], c, cx, cy, cz);
 		uint32_t *fl = L.flist + sph_list_base(s, c.kmax);
-		uint16_t *fl16 = L.flist16 + sph_list_base(s, c.kmax);
-		const bool tiled = tile.ok != 0;
-		float rho_f = 0.001f; // SB:44
-		f3 ss = F3(0.0f, 0.0f, 0.0f);
-		float sq = 0.0f;
+		uint32_t *bl = L.blist + sph_list_base(s, c.kbmax);
+		// ---- phase 1: the 27-cell traversal only culls and appends (a 15 % hit rate would otherwise run
+		// ---- the kernel-function arithmetic at 15 % lane utilisation on every candidate) -----------------
 		int ncount = 0; // get_neighbour_count (PS:424-445)
 		int i_orig = RIGID ? sorted_id[s] : 0;
 		SPH_FOR_27(c, cx, cy, cz, c1) {
 			int a = cstart[c1], b = cstart[c1 + 1];
 			for (int e = a; e < b; ++e) {
 				if (e == s) continue; // PS:461
-				float4 pj = spos[e];
-				Pair p = make_pair(pi, pj);
+				Pair p = make_pair(pi, spos[e]);
 				if (culled(p, c)) continue; // PS:466
-				if (nf < c.kmax) {
-					fl[(size_t)nf * 32] = (uint32_t)e;
-					if (tiled) {
-						int r = (dy_ + 1) * 3 + (dz_ + 1); // run of the tile that holds cell c1
-						fl16[(size_t)nf * 32] = (uint16_t)(e - tile.start[r] + tile.off[r]);
-					}
-				}
+				if (nf < c.kmax) fl[(size_t)nf * 32] = (uint32_t)e;
 				nf++;
 				ncount++;
-				rho_f += c.m * cubic_w(p, c); // SB:62
-				if (ALPHA) {
-					f3 g = c.m * cubic_dw(p, c); // DF:58, 70
-					ss = ss + g;
-					sq += dot(g, g);
-				}
 			}
 			if (RIGID) {
 				// rigid particles follow the fluid ones inside a cell (second append kernel, PS:385-386)
@@ -218,56 +164,75 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 					// distance to the FLUID particle with that index (SURVEY B-7)
 					int k = rg.rsorted_id[e];
 					if (k != i_orig) {
-						float4 pq = rg.pos_orig[min(k, c.N_owned - 1)];
-						Pair q = make_pair(pi, pq);
+						Pair q = make_pair(pi, rg.pos_orig[min(k, c.N_owned - 1)]);
 						if (!culled(q, c)) ncount++;
 					}
-					float4 pj = rg.rspos[e];
-					Pair p = make_pair(pi, pj);
+					Pair p = make_pair(pi, rg.rspos[e]);
 					if (culled(p, c)) continue;
 					if (c.fs_couple != 1) continue; // SB:64: the tasks return 0
-					if (nf < c.kmax) {
-						fl[(size_t)nf * 32] = (uint32_t)e | SPH_RIGID_BIT;
-						if (tiled) fl16[(size_t)nf * 32] = (uint16_t)(e | 0x8000);
-					}
+					if (nf < c.kmax) fl[(size_t)nf * 32] = (uint32_t)e | SPH_RIGID_BIT;
 					nf++;
-					rho_f += (pj.w * cubic_w(p, c)) * SPH_RHO0; // SB:65
-					if (ALPHA) {
-						f3 g = (pj.w * SPH_RHO0) * cubic_dw(p, c); // DF:62, 75
-						ss = ss + g;
-						sq += dot(g, g);
-					}
 				}
+			}
+		}
+		if (c.boundary_handle == 1) {
+			SPH_FOR_27(c, cx, cy, cz, c1) {
+				int a = bstart[c1], b = bstart[c1 + 1];
+				for (int e = a; e < b; ++e) {
+					Pair p = make_pair(pi, bspos[e]);
+					if (culled(p, c)) continue; // PS:364
+					if (nb < c.kbmax) bl[(size_t)nb * 32] = (uint32_t)e;
+					nb++;
+				}
+			}
+		}
+		int nfl = min(nf, c.kmax), nbl = min(nb, c.kbmax);
+		// ---- phase 2: walk the fresh lists (canonical order, every lane busy): rho (SB:41-72), alpha (DF:32-89)
+		float rho_f = 0.001f; // SB:44
+		f3 ss = F3(0.0f, 0.0f, 0.0f);
+		float sq = 0.0f;
+		for (int k = 0; k < nfl; ++k) {
+			uint32_t j = fl[(size_t)k * 32];
+			if (RIGID && (j & SPH_RIGID_BIT)) {
+				float4 pj = rg.rspos[j & ~SPH_RIGID_BIT];
+				Pair p = make_pair(pi, pj);
+				rho_f += (pj.w * cubic_w(p, c)) * SPH_RHO0; // SB:65
+				if (ALPHA) {
+					f3 g = (pj.w * SPH_RHO0) * cubic_dw(p, c); // DF:62, 75
+					ss = ss + g;
+					sq += dot(g, g);
+				}
+				continue;
+			}
+			Pair p = make_pair(pi, spos[j]);
+			rho_f += c.m * cubic_w(p, c); // SB:62
+			if (ALPHA) {
+				f3 g = c.m * cubic_dw(p, c); // DF:58, 70
+				ss = ss + g;
+				sq += dot(g, g);
 			}
 		}
 		float rho_i = rho_f;
 		float den = dot(ss, ss) + sq;
 		if (c.boundary_handle == 1) {
-			uint32_t *bl = L.blist + sph_list_base(s, c.kbmax);
 			float rho_b = 0.0f;
 			f3 ssb = F3(0.0f, 0.0f, 0.0f);
 			float sqb = 0.0f;
-			SPH_FOR_27(c, cx, cy, cz, c1) {
-				int a = bstart[c1], b = bstart[c1 + 1];
-				for (int e = a; e < b; ++e) {
-					float4 pj = bspos[e];
-					Pair p = make_pair(pi, pj);
-					if (culled(p, c)) continue; // PS:364
-					if (nb < c.kbmax) bl[(size_t)nb * 32] = (uint32_t)e;
-					nb++;
-					rho_b += pj.w * cubic_w(p, c); // SB:71
-					if (ALPHA) {
-						f3 g = (pj.w * SPH_RHO0) * cubic_dw(p, c); // DF:82, 88
-						ssb = ssb + g;
-						sqb += dot(g, g);
-					}
+			for (int k = 0; k < nbl; ++k) {
+				float4 pj = bspos[bl[(size_t)k * 32]];
+				Pair p = make_pair(pi, pj);
+				rho_b += pj.w * cubic_w(p, c); // SB:71
+				if (ALPHA) {
+					f3 g = (pj.w * SPH_RHO0) * cubic_dw(p, c); // DF:82, 88
+					ssb = ssb + g;
+					sqb += dot(g, g);
 				}
 			}
 			rho_i = rho_f + rho_b * SPH_RHO0; // SB:49
 			den = ((dot(ss, ss) + sq) + sqb) + dot(ssb, ssb); // DF:45
 		}
-		L.fcount[s] = min(nf, c.kmax);
-		L.bcount[s] = min(nb, c.kbmax);
+		L.fcount[s] = nfl;
+		L.bcount[s] = nbl;
 		nbr_count[s] = ncount;
 		rho[s] = rho_i;
 		posR[s] = make_float4(pi.x, pi.y, pi.z, rho_i);
@@ -299,7 +264,7 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 	k_build_lists<A, R><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,  \
 	                                              h->fg.sorted_id, h->bspos, h->bg.cell_start, h->L, rg,           \
 	                                              h->nbr_count, h->a1[A1_RHO], h->a1[A1_ALPHA], h->a4[A4_PR],      \
-	                                              h->a4[A4_T1], h->ctl)
+	                                              h->a4[A4_T1], h->pv, h->ctl)
 	if (al && rg.active) SPH_BL(true, true);
 	else if (al) SPH_BL(true, false);
 	else if (rg.active) SPH_BL(false, true);
@@ -322,52 +287,16 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 // DFSPH (dfsph_solver.py)
 // =============================================================================================
 
-// ---------------------------------------------------------------------------------------------
-// Neighbour walker shared by the DFSPH sweeps.  Tiled blocks read 16-bit tile-local indices and gather
-// with LDS.128 from the staged runs; the others read the 32-bit lists and gather from global memory.
-// A rigid neighbour is an entry with the tag bit set (0x8000 / SPH_RIGID_BIT) holding the sorted rigid
-// slot; entries keep the reference's canonical order in both lists.
-// ---------------------------------------------------------------------------------------------
-template <bool RIGID, bool TWO, class FluidFn, class RigidFn>
-__device__ __forceinline__ void walk_fluid(const SphConsts &c, const SphLists &L, int s, const SphTile *tile,
-                                           const float4 *tileA, const float4 *tileB, const float4 *__restrict__ gA,
-                                           const float4 *__restrict__ gB, FluidFn &&fluid, RigidFn &&rigid) {
-	const int n = L.fcount[s];
-	const size_t base = sph_list_base(s, c.kmax);
-	const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-	if (tile->ok) {
-		const uint16_t *lp = L.flist16 + base;
-		for (int k = 0; k < n; ++k) {
-			uint32_t j = lp[(size_t)k * 32];
-			if (RIGID && (j & 0x8000u)) { rigid(j & 0x7fffu); continue; }
-			fluid(tileA[j], TWO ? tileB[j] : zero);
-		}
-	} else {
-		const uint32_t *lp = L.flist + base;
-		for (int k = 0; k < n; ++k) {
-			uint32_t j = lp[(size_t)k * 32];
-			if (RIGID && (j & SPH_RIGID_BIT)) { rigid(j & ~SPH_RIGID_BIT); continue; }
-			fluid(__ldg(&gA[j]), TWO ? __ldg(&gB[j]) : zero);
-		}
-	}
-}
-
-struct SphGridView {
-	const int *scell;   // sorted slot -> 1-D cell id
-	const int *cstart;  // CSR of the fluid grid
-};
+// A rigid neighbour entry of the fluid list: sorted rigid slot with SPH_RIGID_BIT set.
+#define SPH_IS_RIGID(j) (RIGID && ((j) & SPH_RIGID_BIT))
+#define SPH_RIGID_SLOT(j) ((j) & ~SPH_RIGID_BIT)
 
 // DF:314-355 divergence_warm_start.  Reads neighbour payload t1 = (k/dt)/rho from posT1.w.
 template <bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK)
-k_df_warm_start(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const float4 *__restrict__ posT1,
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
+k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT1,
                 const float4 *__restrict__ bspos, const float *__restrict__ rho, float4 *__restrict__ svel,
-                const SphCtl *__restrict__ ctl) {
-	extern __shared__ float4 smem[];
-	__shared__ SphTile tile;
-	tile_setup(c, gv.scell, gv.cstart, &tile);
-	if (tile.ok) tile_load(&tile, posT1, smem);
-	__syncthreads();
+                float4 *__restrict__ pv, const SphCtl *__restrict__ ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N || L.fcount[s] < 0) return;
 	float dt = ctl->dt;
@@ -376,22 +305,23 @@ k_df_warm_start(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const 
 	float k_i = vi.w / dt; // DF:333, 342, 353
 	float rho_i = rho[s];
 	f3 va = F3(0.0f, 0.0f, 0.0f);
-	walk_fluid<RIGID, false>(c, L, s, &tile, smem, nullptr, posT1, nullptr,
-		[&](const float4 &pj, const float4 &) {
-			Pair p = sweep_pair(pi, pj);
-			va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:337
-		},
-		[&](uint32_t r) {
-			float4 pj = __ldg(&rg.rspos[r]);
-			Pair p = sweep_pair(pi, pj);
+	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			Pair p = make_pair(pi, pj);
 			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * cubic_dw(p, c); // DF:345
-		});
+			continue;
+		}
+		float4 pj = __ldg(&posT1[j]);
+		Pair p = make_pair(pi, pj);
+		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:337
+	}
 	f3 v = xyz(vi);
 	if (c.boundary_handle == 1) {
 		f3 vb = F3(0.0f, 0.0f, 0.0f);
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
-			Pair p = sweep_pair(pi, pj);
+			Pair p = make_pair(pi, pj);
 			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:354
 		}
 		v = v - (va + vb * SPH_RHO0) * dt; // DF:322
@@ -399,23 +329,19 @@ k_df_warm_start(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const 
 		v = v - va * dt; // DF:324
 	}
 	svel[s] = F4(v, 0.0f); // DF:325 warm_start_k.fill(0)
+	pv[2 * (size_t)s + 1] = F4(v, 0.0f);
 }
 
 // DF:252-300 derivative_iter_all_rho.  Writes drho and the payload t2 = ((drho*alpha)/dt)/rho of
 // the following divergence iteration (DF:363-367); block partials feed the device-side average.
 template <bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK)
-k_df_drho(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const float4 *__restrict__ spos,
-          const float4 *__restrict__ svel, const float4 *__restrict__ bspos, const int *__restrict__ nbr_count,
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
+k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ spos,
+          const float4 *__restrict__ svel, const SphPV *__restrict__ pv, const float4 *__restrict__ bspos,
+          const int *__restrict__ nbr_count,
           const float *__restrict__ rho, const float *__restrict__ alpha, float *__restrict__ drho,
           float4 *__restrict__ posT2, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
-	extern __shared__ float4 smem[];
-	__shared__ SphTile tile;
 	if (gated && !ctl->div_active) return;
-	tile_setup(c, gv.scell, gv.cstart, &tile);
-	float4 *tileV = smem + SPH_TILE_CAP;
-	if (tile.ok) { tile_load(&tile, spos, smem); tile_load(&tile, svel, tileV); }
-	__syncthreads();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	double psum = 0.0;
 	int pcnt = 0;
@@ -426,22 +352,23 @@ k_df_drho(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const float4
 		if (nbr_count[s] >= 20) { // DF:258-261
 			f3 vi = xyz(svel[s]);
 			float rd = 0.0f;
-			walk_fluid<RIGID, true>(c, L, s, &tile, smem, tileV, spos, svel,
-				[&](const float4 &pj, const float4 &vj) {
-					Pair p = sweep_pair(pi, pj);
-					rd += c.m * dot(vi - xyz(vj), cubic_dw(p, c)); // DF:287
-				},
-				[&](uint32_t r) {
-					float4 pj = __ldg(&rg.rspos[r]);
-					Pair p = sweep_pair(pi, pj);
+			SPH_FOR_FLUID(L, c, s, j) {
+				if (SPH_IS_RIGID(j)) {
+					float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+					Pair p = make_pair(pi, pj);
 					f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, false);             // DF:292-293
 					rd += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));        // DF:294
-				});
+					continue;
+				}
+				SphPV nj = ldg256(&pv[j]);
+				Pair p = make_pair(pi, nj.p);
+				rd += c.m * dot(vi - xyz(nj.v), cubic_dw(p, c)); // DF:287
+			}
 			if (c.boundary_handle == 1) {
 				float rdb = 0.0f;
 				SPH_FOR_BOUNDARY(L, c, s, j) {
 					float4 pj = __ldg(&bspos[j]);
-					Pair p = sweep_pair(pi, pj);
+					Pair p = make_pair(pi, pj);
 					rdb += pj.w * dot(vi, cubic_dw(p, c)); // DF:300
 				}
 				out = fmaxf(rd + rdb * SPH_RHO0, 0.0f); // DF:267
@@ -458,16 +385,12 @@ k_df_drho(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const float4
 
 // DF:302-312, 357-391 divergence_iter_all_vel_adv fused with DF:381-384 sum_up_stiff
 template <bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK)
-k_df_div_iter(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const float4 *__restrict__ posT2,
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
+k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT2,
               const float4 *__restrict__ bspos, const float *__restrict__ rho, const float *__restrict__ alpha,
-              const float *__restrict__ drho, float4 *__restrict__ svel, const SphCtl *__restrict__ ctl) {
-	extern __shared__ float4 smem[];
-	__shared__ SphTile tile;
+              const float *__restrict__ drho, float4 *__restrict__ svel, float4 *__restrict__ pv,
+              const SphCtl *__restrict__ ctl) {
 	if (!ctl->div_active) return;
-	tile_setup(c, gv.scell, gv.cstart, &tile);
-	if (tile.ok) tile_load(&tile, posT2, smem);
-	__syncthreads();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N || L.fcount[s] < 0) return;
 	float dt = ctl->dt;
@@ -477,24 +400,25 @@ k_df_div_iter(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const fl
 	float k_i = da / dt; // DF:363, 374, 388
 	float rho_i = rho[s];
 	f3 va = F3(0.0f, 0.0f, 0.0f);
-	walk_fluid<RIGID, false>(c, L, s, &tile, smem, nullptr, posT2, nullptr,
-		[&](const float4 &pj, const float4 &) {
-			Pair p = sweep_pair(pi, pj);
-			float f = pi.w + pj.w;
-			f3 dw = cubic_dw(p, c);
-			if (f > 1e-5f) va = va + (c.m * f) * dw; // DF:367-369
-		},
-		[&](uint32_t r) {
-			float4 pj = __ldg(&rg.rspos[r]);
-			Pair p = sweep_pair(pi, pj);
+	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			Pair p = make_pair(pi, pj);
 			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * cubic_dw(p, c); // DF:377
-		});
+			continue;
+		}
+		float4 pj = __ldg(&posT2[j]);
+		Pair p = make_pair(pi, pj);
+		float f = pi.w + pj.w;
+		f3 dw = cubic_dw(p, c);
+		if (f > 1e-5f) va = va + (c.m * f) * dw; // DF:367-369
+	}
 	f3 v = xyz(vi);
 	if (c.boundary_handle == 1) {
 		f3 vb = F3(0.0f, 0.0f, 0.0f);
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
-			Pair p = sweep_pair(pi, pj);
+			Pair p = make_pair(pi, pj);
 			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:390
 		}
 		v = v - (va + vb * SPH_RHO0) * dt; // DF:310
@@ -502,14 +426,17 @@ k_df_div_iter(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const fl
 		v = v - va * dt;
 	}
 	svel[s] = F4(v, vi.w + da); // DF:384
+	pv[2 * (size_t)s + 1] = F4(v, vi.w + da);
 }
 
 // SB:190-201: viscosity contribution of a rigid neighbour (uses rho[particle_j.index], SURVEY B-6)
-__device__ __forceinline__ void rigid_viscosity(const SphConsts &c, const SphRigidArgs &rg, uint32_t r,
+template <bool RIGID>
+__device__ __forceinline__ void rigid_viscosity(const SphConsts &c, const SphRigidArgs &rg, uint32_t j,
                                                 const float4 &pi, const f3 &vi, float rho_i,
                                                 const float *__restrict__ rho, f3 &visc) {
+	uint32_t r = SPH_RIGID_SLOT(j);
 	float4 pj = __ldg(&rg.rspos[r]);
-	Pair p = sweep_pair(pi, pj);
+	Pair p = make_pair(pi, pj);
 	f3 v_ij = vi - ld3(rg.st->vel);
 	float shear = dot(v_ij, p.r);
 	if (shear < 0.0f) {
@@ -525,16 +452,10 @@ __device__ __forceinline__ void rigid_viscosity(const SphConsts &c, const SphRig
 // DF:91-122: tension (SB:204-217) + viscosity (SB:170-202) + f_ext + v* = v + dt f / m, and the
 // block maxima of |v*| for the adaptive time step.
 template <bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK)
-k_df_ext_force(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const float4 *__restrict__ posR,
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
+k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posR,
                const float4 *__restrict__ svel, const float *__restrict__ rho, float4 *__restrict__ svadv,
                float4 *__restrict__ fext, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials) {
-	extern __shared__ float4 smem[];
-	__shared__ SphTile tile;
-	tile_setup(c, gv.scell, gv.cstart, &tile);
-	float4 *tileV = smem + SPH_TILE_CAP;
-	if (tile.ok) { tile_load(&tile, posR, smem); tile_load(&tile, svel, tileV); }
-	__syncthreads();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	float vmax = -INFINITY;
 	if (s < c.N && L.fcount[s] >= 0) {
@@ -542,25 +463,29 @@ k_df_ext_force(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const f
 		float4 pi = posR[s];
 		f3 vi = xyz(svel[s]);
 		f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
-		walk_fluid<RIGID, true>(c, L, s, &tile, smem, tileV, posR, svel,
-			[&](const float4 &pj, const float4 &vj4) {
-				Pair p = sweep_pair(pi, pj);
-				ten = ten + (c.tension_coef * cubic_w(p, c)) * p.r; // SB:216
-				f3 v_ij = vi - xyz(vj4);
-				float shear = dot(v_ij, p.r); // SB:183
-				if (shear < 0.0f) {
+		SPH_FOR_FLUID(L, c, s, j) {
+			if (SPH_IS_RIGID(j)) {
+				rigid_viscosity<RIGID>(c, rg, j, pi, vi, pi.w, rho, visc);
+				continue;
+			}
+			float4 pj = __ldg(&posR[j]);
+			f3 vj = xyz(__ldg(&svel[j]));
+			Pair p = make_pair(pi, pj);
+			ten = ten + (c.tension_coef * cubic_w(p, c)) * p.r; // SB:216
+			f3 v_ij = vi - vj;
+			float shear = dot(v_ij, p.r); // SB:183
+			if (shear < 0.0f) {
 #if SPH_STRICT
-					float q = sqrtf(p.r2);
-					float q2 = q * q;
+				float q = sqrtf(p.r2);
+				float q2 = q * q;
 #else
-					float q2 = p.r2;
+				float q2 = p.r2;
 #endif
-					float nu = c.visc_num / (pi.w + pj.w);                 // SB:187
-					float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);  // SB:188
-					visc = visc + (c.neg_m * pi_ij) * cubic_dw(p, c);      // SB:189
-				}
-			},
-			[&](uint32_t r) { rigid_viscosity(c, rg, r, pi, vi, pi.w, rho, visc); });
+				float nu = c.visc_num / (pi.w + pj.w);                 // SB:187
+				float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);  // SB:188
+				visc = visc + (c.neg_m * pi_ij) * cubic_dw(p, c);      // SB:189
+			}
+		}
 		f3 tension = ten * c.m;  // SB:209
 		f3 viscosity = visc * c.m; // SB:175
 		f3 g = F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
@@ -576,18 +501,12 @@ k_df_ext_force(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const f
 // DF:124-176 compute_all_rho_adv.  Writes rho_adv and the payload t3 = (((rho_adv-rho0)*alpha)/dt2)/rho
 // of iter_all_vel_adv (DF:199-203).
 template <bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK)
-k_df_rho_adv(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const float4 *__restrict__ spos,
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
+k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ spos,
              const float4 *__restrict__ svadv, const float4 *__restrict__ bspos, const float *__restrict__ rho,
              const float *__restrict__ alpha, float *__restrict__ rho_adv, float4 *__restrict__ posT3,
              const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
-	extern __shared__ float4 smem[];
-	__shared__ SphTile tile;
 	if (gated && !ctl->den_active) return;
-	tile_setup(c, gv.scell, gv.cstart, &tile);
-	float4 *tileV = smem + SPH_TILE_CAP;
-	if (tile.ok) { tile_load(&tile, spos, smem); tile_load(&tile, svadv, tileV); }
-	__syncthreads();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	double psum = 0.0;
 	int pcnt = 0;
@@ -596,24 +515,26 @@ k_df_rho_adv(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const flo
 		float4 pi = spos[s];
 		f3 vi = xyz(svadv[s]);
 		float delta = 0.0f;
-		walk_fluid<RIGID, true>(c, L, s, &tile, smem, tileV, spos, svadv,
-			[&](const float4 &pj, const float4 &vj) {
-				Pair p = sweep_pair(pi, pj);
-				delta += c.m * dot(vi - xyz(vj), cubic_dw(p, c)); // DF:162
-			},
-			[&](uint32_t r) {
-				float4 pj = __ldg(&rg.rspos[r]);
-				Pair p = sweep_pair(pi, pj);
+		SPH_FOR_FLUID(L, c, s, j) {
+			if (SPH_IS_RIGID(j)) {
+				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+				Pair p = make_pair(pi, pj);
 				f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, true);                  // DF:168-169
 				delta += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));         // DF:170
-			});
+				continue;
+			}
+			float4 pj = __ldg(&spos[j]);
+			f3 vj = xyz(__ldg(&svadv[j]));
+			Pair p = make_pair(pi, pj);
+			delta += c.m * dot(vi - vj, cubic_dw(p, c)); // DF:162
+		}
 		float rho_i = rho[s];
 		float ra;
 		if (c.boundary_handle == 1) {
 			float db = 0.0f;
 			SPH_FOR_BOUNDARY(L, c, s, j) {
 				float4 pj = __ldg(&bspos[j]);
-				Pair p = sweep_pair(pi, pj);
+				Pair p = make_pair(pi, pj);
 				db += pj.w * dot(vi, cubic_dw(p, c)); // DF:176
 			}
 			ra = fmaxf(rho_i + dt * (delta + db * SPH_RHO0), SPH_RHO0); // DF:135
@@ -630,17 +551,12 @@ k_df_rho_adv(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const flo
 // DF:178-219 iter_all_vel_adv (fluid + boundary part; the rigid force scatter DF:212 is the gather
 // kernel k_rigid_force_df in sph_rigid.cuh)
 template <bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK)
-k_df_vel_adv_iter(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, const float4 *__restrict__ posT3,
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
+k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT3,
                   const float4 *__restrict__ bspos, const float *__restrict__ rho, const float *__restrict__ alpha,
                   const float *__restrict__ rho_adv, float4 *__restrict__ svadv, const SphCtl *__restrict__ ctl,
                   int gated) {
-	extern __shared__ float4 smem[];
-	__shared__ SphTile tile;
 	if (gated && !ctl->den_active) return;
-	tile_setup(c, gv.scell, gv.cstart, &tile);
-	if (tile.ok) tile_load(&tile, posT3, smem);
-	__syncthreads();
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N || L.fcount[s] < 0) return;
 	float dt = ctl->dt, dt2 = ctl->dt2;
@@ -648,22 +564,23 @@ k_df_vel_adv_iter(SphConsts c, SphLists L, SphGridView gv, SphRigidArgs rg, cons
 	float rho_i = rho[s];
 	float k_i = ((rho_adv[s] - SPH_RHO0) * alpha[s]) / dt2; // DF:199, 208, 217
 	f3 va = F3(0.0f, 0.0f, 0.0f);
-	walk_fluid<RIGID, false>(c, L, s, &tile, smem, nullptr, posT3, nullptr,
-		[&](const float4 &pj, const float4 &) {
-			Pair p = sweep_pair(pi, pj);
-			va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:203
-		},
-		[&](uint32_t r) {
-			float4 pj = __ldg(&rg.rspos[r]);
-			Pair p = sweep_pair(pi, pj);
+	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			Pair p = make_pair(pi, pj);
 			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * cubic_dw(p, c); // DF:211
-		});
+			continue;
+		}
+		float4 pj = __ldg(&posT3[j]);
+		Pair p = make_pair(pi, pj);
+		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:203
+	}
 	f3 delta = va;
 	if (c.boundary_handle == 1) {
 		f3 vb = F3(0.0f, 0.0f, 0.0f);
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
-			Pair p = sweep_pair(pi, pj);
+			Pair p = make_pair(pi, pj);
 			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:219
 		}
 		delta = va + vb * SPH_RHO0; // DF:187
@@ -805,19 +722,10 @@ __global__ void k_df_ctl_den_next(SphCtl *ctl) {
 
 // ---- DFSPH drivers -----------------------------------------------------------------------------
 // launch a kernel templated on RIGID with the instantiation the scene needs
-#define SPH_SMEM1 (SPH_TILE_CAP * sizeof(float4))
-#define SPH_SMEM2 (2 * SPH_TILE_CAP * sizeof(float4))
-#define SPH_LAUNCH_R(K, GRID, SMEM, ...)                                                  \
+#define SPH_LAUNCH_R(K, GRID, ...)                                                        \
 	do {                                                                                  \
-		static bool attr_done_ = false;                                                   \
-		if (!attr_done_) {                                                                \
-			cudaFuncSetAttribute(K<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM));  \
-			cudaFuncSetAttribute(K<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM)); \
-			attr_done_ = true;                                                            \
-		}                                                                                 \
-		size_t smem_ = c.use_tiles ? (size_t)(SMEM) : 0;                                  \
-		if (rg.active) K<true><<<GRID, SPH_BLOCK, smem_, st>>>(__VA_ARGS__);              \
-		else K<false><<<GRID, SPH_BLOCK, smem_, st>>>(__VA_ARGS__);                       \
+		if (rg.active) K<true><<<GRID, SPH_BLOCK, 0, st>>>(__VA_ARGS__);                  \
+		else K<false><<<GRID, SPH_BLOCK, 0, st>>>(__VA_ARGS__);                           \
 	} while (0)
 
 void rigid_lists(SphHandle *h, cudaStream_t st);
@@ -827,31 +735,30 @@ static void df_divergence(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
-	SphGridView gv = {h->fg.scell, h->fg.cell_start};
 	sph_prof_begin(h, KC_DF_WARM, st);
-	SPH_LAUNCH_R(k_df_warm_start, nb, SPH_SMEM1, c, h->L, gv, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl);
+	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->pv, h->ctl);
 	sph_prof_end(h, st);
 	mg_exchange(h, MG_F4_VEL, st);
 	sph_prof_begin(h, KC_DF_DRHO, st);
-	SPH_LAUNCH_R(k_df_drho, nb, SPH_SMEM2, c, h->L, gv, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
+	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], (const SphPV *)h->pv, h->bspos, h->nbr_count,
+	             h->a1[A1_RHO],
 	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 0);
 	sph_prof_end(h, st);
-	mg_exchange(h, MG_F4_T2, st);
-	mg_allreduce(h, nb, st);
+	mg_exchange_reduce(h, MG_F4_T2, nb, st);
 	k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0, h->comm ? h->red : nullptr);
 	h->launches += 3;
 	for (int it = 0; it < 15; ++it) { // max_iteration_density_divergence (DF:24); gated on ctl->div_active
 		sph_prof_begin(h, KC_DF_DIV, st);
-		SPH_LAUNCH_R(k_df_div_iter, nb, SPH_SMEM1, c, h->L, gv, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-		             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
+		SPH_LAUNCH_R(k_df_div_iter, nb, c, h->L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
+		             h->a1[A1_DRHO], h->a4[A4_VEL], h->pv, h->ctl);
 		sph_prof_end(h, st);
 		mg_exchange(h, MG_F4_VEL, st);
 		sph_prof_begin(h, KC_DF_DRHO, st);
-		SPH_LAUNCH_R(k_df_drho, nb, SPH_SMEM2, c, h->L, gv, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
+		SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], (const SphPV *)h->pv, h->bspos, h->nbr_count,
+	             h->a1[A1_RHO],
 		             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 1);
 		sph_prof_end(h, st);
-		mg_exchange(h, MG_F4_T2, st);
-		mg_allreduce(h, nb, st);
+		mg_exchange_reduce(h, MG_F4_T2, nb, st);
 		k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1, h->comm ? h->red : nullptr);
 		h->launches += 3;
 	}
@@ -861,16 +768,14 @@ static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
-	SphGridView gv = {h->fg.scell, h->fg.cell_start};
 	sph_prof_begin(h, KC_DF_EXT, st);
-	SPH_LAUNCH_R(k_df_ext_force, nb, SPH_SMEM2, c, h->L, gv, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->a4[A4_VADV],
+	SPH_LAUNCH_R(k_df_ext_force, nb, c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->a4[A4_VADV],
 	             h->a4[A4_FA], h->ctl, h->partials);
 	sph_prof_end(h, st);
 	// DF:105-110 loops over all rigid particles whenever a rigid body exists, active or not
-	mg_allreduce(h, nb, st);
+	mg_exchange_reduce(h, MG_F4_VADV, nb, st);
 	k_df_ctl_dt<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, c, h->rstate, (c.Nr > 0 && h->rigid_ready) ? 1 : 0,
 	                               h->comm ? h->red : nullptr);
-	mg_exchange(h, MG_F4_VADV, st);
 	h->launches += 2;
 }
 
@@ -878,18 +783,16 @@ static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
-	SphGridView gv = {h->fg.scell, h->fg.cell_start};
 	for (int it = first; it < first + count; ++it) {
 		int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
 		sph_prof_begin(h, KC_DF_RHOADV, st);
-		SPH_LAUNCH_R(k_df_rho_adv, nb, SPH_SMEM2, c, h->L, gv, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
+		SPH_LAUNCH_R(k_df_rho_adv, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
 		             h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated);
 		sph_prof_end(h, st);
-		mg_allreduce(h, nb, st);
+		mg_exchange_reduce(h, MG_F4_T3, nb, st);
 		k_df_ctl_den<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, h->comm ? h->red : nullptr);
-		mg_exchange(h, MG_F4_T3, st);
 		sph_prof_begin(h, KC_DF_VELADV, st);
-		SPH_LAUNCH_R(k_df_vel_adv_iter, nb, SPH_SMEM1, c, h->L, gv, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
+		SPH_LAUNCH_R(k_df_vel_adv_iter, nb, c, h->L, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
 		             h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
 		sph_prof_end(h, st);
 		mg_exchange(h, MG_F4_VADV, st);
