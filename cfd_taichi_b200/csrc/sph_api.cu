@@ -275,8 +275,6 @@ static int require_state(SphHandle *h) {
 	if (!h->pos || !h->vel) return sph_fail(h, SPH_ENOTBOUND, "fluid pos/vel are not bound (sph_bind)");
 	if (h->c.Nb > 0 && h->c.boundary_handle == 1 && !h->boundary_ready)
 		return sph_fail(h, SPH_ESTATE, "boundary particles are not initialised (sph_init_boundary)");
-	if (h->c.Nr > 0 && h->c.active_rigid && h->c.solver != SPH_SOLVER_DFSPH)
-		return sph_fail(h, SPH_ESTATE, "rigid-fluid coupling is built for the DFSPH solver only in this round");
 	return SPH_OK;
 }
 

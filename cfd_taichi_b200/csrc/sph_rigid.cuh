@@ -177,6 +177,55 @@ k_rigid_force_df(SphConsts c, const float4 *__restrict__ rspos, const int *__res
 	rforce[jr] = F4(f, 0.0f);
 }
 
+// The same gather for the other solvers' scatter sites: WC:124-126, PC:185-186, II:158-159.
+enum { RF_WC = 1, RF_PC = 2, RF_II = 3 };
+template <int MODE>
+__global__ void __launch_bounds__(SPH_BLOCK)
+k_rigid_force(SphConsts c, const float4 *__restrict__ rspos, const int *__restrict__ rsorted_id,
+              const uint32_t *__restrict__ rl_list, const int *__restrict__ rl_count, int cap,
+              const float4 *__restrict__ spos, const float *__restrict__ rho, const float *__restrict__ press,
+              float4 *__restrict__ rforce, const SphCtl *__restrict__ ctl, int gated) {
+	if (gated && MODE == RF_PC && !ctl->pc_active) return;
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= c.Nr) return;
+	int n = rl_count[s];
+	if (n == 0) return;
+	float4 pr = rspos[s];
+	int jr = rsorted_id[s];
+	f3 f = xyz(rforce[jr]);
+	const uint32_t *lp = rl_list + sph_list_base(s, cap);
+	for (int k = 0; k < n; ++k) {
+		uint32_t i = lp[(size_t)k * 32];
+		Pair p = make_pair(spos[i], pr);
+		float rho_i = rho[i], p_i = press[i];
+		f3 dw = cubic_dw(p, c);
+		if (MODE == RF_WC) {
+			f3 ret = ((((-pr.w) * p_i) / (rho_i * rho_i)) * dw) * SPH_RHO0; // WC:124
+			f = f + neg(ret) * c.m;                                          // WC:126
+		} else if (MODE == RF_PC) {
+			f3 ret = (((pr.w * SPH_RHO0) * p_i) * dw) / (rho_i * rho_i);    // PC:185
+			f = f + ret * c.m;                                               // PC:186
+		} else {
+			f3 force = (((pr.w * SPH_RHO0) / (rho_i * rho_i)) * dw) * p_i;  // II:158
+			f = f + force * c.m;                                             // II:159
+		}
+	}
+	rforce[jr] = F4(f, 0.0f);
+}
+
+void rigid_force(SphHandle *h, int mode, int gated, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.Nr, SPH_BLOCK);
+	sph_prof_begin(h, KC_RIGID, st);
+#define RF_ARGS c, h->rspos, h->rg.sorted_id, h->rl_list, h->rl_count, h->rl_cap, h->a4[A4_POS], h->a1[A1_RHO], h->a1[A1_P], h->rforce, h->ctl, gated
+	if (mode == RF_WC) k_rigid_force<RF_WC><<<nb, SPH_BLOCK, 0, st>>>(RF_ARGS);
+	else if (mode == RF_PC) k_rigid_force<RF_PC><<<nb, SPH_BLOCK, 0, st>>>(RF_ARGS);
+	else k_rigid_force<RF_II><<<nb, SPH_BLOCK, 0, st>>>(RF_ARGS);
+#undef RF_ARGS
+	sph_prof_end(h, st);
+	h->launches++;
+}
+
 void rigid_force_df(SphHandle *h, int gated, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	sph_prof_begin(h, KC_RIGID, st);

@@ -7,11 +7,15 @@ namespace SPH_NS {
 
 // shared non-pressure force pass: tension (SB:204-217) + viscosity (SB:170-202) for fluid neighbours.
 // posR.w = rho (written by k_build_lists).
-__device__ __forceinline__ void tension_viscosity(const SphConsts &c, const SphLists &L, int s,
+#define SPH_RIGID_ENTRY(j) (rg.active && ((j) & SPH_RIGID_BIT))
+
+__device__ __forceinline__ void tension_viscosity(const SphConsts &c, const SphLists &L, const SphRigidArgs &rg, int s,
                                                   const float4 *__restrict__ posR, const float4 *__restrict__ svel,
-                                                  const float4 &pi, const f3 &vi, f3 &tension, f3 &viscosity) {
+                                                  const float *__restrict__ rho, const float4 &pi, const f3 &vi,
+                                                  f3 &tension, f3 &viscosity) {
 	f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
 	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_RIGID_ENTRY(j)) { rigid_viscosity<true>(c, rg, j, pi, vi, pi.w, rho, visc); continue; } // SB:190-201
 		float4 pj = __ldg(&posR[j]);
 		f3 vj = xyz(__ldg(&svel[j]));
 		Pair p = make_pair(pi, pj);
@@ -68,8 +72,9 @@ k_wc_pressure(SphConsts c, const float4 *__restrict__ posR, const float4 *__rest
 // WC:70-84 + 92-129 pressure gradient / boundary pressure, fused with viscosity and tension
 // (separate accumulators, so each sum keeps the reference's order).
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_wc_force(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float4 *__restrict__ velR,
-           const float4 *__restrict__ bspos, const float *__restrict__ pressure,
+k_wc_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT1,
+           const float4 *__restrict__ velR, const float4 *__restrict__ bspos, const float *__restrict__ pressure,
+           const float *__restrict__ rho,
            float4 *__restrict__ pgrad, float4 *__restrict__ visc_out, float4 *__restrict__ ten_out,
            float4 *__restrict__ bacc_out) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -79,7 +84,17 @@ k_wc_force(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const floa
 	f3 vi = xyz(vr);
 	float rho_i = vr.w;
 	f3 acc = F3(0.0f, 0.0f, 0.0f), ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
+	float p_i = pressure[s];
+	float rho_i_2 = rho_i * rho_i;
 	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_RIGID_ENTRY(j)) {
+			float4 pj = __ldg(&rg.rspos[j & ~SPH_RIGID_BIT]);
+			Pair p = make_pair(pi, pj);
+			acc = acc + ((((-pj.w) * p_i) / rho_i_2) * cubic_dw(p, c)) * SPH_RHO0; // WC:124
+			float4 pr = make_float4(pi.x, pi.y, pi.z, rho_i);
+			rigid_viscosity<true>(c, rg, j, pr, vi, rho_i, rho, visc);
+			continue;
+		}
 		float4 pj = __ldg(&posT1[j]);
 		float4 vj4 = __ldg(&velR[j]);
 		Pair p = make_pair(pi, pj);
@@ -102,8 +117,6 @@ k_wc_force(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const floa
 	}
 	f3 bacc = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
-		float p_i = pressure[s];
-		float rho_i_2 = rho_i * rho_i;
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
@@ -149,10 +162,12 @@ void wc_phase(SphHandle *h, int phase, cudaStream_t st) {
 		build_lists(h, st);
 		sph_prof_begin(h, KC_WC_FORCE, st);
 		k_wc_pressure<<<nba, SPH_BLOCK, 0, st>>>(c, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_P], h->a4[A4_T1], h->a4[A4_VADV]);
-		k_wc_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a4[A4_VADV], h->bspos, h->a1[A1_P], h->a4[A4_FA],
-		                                     h->a4[A4_FB], h->a4[A4_FC], h->a4[A4_FD]);
+		SphRigidArgs rg = rigid_args(h);
+		k_wc_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->a4[A4_VADV], h->bspos, h->a1[A1_P],
+		                                     h->a1[A1_RHO], h->a4[A4_FA], h->a4[A4_FB], h->a4[A4_FC], h->a4[A4_FD]);
 		sph_prof_end(h, st);
 		h->launches += 2;
+		if (rg.active) { rigid_lists(h, st); rigid_force(h, RF_WC, 0, st); } // WC:126, gather form
 	} else if (phase == SPH_PH_WC_KINEMATIC) {
 		sph_prof_begin(h, KC_WC_KIN, st);
 		k_wc_kinematic<<<nba, SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA],
@@ -169,8 +184,8 @@ void wc_phase(SphHandle *h, int phase, cudaStream_t st) {
 // PC:220-226 compute_ext_force (rho comes from k_build_lists) + PC:228-231 reset + first
 // PC:72-87 predict_vel_pos (press_force = 0)
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_pc_ext_force(SphConsts c, SphLists L, const float4 *__restrict__ posR, const float4 *__restrict__ svel,
-               float4 *__restrict__ ext_force, float4 *__restrict__ press_force, float *__restrict__ press,
+k_pc_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posR,
+               const float4 *__restrict__ svel, const float *__restrict__ rho, float4 *__restrict__ ext_force, float4 *__restrict__ press_force, float *__restrict__ press,
                float4 *__restrict__ posT1) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N) return;
@@ -181,7 +196,7 @@ k_pc_ext_force(SphConsts c, SphLists L, const float4 *__restrict__ posR, const f
 	if (s >= c.N_owned) return;
 	f3 vi = xyz(svel[s]);
 	f3 tension, viscosity;
-	tension_viscosity(c, L, s, posR, svel, pi, vi, tension, viscosity);
+	tension_viscosity(c, L, rg, s, posR, svel, rho, pi, vi, tension, viscosity);
 	f3 g = F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
 	ext_force[s] = F4((g + tension) + viscosity, 0.0f); // PC:226
 }
@@ -209,7 +224,8 @@ k_pc_predict(SphConsts c, const float4 *__restrict__ spos, const float4 *__restr
 // PC:89-101 predict_rho (+ PC:121-133 residual partials, + speculative PC:103-107 iter_press into
 // p_next: it is committed by the next force pass only if the loop continues)
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_pc_predict_rho(SphConsts c, SphLists L, const float4 *__restrict__ pos_predict, const float4 *__restrict__ bspos,
+k_pc_predict_rho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ pos_predict,
+                 const float4 *__restrict__ bspos,
                  float *__restrict__ rho_predict, float *__restrict__ rho_err, const float *__restrict__ press,
                  float *__restrict__ p_next, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials,
                  int gated) {
@@ -221,6 +237,13 @@ k_pc_predict_rho(SphConsts c, SphLists L, const float4 *__restrict__ pos_predict
 		float4 pi = pos_predict[s];
 		float rp = 0.0f;
 		SPH_FOR_FLUID(L, c, s, j) {
+			if (SPH_RIGID_ENTRY(j)) {
+				float4 pj = __ldg(&rg.rspos[j & ~SPH_RIGID_BIT]);
+				f3 d = xyz(pi) - xyz(pj);
+				float q = sqrtf(dot(d, d));                      // PC:146
+				rp += (cubic_w_r(q, c) * pj.w) * SPH_RHO0;       // PC:147
+				continue;
+			}
 			float4 pj = __ldg(&pos_predict[j]);
 			f3 d = xyz(pi) - xyz(pj);
 			float q = sqrtf(dot(d, d));          // PC:141
@@ -261,7 +284,8 @@ k_pc_commit_press(SphConsts c, const float *__restrict__ p_next, float *__restri
 
 // PC:109-119 update_press_force fused with the following PC:72-87 predict_vel_pos
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_pc_press_force(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float4 *__restrict__ bspos,
+k_pc_press_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT1,
+                 const float4 *__restrict__ bspos,
                  const float *__restrict__ rho, const float4 *__restrict__ svel, const float4 *__restrict__ ext_force,
                  float4 *__restrict__ press_force, float4 *__restrict__ pos_predict, float4 *__restrict__ vel_predict,
                  const SphCtl *__restrict__ ctl) {
@@ -270,15 +294,22 @@ k_pc_press_force(SphConsts c, SphLists L, const float4 *__restrict__ posT1, cons
 	if (s >= c.N_owned) return;
 	float4 pi = posT1[s];
 	f3 pf = F3(0.0f, 0.0f, 0.0f);
+	float rho_i = rho[s];
+	float rho_i_2 = rho_i * rho_i;
 	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_RIGID_ENTRY(j)) {
+			float4 pj = __ldg(&rg.rspos[j & ~SPH_RIGID_BIT]);
+			Pair p = make_pair(pi, pj);
+			f3 ret = (((pj.w * SPH_RHO0) * pi.w) * cubic_dw(p, c)) / rho_i_2; // PC:185
+			pf = pf + ret * c.m;                                                // PC:187
+			continue;
+		}
 		float4 pj = __ldg(&posT1[j]);
 		Pair p = make_pair(pi, pj);
 		pf = pf + ((((pi.w + pj.w) * cubic_dw(p, c)) / 1000000.0f) * c.m) * c.m; // PC:177
 	}
 	f3 out = neg(pf);
 	if (c.boundary_handle == 1) {
-		float rho_i = rho[s];
-		float rho_i_2 = rho_i * rho_i;
 		f3 bacc = F3(0.0f, 0.0f, 0.0f);
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
@@ -326,15 +357,15 @@ k_pc_integration(SphConsts c, const int *__restrict__ sorted_id, const float4 *_
 
 // PC:39-45 pre_compute_delta for the particle with original index `target` (un-weighted sums, PC:156-167)
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_pc_delta(SphConsts c, SphLists L, const float4 *__restrict__ spos, const int *__restrict__ sorted_id, int target,
-           SphCtl *ctl) {
+k_pc_delta(SphConsts c, SphLists L, const float4 *__restrict__ spos, const float4 *__restrict__ rspos,
+           const int *__restrict__ sorted_id, int target, SphCtl *ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N || sorted_id[s] != target) return;
 	float4 pi = spos[s];
 	f3 sum = F3(0.0f, 0.0f, 0.0f);
 	float sq = 0.0f;
 	SPH_FOR_FLUID(L, c, s, j) {
-		Pair p = make_pair(pi, spos[j]);
+		Pair p = make_pair(pi, (j & SPH_RIGID_BIT) ? rspos[j & ~SPH_RIGID_BIT] : spos[j]); // no material test (PC:156-167)
 		f3 dw = cubic_dw(p, c);
 		sum = sum + dw;
 		sq += dot(dw, dw);
@@ -351,7 +382,7 @@ void pc_precompute(SphHandle *h, cudaStream_t st) {
 
 void pc_set_delta(SphHandle *h, int target, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	k_pc_delta<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->fg.sorted_id, target, h->ctl);
+	k_pc_delta<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->rspos, h->fg.sorted_id, target, h->ctl);
 	h->launches++;
 }
 
@@ -359,12 +390,14 @@ static void pc_iteration(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N_owned, SPH_BLOCK), nba = cdiv(c.N, SPH_BLOCK);
 	float4 *pos_predict = h->a4[A4_T2], *vel_predict = h->a4[A4_VADV];
+	SphRigidArgs rg = rigid_args(h);
+	if (rg.active) rigid_lists(h, st);
 	sph_prof_begin(h, KC_PC_PREDICT, st);
 	k_pc_predict<<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA], h->a4[A4_FB], pos_predict,
 	                                       vel_predict, h->ctl);
 	sph_prof_end(h, st);
 	sph_prof_begin(h, KC_PC_RHO, st);
-	k_pc_predict_rho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB], h->a1[A1_P],
+	k_pc_predict_rho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB], h->a1[A1_P],
 	                                           h->a1[A1_SC], h->ctl, h->partials, 0);
 	sph_prof_end(h, st);
 	k_pc_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0);
@@ -375,11 +408,12 @@ static void pc_iteration(SphHandle *h, cudaStream_t st) {
 		for (int it = 0; it < chunk && done < 80; ++it, ++done) { // max_iteration (PC:21); gated on ctl->pc_active
 			k_pc_commit_press<<<nba, SPH_BLOCK, 0, st>>>(c, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
 			sph_prof_begin(h, KC_PC_FORCE, st);
-			k_pc_press_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
+			k_pc_press_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
 			                                           h->a4[A4_FA], h->a4[A4_FB], pos_predict, vel_predict, h->ctl);
 			sph_prof_end(h, st);
+			if (rg.active) rigid_force(h, RF_PC, 1, st); // PC:186, gather form
 			sph_prof_begin(h, KC_PC_RHO, st);
-			k_pc_predict_rho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB],
+			k_pc_predict_rho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB],
 			                                           h->a1[A1_P], h->a1[A1_SC], h->ctl, h->partials, 1);
 			sph_prof_end(h, st);
 			k_pc_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1);
@@ -402,8 +436,8 @@ void pc_phase(SphHandle *h, int phase, cudaStream_t st) {
 	if (phase == SPH_PH_PC_EXT_FORCE) {
 		build_lists(h, st);
 		sph_prof_begin(h, KC_PC_EXT, st);
-		k_pc_ext_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_PR], h->a4[A4_VEL], h->a4[A4_FA], h->a4[A4_FB],
-		                                          h->a1[A1_P], h->a4[A4_T1]);
+		k_pc_ext_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO],
+		                                          h->a4[A4_FA], h->a4[A4_FB], h->a1[A1_P], h->a4[A4_T1]);
 		sph_prof_end(h, st);
 		h->launches++;
 	} else if (phase == SPH_PH_PC_ITERATION) {
@@ -428,8 +462,8 @@ __device__ __forceinline__ float ii_dji_coef(const SphConsts &c, float dt, float
 
 // II:42-55: tension, viscosity, f_adv, v_adv and d_ii in one pass over the lists
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_ii_advect(SphConsts c, SphLists L, const float4 *__restrict__ posR, const float4 *__restrict__ svel,
-            const float4 *__restrict__ bspos, float4 *__restrict__ f_adv, float4 *__restrict__ v_adv,
+k_ii_advect(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posR,
+            const float4 *__restrict__ svel, const float *__restrict__ rho, const float4 *__restrict__ bspos, float4 *__restrict__ f_adv, float4 *__restrict__ v_adv,
             float4 *__restrict__ d_ii, const SphCtl *__restrict__ ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N_owned) return;
@@ -440,6 +474,13 @@ k_ii_advect(SphConsts c, SphLists L, const float4 *__restrict__ posR, const floa
 	f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f), dii = F3(0.0f, 0.0f, 0.0f);
 	float cf = (-c.m) / (rho_i * rho_i); // II:261
 	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_RIGID_ENTRY(j)) {
+			float4 pj = __ldg(&rg.rspos[j & ~SPH_RIGID_BIT]);
+			Pair p = make_pair(pi, pj);
+			rigid_viscosity<true>(c, rg, j, pi, vi, rho_i, rho, visc);
+			dii = dii + (((-pj.w) * SPH_RHO0) / (rho_i * rho_i)) * cubic_dw(p, c); // II:267
+			continue;
+		}
 		float4 pj = __ldg(&posR[j]);
 		f3 vj = xyz(__ldg(&svel[j]));
 		Pair p = make_pair(pi, pj);
@@ -479,7 +520,8 @@ k_ii_advect(SphConsts c, SphLists L, const float4 *__restrict__ posR, const floa
 
 // II:57-75: rho_adv, p_iter = 0.5 p_past, a_ii
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_ii_rho_adv_aii(SphConsts c, SphLists L, const float4 *__restrict__ posR, const float4 *__restrict__ v_adv,
+k_ii_rho_adv_aii(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posR,
+                 const float4 *__restrict__ v_adv,
                  const float4 *__restrict__ bspos, const float4 *__restrict__ d_ii, const float4 *__restrict__ svel,
                  float *__restrict__ rho_adv, float *__restrict__ a_ii, float *__restrict__ press,
                  float4 *__restrict__ posT1, const SphCtl *__restrict__ ctl) {
@@ -497,6 +539,16 @@ k_ii_rho_adv_aii(SphConsts c, SphLists L, const float4 *__restrict__ posR, const
 	float coef = ii_dji_coef(c, dt, rho_i);
 	float ra = 0.0f, aii = 0.0f;
 	SPH_FOR_FLUID(L, c, s, j) {
+		if (SPH_RIGID_ENTRY(j)) {
+			float4 pj = __ldg(&rg.rspos[j & ~SPH_RIGID_BIT]);
+			Pair p = make_pair(pi, pj);
+			f3 dw = cubic_dw(p, c);
+			f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, true);      // II:328-330
+			ra += (pj.w * dot(va - v_j, dw)) * SPH_RHO0;            // II:333
+			f3 d_ji = coef * neg(dw);                               // II:291-292
+			aii += (pj.w * dot(dii - d_ji, dw)) * SPH_RHO0;         // II:293
+			continue;
+		}
 		float4 pj = __ldg(&posR[j]);
 		f3 vj = xyz(__ldg(&v_adv[j]));
 		Pair p = make_pair(pi, pj);
@@ -534,6 +586,7 @@ k_ii_dij(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float 
 	float4 pi = posT1[s];
 	f3 dij = F3(0.0f, 0.0f, 0.0f);
 	SPH_FOR_FLUID(L, c, s, j) {
+		if (j & SPH_RIGID_BIT) continue; // II:308: fluid neighbours only
 		float4 pj = __ldg(&posT1[j]);
 		float rho_j = __ldg(&rho[j]);
 		Pair p = make_pair(pi, pj);
@@ -545,7 +598,8 @@ k_ii_dij(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float 
 // II:128-147 update_p (sum_factor II:228-253) + residual partials (II:102-113); p_next is committed
 // by k_ii_commit so that neighbours keep reading the current iterate.
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_ii_update_p(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float4 *__restrict__ bspos,
+k_ii_update_p(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT1,
+              const float4 *__restrict__ bspos,
               const float *__restrict__ rho, const float4 *__restrict__ d_ij, const float4 *__restrict__ d_ii,
               const float *__restrict__ a_ii, const float *__restrict__ rho_adv, float *__restrict__ r_sum,
               float *__restrict__ p_next, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials) {
@@ -561,6 +615,12 @@ k_ii_update_p(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const f
 		float coef = ii_dji_coef(c, dt, rho_i);
 		float sum = 0.0f;
 		SPH_FOR_FLUID(L, c, s, j) {
+			if (SPH_RIGID_ENTRY(j)) {
+				float4 pj = __ldg(&rg.rspos[j & ~SPH_RIGID_BIT]);
+				Pair p = make_pair(pi, pj);
+				sum += (dot(dij_i, cubic_dw(p, c)) * pj.w) * SPH_RHO0; // II:252
+				continue;
+			}
 			float4 pj = __ldg(&posT1[j]);
 			f3 dij_j = xyz(__ldg(&d_ij[j]));
 			f3 dii_j = xyz(__ldg(&d_ii[j]));
@@ -658,7 +718,7 @@ static void ii_pressure_solve(SphHandle *h, cudaStream_t st) {
 			k_ii_dij<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->ctl);
 			sph_prof_end(h, st);
 			sph_prof_begin(h, KC_II_UPDATE, st);
-			k_ii_update_p<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
+			k_ii_update_p<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
 			                                        h->a4[A4_FC], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
 			                                        h->a1[A1_SC], h->ctl, h->partials);
 			sph_prof_end(h, st);
@@ -681,11 +741,12 @@ void ii_phase(SphHandle *h, int phase, cudaStream_t st) {
 	if (phase == SPH_PH_II_PREDICT_ADVECTION) {
 		build_lists(h, st);
 		sph_prof_begin(h, KC_II_ADV, st);
-		k_ii_advect<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_PR], h->a4[A4_VEL], h->bspos, h->a4[A4_FA], h->a4[A4_VADV],
-		                                      h->a4[A4_FC], h->ctl);
+		SphRigidArgs rg = rigid_args(h);
+		k_ii_advect<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->bspos, h->a4[A4_FA],
+		                                      h->a4[A4_VADV], h->a4[A4_FC], h->ctl);
 		sph_prof_end(h, st);
 		sph_prof_begin(h, KC_II_AII, st);
-		k_ii_rho_adv_aii<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_PR], h->a4[A4_VADV], h->bspos, h->a4[A4_FC],
+		k_ii_rho_adv_aii<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_PR], h->a4[A4_VADV], h->bspos, h->a4[A4_FC],
 		                                            h->a4[A4_VEL], h->a1[A1_RHOADV], h->a1[A1_SA], h->a1[A1_P],
 		                                            h->a4[A4_T1], h->ctl);
 		sph_prof_end(h, st);
@@ -693,6 +754,7 @@ void ii_phase(SphHandle *h, int phase, cudaStream_t st) {
 	} else if (phase == SPH_PH_II_PRESSURE_SOLVE) {
 		ii_pressure_solve(h, st);
 	} else if (phase == SPH_PH_II_INTEGRATION) {
+		if (rigid_args(h).active) { rigid_lists(h, st); rigid_force(h, RF_II, 0, st); } // II:159, gather form
 		sph_prof_begin(h, KC_II_INT, st);
 		k_ii_integration<<<nba, SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VADV], h->a4[A4_FB],
 		                                            h->a4[A4_FC], h->a1[A1_P], h->a4[A4_FD], h->pos, h->vel, h->ctl);

@@ -126,3 +126,34 @@ def test_dam_flush_cube_scene(built, monkeypatch):
         assert np.array_equal(ps.fluid_particles.pos.to_numpy(), o.field("pos"))
         assert np.array_equal(ps.rigid_particles.pos.to_numpy(), o.field("rpos"))
     ps.close(); o.close()
+
+
+@pytest.mark.parametrize("solver", ["wcsph", "pcisph", "iisph"])
+def test_other_solvers_coupled_strict_bit_exact(built, monkeypatch, solver):
+    """The other three scatter sites (WC:126, PC:186, II:159) in gather form, plus the rigid terms of every
+    sweep of those solvers, against the oracle."""
+    from cfd_taichi_b200.iisph_solver import iisph_solver
+    from cfd_taichi_b200.pcisph_solver import pcisph_solver
+    from cfd_taichi_b200.wcsph_solver import wcsph_solver
+    cls = {"wcsph": wcsph_solver, "pcisph": pcisph_solver, "iisph": iisph_solver}[solver]
+    cfg, pts, verts = rigid_scene()
+    cfg["solver"]["name"] = solver
+    cfg["solver"]["delta_time"] = {"wcsph": 2.5e-4, "pcisph": 1e-4, "iisph": 2.5e-4}[solver]
+    monkeypatch.setattr(scene, "rigid_points_from_config", lambda solid, base_dir=".": (pts, verts, None))
+    ps = quiet_ps(cfg, strict=True, solver_name=solver)
+    sol = quiet_solver(cls, ps, cfg)
+    rs = rigid_solver(ps, cfg)
+    o = O.Oracle(cfg, solver=solver, rigid_points=pts, rigid_vertices=verts, threads=1)
+    if solver == "pcisph":
+        assert sol.stats().pc_max_index == int(o.scalar("pc_max_index"))
+        assert np.float32(sol.delta[None]) == np.float32(o.scalar("pc_delta"))
+    for step in range(4):
+        sol.step()
+        f_ref = o_force_after_fluid(o)
+        assert np.array_equal(ps.rigid_particles.force.to_numpy(), f_ref), "step %d rigid forces" % step
+        rs.step()
+        assert sol.stats().error_flags == 0
+        assert np.array_equal(ps.fluid_particles.pos.to_numpy(), o.field("pos")), "step %d fluid pos" % step
+        assert np.array_equal(ps.fluid_particles.vel.to_numpy(), o.field("vel")), "step %d fluid vel" % step
+        assert np.array_equal(ps.rigid_particles.pos.to_numpy(), o.field("rpos")), "step %d rigid pos" % step
+    ps.close(); o.close()
