@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "libsph_b200.so")
+# SPH_B200_LIB: developer knob to A/B a variant build of the same library (never a different backend)
+LIB_PATH = os.environ.get("SPH_B200_LIB") or os.path.join(_HERE, "_build", "libsph_b200.so")
 
 SOLVER_IDS = {"wcsph": 0, "pcisph": 1, "iisph": 2, "dfsph": 3}
 

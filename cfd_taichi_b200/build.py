@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "_build")
+OUT = os.environ.get("SPH_BUILD_DIR") or os.path.join(HERE, "_build")  # SPH_BUILD_DIR: variant builds for A/B runs
 LIB = os.path.join(OUT, "libsph_b200.so")
 
 def _nccl_include():

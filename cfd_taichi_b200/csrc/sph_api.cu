@@ -84,6 +84,8 @@ static void fill_consts(const SphConfig &cfg, SphConsts &c) {
 	c.Nr = cfg.n_rigid;
 	c.kmax = cfg.max_neighbors > 0 ? cfg.max_neighbors : 96;
 	c.kbmax = cfg.max_boundary_neighbors > 0 ? cfg.max_boundary_neighbors : 48;
+	c.kmax = (c.kmax + 31) & ~31;   // quad-interleaved lists with up to 8 lanes per particle (sph_list_word)
+	c.kbmax = (c.kbmax + 31) & ~31;
 	c.krmax = 48;
 	c.boundary_handle = cfg.boundary_handle ? 1 : 0;
 	c.fs_couple = cfg.fs_couple ? 1 : 0;
@@ -187,7 +189,7 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	SPH_CUDA_CHECK(h, dalloc(&h->nbr_count, ncap));
 	SPH_CUDA_CHECK(h, dalloc(&h->ctl, 1));
 	SPH_CUDA_CHECK(h, cudaMallocHost((void **)&h->ctl_host, sizeof(SphCtl)));
-	h->n_partials = cdiv((int)(ncap ? ncap : 1), SPH_BLOCK) + 1;
+	h->n_partials = 8 * (cdiv((int)(ncap ? ncap : 1), SPH_BLOCK) + 1); // up to 8 lanes per particle (DF_LPP)
 	SPH_CUDA_CHECK(h, dalloc(&h->partials, (size_t)h->n_partials));
 	SPH_CUDA_CHECK(h, dalloc(&h->red, 4));
 	memset(h->ctl_host, 0, sizeof(SphCtl));

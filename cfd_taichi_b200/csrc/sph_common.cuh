@@ -108,8 +108,13 @@ struct SphPartial {
 	float maxv;
 };
 
-// Per-step neighbour lists, warp-interleaved: entry k of sorted particle s lives at
-// list[((s >> 5) * cap + k) * 32 + (s & 31)], so that lane l of a warp reads consecutive words.
+// Per-step neighbour lists, quad-interleaved per warp.  LPP ("lanes per particle", a power of two <= 8)
+// consecutive lanes of a warp share one particle: with PPW = 32 / LPP particles per warp, entry n of
+// sorted particle s belongs to lane  (s % PPW) * LPP + n % LPP  of warp  s / PPW  and is word
+// (n / LPP) % 4 of that lane's quad (n / LPP) / 4:
+//   list4[((s / PPW) * (cap / (4 LPP)) + quad) * 32 + lane]          (cap is a multiple of 32)
+// so one 128-bit load brings four entries of a lane and a warp reads 512 contiguous bytes per request.
+// LPP = 1 (one lane per particle) is the layout of the strict kernels and of WCSPH / PCISPH / IISPH.
 struct SphLists {
 	uint32_t *flist; int *fcount;   // fluid neighbours (indices into the sorted fluid arrays)
 	uint32_t *blist; int *bcount;   // boundary neighbours (indices into the sorted boundary arrays)
@@ -118,6 +123,15 @@ struct SphLists {
 
 __host__ __device__ inline size_t sph_list_base(int s, int cap) {
 	return ((size_t)(s >> 5) * (size_t)cap) * 32u + (size_t)(s & 31);
+}
+
+// word offset of entry n of sorted particle s in a quad-interleaved list with LPP lanes per particle
+template <int LPP>
+__host__ __device__ inline size_t sph_list_word(int s, int cap, int n) {
+	constexpr int PPW = 32 / LPP;
+	int lane = (s % PPW) * LPP + (n % LPP);
+	int m = n / LPP;
+	return ((((size_t)(s / PPW) * (size_t)(cap / (4 * LPP)) + (size_t)(m >> 2)) * 32u + (size_t)lane) << 2) + (size_t)(m & 3);
 }
 
 #define SPH_CUDA_CHECK(h, expr)                                                         \

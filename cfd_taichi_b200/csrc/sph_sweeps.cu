@@ -20,6 +20,19 @@ namespace SPH_NS {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Lanes per particle of the DFSPH sweeps.  Strict kernels: 1 (the reference's summation order).  Fast
+// kernels: DF_LPP adjacent lanes share a particle and take every DF_LPP-th entry of its address-ordered
+// list, so that the gathers of one warp request fall into a few cache lines instead of 32 unrelated ones
+// (the L1 data pipe, not DRAM or the FP32 pipe, bounds these kernels: profiles/r1c_ncu_dfsph_1M.md).
+#if SPH_STRICT
+#define SPH_DF_LPP 1
+#elif !defined(SPH_DF_LPP)
+#define SPH_DF_LPP 4
+#endif
+constexpr int DF_LPP = SPH_DF_LPP;
+constexpr int DF_PPB = SPH_BLOCK / DF_LPP; // particles per block
+
+
 // decode the 1-D cell id (PS:102) back into (x, y, z)
 __device__ __forceinline__ void cell_xyz(int cid, const SphConsts &c, int &cx, int &cy, int &cz) {
 	cy = cid / c.gxz;
@@ -67,6 +80,15 @@ static inline SphRigidArgs rigid_args(const SphHandle *h) {
 
 // Iterate the 27 cells around (cx,cy,cz) in the reference's order: ndrange((-1,2),(-1,2),(-1,2)),
 // dx outermost, dz innermost (PS:452), skipping out-of-range cells (PS:453-456).
+// The fast DFSPH kernels walk address-ordered lists (cell id = x + gx z + gx gz y ascending: dy outermost,
+// dx innermost); any other consumer keeps the canonical order below.
+#define SPH_FOR_27_ADDR(c, cx, cy, cz, C1)                                              \
+	for (int dy_ = -1; dy_ <= 1; ++dy_)                                                 \
+		for (int dz_ = -1; dz_ <= 1; ++dz_)                                             \
+			for (int dx_ = -1; dx_ <= 1; ++dx_)                                         \
+				if ((unsigned)((cx) + dx_) < (unsigned)(c).gx && (unsigned)((cy) + dy_) < (unsigned)(c).gy && \
+				    (unsigned)((cz) + dz_) < (unsigned)(c).gz)                          \
+					for (int C1 = ((cx) + dx_) + ((cy) + dy_) * (c).gxz + ((cz) + dz_) * (c).gx, once_ = 1; once_; once_ = 0)
 #define SPH_FOR_27(c, cx, cy, cz, C1)                                                   \
 	for (int dx_ = -1; dx_ <= 1; ++dx_)                                                 \
 		for (int dy_ = -1; dy_ <= 1; ++dy_)                                             \
@@ -140,19 +162,26 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		float4 pi = spos[s];
 		int cx, cy, cz;
 		cell_xyz(scell[s], c, cx, cy, cz);
-		uint32_t *fl = L.flist + sph_list_base(s, c.kmax);
-		uint32_t *bl = L.blist + sph_list_base(s, c.kbmax);
+		// list layout: DFSPH lists are shared by DF_LPP lanes per particle (fast kernels), all others by one
+		constexpr int LPP = ALPHA ? DF_LPP : 1;
+		uint32_t *fl = L.flist, *bl = L.blist;
+#define SPH_FLW(n) fl[sph_list_word<LPP>(s, c.kmax, n)]
+#define SPH_BLW(n) bl[sph_list_word<LPP>(s, c.kbmax, n)]
 		// ---- phase 1: the 27-cell traversal only culls and appends (a 15 % hit rate would otherwise run
 		// ---- the kernel-function arithmetic at 15 % lane utilisation on every candidate) -----------------
 		int ncount = 0; // get_neighbour_count (PS:424-445)
 		int i_orig = RIGID ? sorted_id[s] : 0;
+#if SPH_STRICT
 		SPH_FOR_27(c, cx, cy, cz, c1) {
+#else
+		SPH_FOR_27_ADDR(c, cx, cy, cz, c1) {
+#endif
 			int a = cstart[c1], b = cstart[c1 + 1];
 			for (int e = a; e < b; ++e) {
 				if (e == s) continue; // PS:461
 				Pair p = make_pair(pi, spos[e]);
 				if (culled(p, c)) continue; // PS:466
-				if (nf < c.kmax) fl[(size_t)nf * 32] = (uint32_t)e;
+				if (nf < c.kmax) SPH_FLW(nf) = (uint32_t)e;
 				nf++;
 				ncount++;
 			}
@@ -170,18 +199,22 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 					Pair p = make_pair(pi, rg.rspos[e]);
 					if (culled(p, c)) continue;
 					if (c.fs_couple != 1) continue; // SB:64: the tasks return 0
-					if (nf < c.kmax) fl[(size_t)nf * 32] = (uint32_t)e | SPH_RIGID_BIT;
+					if (nf < c.kmax) SPH_FLW(nf) = (uint32_t)e | SPH_RIGID_BIT;
 					nf++;
 				}
 			}
 		}
 		if (c.boundary_handle == 1) {
+#if SPH_STRICT
 			SPH_FOR_27(c, cx, cy, cz, c1) {
+#else
+			SPH_FOR_27_ADDR(c, cx, cy, cz, c1) {
+#endif
 				int a = bstart[c1], b = bstart[c1 + 1];
 				for (int e = a; e < b; ++e) {
 					Pair p = make_pair(pi, bspos[e]);
 					if (culled(p, c)) continue; // PS:364
-					if (nb < c.kbmax) bl[(size_t)nb * 32] = (uint32_t)e;
+					if (nb < c.kbmax) SPH_BLW(nb) = (uint32_t)e;
 					nb++;
 				}
 			}
@@ -192,7 +225,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		f3 ss = F3(0.0f, 0.0f, 0.0f);
 		float sq = 0.0f;
 		for (int k = 0; k < nfl; ++k) {
-			uint32_t j = fl[(size_t)k * 32];
+			uint32_t j = SPH_FLW(k);
 			if (RIGID && (j & SPH_RIGID_BIT)) {
 				float4 pj = rg.rspos[j & ~SPH_RIGID_BIT];
 				Pair p = make_pair(pi, pj);
@@ -219,7 +252,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 			f3 ssb = F3(0.0f, 0.0f, 0.0f);
 			float sqb = 0.0f;
 			for (int k = 0; k < nbl; ++k) {
-				float4 pj = bspos[bl[(size_t)k * 32]];
+				float4 pj = bspos[SPH_BLW(k)];
 				Pair p = make_pair(pi, pj);
 				rho_b += pj.w * cubic_w(p, c); // SB:71
 				if (ALPHA) {
@@ -243,6 +276,8 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 			float k = svel[s].w;
 			posT1[s] = make_float4(pi.x, pi.y, pi.z, (k / ctl->dt) / rho_i);
 		}
+#undef SPH_FLW
+#undef SPH_BLW
 	}
 	int mf = warp_max_i(nf), mb = warp_max_i(nb);
 	if ((threadIdx.x & 31) == 0) {
@@ -276,12 +311,92 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 }
 
 // list walkers ---------------------------------------------------------------------------------
-#define SPH_FOR_FLUID(L, c, s, J)                                               \
-	for (int k_ = 0, n_ = (L).fcount[s]; k_ < n_; ++k_)                         \
-		for (uint32_t J = (L).flist[sph_list_base(s, (c).kmax) + (size_t)k_ * 32], once_ = 1; once_; once_ = 0)
-#define SPH_FOR_BOUNDARY(L, c, s, J)                                            \
-	for (int k_ = 0, n_ = (L).bcount[s]; k_ < n_; ++k_)                         \
-		for (uint32_t J = (L).blist[sph_list_base(s, (c).kbmax) + (size_t)k_ * 32], once_ = 1; once_; once_ = 0)
+// Lists are quad-interleaved (sph_list_word): one 128-bit load brings four entries of a particle and a
+// warp reads 512 contiguous bytes.  The list stream comes from DRAM (it is larger than L2), so the
+// walker keeps two quads in flight ahead of the one being consumed; entries bypass L1 allocation
+// (LDG.E.NA) and are marked evict-first in L2 so that the stream does not displace the particle
+// records the gathers hit.  The four bodies of a full quad are straight-line code, so ptxas issues
+// their gathers back to back; the tail (count % 4 entries) is guarded.
+#ifndef SPH_LIST_HINTS
+#define SPH_LIST_HINTS 2 // 0: plain ld.global.nc, 1: + L1::no_allocate, 2: + L2 evict-first policy
+#endif
+__device__ __forceinline__ uint64_t list_policy() {
+	uint64_t pol = 0;
+#if SPH_LIST_HINTS == 2
+	asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+	return pol;
+}
+__device__ __forceinline__ uint4 ld_list(const uint4 *p, uint64_t pol) {
+	uint4 r;
+#if SPH_LIST_HINTS == 2
+	asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+	    : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+	    : "l"(p), "l"(pol));
+#elif SPH_LIST_HINTS == 1
+	asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#else
+	asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#endif
+	return r;
+}
+struct ListRange {
+	const uint4 *p; // quad 0 of this lane
+	int n;          // entries of this lane
+};
+// the share of sub-lane `sub` (0 <= sub < LPP) of the list of sorted particle s: entries sub, sub + LPP, ...
+template <int LPP>
+__device__ __forceinline__ ListRange list_range(const uint32_t *list, int cap, int s, int sub, int n) {
+	constexpr int PPW = 32 / LPP;
+	ListRange r;
+	r.p = reinterpret_cast<const uint4 *>(list) + ((size_t)(s / PPW) * (size_t)(cap / (4 * LPP))) * 32u +
+	      (size_t)((s % PPW) * LPP + sub);
+	r.n = n > sub ? (n - sub + LPP - 1) / LPP : 0;
+	return r;
+}
+template <class F>
+__device__ __forceinline__ void operator<<(ListRange r, F &&f) {
+	if (r.n <= 0) return;
+	const uint64_t pol = list_policy();
+	const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+	const uint4 *p = r.p;
+	uint4 cur = ld_list(p, pol);
+	uint4 nx1 = r.n > 4 ? ld_list(p + 32, pol) : zero;
+	int k = 0;
+	for (; k + 4 <= r.n; k += 4) {
+		uint4 nx2 = k + 8 < r.n ? ld_list(p + 64, pol) : zero;
+		p += 32;
+		f(cur.x); f(cur.y); f(cur.z); f(cur.w);
+		cur = nx1;
+		nx1 = nx2;
+	}
+	int m = r.n - k;
+	if (m > 0) {
+		f(cur.x);
+		if (m > 1) {
+			f(cur.y);
+			if (m > 2) f(cur.z);
+		}
+	}
+}
+// usage:  SPH_FOR_FLUID(L, c, s, j) { ...body, `return` skips to the next neighbour... };
+#define SPH_FOR_FLUID(L, c, s, J) list_range<1>((L).flist, (c).kmax, s, 0, (L).fcount[s]) << [&](uint32_t J)
+#define SPH_FOR_BOUNDARY(L, c, s, J) list_range<1>((L).blist, (c).kbmax, s, 0, (L).bcount[s]) << [&](uint32_t J)
+// cooperative form: LPP lanes share particle s, each walks its share; reduce with sub_sum afterwards
+#define SPH_FOR_FLUID_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).flist, (c).kmax, s, sub, n) << [&](uint32_t J)
+#define SPH_FOR_BOUNDARY_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).blist, (c).kbmax, s, sub, n) << [&](uint32_t J)
+
+// sum over the DF_LPP lanes that share a particle (no-op for one lane per particle)
+template <int LPP>
+__device__ __forceinline__ float sub_sum(float v) {
+#pragma unroll
+	for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+template <int LPP>
+__device__ __forceinline__ f3 sub_sum(f3 v) {
+	return F3(sub_sum<LPP>(v.x), sub_sum<LPP>(v.y), sub_sum<LPP>(v.z));
+}
 
 // =============================================================================================
 // DFSPH (dfsph_solver.py)
@@ -291,43 +406,54 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 #define SPH_IS_RIGID(j) (RIGID && ((j) & SPH_RIGID_BIT))
 #define SPH_RIGID_SLOT(j) ((j) & ~SPH_RIGID_BIT)
 
+// ---- DFSPH sweeps.  Thread t of the grid serves sorted particle s = t / DF_LPP as sub-lane t % DF_LPP
+// ---- (DF_LPP = 1 in the strict kernels); every lane of a warp stays alive until the sub-lane sums.
+#define SPH_DF_THREAD()                                        \
+	const int t_ = blockIdx.x * blockDim.x + threadIdx.x;      \
+	const int s = t_ / DF_LPP, sub = t_ % DF_LPP;              \
+	const int nf_ = s < c.N ? L.fcount[s] : -1;                \
+	const bool live = nf_ >= 0; /* owned particle (ghost copies carry fcount < 0) */ \
+	const int nb_ = live ? L.bcount[s] : 0;                    \
+	(void)sub; (void)nb_
+
 // DF:314-355 divergence_warm_start.  Reads neighbour payload t1 = (k/dt)/rho from posT1.w.
 template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
 k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT1,
                 const float4 *__restrict__ bspos, const float *__restrict__ rho, float4 *__restrict__ svel,
                 float4 *__restrict__ pv, const SphCtl *__restrict__ ctl) {
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N || L.fcount[s] < 0) return;
+	SPH_DF_THREAD();
 	float dt = ctl->dt;
-	float4 pi = posT1[s];
-	float4 vi = svel[s];
+	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vi = pi;
+	float rho_i = 1.0f;
+	if (live) { pi = posT1[s]; vi = svel[s]; rho_i = rho[s]; }
 	float k_i = vi.w / dt; // DF:333, 342, 353
-	float rho_i = rho[s];
 	f3 va = F3(0.0f, 0.0f, 0.0f);
-	SPH_FOR_FLUID(L, c, s, j) {
+	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			Pair p = make_pair(pi, pj);
 			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * cubic_dw(p, c); // DF:345
-			continue;
+			return;
 		}
 		float4 pj = __ldg(&posT1[j]);
 		Pair p = make_pair(pi, pj);
 		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:337
-	}
-	f3 v = xyz(vi);
+	};
+	f3 vb = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
-		f3 vb = F3(0.0f, 0.0f, 0.0f);
-		SPH_FOR_BOUNDARY(L, c, s, j) {
+		SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:354
-		}
-		v = v - (va + vb * SPH_RHO0) * dt; // DF:322
-	} else {
-		v = v - va * dt; // DF:324
+		};
 	}
+	va = sub_sum<DF_LPP>(va);
+	vb = sub_sum<DF_LPP>(vb);
+	if (!live || sub != 0) return;
+	f3 v = xyz(vi);
+	if (c.boundary_handle == 1) v = v - (va + vb * SPH_RHO0) * dt; // DF:322
+	else v = v - va * dt;                                          // DF:324
 	svel[s] = F4(v, 0.0f); // DF:325 warm_start_k.fill(0)
 	pv[2 * (size_t)s + 1] = F4(v, 0.0f);
 }
@@ -342,40 +468,45 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
           const float *__restrict__ rho, const float *__restrict__ alpha, float *__restrict__ drho,
           float4 *__restrict__ posT2, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
 	if (gated && !ctl->div_active) return;
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	SPH_DF_THREAD();
 	double psum = 0.0;
 	int pcnt = 0;
-	if (s < c.N && L.fcount[s] >= 0) {
-		float4 pi = spos[s];
-		float out = 0.0f;
-		float dt = ctl->dt;
-		if (nbr_count[s] >= 20) { // DF:258-261
-			f3 vi = xyz(svel[s]);
-			float rd = 0.0f;
-			SPH_FOR_FLUID(L, c, s, j) {
-				if (SPH_IS_RIGID(j)) {
-					float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
-					Pair p = make_pair(pi, pj);
-					f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, false);             // DF:292-293
-					rd += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));        // DF:294
-					continue;
-				}
-				SphPV nj = ldg256(&pv[j]);
-				Pair p = make_pair(pi, nj.p);
-				rd += c.m * dot(vi - xyz(nj.v), cubic_dw(p, c)); // DF:287
+	float dt = ctl->dt;
+	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	f3 vi = F3(0.0f, 0.0f, 0.0f);
+	bool enough = false;
+	if (live) {
+		pi = spos[s];
+		vi = xyz(svel[s]);
+		enough = nbr_count[s] >= 20; // DF:258-261
+	}
+	float rd = 0.0f, rdb = 0.0f;
+	if (enough) {
+		SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
+			if (SPH_IS_RIGID(j)) {
+				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+				Pair p = make_pair(pi, pj);
+				f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, false);             // DF:292-293
+				rd += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));        // DF:294
+				return;
 			}
-			if (c.boundary_handle == 1) {
-				float rdb = 0.0f;
-				SPH_FOR_BOUNDARY(L, c, s, j) {
-					float4 pj = __ldg(&bspos[j]);
-					Pair p = make_pair(pi, pj);
-					rdb += pj.w * dot(vi, cubic_dw(p, c)); // DF:300
-				}
-				out = fmaxf(rd + rdb * SPH_RHO0, 0.0f); // DF:267
-			} else {
-				out = fmaxf(rd, 0.0f);
-			}
+			SphPV nj = ldg256(&pv[j]);
+			Pair p = make_pair(pi, nj.p);
+			rd += c.m * dot(vi - xyz(nj.v), cubic_dw(p, c)); // DF:287
+		};
+		if (c.boundary_handle == 1) {
+			SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
+				float4 pj = __ldg(&bspos[j]);
+				Pair p = make_pair(pi, pj);
+				rdb += pj.w * dot(vi, cubic_dw(p, c)); // DF:300
+			};
 		}
+	}
+	rd = sub_sum<DF_LPP>(rd);
+	rdb = sub_sum<DF_LPP>(rdb);
+	if (live && sub == 0) {
+		float out = 0.0f;
+		if (enough) out = c.boundary_handle == 1 ? fmaxf(rd + rdb * SPH_RHO0, 0.0f) : fmaxf(rd, 0.0f); // DF:267
 		drho[s] = out;
 		posT2[s] = make_float4(pi.x, pi.y, pi.z, ((out * alpha[s]) / dt) / rho[s]);
 		if (out > 0.0f) { psum = (double)out; pcnt = 1; } // DF:275-277
@@ -391,40 +522,41 @@ k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
               const float *__restrict__ drho, float4 *__restrict__ svel, float4 *__restrict__ pv,
               const SphCtl *__restrict__ ctl) {
 	if (!ctl->div_active) return;
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N || L.fcount[s] < 0) return;
+	SPH_DF_THREAD();
 	float dt = ctl->dt;
-	float4 pi = posT2[s];
-	float4 vi = svel[s];
-	float da = drho[s] * alpha[s];
+	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	float da = 0.0f, rho_i = 1.0f;
+	if (live) { pi = posT2[s]; da = drho[s] * alpha[s]; rho_i = rho[s]; }
 	float k_i = da / dt; // DF:363, 374, 388
-	float rho_i = rho[s];
 	f3 va = F3(0.0f, 0.0f, 0.0f);
-	SPH_FOR_FLUID(L, c, s, j) {
+	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			Pair p = make_pair(pi, pj);
 			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * cubic_dw(p, c); // DF:377
-			continue;
+			return;
 		}
 		float4 pj = __ldg(&posT2[j]);
 		Pair p = make_pair(pi, pj);
 		float f = pi.w + pj.w;
 		f3 dw = cubic_dw(p, c);
 		if (f > 1e-5f) va = va + (c.m * f) * dw; // DF:367-369
-	}
-	f3 v = xyz(vi);
+	};
+	f3 vb = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
-		f3 vb = F3(0.0f, 0.0f, 0.0f);
-		SPH_FOR_BOUNDARY(L, c, s, j) {
+		SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:390
-		}
-		v = v - (va + vb * SPH_RHO0) * dt; // DF:310
-	} else {
-		v = v - va * dt;
+		};
 	}
+	va = sub_sum<DF_LPP>(va);
+	vb = sub_sum<DF_LPP>(vb);
+	if (!live || sub != 0) return;
+	float4 vi = svel[s];
+	f3 v = xyz(vi);
+	if (c.boundary_handle == 1) v = v - (va + vb * SPH_RHO0) * dt; // DF:310
+	else v = v - va * dt;
 	svel[s] = F4(v, vi.w + da); // DF:384
 	pv[2 * (size_t)s + 1] = F4(v, vi.w + da);
 }
@@ -456,36 +588,39 @@ __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
 k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posR,
                const float4 *__restrict__ svel, const float *__restrict__ rho, float4 *__restrict__ svadv,
                float4 *__restrict__ fext, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials) {
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	SPH_DF_THREAD();
 	float vmax = -INFINITY;
-	if (s < c.N && L.fcount[s] >= 0) {
-		float dt = ctl->dt;
-		float4 pi = posR[s];
-		f3 vi = xyz(svel[s]);
-		f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
-		SPH_FOR_FLUID(L, c, s, j) {
-			if (SPH_IS_RIGID(j)) {
-				rigid_viscosity<RIGID>(c, rg, j, pi, vi, pi.w, rho, visc);
-				continue;
-			}
-			float4 pj = __ldg(&posR[j]);
-			f3 vj = xyz(__ldg(&svel[j]));
-			Pair p = make_pair(pi, pj);
-			ten = ten + (c.tension_coef * cubic_w(p, c)) * p.r; // SB:216
-			f3 v_ij = vi - vj;
-			float shear = dot(v_ij, p.r); // SB:183
-			if (shear < 0.0f) {
-#if SPH_STRICT
-				float q = sqrtf(p.r2);
-				float q2 = q * q;
-#else
-				float q2 = p.r2;
-#endif
-				float nu = c.visc_num / (pi.w + pj.w);                 // SB:187
-				float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);  // SB:188
-				visc = visc + (c.neg_m * pi_ij) * cubic_dw(p, c);      // SB:189
-			}
+	float dt = ctl->dt;
+	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+	f3 vi = F3(0.0f, 0.0f, 0.0f);
+	if (live) { pi = posR[s]; vi = xyz(svel[s]); }
+	f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
+	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
+		if (SPH_IS_RIGID(j)) {
+			rigid_viscosity<RIGID>(c, rg, j, pi, vi, pi.w, rho, visc);
+			return;
 		}
+		float4 pj = __ldg(&posR[j]);
+		f3 vj = xyz(__ldg(&svel[j]));
+		Pair p = make_pair(pi, pj);
+		ten = ten + (c.tension_coef * cubic_w(p, c)) * p.r; // SB:216
+		f3 v_ij = vi - vj;
+		float shear = dot(v_ij, p.r); // SB:183
+		if (shear < 0.0f) {
+#if SPH_STRICT
+			float q = sqrtf(p.r2);
+			float q2 = q * q;
+#else
+			float q2 = p.r2;
+#endif
+			float nu = c.visc_num / (pi.w + pj.w);                 // SB:187
+			float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);  // SB:188
+			visc = visc + (c.neg_m * pi_ij) * cubic_dw(p, c);      // SB:189
+		}
+	};
+	ten = sub_sum<DF_LPP>(ten);
+	visc = sub_sum<DF_LPP>(visc);
+	if (live && sub == 0) {
 		f3 tension = ten * c.m;  // SB:209
 		f3 viscosity = visc * c.m; // SB:175
 		f3 g = F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
@@ -507,40 +642,41 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
              const float *__restrict__ alpha, float *__restrict__ rho_adv, float4 *__restrict__ posT3,
              const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
 	if (gated && !ctl->den_active) return;
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	SPH_DF_THREAD();
 	double psum = 0.0;
 	int pcnt = 0;
-	if (s < c.N && L.fcount[s] >= 0) {
-		float dt = ctl->dt, dt2 = ctl->dt2;
-		float4 pi = spos[s];
-		f3 vi = xyz(svadv[s]);
-		float delta = 0.0f;
-		SPH_FOR_FLUID(L, c, s, j) {
-			if (SPH_IS_RIGID(j)) {
-				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
-				Pair p = make_pair(pi, pj);
-				f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, true);                  // DF:168-169
-				delta += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));         // DF:170
-				continue;
-			}
-			float4 pj = __ldg(&spos[j]);
-			f3 vj = xyz(__ldg(&svadv[j]));
+	float dt = ctl->dt, dt2 = ctl->dt2;
+	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	f3 vi = F3(0.0f, 0.0f, 0.0f);
+	if (live) { pi = spos[s]; vi = xyz(svadv[s]); }
+	float delta = 0.0f, db = 0.0f;
+	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			Pair p = make_pair(pi, pj);
-			delta += c.m * dot(vi - vj, cubic_dw(p, c)); // DF:162
+			f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, true);                  // DF:168-169
+			delta += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));         // DF:170
+			return;
 		}
+		float4 pj = __ldg(&spos[j]);
+		f3 vj = xyz(__ldg(&svadv[j]));
+		Pair p = make_pair(pi, pj);
+		delta += c.m * dot(vi - vj, cubic_dw(p, c)); // DF:162
+	};
+	if (c.boundary_handle == 1) {
+		SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
+			float4 pj = __ldg(&bspos[j]);
+			Pair p = make_pair(pi, pj);
+			db += pj.w * dot(vi, cubic_dw(p, c)); // DF:176
+		};
+	}
+	delta = sub_sum<DF_LPP>(delta);
+	db = sub_sum<DF_LPP>(db);
+	if (live && sub == 0) {
 		float rho_i = rho[s];
 		float ra;
-		if (c.boundary_handle == 1) {
-			float db = 0.0f;
-			SPH_FOR_BOUNDARY(L, c, s, j) {
-				float4 pj = __ldg(&bspos[j]);
-				Pair p = make_pair(pi, pj);
-				db += pj.w * dot(vi, cubic_dw(p, c)); // DF:176
-			}
-			ra = fmaxf(rho_i + dt * (delta + db * SPH_RHO0), SPH_RHO0); // DF:135
-		} else {
-			ra = fmaxf(rho_i + dt * delta, SPH_RHO0); // DF:137
-		}
+		if (c.boundary_handle == 1) ra = fmaxf(rho_i + dt * (delta + db * SPH_RHO0), SPH_RHO0); // DF:135
+		else ra = fmaxf(rho_i + dt * delta, SPH_RHO0);                                          // DF:137
 		rho_adv[s] = ra;
 		posT3[s] = make_float4(pi.x, pi.y, pi.z, (((ra - SPH_RHO0) * alpha[s]) / dt2) / rho_i);
 		if (!(ra == SPH_RHO0)) { psum = (double)ra; pcnt = 1; } // DF:139-141
@@ -557,34 +693,39 @@ k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__rest
                   const float *__restrict__ rho_adv, float4 *__restrict__ svadv, const SphCtl *__restrict__ ctl,
                   int gated) {
 	if (gated && !ctl->den_active) return;
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N || L.fcount[s] < 0) return;
+	SPH_DF_THREAD();
 	float dt = ctl->dt, dt2 = ctl->dt2;
-	float4 pi = posT3[s];
-	float rho_i = rho[s];
-	float k_i = ((rho_adv[s] - SPH_RHO0) * alpha[s]) / dt2; // DF:199, 208, 217
+	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	float rho_i = 1.0f, k_i = 0.0f;
+	if (live) {
+		pi = posT3[s];
+		rho_i = rho[s];
+		k_i = ((rho_adv[s] - SPH_RHO0) * alpha[s]) / dt2; // DF:199, 208, 217
+	}
 	f3 va = F3(0.0f, 0.0f, 0.0f);
-	SPH_FOR_FLUID(L, c, s, j) {
+	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			Pair p = make_pair(pi, pj);
 			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * cubic_dw(p, c); // DF:211
-			continue;
+			return;
 		}
 		float4 pj = __ldg(&posT3[j]);
 		Pair p = make_pair(pi, pj);
 		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:203
-	}
-	f3 delta = va;
+	};
+	f3 vb = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
-		f3 vb = F3(0.0f, 0.0f, 0.0f);
-		SPH_FOR_BOUNDARY(L, c, s, j) {
+		SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:219
-		}
-		delta = va + vb * SPH_RHO0; // DF:187
+		};
 	}
+	va = sub_sum<DF_LPP>(va);
+	vb = sub_sum<DF_LPP>(vb);
+	if (!live || sub != 0) return;
+	f3 delta = c.boundary_handle == 1 ? va + vb * SPH_RHO0 : va; // DF:187
 	float4 v = svadv[s];
 	svadv[s] = F4(xyz(v) - delta * dt, 0.0f); // DF:191
 }
@@ -733,7 +874,7 @@ void rigid_force_df(SphHandle *h, int gated, cudaStream_t st);
 
 static void df_divergence(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N, SPH_BLOCK);
+	int nb = cdiv(c.N, DF_PPB); // DF_LPP lanes per particle
 	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_WARM, st);
 	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->pv, h->ctl);
@@ -766,7 +907,7 @@ static void df_divergence(SphHandle *h, cudaStream_t st) {
 
 static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N, SPH_BLOCK);
+	int nb = cdiv(c.N, DF_PPB); // DF_LPP lanes per particle
 	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_EXT, st);
 	SPH_LAUNCH_R(k_df_ext_force, nb, c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->a4[A4_VADV],
@@ -781,7 +922,7 @@ static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 
 static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N, SPH_BLOCK);
+	int nb = cdiv(c.N, DF_PPB); // DF_LPP lanes per particle
 	SphRigidArgs rg = rigid_args(h);
 	for (int it = first; it < first + count; ++it) {
 		int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)

@@ -15,7 +15,7 @@ __device__ __forceinline__ void tension_viscosity(const SphConsts &c, const SphL
                                                   f3 &tension, f3 &viscosity) {
 	f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
 	SPH_FOR_FLUID(L, c, s, j) {
-		if (SPH_RIGID_ENTRY(j)) { rigid_viscosity<true>(c, rg, j, pi, vi, pi.w, rho, visc); continue; } // SB:190-201
+		if (SPH_RIGID_ENTRY(j)) { rigid_viscosity<true>(c, rg, j, pi, vi, pi.w, rho, visc); return; } // SB:190-201
 		float4 pj = __ldg(&posR[j]);
 		f3 vj = xyz(__ldg(&svel[j]));
 		Pair p = make_pair(pi, pj);
@@ -33,7 +33,7 @@ __device__ __forceinline__ void tension_viscosity(const SphConsts &c, const SphL
 			float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2); // SB:188
 			visc = visc + (c.neg_m * pi_ij) * cubic_dw(p, c);     // SB:189
 		}
-	}
+	};
 	tension = ten * c.m;    // SB:209
 	viscosity = visc * c.m; // SB:175
 }
@@ -93,7 +93,7 @@ k_wc_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ 
 			acc = acc + ((((-pj.w) * p_i) / rho_i_2) * cubic_dw(p, c)) * SPH_RHO0; // WC:124
 			float4 pr = make_float4(pi.x, pi.y, pi.z, rho_i);
 			rigid_viscosity<true>(c, rg, j, pr, vi, rho_i, rho, visc);
-			continue;
+			return;
 		}
 		float4 pj = __ldg(&posT1[j]);
 		float4 vj4 = __ldg(&velR[j]);
@@ -114,14 +114,14 @@ k_wc_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ 
 			float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);
 			visc = visc + (c.neg_m * pi_ij) * dw;
 		}
-	}
+	};
 	f3 bacc = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			bacc = bacc - ((pj.w * p_i) / rho_i_2) * cubic_dw(p, c); // WC:99
-		}
+		};
 		bacc = bacc * SPH_RHO0; // WC:83
 	}
 	pgrad[s] = F4(acc, 0.0f);
@@ -242,13 +242,13 @@ k_pc_predict_rho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 				f3 d = xyz(pi) - xyz(pj);
 				float q = sqrtf(dot(d, d));                      // PC:146
 				rp += (cubic_w_r(q, c) * pj.w) * SPH_RHO0;       // PC:147
-				continue;
+				return;
 			}
 			float4 pj = __ldg(&pos_predict[j]);
 			f3 d = xyz(pi) - xyz(pj);
 			float q = sqrtf(dot(d, d));          // PC:141
 			rp += cubic_w_r(q, c) * c.m;         // PC:142
-		}
+		};
 		float out = rp;
 		if (c.boundary_handle == 1) {
 			float rb = 0.0f;
@@ -257,7 +257,7 @@ k_pc_predict_rho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 				f3 d = xyz(pi) - xyz(pj);
 				float q = sqrtf(dot(d, d));      // PC:152
 				rb += cubic_w_r(q, c) * pj.w;    // PC:153
-			}
+			};
 			out = rp + rb * SPH_RHO0;            // PC:98
 		}
 		float err = out - SPH_RHO0;              // PC:101
@@ -302,12 +302,12 @@ k_pc_press_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 			Pair p = make_pair(pi, pj);
 			f3 ret = (((pj.w * SPH_RHO0) * pi.w) * cubic_dw(p, c)) / rho_i_2; // PC:185
 			pf = pf + ret * c.m;                                                // PC:187
-			continue;
+			return;
 		}
 		float4 pj = __ldg(&posT1[j]);
 		Pair p = make_pair(pi, pj);
 		pf = pf + ((((pi.w + pj.w) * cubic_dw(p, c)) / 1000000.0f) * c.m) * c.m; // PC:177
-	}
+	};
 	f3 out = neg(pf);
 	if (c.boundary_handle == 1) {
 		f3 bacc = F3(0.0f, 0.0f, 0.0f);
@@ -315,7 +315,7 @@ k_pc_press_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			bacc = bacc - ((pj.w * pi.w) / rho_i_2) * cubic_dw(p, c); // PC:197
-		}
+		};
 		out = neg(pf) + (bacc * SPH_RHO0) * c.m; // PC:117
 	}
 	press_force[s] = F4(out, 0.0f);
@@ -369,7 +369,7 @@ k_pc_delta(SphConsts c, SphLists L, const float4 *__restrict__ spos, const float
 		f3 dw = cubic_dw(p, c);
 		sum = sum + dw;
 		sq += dot(dw, dw);
-	}
+	};
 	ctl->pc_delta = 1.0f / ((dot(sum, sum) + sq) * c.pc_beta); // PC:45
 	ctl->pc_max_index = target;
 }
@@ -479,7 +479,7 @@ k_ii_advect(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__
 			Pair p = make_pair(pi, pj);
 			rigid_viscosity<true>(c, rg, j, pi, vi, rho_i, rho, visc);
 			dii = dii + (((-pj.w) * SPH_RHO0) / (rho_i * rho_i)) * cubic_dw(p, c); // II:267
-			continue;
+			return;
 		}
 		float4 pj = __ldg(&posR[j]);
 		f3 vj = xyz(__ldg(&svel[j]));
@@ -500,7 +500,7 @@ k_ii_advect(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__
 			visc = visc + (c.neg_m * pi_ij) * dw;
 		}
 		dii = dii + cf * dw;
-	}
+	};
 	f3 g = F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
 	f3 f = (g + ten * c.m) + visc * c.m;      // II:45
 	f_adv[s] = F4(f, 0.0f);
@@ -511,7 +511,7 @@ k_ii_advect(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			db = db + ((-pj.w) / (rho_i * rho_i)) * cubic_dw(p, c); // II:273
-		}
+		};
 		d_ii[s] = F4(((dii + db * SPH_RHO0) * dt) * dt, 0.0f); // II:53
 	} else {
 		d_ii[s] = F4((dii * dt) * dt, 0.0f);
@@ -547,7 +547,7 @@ k_ii_rho_adv_aii(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 			ra += (pj.w * dot(va - v_j, dw)) * SPH_RHO0;            // II:333
 			f3 d_ji = coef * neg(dw);                               // II:291-292
 			aii += (pj.w * dot(dii - d_ji, dw)) * SPH_RHO0;         // II:293
-			continue;
+			return;
 		}
 		float4 pj = __ldg(&posR[j]);
 		f3 vj = xyz(__ldg(&v_adv[j]));
@@ -556,7 +556,7 @@ k_ii_rho_adv_aii(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 		ra += c.m * dot(va - vj, dw);           // II:324
 		f3 d_ji = coef * neg(dw);               // II:283-284: kernel derivative of -q is the negated vector
 		aii += c.m * dot(dii - d_ji, dw);       // II:285
-	}
+	};
 	if (c.boundary_handle == 1) {
 		float rab = 0.0f, ab = 0.0f;
 		SPH_FOR_BOUNDARY(L, c, s, j) {
@@ -566,7 +566,7 @@ k_ii_rho_adv_aii(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 			rab += pj.w * dot(va, dw);          // II:340
 			f3 d_ji = coef * neg(dw);
 			ab += pj.w * dot(dii - d_ji, dw);   // II:303
-		}
+		};
 		rho_adv[s] = (ra + rab * SPH_RHO0) * dt + rho_i; // II:63
 		a_ii[s] = aii + ab * SPH_RHO0;                    // II:73
 	} else {
@@ -586,12 +586,12 @@ k_ii_dij(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float 
 	float4 pi = posT1[s];
 	f3 dij = F3(0.0f, 0.0f, 0.0f);
 	SPH_FOR_FLUID(L, c, s, j) {
-		if (j & SPH_RIGID_BIT) continue; // II:308: fluid neighbours only
+		if (j & SPH_RIGID_BIT) return; // II:308: fluid neighbours only
 		float4 pj = __ldg(&posT1[j]);
 		float rho_j = __ldg(&rho[j]);
 		Pair p = make_pair(pi, pj);
 		dij = dij + (((-c.m) * pj.w) * cubic_dw(p, c)) / (rho_j * rho_j); // II:313
-	}
+	};
 	d_ij[s] = F4((dij * dt) * dt, 0.0f); // II:126
 }
 
@@ -619,7 +619,7 @@ k_ii_update_p(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 				float4 pj = __ldg(&rg.rspos[j & ~SPH_RIGID_BIT]);
 				Pair p = make_pair(pi, pj);
 				sum += (dot(dij_i, cubic_dw(p, c)) * pj.w) * SPH_RHO0; // II:252
-				continue;
+				return;
 			}
 			float4 pj = __ldg(&posT1[j]);
 			f3 dij_j = xyz(__ldg(&d_ij[j]));
@@ -629,7 +629,7 @@ k_ii_update_p(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 			f3 d_ji = (coef * neg(w_ij)) * pi.w;                       // II:244-245
 			f3 t = (dij_i - dii_j * pj.w) - (dij_j - d_ji);            // II:246
 			sum += c.m * dot(t, w_ij);
-		}
+		};
 		float rs = sum;
 		if (c.boundary_handle == 1) {
 			float bsum = 0.0f;
@@ -637,7 +637,7 @@ k_ii_update_p(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 				float4 pj = __ldg(&bspos[j]);
 				Pair p = make_pair(pi, pj);
 				bsum += (dot(dij_i, cubic_dw(p, c)) * pj.w) * SPH_RHO0; // II:232
-			}
+			};
 			rs = sum + bsum; // II:136
 		}
 		r_sum[s] = rs;
