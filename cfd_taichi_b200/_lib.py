@@ -31,7 +31,7 @@ PH_WRITEBACK = 90
 KERNEL_CLASSES = ["grid", "lists", "df_warm_start", "df_drho", "df_div_iter", "df_ext_force", "df_rho_adv",
                   "df_vel_adv_iter", "df_position", "ctl", "wc_force", "wc_kinematic", "pc_ext", "pc_predict",
                   "pc_rho", "pc_force", "pc_integrate", "ii_adv", "ii_aii", "ii_dij", "ii_update", "ii_integrate",
-                  "rigid", "other"]
+                  "rigid", "other", "mg_exchange", "mg_begin_step", "mg_wait"]
 
 
 class SphConfig(ctypes.Structure):

@@ -84,8 +84,8 @@ static void fill_consts(const SphConfig &cfg, SphConsts &c) {
 	c.Nr = cfg.n_rigid;
 	c.kmax = cfg.max_neighbors > 0 ? cfg.max_neighbors : 96;
 	c.kbmax = cfg.max_boundary_neighbors > 0 ? cfg.max_boundary_neighbors : 48;
-	c.kmax = (c.kmax + 31) & ~31;   // quad-interleaved lists with up to 8 lanes per particle (sph_list_word)
-	c.kbmax = (c.kbmax + 31) & ~31;
+	c.kstride = (c.kmax + 31) & ~31;   // quad-interleaved lists with up to 8 lanes per particle (sph_list_word)
+	c.kbstride = (c.kbmax + 31) & ~31;
 	c.krmax = 48;
 	c.boundary_handle = cfg.boundary_handle ? 1 : 0;
 	c.fs_couple = cfg.fs_couple ? 1 : 0;
@@ -177,8 +177,8 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 		SPH_CUDA_CHECK(h, cudaMemset(h->a1[k], 0, sizeof(float) * (ncap ? ncap : 1)));
 	}
 	size_t nwarps = (ncap + 31) / 32;
-	SPH_CUDA_CHECK(h, dalloc(&h->L.flist, nwarps * 32 * (size_t)c.kmax));
-	SPH_CUDA_CHECK(h, dalloc(&h->L.blist, nwarps * 32 * (size_t)c.kbmax));
+	SPH_CUDA_CHECK(h, dalloc(&h->L.flist, nwarps * 32 * (size_t)c.kstride));
+	SPH_CUDA_CHECK(h, dalloc(&h->L.blist, nwarps * 32 * (size_t)c.kbstride));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.rlist, c.Nr > 0 ? nwarps * 32 * (size_t)c.krmax : 1));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.fcount, ncap));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.bcount, ncap));

@@ -16,6 +16,7 @@
 #define SPH_ERR_BLIST_OVERFLOW 4
 #define SPH_ERR_DENSITY_CAP 8
 #define SPH_ERR_NONFINITE 16
+#define SPH_ERR_COMM_TIMEOUT 32 // a peer did not raise its exchange flag within 10 s (multi-GPU windows)
 
 // Constants the reference evaluates in Python scope (fp64) and then casts to f32 where they meet
 // an f32 expression.  Filled once on the host in sph_api.cu.
@@ -43,7 +44,8 @@ struct SphConsts {
 	int N;              // fluid particles handled by this handle (owned + ghost)
 	int N_owned;        // owned fluid particles (== N on one GPU)
 	int Nb, Nr;
-	int kmax, kbmax, krmax; // neighbour-list capacities
+	int kmax, kbmax, krmax; // neighbour-list capacities (entries a particle may hold before the overflow flag)
+	int kstride, kbstride;  // storage capacities of the quad-interleaved lists: kmax / kbmax rounded up to 32
 	int boundary_handle, fs_couple, solver;
 	int active_rigid;
 };
@@ -69,7 +71,8 @@ struct SphCtl {
 	float ii_residual, ii_last;
 	int max_nbr, max_bnbr;
 	float max_vel;
-	int graph_cond; // scratch for conditional graph nodes
+	int graph_cond; // unused
+	int blocks_done; // blocks-finished counter of the sweep tails (sph_ctl.cuh), zero between launches
 };
 
 // Device-resident rigid-body state (rigid_solver.py:12-31 + the uniform per-particle fields the

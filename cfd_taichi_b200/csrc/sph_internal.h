@@ -37,7 +37,7 @@ struct SphGrid {
 enum {
 	KC_GRID = 0, KC_LISTS, KC_DF_WARM, KC_DF_DRHO, KC_DF_DIV, KC_DF_EXT, KC_DF_RHOADV, KC_DF_VELADV, KC_DF_POS,
 	KC_CTL, KC_WC_FORCE, KC_WC_KIN, KC_PC_EXT, KC_PC_PREDICT, KC_PC_RHO, KC_PC_FORCE, KC_PC_INT,
-	KC_II_ADV, KC_II_AII, KC_II_DIJ, KC_II_UPDATE, KC_II_INT, KC_RIGID, KC_OTHER
+	KC_II_ADV, KC_II_AII, KC_II_DIJ, KC_II_UPDATE, KC_II_INT, KC_RIGID, KC_OTHER, KC_MG_EXCHANGE, KC_MG_STEP, KC_MG_WAIT
 };
 struct SphProf {
 	bool on;
@@ -121,8 +121,9 @@ void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaSt
 // Every call is a no-op (returns immediately) when h->comm is null.
 enum { MG_F4_T1R = 0 /* posT1.w + posR.w */, MG_F4_VEL, MG_F4_T2, MG_F4_VADV, MG_F4_T3 };
 void mg_exchange(SphHandle *h, int what, cudaStream_t st);       // ghost values of one field, both neighbours
-void mg_allreduce(SphHandle *h, int n_blocks, cudaStream_t st);  // partials -> h->red (sum, cnt, max) over ranks
-void mg_exchange_reduce(SphHandle *h, int what, int n_blocks, cudaStream_t st); // both in one NCCL group
+// ghost values + the all-reduce of the sweep's n_blocks block partials + the loop decision `ctl_kind`
+// (sph_ctl.cuh) applied on every rank
+void mg_exchange_reduce(SphHandle *h, int what, int ctl_kind, int n_blocks, cudaStream_t st);
 int mg_begin_step(SphHandle *h, cudaStream_t st);                // migration + ghost exchange + counts
 void mg_after_grid(SphHandle *h, cudaStream_t st);               // sorted slots of the send / recv lists
 void mg_destroy(SphHandle *h);

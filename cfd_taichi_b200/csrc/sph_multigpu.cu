@@ -8,6 +8,17 @@
 // rank executes the single-domain iteration counts.  Nothing here synchronises the host except the one
 // count read-back per step in mg_begin_step.  NCCL is bound at run time with dlopen (the torch-bundled
 // libnccl.so.2 that the process already maps); a missing library is an error, never a fallback.
+//
+// Transport of (2) and (3) inside a step: the ~57 exchanges per DFSPH step are 0.3 MB each, i.e. pure
+// latency, so they do not go through NCCL.  Every rank owns a "window" of device memory that its peers
+// map with CUDA IPC; the pack kernel stores the ghost values (and the rank's loop partials) straight into
+// the neighbour's window over NVLink and the last block raises an epoch flag there; the unpack kernel of
+// the receiver spins on its local flag, scatters the values and sums the partials of all ranks in rank
+// order (deterministic, identical on every rank).  Two kernels per exchange, no host involvement, no
+// proxy thread.  Windows are double-buffered by epoch parity: a full handshake with both neighbours per
+// exchange means a rank can be at most one exchange ahead of a peer.  NCCL keeps the two variable-size
+// particle messages per step (migration, ghost particles).  SPH_MG_TRANSPORT=nccl selects NCCL for
+// everything (A/B measurements).
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -16,6 +27,9 @@
 #include <new>
 
 #include "sph_internal.h"
+#include "sph_ctl.cuh"
+
+#define SPH_MG_MAX_RANKS 16
 
 struct NcclApi {
 	void *lib;
@@ -27,6 +41,7 @@ struct NcclApi {
 	ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
 	ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
 	ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+	ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
 	const char *(*GetErrorString)(ncclResult_t);
 };
 static NcclApi g_nccl = {};
@@ -37,7 +52,7 @@ static int nccl_load(SphHandle *h) {
 	if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
 	if (!lib) return sph_fail(h, SPH_ESTATE, "multi-GPU: cannot dlopen libnccl.so.2 (%s)", dlerror());
 #define L(sym) *(void **)(&g_nccl.sym) = dlsym(lib, "nccl" #sym); if (!g_nccl.sym) return sph_fail(h, SPH_ESTATE, "multi-GPU: nccl" #sym " not found")
-	L(GetUniqueId); L(CommInitRank); L(CommDestroy); L(GroupStart); L(GroupEnd); L(Send); L(Recv); L(AllReduce); L(GetErrorString);
+	L(GetUniqueId); L(CommInitRank); L(CommDestroy); L(GroupStart); L(GroupEnd); L(Send); L(Recv); L(AllReduce); L(AllGather); L(GetErrorString);
 #undef L
 	g_nccl.lib = lib;
 	return SPH_OK;
@@ -60,8 +75,26 @@ struct SphComm {
 	int *tmp_gid;
 	int *send_orig[2];      // original (local) index of the k-th particle packed for each side
 	int n_send[2], n_recv[2];
-	float4 *xsend[2], *xrecv[2]; // per-sweep ghost values
+	float4 *xsend[2], *xrecv[2]; // per-sweep ghost values (NCCL transport)
+	// peer-memory transport (CUDA IPC windows over NVLink)
+	int p2p;                     // 1: per-sweep values and loop partials go through the windows
+	char *win;                   // this rank's window (cudaMalloc, exported with cudaIpcGetMemHandle)
+	char *peer_win[SPH_MG_MAX_RANKS]; // every rank's window mapped into this process ([rank] == win)
+	size_t win_bytes;
+	int epoch;                   // exchanges issued so far (same sequence on every rank)
 };
+
+// ---- window layout (identical on every rank) ----------------------------------------------------------
+//   [0, 4096)            loop partials: rslot[2 parity][MAX_RANKS] = {sum | tag}, {count, max | tag}
+//   [4096, ...)          float4 xr[2 parity][2 side][cap_halo], .w = epoch tag
+struct MgCtlWin {
+	double rslot[2][SPH_MG_MAX_RANKS][4]; // two tagged 16-byte slots per (parity, source rank)
+};
+static_assert(sizeof(MgCtlWin) <= 4096, "window control block");
+__host__ __device__ static inline MgCtlWin *win_ctl(char *w) { return (MgCtlWin *)w; }
+__host__ __device__ static inline float4 *win_xr(char *w, int cap, int parity, int side) {
+	return (float4 *)(w + 4096) + ((size_t)parity * 2 + (size_t)side) * (size_t)cap;
+}
 
 #define NCCL_OK(h, expr)                                                                                 \
 	do {                                                                                                 \
@@ -233,6 +266,133 @@ k_mg_unpack_values(int what, const int *__restrict__ slot_of, int first_orig, in
 	}
 }
 
+// ---- peer-memory transport ------------------------------------------------------------------------
+// "LL16" protocol: every 16-byte slot carries its own epoch tag in the last word and is written with ONE
+// 128-bit store, which NVLink delivers atomically (the assumption NCCL's LL / LL128 protocols make for 8-
+// and 128-byte stores).  The receiver polls each slot until the tag equals the epoch: no fence, no
+// separate flag, no "last block" -- the fence.sys + flag version of this kernel took 23 us per exchange,
+// this one is bounded by the NVLink round trip.  Ghost values never need their .w (velocities: the
+// warm-start scalar of a ghost is not read; payloads: one or two scalars), so the tag costs no bandwidth.
+struct MgPeers {
+	char *w[SPH_MG_MAX_RANKS];
+};
+__device__ __forceinline__ void st_slot(void *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+	asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_slot(const void *p) {
+	uint4 r;
+	asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+	return r;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+// poll a slot until its tag word (.w) equals `epoch`; gives up after 10 s (a dead peer must not hang the
+// GPU) and latches SPH_ERR_COMM_TIMEOUT
+__device__ __forceinline__ uint4 wait_slot(const void *p, int epoch, SphCtl *ctl) {
+	uint4 v = ld_slot(p);
+	if ((int)v.w == epoch) return v;
+	unsigned long long t0 = global_ns();
+	for (;;) {
+		v = ld_slot(p);
+		if ((int)v.w == epoch) return v;
+		if (global_ns() - t0 > 10000000000ull) { atomicOr(&ctl->error_flags, SPH_ERR_COMM_TIMEOUT); return v; }
+	}
+}
+
+// One kernel per exchange.  Blocks 0 .. gridDim-2 (or all, without a reduction): store this rank's values of
+// the sent particles straight into the neighbours' windows, then poll the slots the neighbours fill and
+// scatter them into the ghost slots.  Last block (when do_reduce): reduce the sweep's block partials, store
+// {sum, count, max} into every rank's window, poll all ranks' slots, sum in rank order and take the loop
+// decision.  A block pushes before it polls and the grid is far smaller than one resident wave, so two
+// ranks can never wait for each other's unscheduled blocks.
+__global__ void __launch_bounds__(256)
+k_mg_exchange(int what, const int *__restrict__ send_orig_l, const int *__restrict__ send_orig_r,
+              const int *__restrict__ slot_of, int nsl, int nsr, int first_orig, int nrl, int nrr,
+              const float4 *src_a, const float4 *src_b, float4 *dst_a, float4 *dst_b, const float4 *__restrict__ spos,
+              float4 *pv, MgPeers peers, char *win, int cap, int rank, int nranks, int epoch, int do_reduce,
+              const SphPartial *__restrict__ partials, int n_partials, int ctl_kind, SphCtlArgs cargs,
+              double *__restrict__ red, SphCtl *ctl) {
+	const int parity = epoch & 1;
+	if (do_reduce && blockIdx.x == gridDim.x - 1) {
+		double sum; int cnt; float mx;
+		sph_reduce_partials<256>(partials, n_partials, sum, cnt, mx);
+		__shared__ double s_sum[SPH_MG_MAX_RANKS];
+		__shared__ int s_cnt[SPH_MG_MAX_RANKS];
+		__shared__ float s_max[SPH_MG_MAX_RANKS];
+		if (threadIdx.x < nranks) { // one thread per destination rank: two tagged 16-byte slots
+			char *slot = (char *)win_ctl(peers.w[threadIdx.x])->rslot[parity][rank];
+			unsigned long long sb = (unsigned long long)__double_as_longlong(sum);
+			st_slot(slot, (uint32_t)sb, (uint32_t)(sb >> 32), 0u, (uint32_t)epoch);
+			st_slot(slot + 16, (uint32_t)cnt, __float_as_uint(mx), 0u, (uint32_t)epoch);
+		}
+		if (threadIdx.x < nranks) { // ... and one thread per source rank
+			const char *slot = (const char *)win_ctl(win)->rslot[parity][threadIdx.x];
+			uint4 a = wait_slot(slot, epoch, ctl), b = wait_slot(slot + 16, epoch, ctl);
+			s_sum[threadIdx.x] = __longlong_as_double((long long)(((unsigned long long)a.y << 32) | a.x));
+			s_cnt[threadIdx.x] = (int)b.x;
+			s_max[threadIdx.x] = __uint_as_float(b.y);
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			double tsum = 0.0;
+			int tcnt = 0;
+			float tmax = -INFINITY;
+			for (int r = 0; r < nranks; ++r) { tsum += s_sum[r]; tcnt += s_cnt[r]; tmax = fmaxf(tmax, s_max[r]); }
+			red[0] = tsum; red[1] = (double)tcnt; red[2] = (double)tmax;
+			sph_ctl_apply(ctl_kind, ctl, tsum, tcnt, tmax, cargs); // every rank takes the same decision
+		}
+		return;
+	}
+	if (!src_a) return;
+	const int nblk = (int)gridDim.x - (do_reduce ? 1 : 0);
+	const int stride = nblk * (int)blockDim.x;
+	const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+	// phase 1: push.  My left neighbour receives on its right side (1), my right neighbour on its left side (0).
+	for (int k = t0; k < nsl + nsr; k += stride) {
+		bool left = k < nsl;
+		int kk = left ? k : k - nsl;
+		int s = slot_of[(left ? send_orig_l : send_orig_r)[kk]];
+		float4 v;
+		if (what == MG_F4_T1R) v = make_float4(src_a[s].w, src_b[s].w, 0.0f, 0.0f); // posT1.w, posR.w
+		else if (what == MG_F4_T2 || what == MG_F4_T3) v = make_float4(src_a[s].w, 0.0f, 0.0f, 0.0f);
+		else v = src_a[s];
+		float4 *dst = left ? win_xr(peers.w[rank - 1], cap, parity, 1) : win_xr(peers.w[rank + 1], cap, parity, 0);
+		st_slot(&dst[kk], __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), (uint32_t)epoch);
+	}
+	// phase 2: poll + unpack.  Ghosts are stored left block first, then right block.
+	for (int k = t0; k < nrl + nrr; k += stride) {
+		int s = slot_of[first_orig + k];
+		uint4 u = k < nrl ? wait_slot(&win_xr(win, cap, parity, 0)[k], epoch, ctl)
+		                  : wait_slot(&win_xr(win, cap, parity, 1)[k - nrl], epoch, ctl);
+		float4 p = spos[s]; // the payload buffers carry a position copy; ghosts get theirs here
+		float vx = __uint_as_float(u.x), vy = __uint_as_float(u.y), vz = __uint_as_float(u.z);
+		if (what == MG_F4_T1R) { dst_a[s] = make_float4(p.x, p.y, p.z, vx); dst_b[s] = make_float4(p.x, p.y, p.z, vy); }
+		else if (what == MG_F4_T2 || what == MG_F4_T3) dst_a[s] = make_float4(p.x, p.y, p.z, vx);
+		else {
+			float4 v = make_float4(vx, vy, vz, 0.0f);
+			dst_a[s] = v;
+			if (what == MG_F4_VEL) pv[2 * (size_t)s + 1] = v; // the 256-bit (pos, vel) records of k_df_drho
+		}
+	}
+}
+
+// NCCL transport: this rank's partial before, and the decision after, the all-reduce
+__global__ void __launch_bounds__(256) k_mg_reduce_partials(const SphPartial *partials, int n, double *red) {
+	double sum; int cnt; float mx;
+	sph_reduce_partials<256>(partials, n, sum, cnt, mx);
+	if (threadIdx.x == 0) { red[0] = sum; red[1] = (double)cnt; red[2] = (double)mx; }
+}
+void sph_reduce_partials_launch(SphHandle *h, int n_blocks, cudaStream_t st) {
+	k_mg_reduce_partials<<<1, 256, 0, st>>>(h->partials, n_blocks, h->red);
+	h->launches++;
+}
+__global__ void k_mg_ctl_apply(int ctl_kind, SphCtlArgs cargs, const double *__restrict__ red, SphCtl *ctl) {
+	sph_ctl_apply(ctl_kind, ctl, red[0], (int)red[1], (float)red[2], cargs);
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 extern "C" int sph_comm_unique_id(char *out128) {
 	if (!out128) return SPH_EINVAL;
@@ -242,6 +402,36 @@ extern "C" int sph_comm_unique_id(char *out128) {
 	if (g_nccl.GetUniqueId(&id) != ncclSuccess) return sph_fail(nullptr, SPH_ECUDA, "ncclGetUniqueId failed");
 	static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
 	memcpy(out128, &id, 128);
+	return SPH_OK;
+}
+
+// Allocate this rank's window, exchange the IPC handles (one NCCL all-gather at start-up) and map the peers'.
+static int mg_open_windows(SphHandle *h, SphComm *m) {
+	if (m->nranks > SPH_MG_MAX_RANKS) return sph_fail(h, SPH_EINVAL, "multi-GPU: at most %d ranks", SPH_MG_MAX_RANKS);
+	m->win_bytes = 4096 + sizeof(float4) * 4 * (size_t)m->cap_halo;
+	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->win, m->win_bytes));
+	SPH_CUDA_CHECK(h, cudaMemset(m->win, 0, m->win_bytes));
+	cudaIpcMemHandle_t mine;
+	SPH_CUDA_CHECK(h, cudaIpcGetMemHandle(&mine, m->win));
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+	char *dbuf = nullptr;
+	SPH_CUDA_CHECK(h, cudaMalloc((void **)&dbuf, 64 * (size_t)m->nranks));
+	SPH_CUDA_CHECK(h, cudaMemcpy(dbuf + 64 * (size_t)m->rank, &mine, 64, cudaMemcpyHostToDevice));
+	SPH_CUDA_CHECK(h, cudaDeviceSynchronize()); // the memsets above must have landed before any peer can write
+	NCCL_OK(h, g_nccl.AllGather(dbuf + 64 * (size_t)m->rank, dbuf, 64, ncclChar, m->comm, 0));
+	SPH_CUDA_CHECK(h, cudaStreamSynchronize(0));
+	cudaIpcMemHandle_t all[SPH_MG_MAX_RANKS];
+	SPH_CUDA_CHECK(h, cudaMemcpy(all, dbuf, 64 * (size_t)m->nranks, cudaMemcpyDeviceToHost));
+	cudaFree(dbuf);
+	for (int r = 0; r < m->nranks; ++r) {
+		if (r == m->rank) { m->peer_win[r] = m->win; continue; }
+		cudaError_t e = cudaIpcOpenMemHandle((void **)&m->peer_win[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+		if (e != cudaSuccess)
+			return sph_fail(h, SPH_ECUDA, "multi-GPU: cudaIpcOpenMemHandle(rank %d) failed: %s (peer access over NVLink is "
+			                              "required; SPH_MG_TRANSPORT=nccl selects the NCCL transport)", r, cudaGetErrorString(e));
+	}
+	m->p2p = 1;
+	m->epoch = 0;
 	return SPH_OK;
 }
 
@@ -282,6 +472,11 @@ extern "C" int sph_comm_init(SphHandle *h, const char *id128, int rank, int nran
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->tmp_vel, sizeof(float4) * ncap));
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->tmp_gid, sizeof(int) * ncap));
 	h->comm = m;
+	const char *tr = getenv("SPH_MG_TRANSPORT");
+	if (!(tr && strcmp(tr, "nccl") == 0)) {
+		int rc2 = mg_open_windows(h, m);
+		if (rc2 != SPH_OK) { mg_destroy(h); return rc2; }
+	}
 	return SPH_OK;
 }
 
@@ -292,6 +487,12 @@ void mg_destroy(SphHandle *h) {
 		cudaFree(m->msg_send[d]); cudaFree(m->msg_recv[d]); cudaFree(m->send_orig[d]); cudaFree(m->xsend[d]); cudaFree(m->xrecv[d]);
 	}
 	cudaFree(m->counters); cudaFreeHost(m->counters_host); cudaFree(m->tmp_pos); cudaFree(m->tmp_vel); cudaFree(m->tmp_gid);
+	if (m->p2p) {
+		cudaDeviceSynchronize();
+		for (int r = 0; r < m->nranks; ++r)
+			if (r != m->rank && m->peer_win[r]) cudaIpcCloseMemHandle(m->peer_win[r]);
+	}
+	cudaFree(m->win);
 	if (m->comm) g_nccl.CommDestroy(m->comm);
 	delete m;
 	h->comm = nullptr;
@@ -321,6 +522,7 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 	int capacity_owned = h->cfg.n_fluid;
 	int capacity_all = h->cfg.n_fluid + h->cfg.n_ghost_capacity;
 	int n = c.N_owned;
+	sph_prof_begin(h, KC_MG_STEP, st);
 	cudaMemsetAsync(m->counters, 0, sizeof(int) * MC_COUNT, st);
 	// (1) migration
 	k_mg_classify<<<cdiv(n > 0 ? n : 1, 256), 256, 0, st>>>(h->pos, h->vel, h->gid, n, c.h, m->col_lo, m->col_hi, has_left,
@@ -344,6 +546,7 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 	h->launches += 6;
 	// (3) the one host read-back of the step
 	SPH_CUDA_CHECK(h, cudaMemcpyAsync(m->counters_host, m->counters, sizeof(int) * MC_COUNT, cudaMemcpyDeviceToHost, st));
+	sph_prof_end(h, st);
 	SPH_CUDA_CHECK(h, cudaStreamSynchronize(st));
 	const int *k = m->counters_host;
 	if (k[MC_OVERFLOW]) return sph_fail(h, SPH_ESTATE, "multi-GPU: message or slab capacity exceeded (flags %d)", k[MC_OVERFLOW]);
@@ -358,12 +561,15 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 
 void mg_after_grid(SphHandle *h, cudaStream_t st) { (void)h; (void)st; }
 
-void sph_reduce_partials_launch(SphHandle *h, int n_blocks, cudaStream_t st); // sph_sweeps.cu
-
-// Ghost values of one field to / from both neighbours; when reduce_blocks > 0 the loop-decision
-// all-reduce of the same sweep's block partials rides in the same NCCL group (one launch of the
-// communication kernel instead of two).
-static void mg_exchange_impl(SphHandle *h, int what, int reduce_blocks, cudaStream_t st) {
+// Ghost values of one field to / from both neighbours; when ctl_kind != SPH_CTL_NONE the all-reduce of
+// h->red = {sum, count, max} (left there by the tail of the sweep that just ran) rides in the same
+// exchange and the loop decision is applied on every rank.
+static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_blocks, cudaStream_t st) {
+	if (ctl_kind == SPH_CTL_NONE) reduce_blocks = 0;
+	SphCtlArgs cargs;
+	cargs.dt_cfl_c1 = h->c.dt_cfl_c1;
+	cargs.rs = h->rstate;
+	cargs.rigid_exists = (h->c.Nr > 0 && h->rigid_ready) ? 1 : 0;
 	SphComm *m = h->comm;
 	if (!m) return;
 	const float4 *a = nullptr, *b = nullptr;
@@ -377,6 +583,26 @@ static void mg_exchange_impl(SphHandle *h, int what, int reduce_blocks, cudaStre
 	default: break;
 	}
 	int ns = m->n_send[0] + m->n_send[1], nr = m->n_recv[0] + m->n_recv[1];
+	if (m->p2p) {
+		sph_prof_begin(h, KC_MG_EXCHANGE, st);
+		int epoch = ++m->epoch;
+		MgPeers peers;
+		for (int r = 0; r < SPH_MG_MAX_RANKS; ++r) peers.w[r] = r < m->nranks ? m->peer_win[r] : nullptr;
+		int work = ns > nr ? ns : nr;
+		int blocks = a ? cdiv(work > 0 ? work : 1, 256) : 0;
+		if (blocks > 296) blocks = 296; // far below one resident wave: pushing blocks are never queued behind polling ones
+		if (reduce_blocks > 0) blocks += 1;
+		if (blocks > 0) {
+			k_mg_exchange<<<blocks, 256, 0, st>>>(what, m->send_orig[0], m->send_orig[1], h->fg.slot_of, m->n_send[0], m->n_send[1],
+			                                      h->c.N_owned, m->n_recv[0], m->n_recv[1], a, b, wa, wb, h->a4[A4_POS], h->pv, peers,
+			                                      m->win, m->cap_halo, m->rank, m->nranks, epoch, reduce_blocks > 0 ? 1 : 0,
+			                                      h->partials, reduce_blocks, ctl_kind, cargs, h->red, h->ctl);
+			h->launches += 1;
+		}
+		sph_prof_end(h, st);
+		return;
+	}
+	sph_prof_begin(h, KC_MG_EXCHANGE, st);
 	if (a && ns > 0) {
 		k_mg_pack_values<<<cdiv(ns, 256), 256, 0, st>>>(what, m->send_orig[0], m->send_orig[1], h->fg.slot_of, m->n_send[0],
 		                                                m->n_send[1], a, b, m->xsend[0], m->xsend[1]);
@@ -398,16 +624,19 @@ static void mg_exchange_impl(SphHandle *h, int what, int reduce_blocks, cudaStre
 		g_nccl.AllReduce(h->red + 2, h->red + 2, 1, ncclDouble, ncclMax, m->comm, st);
 	}
 	g_nccl.GroupEnd();
+	if (reduce_blocks > 0) { k_mg_ctl_apply<<<1, 1, 0, st>>>(ctl_kind, cargs, h->red, h->ctl); h->launches++; }
 	if (a && nr > 0) {
 		k_mg_unpack_values<<<cdiv(nr, 256), 256, 0, st>>>(what, h->fg.slot_of, h->c.N_owned, m->n_recv[0], m->n_recv[1],
 		                                                  m->xrecv[0], m->xrecv[1], h->a4[A4_POS], wa, wb, h->pv);
 		h->launches++;
 	}
+	sph_prof_end(h, st);
 }
 
-void mg_exchange(SphHandle *h, int what, cudaStream_t st) { mg_exchange_impl(h, what, 0, st); }
-void mg_allreduce(SphHandle *h, int n_blocks, cudaStream_t st) { mg_exchange_impl(h, -1, n_blocks, st); }
-void mg_exchange_reduce(SphHandle *h, int what, int n_blocks, cudaStream_t st) { mg_exchange_impl(h, what, n_blocks, st); }
+void mg_exchange(SphHandle *h, int what, cudaStream_t st) { mg_exchange_impl(h, what, SPH_CTL_NONE, 0, st); }
+void mg_exchange_reduce(SphHandle *h, int what, int ctl_kind, int n_blocks, cudaStream_t st) {
+	mg_exchange_impl(h, what, ctl_kind, n_blocks, st);
+}
 
 extern "C" int sph_comm_info(SphHandle *h, int32_t *out8) {
 	if (!h || !out8) return SPH_EINVAL;

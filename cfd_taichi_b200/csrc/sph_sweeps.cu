@@ -11,6 +11,7 @@
 // brings everything.  No per-pair atomics anywhere; reductions are warp-shuffle + one smem hop.
 #include "sph_math.cuh"
 #include "sph_internal.h"
+#include "sph_ctl.cuh"
 
 #ifndef SPH_MINB
 #define SPH_MINB 1 // minimum resident blocks per SM requested from ptxas for the list-walking sweeps
@@ -27,7 +28,7 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 #if SPH_STRICT
 #define SPH_DF_LPP 1
 #elif !defined(SPH_DF_LPP)
-#define SPH_DF_LPP 4
+#define SPH_DF_LPP 1 // 2, 4, 8 measured slower on B200 (profiles/r1d_coop_lanes.md): 2x the instructions, 66 % lane use
 #endif
 constexpr int DF_LPP = SPH_DF_LPP;
 constexpr int DF_PPB = SPH_BLOCK / DF_LPP; // particles per block
@@ -165,8 +166,8 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		// list layout: DFSPH lists are shared by DF_LPP lanes per particle (fast kernels), all others by one
 		constexpr int LPP = ALPHA ? DF_LPP : 1;
 		uint32_t *fl = L.flist, *bl = L.blist;
-#define SPH_FLW(n) fl[sph_list_word<LPP>(s, c.kmax, n)]
-#define SPH_BLW(n) bl[sph_list_word<LPP>(s, c.kbmax, n)]
+#define SPH_FLW(n) fl[sph_list_word<LPP>(s, c.kstride, n)]
+#define SPH_BLW(n) bl[sph_list_word<LPP>(s, c.kbstride, n)]
 		// ---- phase 1: the 27-cell traversal only culls and appends (a 15 % hit rate would otherwise run
 		// ---- the kernel-function arithmetic at 15 % lane utilisation on every candidate) -----------------
 		int ncount = 0; // get_neighbour_count (PS:424-445)
@@ -380,11 +381,11 @@ __device__ __forceinline__ void operator<<(ListRange r, F &&f) {
 	}
 }
 // usage:  SPH_FOR_FLUID(L, c, s, j) { ...body, `return` skips to the next neighbour... };
-#define SPH_FOR_FLUID(L, c, s, J) list_range<1>((L).flist, (c).kmax, s, 0, (L).fcount[s]) << [&](uint32_t J)
-#define SPH_FOR_BOUNDARY(L, c, s, J) list_range<1>((L).blist, (c).kbmax, s, 0, (L).bcount[s]) << [&](uint32_t J)
+#define SPH_FOR_FLUID(L, c, s, J) list_range<1>((L).flist, (c).kstride, s, 0, (L).fcount[s]) << [&](uint32_t J)
+#define SPH_FOR_BOUNDARY(L, c, s, J) list_range<1>((L).blist, (c).kbstride, s, 0, (L).bcount[s]) << [&](uint32_t J)
 // cooperative form: LPP lanes share particle s, each walks its share; reduce with sub_sum afterwards
-#define SPH_FOR_FLUID_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).flist, (c).kmax, s, sub, n) << [&](uint32_t J)
-#define SPH_FOR_BOUNDARY_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).blist, (c).kbmax, s, sub, n) << [&](uint32_t J)
+#define SPH_FOR_FLUID_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).flist, (c).kstride, s, sub, n) << [&](uint32_t J)
+#define SPH_FOR_BOUNDARY_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).blist, (c).kbstride, s, sub, n) << [&](uint32_t J)
 
 // sum over the DF_LPP lanes that share a particle (no-op for one lane per particle)
 template <int LPP>
@@ -755,110 +756,35 @@ k_df_position(SphConsts c, const int *__restrict__ sorted_id, const float4 *__re
 	vel[i] = F4(v, svel[s].w);
 }
 
-// ---- controller kernels: one block; deterministic reduction of the block partials, then the
-// ---- reference's host-side loop logic evaluated on the device ---------------------------------
-// multi-GPU: partials are reduced by k_reduce_partials, all-reduced with NCCL and handed to the
-// controller kernels through `red` = {sum, count, max}; on one GPU the controller reduces them itself.
-__device__ __forceinline__ void reduce_partials(const SphPartial *p, int n, double &sum, int &cnt, float &mx);
-__device__ __forceinline__ void reduced_or_partials(const double *red, const SphPartial *p, int n, double &sum,
-                                                    int &cnt, float &mx) {
-	if (red) { sum = red[0]; cnt = (int)red[1]; mx = (float)red[2]; __syncthreads(); }
-	else reduce_partials(p, n, sum, cnt, mx);
-}
+// ---- controllers: one block reduces the block partials deterministically and takes the reference's
+// ---- host-side loop decision on the device (sph_ctl.cuh).  On several GPUs the partials travel with the
+// ---- halo exchange and the receive kernel decides (sph_multigpu.cu). -------------------------------------
 __device__ __forceinline__ void reduce_partials(const SphPartial *p, int n, double &sum, int &cnt, float &mx) {
-	__shared__ double ss[256];
-	__shared__ int sc[256];
-	__shared__ float sm[256];
-	double a = 0.0;
-	int b = 0;
-	float m = -INFINITY;
-	for (int i = threadIdx.x; i < n; i += 256) { a += p[i].sum; b += p[i].cnt; m = fmaxf(m, p[i].maxv); }
-	ss[threadIdx.x] = a; sc[threadIdx.x] = b; sm[threadIdx.x] = m;
-	__syncthreads();
-	for (int o = 128; o > 0; o >>= 1) {
-		if (threadIdx.x < o) {
-			ss[threadIdx.x] += ss[threadIdx.x + o];
-			sc[threadIdx.x] += sc[threadIdx.x + o];
-			sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + o]);
-		}
-		__syncthreads();
-	}
-	sum = ss[0]; cnt = sc[0]; mx = sm[0];
+	sph_reduce_partials<256>(p, n, sum, cnt, mx);
 }
-
-__global__ void __launch_bounds__(256) k_reduce_partials(const SphPartial *partials, int n, double *red) {
+__global__ void __launch_bounds__(256) k_df_ctl(int kind, SphCtl *ctl, const SphPartial *partials, int n, SphCtlArgs args) {
+	if ((kind == SPH_CTL_DIV_ITER && !ctl->div_active) || (kind == SPH_CTL_DEN && !ctl->den_active)) return;
 	double sum; int cnt; float mx;
-	reduce_partials(partials, n, sum, cnt, mx);
-	if (threadIdx.x == 0) { red[0] = sum; red[1] = (double)cnt; red[2] = (double)mx; }
+	sph_reduce_partials<256>(partials, n, sum, cnt, mx);
+	if (threadIdx.x == 0) sph_ctl_apply(kind, ctl, sum, cnt, mx, args);
 }
-
-// mode 0: first evaluation (DF:398-399); mode 1: after an iteration (DF:406-414)
-__global__ void __launch_bounds__(256) k_df_ctl_div(SphCtl *ctl, const SphPartial *partials, int n, int mode,
-                                                     const double *red) {
-	if (mode == 1 && !ctl->div_active) return;
-	double sum; int cnt; float mx;
-	reduced_or_partials(red, partials, n, sum, cnt, mx);
-	if (threadIdx.x != 0) return;
-	float avg = cnt > 0 ? (float)(sum / (double)cnt) : 0.0f; // DF:278-279
-	if (mode == 0) {
-		ctl->div_first = avg;
-		ctl->div_err = avg;
-		ctl->div_past = 0.0f;
-		ctl->div_iters = 0;
-		ctl->div_active = 1; // iter_cnt < min_iteration_density_divergence
-	} else {
-		ctl->div_past = ctl->div_err;
-		ctl->div_err = avg;
-		if (fabs((double)avg - (double)ctl->div_past) < 1e-5) { // DF:410-412: break before iter_cnt += 1
-			ctl->div_active = 0;
-		} else {
-			int it = ctl->div_iters + 1;
-			ctl->div_iters = it;
-			ctl->div_active = ((it < 1 || avg > 10.0f) && it < 15) ? 1 : 0; // DF:400
-		}
-	}
-}
-
-// DF:100-119: max |v*| (+ rigid surface speed) -> adaptive dt on the device
-__global__ void __launch_bounds__(256) k_df_ctl_dt(SphCtl *ctl, const SphPartial *partials, int n, SphConsts c,
-                                                    const SphRigidState *rs, int rigid_exists, const double *red) {
-	double sum; int cnt; float mx;
-	reduced_or_partials(red, partials, n, sum, cnt, mx);
-	if (threadIdx.x != 0) return;
-	float max_rigid_vel = rigid_exists ? rs->max_surface_vel : 0.0f; // DF:104-110 (loops over ALL rigid particles)
-	float max_vel = mx + max_rigid_vel;              // DF:111
-	float max_dt = (c.dt_cfl_c1 / max_vel) * 0.2f;   // DF:112
-	float dt;
-	if (max_dt > 1e-3f) dt = 1e-3f;                  // DF:114-115
-	else dt = fmaxf(max_dt, 1e-5f);                  // DF:117
-	ctl->max_vel = max_vel;
-	ctl->dt = dt;
-	ctl->dt2 = dt * dt;                              // DF:118
-	ctl->ps_dt = dt;                                 // DF:119
-	ctl->den_active = 1;
-	ctl->den_iters = 0;
-	ctl->den_avg = INFINITY;
-}
-
-// DF:221-233: evaluated after compute_all_rho_adv of iteration `den_iters`; den_active then tells
-// whether the NEXT iteration runs.  The iter_all_vel_adv of the current iteration always runs, so it
-// is gated on the value den_active had when this iteration started (kept in graph_cond).
-__global__ void __launch_bounds__(256) k_df_ctl_den(SphCtl *ctl, const SphPartial *partials, int n,
-                                                     const double *red) {
-	if (!ctl->den_active) { if (threadIdx.x == 0) ctl->graph_cond = 0; return; }
-	double sum; int cnt; float mx;
-	reduced_or_partials(red, partials, n, sum, cnt, mx);
-	if (threadIdx.x != 0) return;
-	float avg = cnt > 0 ? (float)(sum / (double)cnt) : 1000.0f; // DF:128, 148-149
-	ctl->den_avg = avg;
-	ctl->graph_cond = 1;
-}
+// DF:225 after iter_all_vel_adv of iteration den_iters: does the next iteration run?
 __global__ void k_df_ctl_den_next(SphCtl *ctl) {
-	if (!ctl->graph_cond) return;
+	if (!ctl->den_active) return;
 	int it = ctl->den_iters + 1;
 	ctl->den_iters = it;
 	ctl->den_active = (it < 2 || (double)ctl->den_avg - 1000.0 > 0.1 * 1000 * 0.01) ? 1 : 0; // DF:225
 	if (it >= 1000) { ctl->den_active = 0; atomicOr(&ctl->error_flags, SPH_ERR_DENSITY_CAP); }
+}
+// the loop decision that follows a sweep: one controller launch, or (several GPUs) part of the exchange
+static void df_decide(SphHandle *h, int what, int kind, int nb, cudaStream_t st) {
+	if (h->comm) { mg_exchange_reduce(h, what, kind, nb, st); return; }
+	SphCtlArgs a;
+	a.dt_cfl_c1 = h->c.dt_cfl_c1;
+	a.rs = h->rstate;
+	a.rigid_exists = (h->c.Nr > 0 && h->rigid_ready) ? 1 : 0;
+	k_df_ctl<<<1, 256, 0, st>>>(kind, h->ctl, h->partials, nb, a);
+	h->launches++;
 }
 
 // ---- DFSPH drivers -----------------------------------------------------------------------------
@@ -885,9 +811,8 @@ static void df_divergence(SphHandle *h, cudaStream_t st) {
 	             h->a1[A1_RHO],
 	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 0);
 	sph_prof_end(h, st);
-	mg_exchange_reduce(h, MG_F4_T2, nb, st);
-	k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0, h->comm ? h->red : nullptr);
-	h->launches += 3;
+	df_decide(h, MG_F4_T2, SPH_CTL_DIV_FIRST, nb, st);
+	h->launches += 2;
 	for (int it = 0; it < 15; ++it) { // max_iteration_density_divergence (DF:24); gated on ctl->div_active
 		sph_prof_begin(h, KC_DF_DIV, st);
 		SPH_LAUNCH_R(k_df_div_iter, nb, c, h->L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
@@ -899,9 +824,8 @@ static void df_divergence(SphHandle *h, cudaStream_t st) {
 	             h->a1[A1_RHO],
 		             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 1);
 		sph_prof_end(h, st);
-		mg_exchange_reduce(h, MG_F4_T2, nb, st);
-		k_df_ctl_div<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1, h->comm ? h->red : nullptr);
-		h->launches += 3;
+		df_decide(h, MG_F4_T2, SPH_CTL_DIV_ITER, nb, st);
+		h->launches += 2;
 	}
 }
 
@@ -914,10 +838,8 @@ static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	             h->a4[A4_FA], h->ctl, h->partials);
 	sph_prof_end(h, st);
 	// DF:105-110 loops over all rigid particles whenever a rigid body exists, active or not
-	mg_exchange_reduce(h, MG_F4_VADV, nb, st);
-	k_df_ctl_dt<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, c, h->rstate, (c.Nr > 0 && h->rigid_ready) ? 1 : 0,
-	                               h->comm ? h->red : nullptr);
-	h->launches += 2;
+	df_decide(h, MG_F4_VADV, SPH_CTL_DT, nb, st);
+	h->launches += 1;
 }
 
 static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st) {
@@ -930,8 +852,7 @@ static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st
 		SPH_LAUNCH_R(k_df_rho_adv, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
 		             h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated);
 		sph_prof_end(h, st);
-		mg_exchange_reduce(h, MG_F4_T3, nb, st);
-		k_df_ctl_den<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, h->comm ? h->red : nullptr);
+		df_decide(h, MG_F4_T3, SPH_CTL_DEN, nb, st);
 		sph_prof_begin(h, KC_DF_VELADV, st);
 		SPH_LAUNCH_R(k_df_vel_adv_iter, nb, c, h->L, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
 		             h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
@@ -939,7 +860,7 @@ static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st
 		mg_exchange(h, MG_F4_VADV, st);
 		if (rg.active) rigid_force_df(h, gated, st); // DF:212, gather form
 		k_df_ctl_den_next<<<1, 1, 0, st>>>(h->ctl);
-		h->launches += 4;
+		h->launches += 3;
 	}
 }
 
@@ -1002,10 +923,3 @@ void ii_phase(SphHandle *h, int phase, cudaStream_t st);
 #include "sph_rigid.cuh"
 #include "sph_sweeps_other.cuh"
 
-#if SPH_STRICT
-// mode independent (pure fp64 / int reduction); defined once, in the strict translation unit
-void sph_reduce_partials_launch(SphHandle *h, int n_blocks, cudaStream_t st) {
-	sph_strict::k_reduce_partials<<<1, 256, 0, st>>>(h->partials, n_blocks, h->red);
-	h->launches++;
-}
-#endif
