@@ -363,6 +363,7 @@ static int base_step(SphHandle *h, cudaStream_t st) {
 	sph_prof_begin(h, KC_GRID, st);
 	sphg_build(h, h->fg, h->pos, h->c.N, st, h->comm ? h->gid : nullptr);
 	sphg_gather_fluid(h, st);
+	mg_after_grid(h, st); // multi-GPU: sorted slots of the sent / received particles of this step
 	if (h->c.Nr > 0 && h->c.active_rigid) { // PS:385-386, 399-407
 		sphg_build(h, h->rg, h->rpos, h->c.Nr, st);
 		sphg_gather_rigid(h, st);

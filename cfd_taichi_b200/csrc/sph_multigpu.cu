@@ -82,6 +82,7 @@ struct SphComm {
 	char *peer_win[SPH_MG_MAX_RANKS]; // every rank's window mapped into this process ([rank] == win)
 	size_t win_bytes;
 	int epoch;                   // exchanges issued so far (same sequence on every rank)
+	int *send_slot[2], *recv_slot; // sorted slots of the particles sent to each side / of the ghosts, per step
 };
 
 // ---- window layout (identical on every rank) ----------------------------------------------------------
@@ -309,8 +310,8 @@ __device__ __forceinline__ uint4 wait_slot(const void *p, int epoch, SphCtl *ctl
 // decision.  A block pushes before it polls and the grid is far smaller than one resident wave, so two
 // ranks can never wait for each other's unscheduled blocks.
 __global__ void __launch_bounds__(256)
-k_mg_exchange(int what, const int *__restrict__ send_orig_l, const int *__restrict__ send_orig_r,
-              const int *__restrict__ slot_of, int nsl, int nsr, int first_orig, int nrl, int nrr,
+k_mg_exchange(int what, const int *__restrict__ send_slot_l, const int *__restrict__ send_slot_r,
+              const int *__restrict__ recv_slot, int nsl, int nsr, int nrl, int nrr,
               const float4 *src_a, const float4 *src_b, float4 *dst_a, float4 *dst_b, const float4 *__restrict__ spos,
               float4 *pv, MgPeers peers, char *win, int cap, int rank, int nranks, int epoch, int do_reduce,
               const SphPartial *__restrict__ partials, int n_partials, int ctl_kind, SphCtlArgs cargs,
@@ -354,7 +355,7 @@ k_mg_exchange(int what, const int *__restrict__ send_orig_l, const int *__restri
 	for (int k = t0; k < nsl + nsr; k += stride) {
 		bool left = k < nsl;
 		int kk = left ? k : k - nsl;
-		int s = slot_of[(left ? send_orig_l : send_orig_r)[kk]];
+		int s = (left ? send_slot_l : send_slot_r)[kk];
 		float4 v;
 		if (what == MG_F4_T1R) v = make_float4(src_a[s].w, src_b[s].w, 0.0f, 0.0f); // posT1.w, posR.w
 		else if (what == MG_F4_T2 || what == MG_F4_T3) v = make_float4(src_a[s].w, 0.0f, 0.0f, 0.0f);
@@ -364,7 +365,7 @@ k_mg_exchange(int what, const int *__restrict__ send_orig_l, const int *__restri
 	}
 	// phase 2: poll + unpack.  Ghosts are stored left block first, then right block.
 	for (int k = t0; k < nrl + nrr; k += stride) {
-		int s = slot_of[first_orig + k];
+		int s = recv_slot[k];
 		uint4 u = k < nrl ? wait_slot(&win_xr(win, cap, parity, 0)[k], epoch, ctl)
 		                  : wait_slot(&win_xr(win, cap, parity, 1)[k - nrl], epoch, ctl);
 		float4 p = spos[s]; // the payload buffers carry a position copy; ghosts get theirs here
@@ -409,6 +410,8 @@ extern "C" int sph_comm_unique_id(char *out128) {
 static int mg_open_windows(SphHandle *h, SphComm *m) {
 	if (m->nranks > SPH_MG_MAX_RANKS) return sph_fail(h, SPH_EINVAL, "multi-GPU: at most %d ranks", SPH_MG_MAX_RANKS);
 	m->win_bytes = 4096 + sizeof(float4) * 4 * (size_t)m->cap_halo;
+	for (int d = 0; d < 2; ++d) SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->send_slot[d], sizeof(int) * (size_t)m->cap_halo));
+	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->recv_slot, sizeof(int) * 2 * (size_t)m->cap_halo));
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->win, m->win_bytes));
 	SPH_CUDA_CHECK(h, cudaMemset(m->win, 0, m->win_bytes));
 	cudaIpcMemHandle_t mine;
@@ -492,7 +495,7 @@ void mg_destroy(SphHandle *h) {
 		for (int r = 0; r < m->nranks; ++r)
 			if (r != m->rank && m->peer_win[r]) cudaIpcCloseMemHandle(m->peer_win[r]);
 	}
-	cudaFree(m->win);
+	cudaFree(m->win); cudaFree(m->send_slot[0]); cudaFree(m->send_slot[1]); cudaFree(m->recv_slot);
 	if (m->comm) g_nccl.CommDestroy(m->comm);
 	delete m;
 	h->comm = nullptr;
@@ -559,7 +562,27 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 	return SPH_OK;
 }
 
-void mg_after_grid(SphHandle *h, cudaStream_t st) { (void)h; (void)st; }
+// once per step, after the sort: where the sent particles and the ghosts live in the sorted arrays
+__global__ void __launch_bounds__(256)
+k_mg_slots(const int *__restrict__ send_orig_l, const int *__restrict__ send_orig_r, const int *__restrict__ slot_of,
+           int nsl, int nsr, int first_orig, int nr, int *__restrict__ send_slot_l, int *__restrict__ send_slot_r,
+           int *__restrict__ recv_slot) {
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < nsl) send_slot_l[k] = slot_of[send_orig_l[k]];
+	if (k < nsr) send_slot_r[k] = slot_of[send_orig_r[k]];
+	if (k < nr) recv_slot[k] = slot_of[first_orig + k];
+}
+void mg_after_grid(SphHandle *h, cudaStream_t st) {
+	SphComm *m = h->comm;
+	if (!m || !m->p2p) return;
+	int nr = m->n_recv[0] + m->n_recv[1];
+	int work = nr > m->n_send[0] ? nr : m->n_send[0];
+	if (m->n_send[1] > work) work = m->n_send[1];
+	if (work <= 0) return;
+	k_mg_slots<<<cdiv(work, 256), 256, 0, st>>>(m->send_orig[0], m->send_orig[1], h->fg.slot_of, m->n_send[0], m->n_send[1],
+	                                            h->c.N_owned, nr, m->send_slot[0], m->send_slot[1], m->recv_slot);
+	h->launches++;
+}
 
 // Ghost values of one field to / from both neighbours; when ctl_kind != SPH_CTL_NONE the all-reduce of
 // h->red = {sum, count, max} (left there by the tail of the sweep that just ran) rides in the same
@@ -593,8 +616,8 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 		if (blocks > 296) blocks = 296; // far below one resident wave: pushing blocks are never queued behind polling ones
 		if (reduce_blocks > 0) blocks += 1;
 		if (blocks > 0) {
-			k_mg_exchange<<<blocks, 256, 0, st>>>(what, m->send_orig[0], m->send_orig[1], h->fg.slot_of, m->n_send[0], m->n_send[1],
-			                                      h->c.N_owned, m->n_recv[0], m->n_recv[1], a, b, wa, wb, h->a4[A4_POS], h->pv, peers,
+			k_mg_exchange<<<blocks, 256, 0, st>>>(what, m->send_slot[0], m->send_slot[1], m->recv_slot, m->n_send[0], m->n_send[1],
+			                                      m->n_recv[0], m->n_recv[1], a, b, wa, wb, h->a4[A4_POS], h->pv, peers,
 			                                      m->win, m->cap_halo, m->rank, m->nranks, epoch, reduce_blocks > 0 ? 1 : 0,
 			                                      h->partials, reduce_blocks, ctl_kind, cargs, h->red, h->ctl);
 			h->launches += 1;
