@@ -105,7 +105,7 @@ struct SphRigidArgs {
 	int active;
 };
 
-struct SphPartial {
+struct __align__(16) SphPartial {
 	double sum;
 	int cnt;
 	float maxv;

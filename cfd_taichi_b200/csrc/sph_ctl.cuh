@@ -76,7 +76,16 @@ __device__ __forceinline__ void sph_reduce_partials(const SphPartial *p, int n, 
 	double a = 0.0;
 	int b = 0;
 	float m = -INFINITY;
-	for (int i = threadIdx.x; i < n; i += NT) { a += p[i].sum; b += p[i].cnt; m = fmaxf(m, p[i].maxv); }
+	// eight independent loads in flight per thread (the kernel is pure L2 latency), fixed summation order
+	int i = threadIdx.x;
+	for (; i + 7 * NT < n; i += 8 * NT) {
+		SphPartial q[8];
+#pragma unroll
+		for (int u = 0; u < 8; ++u) q[u] = p[i + u * NT];
+#pragma unroll
+		for (int u = 0; u < 8; ++u) { a += q[u].sum; b += q[u].cnt; m = fmaxf(m, q[u].maxv); }
+	}
+	for (; i < n; i += NT) { a += p[i].sum; b += p[i].cnt; m = fmaxf(m, p[i].maxv); }
 	ss[threadIdx.x] = a; sc[threadIdx.x] = b; sm[threadIdx.x] = m;
 	__syncthreads();
 #pragma unroll

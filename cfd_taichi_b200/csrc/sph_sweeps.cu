@@ -762,10 +762,10 @@ k_df_position(SphConsts c, const int *__restrict__ sorted_id, const float4 *__re
 __device__ __forceinline__ void reduce_partials(const SphPartial *p, int n, double &sum, int &cnt, float &mx) {
 	sph_reduce_partials<256>(p, n, sum, cnt, mx);
 }
-__global__ void __launch_bounds__(256) k_df_ctl(int kind, SphCtl *ctl, const SphPartial *partials, int n, SphCtlArgs args) {
+__global__ void __launch_bounds__(1024) k_df_ctl(int kind, SphCtl *ctl, const SphPartial *partials, int n, SphCtlArgs args) {
 	if ((kind == SPH_CTL_DIV_ITER && !ctl->div_active) || (kind == SPH_CTL_DEN && !ctl->den_active)) return;
 	double sum; int cnt; float mx;
-	sph_reduce_partials<256>(partials, n, sum, cnt, mx);
+	sph_reduce_partials<1024>(partials, n, sum, cnt, mx);
 	if (threadIdx.x == 0) sph_ctl_apply(kind, ctl, sum, cnt, mx, args);
 }
 // DF:225 after iter_all_vel_adv of iteration den_iters: does the next iteration run?
@@ -783,7 +783,7 @@ static void df_decide(SphHandle *h, int what, int kind, int nb, cudaStream_t st)
 	a.dt_cfl_c1 = h->c.dt_cfl_c1;
 	a.rs = h->rstate;
 	a.rigid_exists = (h->c.Nr > 0 && h->rigid_ready) ? 1 : 0;
-	k_df_ctl<<<1, 256, 0, st>>>(kind, h->ctl, h->partials, nb, a);
+	k_df_ctl<<<1, 1024, 0, st>>>(kind, h->ctl, h->partials, nb, a);
 	h->launches++;
 }
 
