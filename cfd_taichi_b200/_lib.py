@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SPH_B200_LIB: developer knob to A/B a variant build of the same library (never a different backend)
 LIB_PATH = os.environ.get("SPH_B200_LIB") or os.path.join(_HERE, "_build", "libsph_b200.so")
 
-SOLVER_IDS = {"wcsph": 0, "pcisph": 1, "iisph": 2, "dfsph": 3}
+SOLVER_IDS = {"wcsph": 0, "pcisph": 1, "iisph": 2, "dfsph": 3, "pbf": 4}
 
 # enum SphField
 F_FLUID_POS, F_FLUID_VEL, F_BOUNDARY_POS, F_RIGID_POS, F_RIGID_VEL, F_RIGID_FORCE, F_FLUID_ACC, F_RIGID_VERTICES, F_FLUID_GID = range(9)
@@ -25,6 +25,7 @@ PH_DF_INITIALIZE, PH_DF_DIVERGENCE, PH_DF_EXT_FORCE_VEL_ADV, PH_DF_DENSITY, PH_D
 PH_WC_PRESSURE, PH_WC_KINEMATIC = 20, 21
 PH_PC_EXT_FORCE, PH_PC_ITERATION, PH_PC_INTEGRATION = 30, 31, 32
 PH_II_PREDICT_ADVECTION, PH_II_PRESSURE_SOLVE, PH_II_INTEGRATION = 40, 41, 42
+PH_PBF_PREDICT, PH_PBF_LAMBDA, PH_PBF_DELTA_POS, PH_PBF_UPDATE_POS = 50, 51, 52, 53
 PH_WRITEBACK = 90
 
 # kernel classes of sph_profile_end (csrc/sph_internal.h)

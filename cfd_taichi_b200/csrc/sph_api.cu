@@ -129,7 +129,7 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 		return sph_fail(nullptr, SPH_EINVAL, "sph_create: grid_num must be positive");
 	if ((long long)cfg->grid_num[0] * cfg->grid_num[1] * cfg->grid_num[2] > 0x7fffffffLL - 2)
 		return sph_fail(nullptr, SPH_EINVAL, "sph_create: grid too large for int32 cell ids");
-	if (cfg->solver < SPH_SOLVER_WCSPH || cfg->solver > SPH_SOLVER_DFSPH)
+	if (cfg->solver < SPH_SOLVER_WCSPH || cfg->solver > SPH_SOLVER_PBF)
 		return sph_fail(nullptr, SPH_EINVAL, "sph_create: unknown solver id %d", cfg->solver);
 	if (!(cfg->particle_radius > 0)) return sph_fail(nullptr, SPH_EINVAL, "sph_create: particle_radius must be > 0");
 	int ndev = 0;
@@ -394,7 +394,7 @@ extern "C" int sph_phase(SphHandle *h, int phase, void *stream) {
 		return check_launch(h, "sph_phase(writeback)");
 	}
 	if (phase != SPH_PH_DF_INITIALIZE && phase != SPH_PH_WC_PRESSURE && phase != SPH_PH_PC_EXT_FORCE &&
-	    phase != SPH_PH_II_PREDICT_ADVECTION && !h->lists_valid)
+	    phase != SPH_PH_II_PREDICT_ADVECTION && phase != SPH_PH_PBF_PREDICT && phase != SPH_PH_PBF_LAMBDA && !h->lists_valid)
 		return sph_fail(h, SPH_ESTATE, "sph_phase: neighbour lists not built (run the solver's first phase)");
 	if (phase >= SPH_PH_DF_INITIALIZE && phase <= SPH_PH_DF_POSITION) {
 		if (h->c.solver != SPH_SOLVER_DFSPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a DFSPH solver");
@@ -408,6 +408,9 @@ extern "C" int sph_phase(SphHandle *h, int phase, void *stream) {
 	} else if (phase >= SPH_PH_II_PREDICT_ADVECTION && phase <= SPH_PH_II_INTEGRATION) {
 		if (h->c.solver != SPH_SOLVER_IISPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not an IISPH solver");
 		if (strict) sph_strict::ii_phase(h, phase, st); else sph_fast::ii_phase(h, phase, st);
+	} else if (phase >= SPH_PH_PBF_PREDICT && phase <= SPH_PH_PBF_UPDATE_POS) {
+		if (h->c.solver != SPH_SOLVER_PBF) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a PBF solver");
+		if (strict) sph_strict::pbf_phase(h, phase, st); else sph_fast::pbf_phase(h, phase, st);
 	} else {
 		return sph_fail(h, SPH_EINVAL, "sph_phase: unknown phase %d", phase);
 	}
@@ -441,6 +444,10 @@ extern "C" int sph_step(SphHandle *h, int n_substeps, void *stream) {
 		case SPH_SOLVER_IISPH:
 			for (int p = SPH_PH_II_PREDICT_ADVECTION; p <= SPH_PH_II_INTEGRATION; ++p)
 				if (strict) sph_strict::ii_phase(h, p, st); else sph_fast::ii_phase(h, p, st);
+			break;
+		case SPH_SOLVER_PBF:
+			for (int p = SPH_PH_PBF_PREDICT; p <= SPH_PH_PBF_UPDATE_POS; ++p)
+				if (strict) sph_strict::pbf_phase(h, p, st); else sph_fast::pbf_phase(h, p, st);
 			break;
 		default: break;
 		}

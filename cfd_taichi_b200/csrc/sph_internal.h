@@ -140,6 +140,7 @@ void mg_destroy(SphHandle *h);
 	void pc_precompute(SphHandle *h, cudaStream_t st);                                      \
 	void pc_set_delta(SphHandle *h, int target, cudaStream_t st);                           \
 	void ii_phase(SphHandle *h, int phase, cudaStream_t st);                                \
+	void pbf_phase(SphHandle *h, int phase, cudaStream_t st);                               \
 	void rigid_init(SphHandle *h, cudaStream_t st);                                         \
 	void rigid_step(SphHandle *h, cudaStream_t st);                                         \
 	}

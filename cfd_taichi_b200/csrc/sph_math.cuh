@@ -20,6 +20,8 @@
 #define SPH_NS sph_fast
 #endif
 
+#define PI_F_DEV ((float)3.141592653589793)
+
 namespace SPH_NS {
 
 struct f3 {

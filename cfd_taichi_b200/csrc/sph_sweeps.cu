@@ -917,9 +917,11 @@ void pc_phase(SphHandle *h, int phase, cudaStream_t st);
 void pc_precompute(SphHandle *h, cudaStream_t st);
 void pc_set_delta(SphHandle *h, int target, cudaStream_t st);
 void ii_phase(SphHandle *h, int phase, cudaStream_t st);
+void pbf_phase(SphHandle *h, int phase, cudaStream_t st);
 
 } // namespace SPH_NS
 
 #include "sph_rigid.cuh"
 #include "sph_sweeps_other.cuh"
+#include "sph_sweeps_pbf.cuh"
 

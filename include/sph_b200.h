@@ -38,6 +38,7 @@ extern "C" {
 #define SPH_SOLVER_PCISPH 1
 #define SPH_SOLVER_IISPH 2
 #define SPH_SOLVER_DFSPH 3
+#define SPH_SOLVER_PBF 4   /* pbf_solver.py with index-based task semantics (stale in the reference, SURVEY B-14) */
 
 /* Mirrors the JSON blocks read by ParticleSystem.__init__ (PS:31-127), solver_base.__init__
  * (SB:7-39) and rigid_solver.__init__ (RS:6-31).  Host-side derived numbers (particle counts,
@@ -115,6 +116,12 @@ enum SphPhase {
 	SPH_PH_II_PREDICT_ADVECTION = 40, /* II:35-75 */
 	SPH_PH_II_PRESSURE_SOLVE,         /* II:78-100 */
 	SPH_PH_II_INTEGRATION,            /* II:184-206 */
+	/* PBF (fetch: rho = SPH_F_RHO, constrain = SCALAR_A, pbf_lambda = SCALAR_B, constrain_derivative =
+	 * FORCE_A, delta_pos = FORCE_B, pos_predict = VEC_C) */
+	SPH_PH_PBF_PREDICT = 50,          /* PBF:26-30 externel_force_predict_pos */
+	SPH_PH_PBF_LAMBDA,                /* PBF:32-52 compute_all_lambda */
+	SPH_PH_PBF_DELTA_POS,             /* PBF:55-65 compute_all_delta_pos */
+	SPH_PH_PBF_UPDATE_POS,            /* PBF:67-96 update_all_pos (move all, then XSPH) */
 	/* commit the sorted work buffers back into the bound original-order state */
 	SPH_PH_WRITEBACK = 90
 };

@@ -40,7 +40,7 @@ def build(force=False):
     """Compile the oracle with the committed Makefile (building the checker is not using it)."""
     if force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
-        for f in ("sph_oracle.c", "sph_oracle_solvers2.inc", "sph_oracle.h")
+        for f in ("sph_oracle.c", "sph_oracle_solvers2.inc", "sph_oracle_pbf.inc", "sph_oracle.h")
     ):
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return _LIB_PATH

@@ -117,6 +117,9 @@ struct OrcSim {
 	float *v_adv, *f_adv, *d_ii, *a_ii, *d_ij, *p_iter, *p_past, *p_new_buff, *r_sum, *f_press;
 	int ii_iters;
 	float ii_residual;
+	/* pbf (index-based semantics, sph_oracle_pbf.inc) */
+	float *pbf_constrain, *pbf_lambda, *pbf_cd, *pbf_delta_pos;
+	int pbf_update_mode;
 	/* scratch */
 	float *scratch;
 };
@@ -1175,6 +1178,7 @@ static void wc_kinematic_phase(OrcSim *s) {
 }
 
 #include "sph_oracle_solvers2.inc"
+#include "sph_oracle_pbf.inc"
 
 /* per-solver reset() (SB:131-134 ; DF:418-421 ; PC:228-231 ; II:31-33) */
 static void solver_reset(OrcSim *s) {
@@ -1194,6 +1198,7 @@ void orc_step(OrcSim *s) {
 	case SOLVER_WCSPH: wc_pressure_phase(s); wc_kinematic_phase(s); break;
 	case SOLVER_PCISPH: pc_compute_ext_force(s); pc_iteration(s); pc_integration(s); break;
 	case SOLVER_IISPH: ii_predict_advection(s); ii_pressure_solve(s); ii_integration(s); break;
+	case SOLVER_PBF: pbf_step(s); break;
 	default: break;
 	}
 }
@@ -1226,6 +1231,10 @@ void orc_phase(OrcSim *s, const char *name) {
 	PH("ii_predict_advection", ii_predict_advection(s))
 	PH("ii_pressure_solve", ii_pressure_solve(s))
 	PH("ii_integration", ii_integration(s))
+	PH("pbf_externel_force_predict_pos", pbf_externel_force_predict_pos(s))
+	PH("pbf_compute_all_lambda", pbf_compute_all_lambda(s))
+	PH("pbf_compute_all_delta_pos", pbf_compute_all_delta_pos(s))
+	PH("pbf_update_all_pos", pbf_update_all_pos(s))
 #undef PH
 	fprintf(stderr, "orc_phase: unknown phase '%s'\n", name);
 	s->error_flags |= 1024;
@@ -1292,6 +1301,7 @@ OrcSim *orc_create(const OrcConfig *cfg, const float *rigid_points, int n_rigid,
 	s->v_adv = falloc(3LL * N); s->f_adv = falloc(3LL * N); s->d_ii = falloc(3LL * N); s->a_ii = falloc(N);
 	s->d_ij = falloc(3LL * N); s->p_iter = falloc(N); s->p_past = falloc(N); s->p_new_buff = falloc(N);
 	s->r_sum = falloc(N); s->f_press = falloc(3LL * N);
+	s->pbf_constrain = falloc(N); s->pbf_lambda = falloc(N); s->pbf_cd = falloc(3LL * N); s->pbf_delta_pos = falloc(3LL * N);
 
 	init_particle_pos(s);                                   /* PS:119 */
 	if (s->exist_rigid == 1) init_rigid_particles_pos(s);   /* PS:120-121 */
@@ -1315,7 +1325,7 @@ void orc_destroy(OrcSim *s) {
 	                &s->force_ext, &s->warm_start_k, &s->pressure, &s->pressure_gradient, &s->boundary_acc,
 	                &s->pos_predict, &s->vel_predict, &s->ext_force, &s->press_force, &s->rho_predict, &s->rho_err,
 	                &s->press_iter, &s->v_adv, &s->f_adv, &s->d_ii, &s->a_ii, &s->d_ij, &s->p_iter, &s->p_past,
-	                &s->p_new_buff, &s->r_sum, &s->f_press};
+	                &s->p_new_buff, &s->r_sum, &s->f_press, &s->pbf_constrain, &s->pbf_lambda, &s->pbf_cd, &s->pbf_delta_pos};
 	for (size_t i = 0; i < sizeof(fp) / sizeof(fp[0]); ++i) free(*fp[i]);
 	int **ip[] = {&s->cell3, &s->cell1, &s->bcell3, &s->rcell3, &s->cell_start, &s->cell_items, &s->bcell_start,
 	              &s->bcell_items, &s->nbr_count};
@@ -1353,6 +1363,8 @@ int orc_field(OrcSim *s, const char *name, void **ptr, long long *n, int *ncomp,
 	FLD("v_adv", s->v_adv, s->N, 3, 1) FLD("f_adv", s->f_adv, s->N, 3, 1) FLD("d_ii", s->d_ii, s->N, 3, 1)
 	FLD("a_ii", s->a_ii, s->N, 1, 1) FLD("d_ij", s->d_ij, s->N, 3, 1) FLD("p_iter", s->p_iter, s->N, 1, 1)
 	FLD("p_past", s->p_past, s->N, 1, 1) FLD("r_sum", s->r_sum, s->N, 1, 1) FLD("f_press", s->f_press, s->N, 3, 1)
+	FLD("pbf_constrain", s->pbf_constrain, s->N, 1, 1) FLD("pbf_lambda", s->pbf_lambda, s->N, 1, 1)
+	FLD("pbf_constrain_derivative", s->pbf_cd, s->N, 3, 1) FLD("pbf_delta_pos", s->pbf_delta_pos, s->N, 3, 1)
 #undef FLD
 	return -1;
 }
@@ -1377,4 +1389,5 @@ void orc_set_scalar(OrcSim *s, const char *name, double v) {
 	if (!strcmp(name, "delta_time")) { s->dt = (float)v; return; }
 	if (!strcmp(name, "delta_time_2")) { s->dt2 = (float)v; return; }
 	if (!strcmp(name, "active_rigid")) { s->active_rigid = (int)v; return; }
+	if (!strcmp(name, "pbf_update_mode")) { s->pbf_update_mode = (int)v; return; }
 }

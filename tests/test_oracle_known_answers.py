@@ -178,3 +178,54 @@ def test_threads_do_not_change_results():
         b.step()
     assert np.array_equal(pa, b.field("pos")) and np.array_equal(va, b.field("vel"))
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# PBF (index-based semantics, oracle/sph_oracle_pbf.inc)
+# ---------------------------------------------------------------------------------------------
+def _poly6(r, h):
+    q = r / h
+    return np.where(q <= 1.0, 315.0 / (64.0 * np.pi * h ** 3) * (1.0 - q * q) ** 3, 0.0)
+
+
+def test_pbf_density_lambda_against_brute_force():
+    cfg = scenes.shipped("small_block", "pbf")
+    o = O.Oracle(cfg, solver="pbf", threads=4)
+    pos = o.field("pos").astype(np.float64)
+    c = pos.mean(axis=0, keepdims=True)
+    o.field("pos")[:] = (c + (pos - c) * 0.86).astype(np.float32)      # compress: constraint active
+    o.base_step()
+    o.phase("pbf_externel_force_predict_pos")
+    o.phase("pbf_compute_all_lambda")
+    pos = o.field("pos").astype(np.float64)
+    bpos, bvol = o.field("bpos").astype(np.float64), o.field("bvol").astype(np.float64)
+    h, m = 0.1, 1000 * 0.025 ** 3 * 8
+    rho, lam, con = o.field("rho"), o.field("pbf_lambda"), o.field("pbf_constrain")
+    for i in (0, 17, 2500, 5878):
+        r = np.linalg.norm(pos - pos[i], axis=1)
+        r[i] = np.inf                                                   # PS:461 self excluded
+        rb = np.linalg.norm(bpos - pos[i], axis=1)
+        brute = 0.001 + m * _poly6(r[r <= h + 1e-9], h).sum() + 1000.0 * (bvol * _poly6(rb, h))[rb <= h + 1e-9].sum()
+        assert abs(brute - rho[i]) <= 2e-4 * brute, (i, brute, rho[i])
+        assert con[i] == np.float32(max(np.float32(rho[i]) / np.float32(1000.0) - np.float32(1.0), 0.0))
+        assert (lam[i] == 0.0) == (con[i] == 0.0) and lam[i] <= 0.0     # PBF:39-52
+    assert (lam < 0).sum() > 100
+    o.close()
+
+
+def test_pbf_update_order_modes():
+    # mode 1 = the reference's literal racy loop in ascending index order (ti.cpu, one thread); mode 0 =
+    # move-all-then-XSPH, the order the CUDA path reproduces.  They differ only through the XSPH term.
+    cfg = scenes.shipped("small_block", "pbf")
+    out = []
+    for mode in (0, 1):
+        o = O.Oracle(cfg, solver="pbf", threads=4)
+        o.set_scalar("pbf_update_mode", mode)
+        rng = np.random.default_rng(5)
+        o.field("vel")[:] = rng.normal(0, 0.5, o.field("vel").shape).astype(np.float32)
+        o.step()
+        out.append((o.field("pos").copy(), o.field("vel").copy()))
+        o.close()
+    assert np.array_equal(out[0][0], out[1][0])                         # positions of one step: identical
+    dv = np.abs(out[0][1] - out[1][1]).max()
+    assert 0.0 < dv < 0.2 * np.abs(out[0][1]).max()
