@@ -283,12 +283,28 @@ class ParticleSystem:
         return scene.derive_sizes(self.config)[1]
 
     def init_particle_pos(self):                                                    # PS:139-195
+        """Fluid lattice and boundary shell generated on the device (sph_init_fluid_lattice /
+        sph_init_boundary_shell); scene.init_*_positions is the numpy statement of the same formulas
+        that the tests compare against."""
         n, nb = self.particle_num, self.boundary_particles_num
-        fp = scene.init_fluid_positions(self.config, n, self._owned_ids)
-        self._pos4[:fp.shape[0], :3].copy_(torch.from_numpy(fp).to(self._device))
+        sc, fl = self.config['scene'], self.config['fluid']
+        lat = _lib.SphLattice()
+        lat.particle_radius = sc['particle_radius']
+        for k in range(3):
+            lat.start_pos[k], lat.water_size[k] = fl['start_pos'][k], fl['water_size'][k]
+            lat.box_min[k], lat.box_max[k] = sc['box_min'][k], sc['box_max'][k]
+        L = _lib.load()
+        dev_index = self._device.index if self._device.index is not None else torch.cuda.current_device()
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        ids, n_local = None, n
+        if self._owned_ids is not None:
+            ids = torch.from_numpy(np.ascontiguousarray(self._owned_ids, dtype=np.int32)).to(self._device)
+            n_local = ids.shape[0]
+        _lib.check(L.sph_init_fluid_lattice(ctypes.byref(lat), n, ids.data_ptr() if ids is not None else None, n_local,
+                                            self._pos4.data_ptr(), dev_index, stream))
         if nb > 0:
-            bp = scene.init_boundary_positions(self.config, nb)
-            self._bpos4[:nb, :3].copy_(torch.from_numpy(bp).to(self._device))
+            _lib.check(L.sph_init_boundary_shell(ctypes.byref(lat), nb, self._bpos4.data_ptr(), dev_index, stream))
+        torch.cuda.current_stream(self._device).synchronize()   # ids may be freed after this call
 
     def init_rigid_particles_pos(self):                                             # PS:198-223
         a = self.rigid_attitude_offset

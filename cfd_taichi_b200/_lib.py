@@ -35,6 +35,11 @@ KERNEL_CLASSES = ["grid", "lists", "df_warm_start", "df_drho", "df_div_iter", "d
                   "rigid", "other", "mg_exchange", "mg_begin_step", "mg_wait"]
 
 
+class SphLattice(ctypes.Structure):
+    _fields_ = [("particle_radius", ctypes.c_double), ("start_pos", ctypes.c_double * 3),
+                ("water_size", ctypes.c_double * 3), ("box_min", ctypes.c_double * 3), ("box_max", ctypes.c_double * 3)]
+
+
 class SphConfig(ctypes.Structure):
     _fields_ = [
         ("box_min", ctypes.c_double * 3),
@@ -111,6 +116,9 @@ PROTOTYPES = [
     ("sph_rigid_state", _i, [_vp, _vp]),
     ("sph_set_delta_time", _i, [_vp, _f, _vp]),
     ("sph_fetch", _i, [_vp, _i, _vp, ctypes.c_size_t, _vp]),
+    ("sph_init_fluid_lattice", _i, [ctypes.POINTER(SphLattice), ctypes.c_longlong, _vp, ctypes.c_size_t, _vp, _i, _vp]),
+    ("sph_init_boundary_shell", _i, [ctypes.POINTER(SphLattice), ctypes.c_size_t, _vp, _i, _vp]),
+    ("sph_visualize", _i, [_vp, _i, _vp, _i, ctypes.c_size_t, _vp]),
     ("sph_upload_state", _i, [_vp, _vp, _vp, _vp]),
     ("sph_download_state", _i, [_vp, _vp, _vp, _vp]),
     ("sph_read_stats", _i, [_vp, ctypes.POINTER(SphStats)]),

@@ -551,6 +551,19 @@ extern "C" int sph_fetch(SphHandle *h, int field, void *dev_out, size_t n, void 
 	return check_launch(h, "sph_fetch");
 }
 
+extern "C" int sph_visualize(SphHandle *h, int what, void *dev_rgb, int stride_floats, size_t n, void *stream) {
+	int rc = require_state(h);
+	if (rc != SPH_OK) return rc;
+	if (!dev_rgb || stride_floats < 3) return sph_fail(h, SPH_EINVAL, "sph_visualize: rgb buffer with a stride of >= 3 floats expected");
+	if (what != SPH_VIS_RHO && what != SPH_VIS_NEIGHBOUR) return sph_fail(h, SPH_EINVAL, "sph_visualize: unknown quantity %d", what);
+	if (n < (size_t)h->c.N_owned) return sph_fail(h, SPH_EINVAL, "sph_visualize: output too small (%zu < %d)", n, h->c.N_owned);
+	if (h->simulate_cnt <= 0 && !h->lists_valid)
+		return sph_fail(h, SPH_ESTATE, "sph_visualize: no density / neighbour counts yet (run a solver step first)");
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	sphg_visualize(h, what, (float *)dev_rgb, stride_floats, (cudaStream_t)stream);
+	return check_launch(h, "sph_visualize");
+}
+
 extern "C" int sph_upload_state(SphHandle *h, const float *host_pos4, const float *host_vel4, void *stream) {
 	if (!h || !h->pos || !h->vel) return h ? sph_fail(h, SPH_ENOTBOUND, "sph_upload_state: state not bound") : SPH_EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;

@@ -294,3 +294,144 @@ void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaSt
 	k_writeback<<<cdiv(n, 256), 256, 0, st>>>(h->fg.sorted_id, n, h->c.N_owned, spos, svel, h->pos, h->vel);
 	h->launches++;
 }
+
+// ---------------------------------------------------------------------------------------------
+// SB:219-245 visualize_rho / visualize_neighbour: min / max of a per-particle quantity (hierarchical:
+// warp shuffles, one smem hop, one atomic per block on order-independent integer keys), then the colour
+// map  rgb[i] = (0, 0.28, (q_i - min) / (max - min))  written in ORIGINAL particle order.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int f2key(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; } // monotone
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+template <bool IS_INT>
+__global__ void __launch_bounds__(256) k_vis_minmax(const void *__restrict__ q, int n, int *__restrict__ mm) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	float v = 0.0f;
+	bool ok = s < n;
+	if (ok) v = IS_INT ? (float)((const int *)q)[s] : ((const float *)q)[s];
+	float lo = ok ? v : INFINITY, hi = ok ? v : -INFINITY;
+	for (int o = 16; o > 0; o >>= 1) {
+		lo = fminf(lo, __shfl_down_sync(0xffffffffu, lo, o));
+		hi = fmaxf(hi, __shfl_down_sync(0xffffffffu, hi, o));
+	}
+	__shared__ float slo[8], shi[8];
+	if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int k = 1; k < 8; ++k) { lo = fminf(lo, slo[k]); hi = fmaxf(hi, shi[k]); }
+		atomicMin(&mm[0], f2key(lo));
+		atomicMax(&mm[1], f2key(hi));
+	}
+}
+__global__ void k_vis_init(int *mm) { mm[0] = f2key(INFINITY); mm[1] = f2key(-INFINITY); }
+
+template <bool IS_INT>
+__global__ void __launch_bounds__(256) k_vis_colour(const void *__restrict__ q, const int *__restrict__ sorted_id, int n,
+                                                     const int *__restrict__ mm, float *__restrict__ rgb, int stride) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	float lo = key2f(mm[0]), hi = key2f(mm[1]);
+	if (!(hi - lo > 0.0f)) return; // SB:230, 244: colours stay as they are
+	float v = IS_INT ? (float)((const int *)q)[s] : ((const float *)q)[s];
+	float *o = rgb + (size_t)sorted_id[s] * stride;
+	o[0] = 0.0f; o[1] = 0.28f; o[2] = (v - lo) / (hi - lo);
+}
+
+// what: 0 = rho (SB:219-232), 1 = neighbour count (SB:234-245); rgb: n x stride floats, original order
+void sphg_visualize(SphHandle *h, int what, float *rgb, int stride, cudaStream_t st) {
+	int n = h->c.N_owned;
+	if (n <= 0) return;
+	int *mm = (int *)h->red; // 32 bytes of device scratch that no kernel uses between steps
+	k_vis_init<<<1, 1, 0, st>>>(mm);
+	if (what == 0) {
+		k_vis_minmax<false><<<cdiv(n, 256), 256, 0, st>>>(h->a1[A1_RHO], n, mm);
+		k_vis_colour<false><<<cdiv(n, 256), 256, 0, st>>>(h->a1[A1_RHO], h->fg.sorted_id, n, mm, rgb, stride);
+	} else {
+		k_vis_minmax<true><<<cdiv(n, 256), 256, 0, st>>>(h->nbr_count, n, mm);
+		k_vis_colour<true><<<cdiv(n, 256), 256, 0, st>>>(h->nbr_count, h->fg.sorted_id, n, mm, rgb, stride);
+	}
+	h->launches += 3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-side scene initialisation: the fluid lattice (PS:142-151) and the one-layer
+// boundary shell (PS:155-195) of init_particle_pos, written straight into the caller's float4 arrays.
+// Stateless (no handle: the reference fills the positions before anything else exists, PS:119).
+// Arithmetic is the reference's, operation by operation, with un-fused IEEE intrinsics.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_init_fluid_lattice(long long total, const int *__restrict__ ids, long long n, float x_num, float z_num, float xz_num,
+                     int xi, int zi, float rad, float sx, float sy, float sz, float4 *__restrict__ pos) {
+	long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	long long id = ids ? (long long)ids[k] : k;
+	float x, y, z;
+	if (total < (1LL << 24)) {
+		float fi = (float)id;                                            // PS:146-149: f32 index arithmetic
+		float qx = floorf(__fdiv_rn(fi, x_num));
+		x = __fsub_rn(fi, __fmul_rn(x_num, qx));                         // i % x_num
+		z = __fsub_rn(qx, __fmul_rn(z_num, floorf(__fdiv_rn(qx, z_num)))); // (i // x_num) % z_num
+		y = (float)(int)__fdiv_rn(fi, xz_num);                           // int(i / xz_num)
+	} else { // the f32 index arithmetic is inexact beyond 2^24: integer lattice
+		x = (float)(id % xi);
+		z = (float)((id / xi) % zi);
+		y = (float)(id / ((long long)xi * zi));
+	}
+	pos[k] = make_float4(__fadd_rn(__fmul_rn(__fmul_rn(x, rad), 2.0f), sx), __fadd_rn(__fmul_rn(__fmul_rn(y, rad), 2.0f), sy),
+	                     __fadd_rn(__fmul_rn(__fmul_rn(z, rad), 2.0f), sz), 0.0f); // PS:150
+}
+
+__global__ void __launch_bounds__(256)
+k_init_boundary_shell(long long nb, long long x_cnt, long long z_cnt, long long bottom, long long one_round, float d,
+                      float box_max_y, float4 *__restrict__ bpos) {
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nb) return;
+	const long long xr = x_cnt - 1, zr = z_cnt - 1;
+	float x = 0.0f, y = 0.0f, z = 0.0f;
+	if (i < bottom) {                                                    // PS:164-168 floor
+		x = __fmul_rn((float)(i % x_cnt), d);
+		z = __fmul_rn(floorf(__fdiv_rn((float)i, (float)x_cnt)), d);
+	} else if (i < nb - bottom) {                                        // PS:169-189 walls, layer by layer
+		long long idx = i - bottom;
+		long long layer = (long long)floorf(__fdiv_rn((float)idx, (float)one_round));
+		y = __fmul_rn(d, (float)(layer + 1));
+		idx = idx - layer * one_round + 1;
+		if (idx <= xr) x = __fmul_rn((float)(idx % xr), d);
+		else if (idx <= xr + zr) { x = __fmul_rn((float)xr, d); z = __fmul_rn((float)((idx - x_cnt) % zr), d); }
+		else if (idx <= 2 * xr + zr) { x = __fmul_rn((float)((2 * xr + zr - idx) % xr + 1), d); z = __fmul_rn((float)zr, d); }
+		else if (idx <= 2 * (xr + zr)) z = __fmul_rn((float)((2 * (xr + zr) - idx) % zr + 1), d);
+	} else {                                                             // PS:190-195 lid
+		long long i2 = i - (nb - bottom);
+		x = __fmul_rn((float)(i2 % x_cnt), d);
+		y = box_max_y;
+		z = __fmul_rn((float)(long long)__fdiv_rn((float)i2, (float)x_cnt), d);
+	}
+	bpos[i] = make_float4(x, y, z, 0.0f);
+}
+
+extern "C" int sph_init_fluid_lattice(const SphLattice *lat, long long particle_num_total, const int32_t *dev_ids, size_t n,
+                                      void *dev_pos4, int device, void *stream) {
+	if (!lat || !dev_pos4) return SPH_EINVAL;
+	if (n == 0) return SPH_OK;
+	if (cudaSetDevice(device) != cudaSuccess) return SPH_ECUDA;
+	double d = lat->particle_radius * 2;
+	double x_num_d = lat->water_size[0] / d, z_num_d = lat->water_size[2] / d;
+	k_init_fluid_lattice<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+	    particle_num_total, dev_ids, (long long)n, (float)x_num_d, (float)z_num_d, (float)(x_num_d * z_num_d),
+	    (int)llround(x_num_d), (int)llround(z_num_d), (float)lat->particle_radius, (float)lat->start_pos[0],
+	    (float)lat->start_pos[1], (float)lat->start_pos[2], (float4 *)dev_pos4);
+	return cudaGetLastError() == cudaSuccess ? SPH_OK : SPH_ECUDA;
+}
+
+extern "C" int sph_init_boundary_shell(const SphLattice *lat, size_t nb, void *dev_bpos4, int device, void *stream) {
+	if (!lat || !dev_bpos4) return SPH_EINVAL;
+	if (nb == 0) return SPH_OK;
+	if (cudaSetDevice(device) != cudaSuccess) return SPH_ECUDA;
+	double dd = lat->particle_radius * 2;
+	long long x_cnt = (long long)((lat->box_max[0] - lat->box_min[0]) / dd + 1); // PS:157-158
+	long long z_cnt = (long long)((lat->box_max[2] - lat->box_min[2]) / dd + 1);
+	long long bottom = x_cnt * z_cnt, one_round = x_cnt * z_cnt - (x_cnt - 2) * (z_cnt - 2);
+	k_init_boundary_shell<<<(unsigned)((nb + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+	    (long long)nb, x_cnt, z_cnt, bottom, one_round, (float)dd, (float)lat->box_max[1], (float4 *)dev_bpos4);
+	return cudaGetLastError() == cudaSuccess ? SPH_OK : SPH_ECUDA;
+}

@@ -116,6 +116,7 @@ void sphg_unsort_f1(SphHandle *h, const SphGrid &g, const float *in, float *out,
 void sphg_unsort_i1(SphHandle *h, const SphGrid &g, const int *in, int *out, int n, cudaStream_t st);
 void sphg_unsort_f4(SphHandle *h, const SphGrid &g, const float4 *in, float4 *out, int n, cudaStream_t st);
 void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaStream_t st);
+void sphg_visualize(SphHandle *h, int what, float *rgb, int stride, cudaStream_t st);
 
 // ---- sph_multigpu.cu: slab decomposition along x, NCCL halo exchange / migration / allreduce -------
 // Every call is a no-op (returns immediately) when h->comm is null.

@@ -62,6 +62,18 @@ class solver_base:
         self.ps.update_grid()
         self.reset()
 
+    def visualize_rho(self):                                                         # SB:219-232
+        """ps.rgb[i] = (0, 0.28, (rho_i - min) / (max - min)); reductions and colour map on the device."""
+        self._visualize(0)
+
+    def visualize_neighbour(self):                                                   # SB:234-245
+        self._visualize(1)
+
+    def _visualize(self, what):
+        rgb = self.ps.rgb.tensor
+        _lib.check(self._lib.sph_visualize(self.ps._h, what, rgb.data_ptr(), rgb.shape[1], rgb.shape[0],
+                                           self.ps._stream()), self.ps._h)
+
     def _full_step(self, n=1):
         self.simulate_cnt[None] += n
         _lib.check(self._lib.sph_step(self.ps._h, n, self.ps._stream()), self.ps._h)

@@ -198,6 +198,31 @@ int sph_set_delta_time(SphHandle *h, float dt, void *stream);
 int sph_fetch(SphHandle *h, int field, void *dev_out, size_t n, void *stream);
 
 /* Host-buffer entry points (the e2e path): pinned or pageable host memory, float4 * n. */
+/* Device-side scene initialisation (init_particle_pos, PS:139-195): the fluid lattice and the one-layer
+ * boundary shell written straight into caller-owned float4 arrays, with the reference's f32 arithmetic.
+ * Stateless: no handle is needed (the reference fills the positions before anything else, PS:119).
+ * dev_ids (optional, int32, device): the global lattice indices to generate (multi-GPU slabs); NULL = 0..n-1.
+ * particle_num_total selects the reference's f32 index arithmetic (< 2^24 particles, where it is exact)
+ * or the integer lattice. */
+typedef struct SphLattice {
+	double particle_radius;
+	double start_pos[3];
+	double water_size[3];
+	double box_min[3];
+	double box_max[3];
+} SphLattice;
+int sph_init_fluid_lattice(const SphLattice *lat, long long particle_num_total, const int32_t *dev_ids, size_t n,
+                           void *dev_pos4, int device, void *stream);
+int sph_init_boundary_shell(const SphLattice *lat, size_t nb, void *dev_bpos4, int device, void *stream);
+
+/* SB:219-245 visualize_rho / visualize_neighbour: rgb[i] = (0, 0.28, (q_i - min q) / (max q - min q)) in
+ * ORIGINAL particle order, q = rho or get_neighbour_count; dev_rgb holds n rows of stride_floats floats
+ * (3 = ps.rgb, 4 = an rgba buffer).  Unchanged when max == min (SB:230, 244).  Uses the density / counts of
+ * the last solver step. */
+#define SPH_VIS_RHO 0
+#define SPH_VIS_NEIGHBOUR 1
+int sph_visualize(SphHandle *h, int what, void *dev_rgb, int stride_floats, size_t n, void *stream);
+
 int sph_upload_state(SphHandle *h, const float *host_pos4, const float *host_vel4, void *stream);
 int sph_download_state(SphHandle *h, float *host_pos4, float *host_vel4, void *stream);
 

@@ -229,3 +229,22 @@ def test_host_buffer_entry_points(built):
     assert np.array_equal(hvel[:, :3].numpy(), o.field("vel"))
     assert np.array_equal(hvel[:, 3].numpy(), o.field("warm_start_k"))
     ps.close(); o.close()
+
+
+def test_visualize_rho_and_neighbour(built):
+    # SB:219-245: colour maps from device-side min / max reductions, original particle order
+    cfg = scenes.shipped("small_block", "dfsph")
+    ps = quiet_ps(cfg, strict=True)
+    sol = quiet_solver(dfsph_solver, ps, cfg)
+    sol.step()
+    rho = sol.rho.to_numpy()
+    sol.visualize_rho()
+    rgb = ps.rgb.to_numpy()
+    b = (rho - rho.min()) / (rho.max() - rho.min())
+    assert np.array_equal(rgb[:, 0], np.zeros_like(b)) and np.allclose(rgb[:, 1], 0.28)
+    assert np.array_equal(rgb[:, 2], b.astype(np.float32))
+    cnt = ps.neighbour_counts().cpu().numpy().astype(np.float32)
+    sol.visualize_neighbour()
+    rgb = ps.rgb.to_numpy()
+    assert np.array_equal(rgb[:, 2], ((cnt - cnt.min()) / (cnt.max() - cnt.min())).astype(np.float32))
+    ps.close()

@@ -130,3 +130,38 @@ def test_full_size_grid_properties_1m(built):
     gx, gz = ps.grid_num[0], ps.grid_num[2]
     assert torch.equal(c3[:, 0] + gx * gz * c3[:, 1] + gx * c3[:, 2], c1.long())
     ps.close()
+
+
+@pytest.mark.parametrize("name,solver", [("small_block", "dfsph"), ("breaking_dam_30k", "wcsph"), ("dam_flush_cube", "dfsph")])
+def test_device_side_init_equals_numpy_statement(built, name, solver):
+    # init_particle_pos (PS:139-195) on the device vs the numpy statement of the same formulas
+    from cfd_taichi_b200 import scene
+    cfg = scenes.shipped(name, solver)
+    cfg.pop("solid", None)            # the mesh asset of dam_flush_cube is not part of this repository
+    ps = quiet_ps(cfg, strict=True)
+    n, nb = ps.particle_num, ps.boundary_particles_num
+    assert np.array_equal(ps._pos4[:n, :3].cpu().numpy(), scene.init_fluid_positions(cfg, n))
+    assert np.array_equal(ps.boundary_particles.pos.to_numpy(), scene.init_boundary_positions(cfg, nb))
+    ps.close()
+
+
+def test_device_side_init_integer_lattice_beyond_2_24(built):
+    # 256^3 = 2^24 particles: the reference's f32 index arithmetic stops being exact, integer lattice instead
+    import ctypes
+    from cfd_taichi_b200 import _lib, scene
+    cfg = scenes.breaking_dam(256)
+    n = scene.derive_sizes(cfg)[0]
+    assert n == 1 << 24
+    lat = _lib.SphLattice()
+    lat.particle_radius = cfg["scene"]["particle_radius"]
+    for k in range(3):
+        lat.start_pos[k], lat.water_size[k] = cfg["fluid"]["start_pos"][k], cfg["fluid"]["water_size"][k]
+        lat.box_min[k], lat.box_max[k] = cfg["scene"]["box_min"][k], cfg["scene"]["box_max"][k]
+    ids = torch.tensor([0, 255, 256, 65535, 65536, (1 << 24) - 1, 12345678], dtype=torch.int32, device="cuda")
+    out = torch.zeros((ids.shape[0], 4), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.load().sph_init_fluid_lattice(ctypes.byref(lat), n, ids.data_ptr(), ids.shape[0], out.data_ptr(), 0,
+                                                  torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    i = ids.cpu().numpy().astype(np.int64)
+    want = np.stack([i % 256, i // 65536, (i // 256) % 256], axis=1).astype(np.float32) * np.float32(0.025) * np.float32(2) + np.float32(0.1)
+    assert np.array_equal(out[:, :3].cpu().numpy(), want)
