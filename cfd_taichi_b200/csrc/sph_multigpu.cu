@@ -9,16 +9,18 @@
 // count read-back per step in mg_begin_step.  NCCL is bound at run time with dlopen (the torch-bundled
 // libnccl.so.2 that the process already maps); a missing library is an error, never a fallback.
 //
-// Transport of (2) and (3) inside a step: the ~57 exchanges per DFSPH step are 0.3 MB each, i.e. pure
+// Transport of (2) and (3) inside a step: the ~40 exchanges per DFSPH step are 0.3 MB each, i.e. pure
 // latency, so they do not go through NCCL.  Every rank owns a "window" of device memory that its peers
-// map with CUDA IPC; the pack kernel stores the ghost values (and the rank's loop partials) straight into
-// the neighbour's window over NVLink and the last block raises an epoch flag there; the unpack kernel of
-// the receiver spins on its local flag, scatters the values and sums the partials of all ranks in rank
-// order (deterministic, identical on every rank).  Two kernels per exchange, no host involvement, no
-// proxy thread.  Windows are double-buffered by epoch parity: a full handshake with both neighbours per
-// exchange means a rank can be at most one exchange ahead of a peer.  NCCL keeps the two variable-size
-// particle messages per step (migration, ghost particles).  SPH_MG_TRANSPORT=nccl selects NCCL for
-// everything (A/B measurements).
+// map with CUDA IPC.  One kernel per exchange (k_mg_exchange): each block stores this rank's ghost values
+// straight into the neighbours' windows over NVLink, then polls the slots its neighbours fill and scatters
+// them into the ghost slots; one extra block reduces the sweep's block partials, stores them into every
+// rank's window, polls all ranks' slots, sums them in rank order (deterministic, identical on every rank)
+// and takes the loop decision (sph_ctl.cuh).  Every 16-byte slot carries the exchange's epoch in its last
+// word and is written with one 128-bit store (the atomicity NCCL's LL protocols rely on), so there is no
+// fence, no flag, no host involvement and no proxy thread.  Windows are double-buffered by epoch parity: a
+// full handshake with both neighbours per exchange means a rank can be at most one exchange ahead of a
+// peer.  NCCL keeps the two variable-size particle messages per step (migration, ghost particles).
+// SPH_MG_TRANSPORT=nccl selects NCCL for everything (A/B measurements).
 #include <dlfcn.h>
 #include <nccl.h>
 
