@@ -179,7 +179,7 @@ class ParticleSystem:
         cfg.strict = 1 if self._strict else 0
         cfg.n_ghost_capacity = self._ghost_capacity
         cfg.rigid_rho = solid_config.get('rho_0', 0.0) if solid_config else 0.0
-        cfg.use_graph = 1 if solver_config.get('use_graph', False) else 0
+        cfg.use_graph = 0   # reserved (include/sph_b200.h)
         h = ctypes.c_void_p()
         with torch.cuda.device(self._device):
             rc = self._lib.sph_create(ctypes.byref(cfg), self._device.index, ctypes.byref(h))

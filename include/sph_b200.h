@@ -65,7 +65,8 @@ typedef struct SphConfig {
 	                             neighbour sets, results within 1e-5) */
 	int32_t n_ghost_capacity; /* multi-GPU: room for ghost fluid particles after the owned ones */
 	double rigid_rho;         /* solid.rho_0 */
-	int32_t use_graph;        /* 1 = run the solver loops as CUDA-graph WHILE nodes (no host sync) */
+	int32_t use_graph;        /* reserved, must be 0: the solver loops are stream-ordered launches gated by device
+	                             flags (one host look per step); CUDA-graph capture is not implemented */
 	int32_t reserved;
 } SphConfig;
 
