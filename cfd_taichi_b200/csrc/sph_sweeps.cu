@@ -135,13 +135,38 @@ void boundary_volume(SphHandle *h, cudaStream_t st) {
 	h->launches++;
 }
 
+// Cull the candidates [a, b) of one contiguous segment of a sorted array against pi, 32 at a time: the loop
+// over candidates only builds a hit mask (branch-free body: with a ~15 % hit rate a conditional append
+// inside it runs for almost every candidate of a warp at a few active lanes), then the mask is expanded in
+// ascending order.  `self` is the slot to skip (PS:461) or NO_SELF.
+#define NO_SELF (-0x40000000)
+template <class Emit>
+__device__ __forceinline__ void scan_segment(const SphConsts &c, const float4 &pi, const float4 *__restrict__ arr, int a,
+                                             int b, int self, Emit &&emit) {
+	for (int base = a; base < b; base += 32) {
+		int len = min(32, b - base);
+		uint32_t mask = 0;
+		for (int k = 0; k < len; ++k) {
+			Pair p = make_pair(pi, arr[base + k]);
+			mask |= (uint32_t)(!culled(p, c)) << k; // PS:466 / PS:364
+		}
+		uint32_t d = (uint32_t)(self - base);
+		if (d < 32u) mask &= ~(1u << d);
+		while (mask) {
+			int k = __ffs(mask) - 1;
+			mask &= mask - 1;
+			emit(base + k);
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_build_lists: the only 27-cell traversal of a step.  Emits the fluid and boundary neighbour
 // lists (canonical order), the neighbour count of get_neighbour_count (PS:424-445), rho
 // (SB:41-72) and, for DFSPH, alpha (DF:32-89) -- all of which depend on positions only.
 // ---------------------------------------------------------------------------------------------
 template <bool ALPHA, bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK)
+__global__ void __launch_bounds__(SPH_BLOCK, 8) // 64 registers: this kernel is issue-bound and wants the warps
 k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__restrict__ svel,
               const int *__restrict__ scell, const int *__restrict__ cstart, const int *__restrict__ sorted_id,
               const float4 *__restrict__ bspos, const int *__restrict__ bstart, SphLists L, SphRigidArgs rg,
@@ -172,21 +197,73 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		// ---- the kernel-function arithmetic at 15 % lane utilisation on every candidate) -----------------
 		int ncount = 0; // get_neighbour_count (PS:424-445)
 		int i_orig = RIGID ? sorted_id[s] : 0;
-#if SPH_STRICT
-		SPH_FOR_27(c, cx, cy, cz, c1) {
-#else
-		SPH_FOR_27_ADDR(c, cx, cy, cz, c1) {
-#endif
-			int a = cstart[c1], b = cstart[c1 + 1];
-			for (int e = a; e < b; ++e) {
-				if (e == s) continue; // PS:461
-				Pair p = make_pair(pi, spos[e]);
-				if (culled(p, c)) continue; // PS:466
-				if (nf < c.kmax) SPH_FLW(nf) = (uint32_t)e;
+		if (!RIGID) {
+			// append cursors: for one lane per particle the word of entry n+1 is 1 further, 125 further after a quad
+			uint32_t *fcur = &SPH_FLW(0), *bcur = &SPH_BLW(0);
+			auto emit_f = [&](int e) {
+				if (nf < c.kmax) *fcur = (uint32_t)e;
+				if (LPP == 1) fcur += (nf & 3) == 3 ? 125 : 1; else fcur = &SPH_FLW(nf + 1);
 				nf++;
-				ncount++;
+			};
+			auto emit_b = [&](int e) {
+				if (nb < c.kbmax) *bcur = (uint32_t)e;
+				if (LPP == 1) bcur += (nb & 3) == 3 ? 125 : 1; else bcur = &SPH_BLW(nb + 1);
+				nb++;
+			};
+#if SPH_STRICT
+			// canonical order of the reference: cell by cell, (dx, dy, dz) with dz fastest
+			SPH_FOR_27(c, cx, cy, cz, c1) { scan_segment(c, pi, spos, cstart[c1], cstart[c1 + 1], s, emit_f); }
+			if (c.boundary_handle == 1)
+				SPH_FOR_27(c, cx, cy, cz, c1) { scan_segment(c, pi, bspos, bstart[c1], bstart[c1 + 1], NO_SELF, emit_b); }
+#else
+			// The 27 cells are 9 runs of up to three x-adjacent cells, contiguous in the sorted arrays (cell id =
+			// x + gx z + gx gz y).  The 18 run bounds of a grid are fetched up front (independent loads instead of
+			// 27 dependent load pairs), then each run is one segment; the list comes out in address order.
+			const int x0 = max(cx - 1, 0), xw = min(cx + 1, c.gx - 1) - x0 + 1;
+			{
+				int ra[9], rb[9];
+#pragma unroll
+				for (int r = 0; r < 9; ++r) {
+					int y = cy + r / 3 - 1, z = cz + r % 3 - 1;
+					bool ok = (unsigned)y < (unsigned)c.gy && (unsigned)z < (unsigned)c.gz;
+					int c0 = x0 + y * c.gxz + z * c.gx;
+					ra[r] = ok ? cstart[c0] : 0;
+					rb[r] = ok ? cstart[c0 + xw] : 0;
+				}
+#pragma unroll
+				for (int r = 0; r < 9; ++r) scan_segment(c, pi, spos, ra[r], rb[r], s, emit_f);
 			}
-			if (RIGID) {
+			if (c.boundary_handle == 1) {
+				int qa[9], qb[9];
+#pragma unroll
+				for (int r = 0; r < 9; ++r) {
+					int y = cy + r / 3 - 1, z = cz + r % 3 - 1;
+					bool ok = (unsigned)y < (unsigned)c.gy && (unsigned)z < (unsigned)c.gz;
+					int c0 = x0 + y * c.gxz + z * c.gx;
+					qa[r] = ok ? bstart[c0] : 0;
+					qb[r] = ok ? bstart[c0 + xw] : 0;
+				}
+#pragma unroll
+				for (int r = 0; r < 9; ++r) scan_segment(c, pi, bspos, qa[r], qb[r], NO_SELF, emit_b);
+			}
+#endif
+			ncount = nf; // no rigid entries: get_neighbour_count (PS:424-445) equals the fluid hits
+		} else {
+			// scenes with an active rigid body: per-cell traversal, rigid particles after the fluid ones of a cell
+#if SPH_STRICT
+			SPH_FOR_27(c, cx, cy, cz, c1) {
+#else
+			SPH_FOR_27_ADDR(c, cx, cy, cz, c1) {
+#endif
+				int a = cstart[c1], b = cstart[c1 + 1];
+				for (int e = a; e < b; ++e) {
+					if (e == s) continue; // PS:461
+					Pair p = make_pair(pi, spos[e]);
+					if (culled(p, c)) continue; // PS:466
+					if (nf < c.kmax) SPH_FLW(nf) = (uint32_t)e;
+					nf++;
+					ncount++;
+				}
 				// rigid particles follow the fluid ones inside a cell (second append kernel, PS:385-386)
 				int ra = rg.rstart[c1], rb = rg.rstart[c1 + 1];
 				for (int e = ra; e < rb; ++e) {
@@ -204,19 +281,19 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 					nf++;
 				}
 			}
-		}
-		if (c.boundary_handle == 1) {
+			if (c.boundary_handle == 1) {
 #if SPH_STRICT
-			SPH_FOR_27(c, cx, cy, cz, c1) {
+				SPH_FOR_27(c, cx, cy, cz, c1) {
 #else
-			SPH_FOR_27_ADDR(c, cx, cy, cz, c1) {
+				SPH_FOR_27_ADDR(c, cx, cy, cz, c1) {
 #endif
-				int a = bstart[c1], b = bstart[c1 + 1];
-				for (int e = a; e < b; ++e) {
-					Pair p = make_pair(pi, bspos[e]);
-					if (culled(p, c)) continue; // PS:364
-					if (nb < c.kbmax) SPH_BLW(nb) = (uint32_t)e;
-					nb++;
+					int a = bstart[c1], b = bstart[c1 + 1];
+					for (int e = a; e < b; ++e) {
+						Pair p = make_pair(pi, bspos[e]);
+						if (culled(p, c)) continue; // PS:364
+						if (nb < c.kbmax) SPH_BLW(nb) = (uint32_t)e;
+						nb++;
+					}
 				}
 			}
 		}
