@@ -179,6 +179,8 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	size_t nwarps = (ncap + 31) / 32;
 	SPH_CUDA_CHECK(h, dalloc(&h->L.flist, nwarps * 32 * (size_t)c.kstride));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.blist, nwarps * 32 * (size_t)c.kbstride));
+	h->L.gw = nullptr;
+	if (c.solver == SPH_SOLVER_DFSPH) SPH_CUDA_CHECK(h, dalloc(&h->L.gw, nwarps * 32 * (size_t)c.kstride));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.rlist, c.Nr > 0 ? nwarps * 32 * (size_t)c.krmax : 1));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.fcount, ncap));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.bcount, ncap));
@@ -220,7 +222,7 @@ extern "C" int sph_destroy(SphHandle *h) {
 	for (int k = 0; k < A4_COUNT; ++k) cudaFree(h->a4[k]);
 	cudaFree(h->pv);
 	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
-	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.rlist);
+	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.rlist); cudaFree(h->L.gw);
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount); cudaFree(h->L.rcount);
 	mg_destroy(h);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);

@@ -122,6 +122,9 @@ struct SphLists {
 	uint32_t *flist; int *fcount;   // fluid neighbours (indices into the sorted fluid arrays)
 	uint32_t *blist; int *bcount;   // boundary neighbours (indices into the sorted boundary arrays)
 	uint32_t *rlist; int *rcount;   // rigid neighbours (indices into the sorted rigid arrays)
+	// DFSPH only (null otherwise): per-pair cache [index | grad W_ij] of the fluid list, one float4 per entry,
+	// entry k of sorted particle s at gw[((s >> 5) * cap + k) * 32 + (s & 31)] (a warp reads 512 contiguous bytes)
+	float4 *gw;
 };
 
 __host__ __device__ inline size_t sph_list_base(int s, int cap) {

@@ -21,6 +21,21 @@ namespace SPH_NS {
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// ---- per-pair gradient cache (DFSPH) -------------------------------------------------------------------------
+// Positions are frozen inside a step, so grad W_ij is too.  The two sweeps that need a neighbour's position AND
+// velocity (k_df_drho, k_df_rho_adv: a 32-byte gather per pair, the costliest access pattern of the step) read
+// [j | grad W_ij] records that k_build_lists wrote once per step instead -- a coalesced 16-byte stream -- and
+// gather only the velocity.  The stored gradient is bit-identical to a recomputation (same function, same
+// inputs), so the strict kernels stay bit-exact.  The sweeps that need one scalar of the neighbour keep the
+// 16-byte (pos, payload) gather: for them the stream would cost more DRAM time than the arithmetic it saves.
+#ifndef SPH_GW
+#define SPH_GW 1
+#endif
+// the interleaved (pos, vel) records serve only the build without the gradient cache (one LDG.E.256 per neighbour)
+#define SPH_USE_PV (!(SPH_GW && SPH_DF_LPP == 1))
+__host__ __device__ inline size_t sph_gw_index(int s, int cap, int k) {
+	return ((size_t)(s >> 5) * (size_t)cap + (size_t)k) * 32u + (size_t)(s & 31);
+}
 // Lanes per particle of the DFSPH sweeps.  Strict kernels: 1 (the reference's summation order).  Fast
 // kernels: DF_LPP adjacent lanes share a particle and take every DF_LPP-th entry of its address-ordered
 // list, so that the gathers of one warp request fall into a few cache lines instead of 32 unrelated ones
@@ -28,7 +43,7 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 #if SPH_STRICT
 #define SPH_DF_LPP 1
 #elif !defined(SPH_DF_LPP)
-#define SPH_DF_LPP 1 // 2, 4, 8 measured slower on B200 (profiles/r1d_coop_lanes.md): 2x the instructions, 66 % lane use
+#define SPH_DF_LPP 1 // 2, 4, 8 measured slower on B200 (profiles/r1d_experiments.md): 2x the instructions, 66 % lane use
 #endif
 constexpr int DF_LPP = SPH_DF_LPP;
 constexpr int DF_PPB = SPH_BLOCK / DF_LPP; // particles per block
@@ -174,7 +189,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
               float4 *__restrict__ posR, float4 *__restrict__ posT1, float4 *__restrict__ pv, SphCtl *ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	int nf = 0, nb = 0;
-	if (s < c.N && ALPHA) { pv[2 * (size_t)s] = spos[s]; pv[2 * (size_t)s + 1] = svel[s]; }
+	if (SPH_USE_PV && s < c.N && ALPHA) { pv[2 * (size_t)s] = spos[s]; pv[2 * (size_t)s + 1] = svel[s]; }
 	if (s < c.N && c.N != c.N_owned && sorted_id[s] >= c.N_owned) {
 		// ghost copy of a neighbour rank's particle (multi-GPU): never a centre particle; its rho / alpha /
 		// payloads arrive through the halo exchange.  fcount < 0 is the ownership flag every sweep tests.
@@ -309,7 +324,9 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 				Pair p = make_pair(pi, pj);
 				rho_f += (pj.w * cubic_w(p, c)) * SPH_RHO0; // SB:65
 				if (ALPHA) {
-					f3 g = (pj.w * SPH_RHO0) * cubic_dw(p, c); // DF:62, 75
+					f3 dw = cubic_dw(p, c);
+					if (SPH_GW && L.gw) L.gw[sph_gw_index(s, c.kstride, k)] = make_float4(__uint_as_float(j), dw.x, dw.y, dw.z);
+					f3 g = (pj.w * SPH_RHO0) * dw; // DF:62, 75
 					ss = ss + g;
 					sq += dot(g, g);
 				}
@@ -318,7 +335,9 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 			Pair p = make_pair(pi, spos[j]);
 			rho_f += c.m * cubic_w(p, c); // SB:62
 			if (ALPHA) {
-				f3 g = c.m * cubic_dw(p, c); // DF:58, 70
+				f3 dw = cubic_dw(p, c);
+				if (SPH_GW && L.gw) L.gw[sph_gw_index(s, c.kstride, k)] = make_float4(__uint_as_float(j), dw.x, dw.y, dw.z);
+				f3 g = c.m * dw; // DF:58, 70
 				ss = ss + g;
 				sq += dot(g, g);
 			}
@@ -464,6 +483,47 @@ __device__ __forceinline__ void operator<<(ListRange r, F &&f) {
 #define SPH_FOR_FLUID_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).flist, (c).kstride, s, sub, n) << [&](uint32_t J)
 #define SPH_FOR_BOUNDARY_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).blist, (c).kbstride, s, sub, n) << [&](uint32_t J)
 
+__device__ __forceinline__ float4 ld_gw(const float4 *p, uint64_t pol) {
+	float4 r;
+#if SPH_LIST_HINTS == 2
+	asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+	    : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+	    : "l"(p), "l"(pol));
+#else
+	asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+#endif
+	return r;
+}
+// f(j, grad W_ij) for the n entries of sorted particle s; four records in flight ahead of the four in use
+template <class F>
+__device__ __forceinline__ void walk_gw(const float4 *__restrict__ gw, int cap, int s, int n, F &&f) {
+	if (n <= 0) return;
+	const uint64_t pol = list_policy();
+	const float4 *p = gw + sph_gw_index(s, cap, 0);
+	const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	float4 c0 = ld_gw(p, pol), c1 = n > 1 ? ld_gw(p + 32, pol) : z, c2 = n > 2 ? ld_gw(p + 64, pol) : z,
+	       c3 = n > 3 ? ld_gw(p + 96, pol) : z;
+	int k = 0;
+	for (; k + 4 <= n; k += 4) {
+		p += 128;
+		float4 n0 = k + 4 < n ? ld_gw(p, pol) : z, n1 = k + 5 < n ? ld_gw(p + 32, pol) : z,
+		       n2 = k + 6 < n ? ld_gw(p + 64, pol) : z, n3 = k + 7 < n ? ld_gw(p + 96, pol) : z;
+		f(__float_as_uint(c0.x), F3(c0.y, c0.z, c0.w));
+		f(__float_as_uint(c1.x), F3(c1.y, c1.z, c1.w));
+		f(__float_as_uint(c2.x), F3(c2.y, c2.z, c2.w));
+		f(__float_as_uint(c3.x), F3(c3.y, c3.z, c3.w));
+		c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+	}
+	int m = n - k;
+	if (m > 0) {
+		f(__float_as_uint(c0.x), F3(c0.y, c0.z, c0.w));
+		if (m > 1) {
+			f(__float_as_uint(c1.x), F3(c1.y, c1.z, c1.w));
+			if (m > 2) f(__float_as_uint(c2.x), F3(c2.y, c2.z, c2.w));
+		}
+	}
+}
+
 // sum over the DF_LPP lanes that share a particle (no-op for one lane per particle)
 template <int LPP>
 __device__ __forceinline__ float sub_sum(float v) {
@@ -533,7 +593,7 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
 	if (c.boundary_handle == 1) v = v - (va + vb * SPH_RHO0) * dt; // DF:322
 	else v = v - va * dt;                                          // DF:324
 	svel[s] = F4(v, 0.0f); // DF:325 warm_start_k.fill(0)
-	pv[2 * (size_t)s + 1] = F4(v, 0.0f);
+	if (SPH_USE_PV) pv[2 * (size_t)s + 1] = F4(v, 0.0f);
 }
 
 // DF:252-300 derivative_iter_all_rho.  Writes drho and the payload t2 = ((drho*alpha)/dt)/rho of
@@ -560,6 +620,17 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 	}
 	float rd = 0.0f, rdb = 0.0f;
 	if (enough) {
+#if SPH_GW && SPH_DF_LPP == 1
+		walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+			if (SPH_IS_RIGID(j)) {
+				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+				f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, false);             // DF:292-293
+				rd += (pj.w * SPH_RHO0) * dot(vi - v_j, dw);                    // DF:294
+				return;
+			}
+			rd += c.m * dot(vi - xyz(__ldg(&svel[j])), dw); // DF:287
+		});
+#else
 		SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
 			if (SPH_IS_RIGID(j)) {
 				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
@@ -572,6 +643,7 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 			Pair p = make_pair(pi, nj.p);
 			rd += c.m * dot(vi - xyz(nj.v), cubic_dw(p, c)); // DF:287
 		};
+#endif
 		if (c.boundary_handle == 1) {
 			SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
 				float4 pj = __ldg(&bspos[j]);
@@ -636,7 +708,7 @@ k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 	if (c.boundary_handle == 1) v = v - (va + vb * SPH_RHO0) * dt; // DF:310
 	else v = v - va * dt;
 	svel[s] = F4(v, vi.w + da); // DF:384
-	pv[2 * (size_t)s + 1] = F4(v, vi.w + da);
+	if (SPH_USE_PV) pv[2 * (size_t)s + 1] = F4(v, vi.w + da);
 }
 
 // SB:190-201: viscosity contribution of a rigid neighbour (uses rho[particle_j.index], SURVEY B-6)
@@ -728,6 +800,17 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
 	f3 vi = F3(0.0f, 0.0f, 0.0f);
 	if (live) { pi = spos[s]; vi = xyz(svadv[s]); }
 	float delta = 0.0f, db = 0.0f;
+#if SPH_GW && SPH_DF_LPP == 1
+	walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, true);                  // DF:168-169
+			delta += (pj.w * SPH_RHO0) * dot(vi - v_j, dw);                     // DF:170
+			return;
+		}
+		delta += c.m * dot(vi - xyz(__ldg(&svadv[j])), dw); // DF:162
+	});
+#else
 	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
@@ -741,6 +824,7 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
 		Pair p = make_pair(pi, pj);
 		delta += c.m * dot(vi - vj, cubic_dw(p, c)); // DF:162
 	};
+#endif
 	if (c.boundary_handle == 1) {
 		SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
 			float4 pj = __ldg(&bspos[j]);
