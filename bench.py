@@ -287,7 +287,10 @@ def run_ours(args):
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic,
+                         "traffic_gbps": (traffic / (avg_ms * 1e-3) / 1e9) if traffic else None,
+                         "traffic_frac": (traffic / (avg_ms * 1e-3) / 1e9 / peak) if traffic else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_particle": alg_bytes.get(dom), "avg_launch_ms": avg_ms,
                          "timing": "CUDA events around every launch, second pass of the same %d steps "
                                    "(%.3f ms/step with the events in the stream)" % (args.steps, ms_profiled / args.steps)},
