@@ -84,8 +84,8 @@ static void fill_consts(const SphConfig &cfg, SphConsts &c) {
 	c.Nr = cfg.n_rigid;
 	c.kmax = cfg.max_neighbors > 0 ? cfg.max_neighbors : 96;
 	c.kbmax = cfg.max_boundary_neighbors > 0 ? cfg.max_boundary_neighbors : 48;
-	c.kstride = (c.kmax + 31) & ~31;   // quad-interleaved lists with up to 8 lanes per particle (sph_list_word)
-	c.kbstride = (c.kbmax + 31) & ~31;
+	c.kstride = (c.kmax + 3) & ~3;   // quad-interleaved lists (sph_list_word)
+	c.kbstride = (c.kbmax + 3) & ~3;
 	c.krmax = 48;
 	c.boundary_handle = cfg.boundary_handle ? 1 : 0;
 	c.fs_couple = cfg.fs_couple ? 1 : 0;
@@ -170,8 +170,6 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 		SPH_CUDA_CHECK(h, dalloc(&h->a4[k], ncap));
 		SPH_CUDA_CHECK(h, cudaMemset(h->a4[k], 0, sizeof(float4) * (ncap ? ncap : 1)));
 	}
-	SPH_CUDA_CHECK(h, dalloc(&h->pv, 2 * ncap));
-	SPH_CUDA_CHECK(h, cudaMemset(h->pv, 0, sizeof(float4) * 2 * (ncap ? ncap : 1)));
 	for (int k = 0; k < A1_COUNT; ++k) {
 		SPH_CUDA_CHECK(h, dalloc(&h->a1[k], ncap));
 		SPH_CUDA_CHECK(h, cudaMemset(h->a1[k], 0, sizeof(float) * (ncap ? ncap : 1)));
@@ -191,7 +189,7 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	SPH_CUDA_CHECK(h, dalloc(&h->nbr_count, ncap));
 	SPH_CUDA_CHECK(h, dalloc(&h->ctl, 1));
 	SPH_CUDA_CHECK(h, cudaMallocHost((void **)&h->ctl_host, sizeof(SphCtl)));
-	h->n_partials = 8 * (cdiv((int)(ncap ? ncap : 1), SPH_BLOCK) + 1); // up to 8 lanes per particle (DF_LPP)
+	h->n_partials = cdiv((int)(ncap ? ncap : 1), SPH_BLOCK) + 1;
 	SPH_CUDA_CHECK(h, dalloc(&h->partials, (size_t)h->n_partials));
 	SPH_CUDA_CHECK(h, dalloc(&h->red, 4));
 	memset(h->ctl_host, 0, sizeof(SphCtl));
@@ -220,7 +218,6 @@ extern "C" int sph_destroy(SphHandle *h) {
 	free_grid(h->fg); free_grid(h->bg); free_grid(h->rg);
 	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rsvel); cudaFree(h->rkin); cudaFree(h->rstate); cudaFree(h->rl_list); cudaFree(h->rl_count);
 	for (int k = 0; k < A4_COUNT; ++k) cudaFree(h->a4[k]);
-	cudaFree(h->pv);
 	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
 	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.rlist); cudaFree(h->L.gw);
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount); cudaFree(h->L.rcount);

@@ -45,7 +45,7 @@ struct SphConsts {
 	int N_owned;        // owned fluid particles (== N on one GPU)
 	int Nb, Nr;
 	int kmax, kbmax, krmax; // neighbour-list capacities (entries a particle may hold before the overflow flag)
-	int kstride, kbstride;  // storage capacities of the quad-interleaved lists: kmax / kbmax rounded up to 32
+	int kstride, kbstride;  // storage capacities of the quad-interleaved lists: kmax / kbmax rounded up to 4
 	int boundary_handle, fs_couple, solver;
 	int active_rigid;
 };
@@ -111,13 +111,9 @@ struct __align__(16) SphPartial {
 	float maxv;
 };
 
-// Per-step neighbour lists, quad-interleaved per warp.  LPP ("lanes per particle", a power of two <= 8)
-// consecutive lanes of a warp share one particle: with PPW = 32 / LPP particles per warp, entry n of
-// sorted particle s belongs to lane  (s % PPW) * LPP + n % LPP  of warp  s / PPW  and is word
-// (n / LPP) % 4 of that lane's quad (n / LPP) / 4:
-//   list4[((s / PPW) * (cap / (4 LPP)) + quad) * 32 + lane]          (cap is a multiple of 32)
-// so one 128-bit load brings four entries of a lane and a warp reads 512 contiguous bytes per request.
-// LPP = 1 (one lane per particle) is the layout of the strict kernels and of WCSPH / PCISPH / IISPH.
+// Per-step neighbour lists, quad-interleaved per warp: entries 4q .. 4q+3 of sorted particle s are the
+// four words of the uint4 at  list4[((s >> 5) * (cap / 4) + q) * 32 + (s & 31)]  (cap is a multiple of 4),
+// so one 128-bit load brings four entries and a warp reads 512 contiguous bytes per request.
 struct SphLists {
 	uint32_t *flist; int *fcount;   // fluid neighbours (indices into the sorted fluid arrays)
 	uint32_t *blist; int *bcount;   // boundary neighbours (indices into the sorted boundary arrays)
@@ -131,13 +127,9 @@ __host__ __device__ inline size_t sph_list_base(int s, int cap) {
 	return ((size_t)(s >> 5) * (size_t)cap) * 32u + (size_t)(s & 31);
 }
 
-// word offset of entry n of sorted particle s in a quad-interleaved list with LPP lanes per particle
-template <int LPP>
+// word offset of entry n of sorted particle s in a quad-interleaved list
 __host__ __device__ inline size_t sph_list_word(int s, int cap, int n) {
-	constexpr int PPW = 32 / LPP;
-	int lane = (s % PPW) * LPP + (n % LPP);
-	int m = n / LPP;
-	return ((((size_t)(s / PPW) * (size_t)(cap / (4 * LPP)) + (size_t)(m >> 2)) * 32u + (size_t)lane) << 2) + (size_t)(m & 3);
+	return ((((size_t)(s >> 5) * (size_t)(cap >> 2) + (size_t)(n >> 2)) * 32u + (size_t)(s & 31)) << 2) + (size_t)(n & 3);
 }
 
 #define SPH_CUDA_CHECK(h, expr)                                                         \

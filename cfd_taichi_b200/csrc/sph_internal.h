@@ -72,7 +72,6 @@ struct SphHandle {
 	bool rigid_ready;
 	// sorted work arrays
 	float4 *a4[A4_COUNT];
-	float4 *pv;     // interleaved (pos, vel) records, 32 B per sorted particle (256-bit gathers)
 	float *a1[A1_COUNT];
 	SphLists L;
 	int *nbr_count; // get_neighbour_count (PS:424-445), sorted order

@@ -254,8 +254,7 @@ k_mg_pack_values(int what, const int *__restrict__ send_orig_l, const int *__res
 __global__ void __launch_bounds__(256)
 k_mg_unpack_values(int what, const int *__restrict__ slot_of, int first_orig, int nl, int nr,
                    const float4 *__restrict__ in_l, const float4 *__restrict__ in_r,
-                   const float4 *__restrict__ spos, float4 *__restrict__ a, float4 *__restrict__ b,
-                   float4 *__restrict__ pv) {
+                   const float4 *__restrict__ spos, float4 *__restrict__ a, float4 *__restrict__ b) {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
 	if (k >= nl + nr) return;
 	int s = slot_of[first_orig + k]; // ghosts are stored left block first, then right block
@@ -263,10 +262,7 @@ k_mg_unpack_values(int what, const int *__restrict__ slot_of, int first_orig, in
 	float4 p = spos[s]; // the payload buffers carry a position copy; ghosts get theirs here
 	if (what == MG_F4_T1R) { a[s] = make_float4(p.x, p.y, p.z, v.x); b[s] = make_float4(p.x, p.y, p.z, v.y); }
 	else if (what == MG_F4_T2 || what == MG_F4_T3) a[s] = make_float4(p.x, p.y, p.z, v.x);
-	else {
-		a[s] = v;
-		if (what == MG_F4_VEL) pv[2 * (size_t)s + 1] = v; // the 256-bit (pos, vel) records of k_df_drho
-	}
+	else a[s] = v;
 }
 
 // ---- peer-memory transport ------------------------------------------------------------------------
@@ -315,7 +311,7 @@ __global__ void __launch_bounds__(256)
 k_mg_exchange(int what, const int *__restrict__ send_slot_l, const int *__restrict__ send_slot_r,
               const int *__restrict__ recv_slot, int nsl, int nsr, int nrl, int nrr,
               const float4 *src_a, const float4 *src_b, float4 *dst_a, float4 *dst_b, const float4 *__restrict__ spos,
-              float4 *pv, MgPeers peers, char *win, int cap, int rank, int nranks, int epoch, int do_reduce,
+              MgPeers peers, char *win, int cap, int rank, int nranks, int epoch, int do_reduce,
               const SphPartial *__restrict__ partials, int n_partials, int ctl_kind, SphCtlArgs cargs,
               double *__restrict__ red, SphCtl *ctl) {
 	const int parity = epoch & 1;
@@ -374,11 +370,7 @@ k_mg_exchange(int what, const int *__restrict__ send_slot_l, const int *__restri
 		float vx = __uint_as_float(u.x), vy = __uint_as_float(u.y), vz = __uint_as_float(u.z);
 		if (what == MG_F4_T1R) { dst_a[s] = make_float4(p.x, p.y, p.z, vx); dst_b[s] = make_float4(p.x, p.y, p.z, vy); }
 		else if (what == MG_F4_T2 || what == MG_F4_T3) dst_a[s] = make_float4(p.x, p.y, p.z, vx);
-		else {
-			float4 v = make_float4(vx, vy, vz, 0.0f);
-			dst_a[s] = v;
-			if (what == MG_F4_VEL) pv[2 * (size_t)s + 1] = v; // the 256-bit (pos, vel) records of k_df_drho
-		}
+		else dst_a[s] = make_float4(vx, vy, vz, 0.0f);
 	}
 }
 
@@ -619,7 +611,7 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 		if (reduce_blocks > 0) blocks += 1;
 		if (blocks > 0) {
 			k_mg_exchange<<<blocks, 256, 0, st>>>(what, m->send_slot[0], m->send_slot[1], m->recv_slot, m->n_send[0], m->n_send[1],
-			                                      m->n_recv[0], m->n_recv[1], a, b, wa, wb, h->a4[A4_POS], h->pv, peers,
+			                                      m->n_recv[0], m->n_recv[1], a, b, wa, wb, h->a4[A4_POS], peers,
 			                                      m->win, m->cap_halo, m->rank, m->nranks, epoch, reduce_blocks > 0 ? 1 : 0,
 			                                      h->partials, reduce_blocks, ctl_kind, cargs, h->red, h->ctl);
 			h->launches += 1;
@@ -652,7 +644,7 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 	if (reduce_blocks > 0) { k_mg_ctl_apply<<<1, 1, 0, st>>>(ctl_kind, cargs, h->red, h->ctl); h->launches++; }
 	if (a && nr > 0) {
 		k_mg_unpack_values<<<cdiv(nr, 256), 256, 0, st>>>(what, h->fg.slot_of, h->c.N_owned, m->n_recv[0], m->n_recv[1],
-		                                                  m->xrecv[0], m->xrecv[1], h->a4[A4_POS], wa, wb, h->pv);
+		                                                  m->xrecv[0], m->xrecv[1], h->a4[A4_POS], wa, wb);
 		h->launches++;
 	}
 	sph_prof_end(h, st);

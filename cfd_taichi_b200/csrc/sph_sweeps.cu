@@ -28,25 +28,9 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // gather only the velocity.  The stored gradient is bit-identical to a recomputation (same function, same
 // inputs), so the strict kernels stay bit-exact.  The sweeps that need one scalar of the neighbour keep the
 // 16-byte (pos, payload) gather: for them the stream would cost more DRAM time than the arithmetic it saves.
-#ifndef SPH_GW
-#define SPH_GW 1
-#endif
-// the interleaved (pos, vel) records serve only the build without the gradient cache (one LDG.E.256 per neighbour)
-#define SPH_USE_PV (!(SPH_GW && SPH_DF_LPP == 1))
 __host__ __device__ inline size_t sph_gw_index(int s, int cap, int k) {
 	return ((size_t)(s >> 5) * (size_t)cap + (size_t)k) * 32u + (size_t)(s & 31);
 }
-// Lanes per particle of the DFSPH sweeps.  Strict kernels: 1 (the reference's summation order).  Fast
-// kernels: DF_LPP adjacent lanes share a particle and take every DF_LPP-th entry of its address-ordered
-// list, so that the gathers of one warp request fall into a few cache lines instead of 32 unrelated ones
-// (the L1 data pipe, not DRAM or the FP32 pipe, bounds these kernels: profiles/r1c_ncu_dfsph_1M.md).
-#if SPH_STRICT
-#define SPH_DF_LPP 1
-#elif !defined(SPH_DF_LPP)
-#define SPH_DF_LPP 1 // 2, 4, 8 measured slower on B200 (profiles/r1d_experiments.md): 2x the instructions, 66 % lane use
-#endif
-constexpr int DF_LPP = SPH_DF_LPP;
-constexpr int DF_PPB = SPH_BLOCK / DF_LPP; // particles per block
 
 
 // decode the 1-D cell id (PS:102) back into (x, y, z)
@@ -58,20 +42,6 @@ __device__ __forceinline__ void cell_xyz(int cid, const SphConsts &c, int &cx, i
 }
 
 __device__ __forceinline__ f3 ld3(const float *p) { return F3(p[0], p[1], p[2]); }
-
-// One 32-byte record per sorted particle: position (+ payload) and velocity side by side, so that the
-// sweeps that need both fetch them with ONE 256-bit load (LDG.E.256 on sm_100a) from one 32-byte sector
-// instead of two 128-bit gathers from two arrays.
-struct __align__(32) SphPV {
-	float4 p, v;
-};
-__device__ __forceinline__ SphPV ldg256(const SphPV *ptr) {
-	SphPV r;
-	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	             : "=f"(r.p.x), "=f"(r.p.y), "=f"(r.p.z), "=f"(r.p.w), "=f"(r.v.x), "=f"(r.v.y), "=f"(r.v.z), "=f"(r.v.w)
-	             : "l"(ptr));
-	return r;
-}
 
 // velocity of a rigid particle as seen by the coupling terms (DF:168-169, 292-293; II:328-330):
 // v_j = (vel + acc*dt) + cross(omega [+ alpha*dt], pos_j - centroid)
@@ -186,10 +156,9 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
               const int *__restrict__ scell, const int *__restrict__ cstart, const int *__restrict__ sorted_id,
               const float4 *__restrict__ bspos, const int *__restrict__ bstart, SphLists L, SphRigidArgs rg,
               int *__restrict__ nbr_count, float *__restrict__ rho, float *__restrict__ alpha,
-              float4 *__restrict__ posR, float4 *__restrict__ posT1, float4 *__restrict__ pv, SphCtl *ctl) {
+              float4 *__restrict__ posR, float4 *__restrict__ posT1, SphCtl *ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	int nf = 0, nb = 0;
-	if (SPH_USE_PV && s < c.N && ALPHA) { pv[2 * (size_t)s] = spos[s]; pv[2 * (size_t)s + 1] = svel[s]; }
 	if (s < c.N && c.N != c.N_owned && sorted_id[s] >= c.N_owned) {
 		// ghost copy of a neighbour rank's particle (multi-GPU): never a centre particle; its rho / alpha /
 		// payloads arrive through the halo exchange.  fcount < 0 is the ownership flag every sweep tests.
@@ -203,26 +172,24 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		float4 pi = spos[s];
 		int cx, cy, cz;
 		cell_xyz(scell[s], c, cx, cy, cz);
-		// list layout: DFSPH lists are shared by DF_LPP lanes per particle (fast kernels), all others by one
-		constexpr int LPP = ALPHA ? DF_LPP : 1;
 		uint32_t *fl = L.flist, *bl = L.blist;
-#define SPH_FLW(n) fl[sph_list_word<LPP>(s, c.kstride, n)]
-#define SPH_BLW(n) bl[sph_list_word<LPP>(s, c.kbstride, n)]
+#define SPH_FLW(n) fl[sph_list_word(s, c.kstride, n)]
+#define SPH_BLW(n) bl[sph_list_word(s, c.kbstride, n)]
 		// ---- phase 1: the 27-cell traversal only culls and appends (a 15 % hit rate would otherwise run
 		// ---- the kernel-function arithmetic at 15 % lane utilisation on every candidate) -----------------
 		int ncount = 0; // get_neighbour_count (PS:424-445)
 		int i_orig = RIGID ? sorted_id[s] : 0;
 		if (!RIGID) {
-			// append cursors: for one lane per particle the word of entry n+1 is 1 further, 125 further after a quad
+			// append cursors: the word of entry n+1 is 1 further, 125 further after a quad (sph_list_word)
 			uint32_t *fcur = &SPH_FLW(0), *bcur = &SPH_BLW(0);
 			auto emit_f = [&](int e) {
 				if (nf < c.kmax) *fcur = (uint32_t)e;
-				if (LPP == 1) fcur += (nf & 3) == 3 ? 125 : 1; else fcur = &SPH_FLW(nf + 1);
+				fcur += (nf & 3) == 3 ? 125 : 1;
 				nf++;
 			};
 			auto emit_b = [&](int e) {
 				if (nb < c.kbmax) *bcur = (uint32_t)e;
-				if (LPP == 1) bcur += (nb & 3) == 3 ? 125 : 1; else bcur = &SPH_BLW(nb + 1);
+				bcur += (nb & 3) == 3 ? 125 : 1;
 				nb++;
 			};
 #if SPH_STRICT
@@ -325,7 +292,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 				rho_f += (pj.w * cubic_w(p, c)) * SPH_RHO0; // SB:65
 				if (ALPHA) {
 					f3 dw = cubic_dw(p, c);
-					if (SPH_GW && L.gw) L.gw[sph_gw_index(s, c.kstride, k)] = make_float4(__uint_as_float(j), dw.x, dw.y, dw.z);
+					if (L.gw) L.gw[sph_gw_index(s, c.kstride, k)] = make_float4(__uint_as_float(j), dw.x, dw.y, dw.z);
 					f3 g = (pj.w * SPH_RHO0) * dw; // DF:62, 75
 					ss = ss + g;
 					sq += dot(g, g);
@@ -336,7 +303,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 			rho_f += c.m * cubic_w(p, c); // SB:62
 			if (ALPHA) {
 				f3 dw = cubic_dw(p, c);
-				if (SPH_GW && L.gw) L.gw[sph_gw_index(s, c.kstride, k)] = make_float4(__uint_as_float(j), dw.x, dw.y, dw.z);
+				if (L.gw) L.gw[sph_gw_index(s, c.kstride, k)] = make_float4(__uint_as_float(j), dw.x, dw.y, dw.z);
 				f3 g = c.m * dw; // DF:58, 70
 				ss = ss + g;
 				sq += dot(g, g);
@@ -396,7 +363,7 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 	k_build_lists<A, R><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,  \
 	                                              h->fg.sorted_id, h->bspos, h->bg.cell_start, h->L, rg,           \
 	                                              h->nbr_count, h->a1[A1_RHO], h->a1[A1_ALPHA], h->a4[A4_PR],      \
-	                                              h->a4[A4_T1], h->pv, h->ctl)
+	                                              h->a4[A4_T1], h->ctl)
 	if (al && rg.active) SPH_BL(true, true);
 	else if (al) SPH_BL(true, false);
 	else if (rg.active) SPH_BL(false, true);
@@ -441,14 +408,10 @@ struct ListRange {
 	const uint4 *p; // quad 0 of this lane
 	int n;          // entries of this lane
 };
-// the share of sub-lane `sub` (0 <= sub < LPP) of the list of sorted particle s: entries sub, sub + LPP, ...
-template <int LPP>
-__device__ __forceinline__ ListRange list_range(const uint32_t *list, int cap, int s, int sub, int n) {
-	constexpr int PPW = 32 / LPP;
+__device__ __forceinline__ ListRange list_range(const uint32_t *list, int cap, int s, int n) {
 	ListRange r;
-	r.p = reinterpret_cast<const uint4 *>(list) + ((size_t)(s / PPW) * (size_t)(cap / (4 * LPP))) * 32u +
-	      (size_t)((s % PPW) * LPP + sub);
-	r.n = n > sub ? (n - sub + LPP - 1) / LPP : 0;
+	r.p = reinterpret_cast<const uint4 *>(list) + ((size_t)(s >> 5) * (size_t)(cap >> 2)) * 32u + (size_t)(s & 31);
+	r.n = n;
 	return r;
 }
 template <class F>
@@ -477,11 +440,11 @@ __device__ __forceinline__ void operator<<(ListRange r, F &&f) {
 	}
 }
 // usage:  SPH_FOR_FLUID(L, c, s, j) { ...body, `return` skips to the next neighbour... };
-#define SPH_FOR_FLUID(L, c, s, J) list_range<1>((L).flist, (c).kstride, s, 0, (L).fcount[s]) << [&](uint32_t J)
-#define SPH_FOR_BOUNDARY(L, c, s, J) list_range<1>((L).blist, (c).kbstride, s, 0, (L).bcount[s]) << [&](uint32_t J)
-// cooperative form: LPP lanes share particle s, each walks its share; reduce with sub_sum afterwards
-#define SPH_FOR_FLUID_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).flist, (c).kstride, s, sub, n) << [&](uint32_t J)
-#define SPH_FOR_BOUNDARY_L(LPP, L, c, s, sub, n, J) list_range<LPP>((L).blist, (c).kbstride, s, sub, n) << [&](uint32_t J)
+#define SPH_FOR_FLUID(L, c, s, J) list_range((L).flist, (c).kstride, s, (L).fcount[s]) << [&](uint32_t J)
+#define SPH_FOR_BOUNDARY(L, c, s, J) list_range((L).blist, (c).kbstride, s, (L).bcount[s]) << [&](uint32_t J)
+// the same with the count already in a register
+#define SPH_FOR_FLUID_N(L, c, s, n, J) list_range((L).flist, (c).kstride, s, n) << [&](uint32_t J)
+#define SPH_FOR_BOUNDARY_N(L, c, s, n, J) list_range((L).blist, (c).kbstride, s, n) << [&](uint32_t J)
 
 __device__ __forceinline__ float4 ld_gw(const float4 *p, uint64_t pol) {
 	float4 r;
@@ -524,18 +487,6 @@ __device__ __forceinline__ void walk_gw(const float4 *__restrict__ gw, int cap, 
 	}
 }
 
-// sum over the DF_LPP lanes that share a particle (no-op for one lane per particle)
-template <int LPP>
-__device__ __forceinline__ float sub_sum(float v) {
-#pragma unroll
-	for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-	return v;
-}
-template <int LPP>
-__device__ __forceinline__ f3 sub_sum(f3 v) {
-	return F3(sub_sum<LPP>(v.x), sub_sum<LPP>(v.y), sub_sum<LPP>(v.z));
-}
-
 // =============================================================================================
 // DFSPH (dfsph_solver.py)
 // =============================================================================================
@@ -544,22 +495,20 @@ __device__ __forceinline__ f3 sub_sum(f3 v) {
 #define SPH_IS_RIGID(j) (RIGID && ((j) & SPH_RIGID_BIT))
 #define SPH_RIGID_SLOT(j) ((j) & ~SPH_RIGID_BIT)
 
-// ---- DFSPH sweeps.  Thread t of the grid serves sorted particle s = t / DF_LPP as sub-lane t % DF_LPP
-// ---- (DF_LPP = 1 in the strict kernels); every lane of a warp stays alive until the sub-lane sums.
+// ---- DFSPH sweeps: one thread per sorted particle; ghost copies (multi-GPU) carry fcount < 0 -------------
 #define SPH_DF_THREAD()                                        \
-	const int t_ = blockIdx.x * blockDim.x + threadIdx.x;      \
-	const int s = t_ / DF_LPP, sub = t_ % DF_LPP;              \
+	const int s = blockIdx.x * blockDim.x + threadIdx.x;       \
 	const int nf_ = s < c.N ? L.fcount[s] : -1;                \
-	const bool live = nf_ >= 0; /* owned particle (ghost copies carry fcount < 0) */ \
+	const bool live = nf_ >= 0;                                \
 	const int nb_ = live ? L.bcount[s] : 0;                    \
-	(void)sub; (void)nb_
+	(void)nb_
 
 // DF:314-355 divergence_warm_start.  Reads neighbour payload t1 = (k/dt)/rho from posT1.w.
 template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
 k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT1,
                 const float4 *__restrict__ bspos, const float *__restrict__ rho, float4 *__restrict__ svel,
-                float4 *__restrict__ pv, const SphCtl *__restrict__ ctl) {
+                const SphCtl *__restrict__ ctl) {
 	SPH_DF_THREAD();
 	float dt = ctl->dt;
 	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vi = pi;
@@ -567,7 +516,7 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
 	if (live) { pi = posT1[s]; vi = svel[s]; rho_i = rho[s]; }
 	float k_i = vi.w / dt; // DF:333, 342, 353
 	f3 va = F3(0.0f, 0.0f, 0.0f);
-	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
+	SPH_FOR_FLUID_N(L, c, s, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			Pair p = make_pair(pi, pj);
@@ -580,20 +529,17 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
 	};
 	f3 vb = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
-		SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
+		SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:354
 		};
 	}
-	va = sub_sum<DF_LPP>(va);
-	vb = sub_sum<DF_LPP>(vb);
-	if (!live || sub != 0) return;
+	if (!live) return;
 	f3 v = xyz(vi);
 	if (c.boundary_handle == 1) v = v - (va + vb * SPH_RHO0) * dt; // DF:322
 	else v = v - va * dt;                                          // DF:324
 	svel[s] = F4(v, 0.0f); // DF:325 warm_start_k.fill(0)
-	if (SPH_USE_PV) pv[2 * (size_t)s + 1] = F4(v, 0.0f);
 }
 
 // DF:252-300 derivative_iter_all_rho.  Writes drho and the payload t2 = ((drho*alpha)/dt)/rho of
@@ -601,7 +547,7 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
 template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
 k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ spos,
-          const float4 *__restrict__ svel, const SphPV *__restrict__ pv, const float4 *__restrict__ bspos,
+          const float4 *__restrict__ svel, const float4 *__restrict__ bspos,
           const int *__restrict__ nbr_count,
           const float *__restrict__ rho, const float *__restrict__ alpha, float *__restrict__ drho,
           float4 *__restrict__ posT2, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
@@ -620,7 +566,6 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 	}
 	float rd = 0.0f, rdb = 0.0f;
 	if (enough) {
-#if SPH_GW && SPH_DF_LPP == 1
 		walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
 			if (SPH_IS_RIGID(j)) {
 				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
@@ -630,31 +575,15 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 			}
 			rd += c.m * dot(vi - xyz(__ldg(&svel[j])), dw); // DF:287
 		});
-#else
-		SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
-			if (SPH_IS_RIGID(j)) {
-				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
-				Pair p = make_pair(pi, pj);
-				f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, false);             // DF:292-293
-				rd += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));        // DF:294
-				return;
-			}
-			SphPV nj = ldg256(&pv[j]);
-			Pair p = make_pair(pi, nj.p);
-			rd += c.m * dot(vi - xyz(nj.v), cubic_dw(p, c)); // DF:287
-		};
-#endif
 		if (c.boundary_handle == 1) {
-			SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
+			SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
 				float4 pj = __ldg(&bspos[j]);
 				Pair p = make_pair(pi, pj);
 				rdb += pj.w * dot(vi, cubic_dw(p, c)); // DF:300
 			};
 		}
 	}
-	rd = sub_sum<DF_LPP>(rd);
-	rdb = sub_sum<DF_LPP>(rdb);
-	if (live && sub == 0) {
+	if (live) {
 		float out = 0.0f;
 		if (enough) out = c.boundary_handle == 1 ? fmaxf(rd + rdb * SPH_RHO0, 0.0f) : fmaxf(rd, 0.0f); // DF:267
 		drho[s] = out;
@@ -669,8 +598,7 @@ template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
 k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT2,
               const float4 *__restrict__ bspos, const float *__restrict__ rho, const float *__restrict__ alpha,
-              const float *__restrict__ drho, float4 *__restrict__ svel, float4 *__restrict__ pv,
-              const SphCtl *__restrict__ ctl) {
+              const float *__restrict__ drho, float4 *__restrict__ svel, const SphCtl *__restrict__ ctl) {
 	if (!ctl->div_active) return;
 	SPH_DF_THREAD();
 	float dt = ctl->dt;
@@ -679,7 +607,7 @@ k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 	if (live) { pi = posT2[s]; da = drho[s] * alpha[s]; rho_i = rho[s]; }
 	float k_i = da / dt; // DF:363, 374, 388
 	f3 va = F3(0.0f, 0.0f, 0.0f);
-	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
+	SPH_FOR_FLUID_N(L, c, s, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			Pair p = make_pair(pi, pj);
@@ -694,21 +622,18 @@ k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 	};
 	f3 vb = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
-		SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
+		SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:390
 		};
 	}
-	va = sub_sum<DF_LPP>(va);
-	vb = sub_sum<DF_LPP>(vb);
-	if (!live || sub != 0) return;
+	if (!live) return;
 	float4 vi = svel[s];
 	f3 v = xyz(vi);
 	if (c.boundary_handle == 1) v = v - (va + vb * SPH_RHO0) * dt; // DF:310
 	else v = v - va * dt;
 	svel[s] = F4(v, vi.w + da); // DF:384
-	if (SPH_USE_PV) pv[2 * (size_t)s + 1] = F4(v, vi.w + da);
 }
 
 // SB:190-201: viscosity contribution of a rigid neighbour (uses rho[particle_j.index], SURVEY B-6)
@@ -745,7 +670,7 @@ k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restric
 	f3 vi = F3(0.0f, 0.0f, 0.0f);
 	if (live) { pi = posR[s]; vi = xyz(svel[s]); }
 	f3 ten = F3(0.0f, 0.0f, 0.0f), visc = F3(0.0f, 0.0f, 0.0f);
-	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
+	SPH_FOR_FLUID_N(L, c, s, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			rigid_viscosity<RIGID>(c, rg, j, pi, vi, pi.w, rho, visc);
 			return;
@@ -768,9 +693,7 @@ k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restric
 			visc = visc + (c.neg_m * pi_ij) * cubic_dw(p, c);      // SB:189
 		}
 	};
-	ten = sub_sum<DF_LPP>(ten);
-	visc = sub_sum<DF_LPP>(visc);
-	if (live && sub == 0) {
+	if (live) {
 		f3 tension = ten * c.m;  // SB:209
 		f3 viscosity = visc * c.m; // SB:175
 		f3 g = F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
@@ -800,7 +723,6 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
 	f3 vi = F3(0.0f, 0.0f, 0.0f);
 	if (live) { pi = spos[s]; vi = xyz(svadv[s]); }
 	float delta = 0.0f, db = 0.0f;
-#if SPH_GW && SPH_DF_LPP == 1
 	walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
@@ -810,31 +732,14 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
 		}
 		delta += c.m * dot(vi - xyz(__ldg(&svadv[j])), dw); // DF:162
 	});
-#else
-	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
-		if (SPH_IS_RIGID(j)) {
-			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
-			Pair p = make_pair(pi, pj);
-			f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, true);                  // DF:168-169
-			delta += (pj.w * SPH_RHO0) * dot(vi - v_j, cubic_dw(p, c));         // DF:170
-			return;
-		}
-		float4 pj = __ldg(&spos[j]);
-		f3 vj = xyz(__ldg(&svadv[j]));
-		Pair p = make_pair(pi, pj);
-		delta += c.m * dot(vi - vj, cubic_dw(p, c)); // DF:162
-	};
-#endif
 	if (c.boundary_handle == 1) {
-		SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
+		SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			db += pj.w * dot(vi, cubic_dw(p, c)); // DF:176
 		};
 	}
-	delta = sub_sum<DF_LPP>(delta);
-	db = sub_sum<DF_LPP>(db);
-	if (live && sub == 0) {
+	if (live) {
 		float rho_i = rho[s];
 		float ra;
 		if (c.boundary_handle == 1) ra = fmaxf(rho_i + dt * (delta + db * SPH_RHO0), SPH_RHO0); // DF:135
@@ -865,7 +770,7 @@ k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__rest
 		k_i = ((rho_adv[s] - SPH_RHO0) * alpha[s]) / dt2; // DF:199, 208, 217
 	}
 	f3 va = F3(0.0f, 0.0f, 0.0f);
-	SPH_FOR_FLUID_L(DF_LPP, L, c, s, sub, nf_, j) {
+	SPH_FOR_FLUID_N(L, c, s, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			Pair p = make_pair(pi, pj);
@@ -878,15 +783,13 @@ k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__rest
 	};
 	f3 vb = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
-		SPH_FOR_BOUNDARY_L(DF_LPP, L, c, s, sub, nb_, j) {
+		SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
 			vb = vb + ((pj.w * k_i) / rho_i) * cubic_dw(p, c); // DF:219
 		};
 	}
-	va = sub_sum<DF_LPP>(va);
-	vb = sub_sum<DF_LPP>(vb);
-	if (!live || sub != 0) return;
+	if (!live) return;
 	f3 delta = c.boundary_handle == 1 ? va + vb * SPH_RHO0 : va; // DF:187
 	float4 v = svadv[s];
 	svadv[s] = F4(xyz(v) - delta * dt, 0.0f); // DF:191
@@ -961,14 +864,14 @@ void rigid_force_df(SphHandle *h, int gated, cudaStream_t st);
 
 static void df_divergence(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N, DF_PPB); // DF_LPP lanes per particle
+	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_WARM, st);
-	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->pv, h->ctl);
+	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl);
 	sph_prof_end(h, st);
 	mg_exchange(h, MG_F4_VEL, st);
 	sph_prof_begin(h, KC_DF_DRHO, st);
-	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], (const SphPV *)h->pv, h->bspos, h->nbr_count,
+	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
 	             h->a1[A1_RHO],
 	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 0);
 	sph_prof_end(h, st);
@@ -977,11 +880,11 @@ static void df_divergence(SphHandle *h, cudaStream_t st) {
 	for (int it = 0; it < 15; ++it) { // max_iteration_density_divergence (DF:24); gated on ctl->div_active
 		sph_prof_begin(h, KC_DF_DIV, st);
 		SPH_LAUNCH_R(k_df_div_iter, nb, c, h->L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-		             h->a1[A1_DRHO], h->a4[A4_VEL], h->pv, h->ctl);
+		             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
 		sph_prof_end(h, st);
 		mg_exchange(h, MG_F4_VEL, st);
 		sph_prof_begin(h, KC_DF_DRHO, st);
-		SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], (const SphPV *)h->pv, h->bspos, h->nbr_count,
+		SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
 	             h->a1[A1_RHO],
 		             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 1);
 		sph_prof_end(h, st);
@@ -992,7 +895,7 @@ static void df_divergence(SphHandle *h, cudaStream_t st) {
 
 static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N, DF_PPB); // DF_LPP lanes per particle
+	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_EXT, st);
 	SPH_LAUNCH_R(k_df_ext_force, nb, c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->a4[A4_VADV],
@@ -1005,7 +908,7 @@ static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 
 static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N, DF_PPB); // DF_LPP lanes per particle
+	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	for (int it = first; it < first + count; ++it) {
 		int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
