@@ -86,7 +86,6 @@ static void fill_consts(const SphConfig &cfg, SphConsts &c) {
 	c.kbmax = cfg.max_boundary_neighbors > 0 ? cfg.max_boundary_neighbors : 48;
 	c.kstride = (c.kmax + 3) & ~3;   // quad-interleaved lists (sph_list_word)
 	c.kbstride = (c.kbmax + 3) & ~3;
-	c.krmax = 48;
 	c.boundary_handle = cfg.boundary_handle ? 1 : 0;
 	c.fs_couple = cfg.fs_couple ? 1 : 0;
 	c.solver = cfg.solver;
@@ -159,8 +158,6 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	SPH_CUDA_CHECK(h, dalloc(&h->scan_sums, (size_t)h->scan_sums_cap));
 	SPH_CUDA_CHECK(h, dalloc(&h->bspos, (size_t)c.Nb));
 	SPH_CUDA_CHECK(h, dalloc(&h->rspos, (size_t)c.Nr));
-	SPH_CUDA_CHECK(h, dalloc(&h->rsvel, (size_t)c.Nr));
-	SPH_CUDA_CHECK(h, dalloc(&h->rkin, (size_t)1));
 	SPH_CUDA_CHECK(h, dalloc(&h->rstate, 1));
 	SPH_CUDA_CHECK(h, cudaMemset(h->rstate, 0, sizeof(SphRigidState)));
 	h->rl_cap = 96;
@@ -179,13 +176,10 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	SPH_CUDA_CHECK(h, dalloc(&h->L.blist, nwarps * 32 * (size_t)c.kbstride));
 	h->L.gw = nullptr;
 	if (c.solver == SPH_SOLVER_DFSPH) SPH_CUDA_CHECK(h, dalloc(&h->L.gw, nwarps * 32 * (size_t)c.kstride));
-	SPH_CUDA_CHECK(h, dalloc(&h->L.rlist, c.Nr > 0 ? nwarps * 32 * (size_t)c.krmax : 1));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.fcount, ncap));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.bcount, ncap));
-	SPH_CUDA_CHECK(h, dalloc(&h->L.rcount, ncap));
 	SPH_CUDA_CHECK(h, cudaMemset(h->L.fcount, 0, sizeof(int) * (ncap ? ncap : 1)));
 	SPH_CUDA_CHECK(h, cudaMemset(h->L.bcount, 0, sizeof(int) * (ncap ? ncap : 1)));
-	SPH_CUDA_CHECK(h, cudaMemset(h->L.rcount, 0, sizeof(int) * (ncap ? ncap : 1)));
 	SPH_CUDA_CHECK(h, dalloc(&h->nbr_count, ncap));
 	SPH_CUDA_CHECK(h, dalloc(&h->ctl, 1));
 	SPH_CUDA_CHECK(h, cudaMallocHost((void **)&h->ctl_host, sizeof(SphCtl)));
@@ -216,11 +210,11 @@ extern "C" int sph_destroy(SphHandle *h) {
 	cudaSetDevice(h->device);
 	cudaDeviceSynchronize();
 	free_grid(h->fg); free_grid(h->bg); free_grid(h->rg);
-	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rsvel); cudaFree(h->rkin); cudaFree(h->rstate); cudaFree(h->rl_list); cudaFree(h->rl_count);
+	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rstate); cudaFree(h->rl_list); cudaFree(h->rl_count);
 	for (int k = 0; k < A4_COUNT; ++k) cudaFree(h->a4[k]);
 	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
-	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.rlist); cudaFree(h->L.gw);
-	cudaFree(h->L.fcount); cudaFree(h->L.bcount); cudaFree(h->L.rcount);
+	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.gw);
+	cudaFree(h->L.fcount); cudaFree(h->L.bcount);
 	mg_destroy(h);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);
 	if (h->ctl_host) cudaFreeHost(h->ctl_host);

@@ -44,7 +44,7 @@ struct SphConsts {
 	int N;              // fluid particles handled by this handle (owned + ghost)
 	int N_owned;        // owned fluid particles (== N on one GPU)
 	int Nb, Nr;
-	int kmax, kbmax, krmax; // neighbour-list capacities (entries a particle may hold before the overflow flag)
+	int kmax, kbmax;        // neighbour-list capacities (entries a particle may hold before the overflow flag)
 	int kstride, kbstride;  // storage capacities of the quad-interleaved lists: kmax / kbmax rounded up to 4
 	int boundary_handle, fs_couple, solver;
 	int active_rigid;
@@ -117,7 +117,6 @@ struct __align__(16) SphPartial {
 struct SphLists {
 	uint32_t *flist; int *fcount;   // fluid neighbours (indices into the sorted fluid arrays)
 	uint32_t *blist; int *bcount;   // boundary neighbours (indices into the sorted boundary arrays)
-	uint32_t *rlist; int *rcount;   // rigid neighbours (indices into the sorted rigid arrays)
 	// DFSPH only (null otherwise): per-pair cache [index | grad W_ij] of the fluid list, one float4 per entry,
 	// entry k of sorted particle s at gw[((s >> 5) * cap + k) * 32 + (s & 31)] (a warp reads 512 contiguous bytes)
 	float4 *gw;

@@ -64,8 +64,6 @@ struct SphHandle {
 	// sorted static boundary / rigid
 	float4 *bspos;  // xyz, w = volume
 	float4 *rspos;  // xyz, w = volume * rho0-free volume
-	float4 *rsvel;  // predicted rigid particle velocity used by the coupling terms
-	float4 *rkin;   // unused
 	SphRigidState *rstate;      // device
 	float4 *rverts; size_t n_rverts; // caller-owned mesh vertices (float4)
 	uint32_t *rl_list; int *rl_count; int rl_cap; // rigid-centric fluid neighbour lists (force gather)
@@ -82,8 +80,6 @@ struct SphHandle {
 	double *red; // device: {sum, cnt, max} of the last reduction (all ranks)
 	bool grid_valid, boundary_ready, lists_valid;
 	int sweep_blocks;
-	// CUDA graph state
-	void *graph_exec;
 	int last_den_chunk;
 	SphProf *prof;
 	struct SphComm *comm; // multi-GPU slab state (sph_multigpu.cu); null on one GPU
