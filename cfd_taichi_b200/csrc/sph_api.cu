@@ -267,7 +267,8 @@ extern "C" int sph_bind(SphHandle *h, int field, void *dev_ptr, size_t n) {
 
 static int require_state(SphHandle *h) {
 	if (!h) return SPH_EINVAL;
-	if (!h->pos || !h->vel) return sph_fail(h, SPH_ENOTBOUND, "fluid pos/vel are not bound (sph_bind)");
+	size_t ncap = (size_t)h->cfg.n_fluid + (size_t)(h->cfg.n_ghost_capacity > 0 ? h->cfg.n_ghost_capacity : 0);
+	if (ncap > 0 && (!h->pos || !h->vel)) return sph_fail(h, SPH_ENOTBOUND, "fluid pos/vel are not bound (sph_bind)");
 	if (h->c.Nb > 0 && h->c.boundary_handle == 1 && !h->boundary_ready)
 		return sph_fail(h, SPH_ESTATE, "boundary particles are not initialised (sph_init_boundary)");
 	return SPH_OK;
@@ -372,6 +373,10 @@ extern "C" int sph_phase(SphHandle *h, int phase, void *stream) {
 	if (rc != SPH_OK) return rc;
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	if (h->c.N <= 0 && !h->comm) { // empty fluid block: nothing to sort or sweep
+		if (phase == SPH_PH_BUILD_GRID) h->simulate_cnt += 1;
+		return SPH_OK;
+	}
 	if (phase == SPH_PH_BUILD_GRID) {
 		if (h->comm) {
 			rc = mg_begin_step(h, st);
@@ -416,6 +421,10 @@ extern "C" int sph_step(SphHandle *h, int n_substeps, void *stream) {
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
 	bool strict = h->cfg.strict != 0;
+	if (h->c.N <= 0 && !h->comm) { // empty fluid block: the counter advances, nothing to sort or sweep
+		h->simulate_cnt += n_substeps;
+		return SPH_OK;
+	}
 	for (int k = 0; k < n_substeps; ++k) {
 		if (h->comm) { // multi-GPU slab: migration + ghost particles first (positions moved last step)
 			rc = mg_begin_step(h, st);

@@ -411,8 +411,9 @@ k_init_boundary_shell(long long nb, long long x_cnt, long long z_cnt, long long 
 
 extern "C" int sph_init_fluid_lattice(const SphLattice *lat, long long particle_num_total, const int32_t *dev_ids, size_t n,
                                       void *dev_pos4, int device, void *stream) {
-	if (!lat || !dev_pos4) return SPH_EINVAL;
+	if (!lat) return SPH_EINVAL;
 	if (n == 0) return SPH_OK;
+	if (!dev_pos4) return SPH_EINVAL;
 	if (cudaSetDevice(device) != cudaSuccess) return SPH_ECUDA;
 	double d = lat->particle_radius * 2;
 	double x_num_d = lat->water_size[0] / d, z_num_d = lat->water_size[2] / d;
@@ -424,8 +425,9 @@ extern "C" int sph_init_fluid_lattice(const SphLattice *lat, long long particle_
 }
 
 extern "C" int sph_init_boundary_shell(const SphLattice *lat, size_t nb, void *dev_bpos4, int device, void *stream) {
-	if (!lat || !dev_bpos4) return SPH_EINVAL;
+	if (!lat) return SPH_EINVAL;
 	if (nb == 0) return SPH_OK;
+	if (!dev_bpos4) return SPH_EINVAL;
 	if (cudaSetDevice(device) != cudaSuccess) return SPH_ECUDA;
 	double dd = lat->particle_radius * 2;
 	long long x_cnt = (long long)((lat->box_max[0] - lat->box_min[0]) / dd + 1); // PS:157-158

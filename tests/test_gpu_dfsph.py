@@ -248,3 +248,38 @@ def test_visualize_rho_and_neighbour(built):
     rgb = ps.rgb.to_numpy()
     assert np.array_equal(rgb[:, 2], ((cnt - cnt.min()) / (cnt.max() - cnt.min())).astype(np.float32))
     ps.close()
+
+
+def test_coincident_particles_strict(built):
+    # r = 0 pairs (collisions): W(0) is finite, grad W is exactly zero for q <= 1e-5 (SB:95); GPU == oracle
+    cfg = scenes.shipped("small_block", "dfsph")
+    ps = quiet_ps(cfg, strict=True)
+    sol = quiet_solver(dfsph_solver, ps, cfg)
+    o = O.Oracle(cfg, solver="dfsph", threads=8)
+    pos = o.field("pos")
+    pos[100] = pos[101]                      # two particles on top of each other
+    pos[2000] = pos[2001]
+    pos[2002] = pos[2001]                    # and a triple
+    ps.fluid_particles.pos.from_numpy(pos)
+    for _ in range(2):
+        sol.step()
+        o.step()
+    assert sol.stats().error_flags == 0
+    assert np.array_equal(sol.rho.to_numpy(), o.field("rho"))
+    assert np.array_equal(ps.fluid_particles.pos.to_numpy(), o.field("pos"))
+    assert np.array_equal(ps.fluid_particles.vel.to_numpy(), o.field("vel"))
+    assert np.isfinite(ps.fluid_particles.pos.to_numpy()).all()
+    ps.close(); o.close()
+
+
+def test_empty_fluid_block(built):
+    # empty input: a scene whose water block holds no particle still builds, steps and reports zero work
+    cfg = scenes.make_scene([1.5, 1.5, 1.5], [0.3, 0.3, 0.3], [0.04, 0.04, 0.04], "dfsph", 1e-3)
+    ps = quiet_ps(cfg, strict=False)
+    assert ps.particle_num == 0
+    sol = quiet_solver(dfsph_solver, ps, cfg)
+    sol.step()
+    st = sol.stats()
+    assert st.error_flags == 0
+    assert ps.fluid_particles.pos.to_numpy().shape == (0, 3)
+    ps.close()
