@@ -232,26 +232,27 @@ def run_ours(args):
     # ---- e2e: host buffers in, host buffers out, through the C-ABI ------------------------------
     n = ps.particle_num if world == 1 else ps.comm_info()["owned"]
     ncap_e2e = n if world == 1 else ps._n_owned_cap
-    hpos = torch.empty((ncap_e2e, 4), dtype=torch.float32).pin_memory()
-    hvel = torch.empty((ncap_e2e, 4), dtype=torch.float32).pin_memory()
+    # host state as the reference's callers hold it: pos / vel as N x 3 float32 (main.py:190), pinned
+    hpos = torch.empty((ncap_e2e, 3), dtype=torch.float32).pin_memory()
+    hvel = torch.empty((ncap_e2e, 3), dtype=torch.float32).pin_memory()
     stream = ps._stream()
-    _lib.check(L.sph_download_state(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
+    _lib.check(L.sph_download_state_xyz(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
     e2e_steps = max(3, min(args.steps, 10))
     restore()
-    _lib.check(L.sph_download_state(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
+    _lib.check(L.sph_download_state_xyz(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        _lib.check(L.sph_upload_state(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
+        _lib.check(L.sph_upload_state_xyz(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
         _lib.check(L.sph_step(h, 1, stream), h)
-        _lib.check(L.sph_download_state(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
+        _lib.check(L.sph_download_state_xyz(h, hpos.data_ptr(), hvel.data_ptr(), stream), h)
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_particles * e2e_steps / float(te.item())
-    bytes_dir = 2 * n * 16
+    bytes_dir = 2 * n * 12
 
     if rank != 0 and os.environ.get("SPH_BENCH_ALL_RANKS"):
         sys.stderr.write("rank %d kernel_ms %s\n" % (rank, json.dumps({_lib.KERNEL_CLASSES[k]: round(float(ms_by[k]), 3)

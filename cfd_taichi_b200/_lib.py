@@ -120,6 +120,8 @@ PROTOTYPES = [
     ("sph_init_boundary_shell", _i, [ctypes.POINTER(SphLattice), ctypes.c_size_t, _vp, _i, _vp]),
     ("sph_visualize", _i, [_vp, _i, _vp, _i, ctypes.c_size_t, _vp]),
     ("sph_upload_state", _i, [_vp, _vp, _vp, _vp]),
+    ("sph_upload_state_xyz", _i, [_vp, _vp, _vp, _vp]),
+    ("sph_download_state_xyz", _i, [_vp, _vp, _vp, _vp]),
     ("sph_download_state", _i, [_vp, _vp, _vp, _vp]),
     ("sph_read_stats", _i, [_vp, ctypes.POINTER(SphStats)]),
     ("sph_profile_begin", _i, [_vp]),

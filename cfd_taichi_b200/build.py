@@ -45,9 +45,9 @@ def build(force=False, verbose=False):
     hdrs.append(os.path.join(HERE, "..", "include", "sph_b200.h"))
     extra = os.environ.get("SPH_EXTRA_NVCC", "").split()
     units = [
-        ("sph_grid.cu", "sph_grid.o", []),
-        ("sph_api.cu", "sph_api.o", []),
-        ("sph_multigpu.cu", "sph_multigpu.o", ["-I", NCCL_INC]),
+        ("sph_grid.cu", "sph_grid.o", extra),
+        ("sph_api.cu", "sph_api.o", extra),
+        ("sph_multigpu.cu", "sph_multigpu.o", ["-I", NCCL_INC] + extra),
         ("sph_sweeps.cu", "sph_sweeps_strict.o", ["-DSPH_STRICT=1", "-fmad=false"] + extra),
         ("sph_sweeps.cu", "sph_sweeps_fast.o", ["-DSPH_STRICT=0", "-fmad=true"] + extra),
     ]

@@ -217,6 +217,7 @@ extern "C" int sph_destroy(SphHandle *h) {
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount);
 	mg_destroy(h);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);
+	cudaFree(h->xyz_stage);
 	if (h->ctl_host) cudaFreeHost(h->ctl_host);
 	if (h->prof) {
 		if (h->prof->created)
@@ -583,6 +584,42 @@ extern "C" int sph_download_state(SphHandle *h, float *host_pos4, float *host_ve
 	size_t bytes = sizeof(float4) * (size_t)h->c.N_owned;
 	if (host_pos4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_pos4, h->pos, bytes, cudaMemcpyDeviceToHost, st));
 	if (host_vel4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_vel4, h->vel, bytes, cudaMemcpyDeviceToHost, st));
+	SPH_CUDA_CHECK(h, cudaStreamSynchronize(st));
+	return SPH_OK;
+}
+
+static int xyz_stage(SphHandle *h) {
+	if (h->xyz_stage) return SPH_OK;
+	size_t n = (size_t)h->cfg.n_fluid;
+	SPH_CUDA_CHECK(h, cudaMalloc((void **)&h->xyz_stage, sizeof(float) * 6 * (n ? n : 1)));
+	return SPH_OK;
+}
+
+extern "C" int sph_upload_state_xyz(SphHandle *h, const float *host_pos3, const float *host_vel3, void *stream) {
+	int rc = require_state(h);
+	if (rc != SPH_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	if ((rc = xyz_stage(h)) != SPH_OK) return rc;
+	size_t n = (size_t)h->c.N_owned, bytes = sizeof(float) * 3 * n;
+	float *p3 = h->xyz_stage, *v3 = h->xyz_stage + 3 * (size_t)h->cfg.n_fluid;
+	if (host_pos3) SPH_CUDA_CHECK(h, cudaMemcpyAsync(p3, host_pos3, bytes, cudaMemcpyHostToDevice, st));
+	if (host_vel3) SPH_CUDA_CHECK(h, cudaMemcpyAsync(v3, host_vel3, bytes, cudaMemcpyHostToDevice, st));
+	sphg_unpack_xyz(h, host_pos3 ? p3 : nullptr, host_vel3 ? v3 : nullptr, (int)n, st);
+	return check_launch(h, "sph_upload_state_xyz");
+}
+
+extern "C" int sph_download_state_xyz(SphHandle *h, float *host_pos3, float *host_vel3, void *stream) {
+	int rc = require_state(h);
+	if (rc != SPH_OK) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	if ((rc = xyz_stage(h)) != SPH_OK) return rc;
+	size_t n = (size_t)h->c.N_owned, bytes = sizeof(float) * 3 * n;
+	float *p3 = h->xyz_stage, *v3 = h->xyz_stage + 3 * (size_t)h->cfg.n_fluid;
+	sphg_pack_xyz(h, host_pos3 ? p3 : nullptr, host_vel3 ? v3 : nullptr, (int)n, st);
+	if (host_pos3) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_pos3, p3, bytes, cudaMemcpyDeviceToHost, st));
+	if (host_vel3) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_vel3, v3, bytes, cudaMemcpyDeviceToHost, st));
 	SPH_CUDA_CHECK(h, cudaStreamSynchronize(st));
 	return SPH_OK;
 }

@@ -7,7 +7,9 @@
 
 #include "../../include/sph_b200.h"
 
+#ifndef SPH_BLOCK
 #define SPH_BLOCK 128            // threads per sweep block (one sorted particle per thread)
+#endif
 #define SPH_RHO0 1000.0f         // solver_base.rho_0 (SB:19)
 
 // error flag bits latched on the device (SphStats.error_flags)

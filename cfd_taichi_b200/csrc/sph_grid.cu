@@ -437,3 +437,33 @@ extern "C" int sph_init_boundary_shell(const SphLattice *lat, size_t nb, void *d
 	    (long long)nb, x_cnt, z_cnt, bottom, one_round, (float)dd, (float)lat->box_max[1], (float4 *)dev_bpos4);
 	return cudaGetLastError() == cudaSuccess ? SPH_OK : SPH_ECUDA;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Host state as the reference's callers see it (pos / vel as N x 3, main.py:190): packed xyz staging so
+// that the PCIe transfers carry 12 instead of 16 bytes per vector.  vel.w (the solver-persistent scalar:
+// DFSPH warm_start_k, IISPH p_past) never leaves the device.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_unpack_xyz(const float *__restrict__ p3, const float *__restrict__ v3, int n,
+                                                     float4 *__restrict__ pos, float4 *__restrict__ vel) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (p3) pos[i] = make_float4(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2], 0.0f);
+	if (v3) vel[i] = make_float4(v3[3 * i], v3[3 * i + 1], v3[3 * i + 2], vel[i].w);
+}
+__global__ void __launch_bounds__(256) k_pack_xyz(const float4 *__restrict__ pos, const float4 *__restrict__ vel, int n,
+                                                   float *__restrict__ p3, float *__restrict__ v3) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	if (p3) { float4 p = pos[i]; p3[3 * i] = p.x; p3[3 * i + 1] = p.y; p3[3 * i + 2] = p.z; }
+	if (v3) { float4 v = vel[i]; v3[3 * i] = v.x; v3[3 * i + 1] = v.y; v3[3 * i + 2] = v.z; }
+}
+void sphg_unpack_xyz(SphHandle *h, const float *p3, const float *v3, int n, cudaStream_t st) {
+	if (n <= 0) return;
+	k_unpack_xyz<<<cdiv(n, 256), 256, 0, st>>>(p3, v3, n, h->pos, h->vel);
+	h->launches++;
+}
+void sphg_pack_xyz(SphHandle *h, float *p3, float *v3, int n, cudaStream_t st) {
+	if (n <= 0) return;
+	k_pack_xyz<<<cdiv(n, 256), 256, 0, st>>>(h->pos, h->vel, n, p3, v3);
+	h->launches++;
+}

@@ -81,6 +81,7 @@ struct SphHandle {
 	bool grid_valid, boundary_ready, lists_valid;
 	int sweep_blocks;
 	int last_den_chunk;
+	float *xyz_stage;     // 2 x 3 floats per fluid particle: staging of sph_upload_state_xyz / sph_download_state_xyz
 	SphProf *prof;
 	struct SphComm *comm; // multi-GPU slab state (sph_multigpu.cu); null on one GPU
 	int *gid;             // caller-owned global particle ids (multi-GPU)
@@ -111,6 +112,8 @@ void sphg_unsort_f1(SphHandle *h, const SphGrid &g, const float *in, float *out,
 void sphg_unsort_i1(SphHandle *h, const SphGrid &g, const int *in, int *out, int n, cudaStream_t st);
 void sphg_unsort_f4(SphHandle *h, const SphGrid &g, const float4 *in, float4 *out, int n, cudaStream_t st);
 void sphg_writeback(SphHandle *h, const float4 *spos, const float4 *svel, cudaStream_t st);
+void sphg_unpack_xyz(SphHandle *h, const float *p3, const float *v3, int n, cudaStream_t st);
+void sphg_pack_xyz(SphHandle *h, float *p3, float *v3, int n, cudaStream_t st);
 void sphg_visualize(SphHandle *h, int what, float *rgb, int stride, cudaStream_t st);
 
 // ---- sph_multigpu.cu: slab decomposition along x, NCCL halo exchange / migration / allreduce -------

@@ -226,6 +226,11 @@ int sph_visualize(SphHandle *h, int what, void *dev_rgb, int stride_floats, size
 
 int sph_upload_state(SphHandle *h, const float *host_pos4, const float *host_vel4, void *stream);
 int sph_download_state(SphHandle *h, float *host_pos4, float *host_vel4, void *stream);
+/* The same with the host arrays the reference's callers hold (pos / vel as N x 3 floats, main.py:190):
+ * 12 instead of 16 bytes per vector over PCIe; vel.w (DFSPH warm_start_k, IISPH p_past) stays on the device.
+ * Either pointer may be NULL. */
+int sph_upload_state_xyz(SphHandle *h, const float *host_pos3, const float *host_vel3, void *stream);
+int sph_download_state_xyz(SphHandle *h, float *host_pos3, float *host_vel3, void *stream);
 
 int sph_read_stats(SphHandle *h, SphStats *out);
 

@@ -283,3 +283,28 @@ def test_empty_fluid_block(built):
     assert st.error_flags == 0
     assert ps.fluid_particles.pos.to_numpy().shape == (0, 3)
     ps.close()
+
+
+def test_state_transfer_xyz_round_trip(built):
+    # sph_download_state_xyz / sph_upload_state_xyz: N x 3 host arrays, vel.w (warm_start_k) stays on the device
+    import ctypes
+    import torch
+    cfg = scenes.shipped("small_block", "dfsph")
+    ps = quiet_ps(cfg, strict=True)
+    sol = quiet_solver(dfsph_solver, ps, cfg)
+    sol.step()
+    n = ps.particle_num
+    L, h, st = ps._lib, ps._h, ps._stream()
+    hp = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    hv = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    _lib.check(L.sph_download_state_xyz(h, hp.data_ptr(), hv.data_ptr(), st), h)
+    assert np.array_equal(hp.numpy(), ps.fluid_particles.pos.to_numpy())
+    assert np.array_equal(hv.numpy(), ps.fluid_particles.vel.to_numpy())
+    w_before = ps._vel4[:n, 3].clone()
+    hp2, hv2 = (hp + 0.001).pin_memory(), (hv * 0.5).pin_memory()
+    _lib.check(L.sph_upload_state_xyz(h, hp2.data_ptr(), hv2.data_ptr(), st), h)
+    torch.cuda.synchronize()
+    assert np.array_equal(ps.fluid_particles.pos.to_numpy(), hp2.numpy())
+    assert np.array_equal(ps.fluid_particles.vel.to_numpy(), hv2.numpy())
+    assert torch.equal(ps._vel4[:n, 3], w_before)
+    ps.close()
