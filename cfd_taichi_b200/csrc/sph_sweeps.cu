@@ -487,6 +487,91 @@ __device__ __forceinline__ void walk_gw(const float4 *__restrict__ gw, int cap, 
 	}
 }
 
+// ---- the same walk with the records staged through shared memory by TMA bulk copies ------------------------
+// The cache rows of a warp are contiguous (512 bytes per entry row), so a stage of four rows is one 2 KB
+// cp.async.bulk (global -> shared, completion on an mbarrier).  Each warp owns a private ring of GW_STAGES
+// stages: lane 0 issues the copies, every lane waits on the stage's barrier parity and reads its own record
+// with one conflict-free LDS.128.  The bytes in flight no longer live in registers (64 instead of 80).
+// Measured on B200 (profiles/r1d_experiments.md section 9): k_df_drho 111 us with two stages, 124 us with three,
+// against 107 us for the register-prefetched walk_gw -- the ring's shared memory is taken from the L1 that
+// the velocity gathers live in.  Compile-time opt-in, off by default.
+#ifndef SPH_GW_BULK
+#define SPH_GW_BULK 0
+#endif
+#ifndef GW_STAGES
+#define GW_STAGES 3
+#endif
+#define GW_STAGE_F4 128 // four rows of 32 records
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_stage(float4 *dst, const float4 *src, uint64_t *bar) {
+	const uint32_t bytes = GW_STAGE_F4 * sizeof(float4);
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(
+	                 smem_u32(bar)),
+	             "r"(parity)
+	             : "memory");
+}
+// every lane of the warp must call (dead lanes with n <= 0); ring / bars are the warp's private slices
+template <class F>
+__device__ __forceinline__ void walk_gw_bulk(const float4 *__restrict__ gw, int cap, int s, int n, float4 *ring, uint64_t *bars,
+                                             F &&f) {
+	const int lane = threadIdx.x & 31;
+	int nmax = max(n, 0);
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+	if (nmax == 0) return;
+	const float4 *src = gw + ((size_t)(s >> 5) * (size_t)cap) * 32u; // row 0 of this warp (s >> 5 is warp-uniform)
+	const int nst = (nmax + 3) >> 2;
+	if (lane == 0) {
+#pragma unroll
+		for (int k = 0; k < GW_STAGES; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[k])));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		for (int k = 0; k < GW_STAGES && k < nst; ++k) bulk_stage(ring + k * GW_STAGE_F4, src + (size_t)k * GW_STAGE_F4, &bars[k]);
+	}
+	__syncwarp();
+	for (int st = 0; st < nst; ++st) {
+		const int slot = st % GW_STAGES;
+		bar_wait(&bars[slot], (uint32_t)((st / GW_STAGES) & 1));
+		const float4 *r = ring + slot * GW_STAGE_F4 + lane;
+		float4 c0 = r[0], c1 = r[32], c2 = r[64], c3 = r[96];
+		__syncwarp();
+		if (lane == 0 && st + GW_STAGES < nst) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			bulk_stage(ring + slot * GW_STAGE_F4, src + (size_t)(st + GW_STAGES) * GW_STAGE_F4, &bars[slot]);
+		}
+		const int k = st * 4;
+		if (k + 4 <= n) {
+			f(__float_as_uint(c0.x), F3(c0.y, c0.z, c0.w));
+			f(__float_as_uint(c1.x), F3(c1.y, c1.z, c1.w));
+			f(__float_as_uint(c2.x), F3(c2.y, c2.z, c2.w));
+			f(__float_as_uint(c3.x), F3(c3.y, c3.z, c3.w));
+		} else if (k < n) {
+			f(__float_as_uint(c0.x), F3(c0.y, c0.z, c0.w));
+			if (k + 1 < n) {
+				f(__float_as_uint(c1.x), F3(c1.y, c1.z, c1.w));
+				if (k + 2 < n) f(__float_as_uint(c2.x), F3(c2.y, c2.z, c2.w));
+			}
+		}
+	}
+}
+#if SPH_GW_BULK
+#define SPH_GW_RING()                                                                              \
+	__shared__ __align__(128) float4 gw_ring_[(SPH_BLOCK / 32) * GW_STAGES * GW_STAGE_F4];         \
+	__shared__ __align__(8) uint64_t gw_bars_[(SPH_BLOCK / 32) * GW_STAGES]
+#define SPH_WALK_GW(L, c, s, n, ...)                                                               \
+	walk_gw_bulk((L).gw, (c).kstride, s, n, gw_ring_ + (threadIdx.x >> 5) * GW_STAGES * GW_STAGE_F4, \
+	             gw_bars_ + (threadIdx.x >> 5) * GW_STAGES, __VA_ARGS__)
+#else
+#define SPH_GW_RING() (void)0
+#define SPH_WALK_GW(L, c, s, n, ...) walk_gw((L).gw, (c).kstride, s, n, __VA_ARGS__)
+#endif
+
 // =============================================================================================
 // DFSPH (dfsph_solver.py)
 // =============================================================================================
@@ -553,6 +638,7 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
           float4 *__restrict__ posT2, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
 	if (gated && !ctl->div_active) return;
 	SPH_DF_THREAD();
+	SPH_GW_RING();
 	double psum = 0.0;
 	int pcnt = 0;
 	float dt = ctl->dt;
@@ -565,8 +651,14 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 		enough = nbr_count[s] >= 20; // DF:258-261
 	}
 	float rd = 0.0f, rdb = 0.0f;
+#if SPH_GW_BULK
+	const int nwalk = enough ? nf_ : 0; // the staged walker needs every lane of the warp: the others walk an empty list
+	{
+#else
+	const int nwalk = nf_;
 	if (enough) {
-		walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+#endif
+		SPH_WALK_GW(L, c, s, nwalk, [&](uint32_t j, f3 dw) {
 			if (SPH_IS_RIGID(j)) {
 				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 				f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, false);             // DF:292-293
@@ -575,7 +667,7 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 			}
 			rd += c.m * dot(vi - xyz(__ldg(&svel[j])), dw); // DF:287
 		});
-		if (c.boundary_handle == 1) {
+		if (enough && c.boundary_handle == 1) {
 			SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
 				float4 pj = __ldg(&bspos[j]);
 				Pair p = make_pair(pi, pj);
@@ -716,6 +808,7 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
              const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
 	if (gated && !ctl->den_active) return;
 	SPH_DF_THREAD();
+	SPH_GW_RING();
 	double psum = 0.0;
 	int pcnt = 0;
 	float dt = ctl->dt, dt2 = ctl->dt2;
@@ -723,7 +816,7 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
 	f3 vi = F3(0.0f, 0.0f, 0.0f);
 	if (live) { pi = spos[s]; vi = xyz(svadv[s]); }
 	float delta = 0.0f, db = 0.0f;
-	walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+	SPH_WALK_GW(L, c, s, nf_, [&](uint32_t j, f3 dw) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, true);                  // DF:168-169
