@@ -304,10 +304,11 @@ __device__ __forceinline__ int f2key(float f) { int i = __float_as_int(f); retur
 __device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 
 template <bool IS_INT>
-__global__ void __launch_bounds__(256) k_vis_minmax(const void *__restrict__ q, int n, int *__restrict__ mm) {
+__global__ void __launch_bounds__(256) k_vis_minmax(const void *__restrict__ q, const int *__restrict__ sorted_id, int n,
+                                                     int n_owned, int *__restrict__ mm) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	float v = 0.0f;
-	bool ok = s < n;
+	bool ok = s < n && sorted_id[s] < n_owned;
 	if (ok) v = IS_INT ? (float)((const int *)q)[s] : ((const float *)q)[s];
 	float lo = ok ? v : INFINITY, hi = ok ? v : -INFINITY;
 	for (int o = 16; o > 0; o >>= 1) {
@@ -327,9 +328,10 @@ __global__ void k_vis_init(int *mm) { mm[0] = f2key(INFINITY); mm[1] = f2key(-IN
 
 template <bool IS_INT>
 __global__ void __launch_bounds__(256) k_vis_colour(const void *__restrict__ q, const int *__restrict__ sorted_id, int n,
-                                                     const int *__restrict__ mm, float *__restrict__ rgb, int stride) {
+                                                     int n_owned, const int *__restrict__ mm, float *__restrict__ rgb,
+                                                     int stride) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= n) return;
+	if (s >= n || sorted_id[s] >= n_owned) return; // ghost copies (multi-GPU slabs) have no colour of their own
 	float lo = key2f(mm[0]), hi = key2f(mm[1]);
 	if (!(hi - lo > 0.0f)) return; // SB:230, 244: colours stay as they are
 	float v = IS_INT ? (float)((const int *)q)[s] : ((const float *)q)[s];
@@ -339,16 +341,16 @@ __global__ void __launch_bounds__(256) k_vis_colour(const void *__restrict__ q, 
 
 // what: 0 = rho (SB:219-232), 1 = neighbour count (SB:234-245); rgb: n x stride floats, original order
 void sphg_visualize(SphHandle *h, int what, float *rgb, int stride, cudaStream_t st) {
-	int n = h->c.N_owned;
+	int n = h->c.N, no = h->c.N_owned; // sorted slots hold owned particles and (multi-GPU) ghost copies
 	if (n <= 0) return;
 	int *mm = (int *)h->red; // 32 bytes of device scratch that no kernel uses between steps
 	k_vis_init<<<1, 1, 0, st>>>(mm);
 	if (what == 0) {
-		k_vis_minmax<false><<<cdiv(n, 256), 256, 0, st>>>(h->a1[A1_RHO], n, mm);
-		k_vis_colour<false><<<cdiv(n, 256), 256, 0, st>>>(h->a1[A1_RHO], h->fg.sorted_id, n, mm, rgb, stride);
+		k_vis_minmax<false><<<cdiv(n, 256), 256, 0, st>>>(h->a1[A1_RHO], h->fg.sorted_id, n, no, mm);
+		k_vis_colour<false><<<cdiv(n, 256), 256, 0, st>>>(h->a1[A1_RHO], h->fg.sorted_id, n, no, mm, rgb, stride);
 	} else {
-		k_vis_minmax<true><<<cdiv(n, 256), 256, 0, st>>>(h->nbr_count, n, mm);
-		k_vis_colour<true><<<cdiv(n, 256), 256, 0, st>>>(h->nbr_count, h->fg.sorted_id, n, mm, rgb, stride);
+		k_vis_minmax<true><<<cdiv(n, 256), 256, 0, st>>>(h->nbr_count, h->fg.sorted_id, n, no, mm);
+		k_vis_colour<true><<<cdiv(n, 256), 256, 0, st>>>(h->nbr_count, h->fg.sorted_id, n, no, mm, rgb, stride);
 	}
 	h->launches += 3;
 }

@@ -78,7 +78,7 @@ k_wc_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ 
            float4 *__restrict__ pgrad, float4 *__restrict__ visc_out, float4 *__restrict__ ten_out,
            float4 *__restrict__ bacc_out) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N_owned) return;
+	if (s >= c.N || L.fcount[s] < 0) return; // ghost copies (multi-GPU slabs) are never centre particles
 	float4 pi = posT1[s];
 	float4 vr = velR[s];
 	f3 vi = xyz(vr);
@@ -160,10 +160,11 @@ void wc_phase(SphHandle *h, int phase, cudaStream_t st) {
 	int nb = cdiv(c.N_owned, SPH_BLOCK), nba = cdiv(c.N, SPH_BLOCK);
 	if (phase == SPH_PH_WC_PRESSURE) {
 		build_lists(h, st);
+		mg_exchange(h, MG_F4_T1R, st); // slabs: rho of the ghost particles (posR.w); p follows from it pointwise
 		sph_prof_begin(h, KC_WC_FORCE, st);
 		k_wc_pressure<<<nba, SPH_BLOCK, 0, st>>>(c, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_P], h->a4[A4_T1], h->a4[A4_VADV]);
 		SphRigidArgs rg = rigid_args(h);
-		k_wc_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->a4[A4_VADV], h->bspos, h->a1[A1_P],
+		k_wc_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->a4[A4_VADV], h->bspos, h->a1[A1_P],
 		                                     h->a1[A1_RHO], h->a4[A4_FA], h->a4[A4_FB], h->a4[A4_FC], h->a4[A4_FD]);
 		sph_prof_end(h, st);
 		h->launches += 2;

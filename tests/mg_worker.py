@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 
 from cfd_taichi_b200 import scenes  # noqa: E402
 from cfd_taichi_b200.ParticleSystem import ParticleSystem  # noqa: E402
-from cfd_taichi_b200.dfsph_solver import dfsph_solver  # noqa: E402
+import importlib  # noqa: E402
 
 
 def random_state(n, seed):
@@ -26,16 +26,18 @@ def random_state(n, seed):
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     strict = (sys.argv[2] if len(sys.argv) > 2 else "strict") == "strict"
+    solver = sys.argv[3] if len(sys.argv) > 3 else "dfsph"
+    solver_cls = getattr(importlib.import_module("cfd_taichi_b200.%s_solver" % solver), "%s_solver" % solver)
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = scenes.shipped("small_block", "dfsph")
+    cfg = scenes.shipped("small_block", solver)
     n_global = 5879
     jit, vel = random_state(n_global, 7)
     with contextlib.redirect_stdout(io.StringIO()):
-        ps = ParticleSystem(cfg, strict=strict, solver_name="dfsph", slab=(rank, world))
-        sol = dfsph_solver(ps, cfg)
+        ps = ParticleSystem(cfg, strict=strict, solver_name=solver, slab=(rank, world))
+        sol = solver_cls(ps, cfg)
     gid, pos, v4 = ps.owned_state()
     n0 = len(gid)
     ps._pos4[:n0, :3] += torch.from_numpy(jit[gid]).to(ps._device)
@@ -56,8 +58,8 @@ def main():
     ok = True
     if rank == 0:
         with contextlib.redirect_stdout(io.StringIO()):
-            ps1 = ParticleSystem(cfg, strict=strict, solver_name="dfsph")
-            sol1 = dfsph_solver(ps1, cfg)
+            ps1 = ParticleSystem(cfg, strict=strict, solver_name=solver)
+            sol1 = solver_cls(ps1, cfg)
         ps1._pos4[:n_global, :3] += torch.from_numpy(jit).to(ps1._device)
         ps1._vel4[:n_global, :3] = torch.from_numpy(vel).to(ps1._device)
         for _ in range(steps):
