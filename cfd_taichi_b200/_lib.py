@@ -110,6 +110,7 @@ PROTOTYPES = [
     ("sph_init_rigid", _i, [_vp, _vp]),
     ("sph_pcisph_precompute", _i, [_vp, _vp]),
     ("sph_pcisph_delta", _i, [_vp, _i, _vp]),
+    ("sph_pcisph_set_delta", _i, [_vp, ctypes.c_float, _i, _vp]),
     ("sph_step", _i, [_vp, _i, _vp]),
     ("sph_phase", _i, [_vp, _i, _vp]),
     ("sph_rigid_step", _i, [_vp, _vp]),

@@ -465,11 +465,29 @@ extern "C" int sph_pcisph_precompute(SphHandle *h, void *stream) {
 	if (rc != SPH_OK) return rc;
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
-	sphg_build(h, h->fg, h->pos, h->c.N, st); // PC:29-31
+	if (h->comm) { // slabs: the ghost layer must be in place for the neighbour counts of the edge columns
+		rc = mg_begin_step(h, st);
+		if (rc != SPH_OK) return rc;
+	}
+	sphg_build(h, h->fg, h->pos, h->c.N, st, h->comm ? h->gid : nullptr); // PC:29-31
 	sphg_gather_fluid(h, st);
+	mg_after_grid(h, st);
 	h->grid_valid = true;
 	if (h->cfg.strict) sph_strict::pc_precompute(h, st); else sph_fast::pc_precompute(h, st);
 	return check_launch(h, "sph_pcisph_precompute");
+}
+
+__global__ void k_set_pc_delta(SphCtl *ctl, float delta, int index) {
+	ctl->pc_delta = delta;
+	ctl->pc_max_index = index;
+}
+
+extern "C" int sph_pcisph_set_delta(SphHandle *h, float delta, int particle_index, void *stream) {
+	if (!h) return SPH_EINVAL;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	k_set_pc_delta<<<1, 1, 0, (cudaStream_t)stream>>>(h->ctl, delta, particle_index);
+	h->launches++;
+	return check_launch(h, "sph_pcisph_set_delta");
 }
 
 extern "C" int sph_pcisph_delta(SphHandle *h, int particle_index, void *stream) {

@@ -8,7 +8,8 @@
 #pragma once
 #include "sph_common.cuh"
 
-enum { SPH_CTL_NONE = 0, SPH_CTL_DIV_FIRST, SPH_CTL_DIV_ITER, SPH_CTL_DT, SPH_CTL_DEN };
+enum { SPH_CTL_NONE = 0, SPH_CTL_DIV_FIRST, SPH_CTL_DIV_ITER, SPH_CTL_DT, SPH_CTL_DEN, SPH_CTL_PC_FIRST, SPH_CTL_PC_ITER,
+       SPH_CTL_II_ITER };
 
 // what a controller needs besides the reduced (sum, count, max)
 struct SphCtlArgs {
@@ -61,6 +62,28 @@ __device__ __forceinline__ void sph_ctl_apply(int kind, SphCtl *ctl, double sum,
 	case SPH_CTL_DEN: { // DF:221-233, evaluated after compute_all_rho_adv of iteration den_iters
 		if (!ctl->den_active) break;
 		ctl->den_avg = cnt > 0 ? (float)(sum / (double)cnt) : 1000.0f; // DF:128, 148-149
+		break;
+	}
+	case SPH_CTL_PC_FIRST:  // PC:54: residual before the loop
+	case SPH_CTL_PC_ITER: { // PC:68-69: end of a loop body
+		if (kind == SPH_CTL_PC_ITER && !ctl->pc_active) break;
+		float avg = cnt > 0 ? (float)(sum / (double)cnt) : 0.0f; // PC:131-132
+		int it = kind == SPH_CTL_PC_FIRST ? 0 : ctl->pc_iters + 1;
+		ctl->pc_iters = it;
+		ctl->pc_err = avg;
+		ctl->pc_active = (((double)avg > 1000 * .1 * 0.01 || it < 1) && it < 80) ? 1 : 0; // PC:56
+		break;
+	}
+	case SPH_CTL_II_ITER: { // II:78-100 after an iteration
+		if (!ctl->ii_active) break;
+		float res = cnt > 0 ? (float)(sum / (double)cnt) : 0.0f; // II:111-112
+		int l = ctl->ii_iters + 1;                                // II:88
+		ctl->ii_iters = l;
+		ctl->ii_residual = res;
+		if (ctl->ii_have_last && (double)res - (double)ctl->ii_last > 0) { ctl->ii_active = 0; break; } // II:91-93
+		ctl->ii_last = res;
+		ctl->ii_have_last = 1;
+		ctl->ii_active = (((double)res > .1 * 1000 * 0.01 || l < 1) && l < 180) ? 1 : 0; // II:83
 		break;
 	}
 	default: break;

@@ -247,7 +247,7 @@ k_mg_pack_values(int what, const int *__restrict__ send_orig_l, const int *__res
 	int s = slot_of[(left ? send_orig_l : send_orig_r)[kk]];
 	float4 v;
 	if (what == MG_F4_T1R) v = make_float4(a[s].w, b[s].w, 0.0f, 0.0f); // posT1.w, posR.w
-	else if (what == MG_F4_T2 || what == MG_F4_T3) v = make_float4(a[s].w, 0.0f, 0.0f, 0.0f);
+	else if (what == MG_F4_T2 || what == MG_F4_T3 || what == MG_F4_T1W) v = make_float4(a[s].w, 0.0f, 0.0f, 0.0f);
 	else v = a[s];
 	(left ? out_l : out_r)[kk] = v;
 }
@@ -261,7 +261,7 @@ k_mg_unpack_values(int what, const int *__restrict__ slot_of, int first_orig, in
 	float4 v = k < nl ? in_l[k] : in_r[k - nl];
 	float4 p = spos[s]; // the payload buffers carry a position copy; ghosts get theirs here
 	if (what == MG_F4_T1R) { a[s] = make_float4(p.x, p.y, p.z, v.x); b[s] = make_float4(p.x, p.y, p.z, v.y); }
-	else if (what == MG_F4_T2 || what == MG_F4_T3) a[s] = make_float4(p.x, p.y, p.z, v.x);
+	else if (what == MG_F4_T2 || what == MG_F4_T3 || what == MG_F4_T1W) a[s] = make_float4(p.x, p.y, p.z, v.x);
 	else a[s] = v;
 }
 
@@ -356,7 +356,7 @@ k_mg_exchange(int what, const int *__restrict__ send_slot_l, const int *__restri
 		int s = (left ? send_slot_l : send_slot_r)[kk];
 		float4 v;
 		if (what == MG_F4_T1R) v = make_float4(src_a[s].w, src_b[s].w, 0.0f, 0.0f); // posT1.w, posR.w
-		else if (what == MG_F4_T2 || what == MG_F4_T3) v = make_float4(src_a[s].w, 0.0f, 0.0f, 0.0f);
+		else if (what == MG_F4_T2 || what == MG_F4_T3 || what == MG_F4_T1W) v = make_float4(src_a[s].w, 0.0f, 0.0f, 0.0f);
 		else v = src_a[s];
 		float4 *dst = left ? win_xr(peers.w[rank - 1], cap, parity, 1) : win_xr(peers.w[rank + 1], cap, parity, 0);
 		st_slot(&dst[kk], __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), (uint32_t)epoch);
@@ -369,7 +369,7 @@ k_mg_exchange(int what, const int *__restrict__ send_slot_l, const int *__restri
 		float4 p = spos[s]; // the payload buffers carry a position copy; ghosts get theirs here
 		float vx = __uint_as_float(u.x), vy = __uint_as_float(u.y), vz = __uint_as_float(u.z);
 		if (what == MG_F4_T1R) { dst_a[s] = make_float4(p.x, p.y, p.z, vx); dst_b[s] = make_float4(p.x, p.y, p.z, vy); }
-		else if (what == MG_F4_T2 || what == MG_F4_T3) dst_a[s] = make_float4(p.x, p.y, p.z, vx);
+		else if (what == MG_F4_T2 || what == MG_F4_T3 || what == MG_F4_T1W) dst_a[s] = make_float4(p.x, p.y, p.z, vx);
 		else dst_a[s] = make_float4(vx, vy, vz, 0.0f);
 	}
 }
@@ -435,8 +435,7 @@ static int mg_open_windows(SphHandle *h, SphComm *m) {
 extern "C" int sph_comm_init(SphHandle *h, const char *id128, int rank, int nranks, int col_lo, int col_hi) {
 	if (!h || !id128) return SPH_EINVAL;
 	if (nranks < 2 || rank < 0 || rank >= nranks) return sph_fail(h, SPH_EINVAL, "sph_comm_init: bad rank %d / %d", rank, nranks);
-	if (h->c.solver != SPH_SOLVER_DFSPH && h->c.solver != SPH_SOLVER_WCSPH)
-		return sph_fail(h, SPH_EINVAL, "multi-GPU slabs are built for the DFSPH and WCSPH solvers");
+	if (h->c.solver == SPH_SOLVER_PBF) return sph_fail(h, SPH_EINVAL, "multi-GPU slabs are not built for the PBF solver");
 	if (h->cfg.n_ghost_capacity <= 0) return sph_fail(h, SPH_EINVAL, "sph_comm_init: create the handle with n_ghost_capacity > 0");
 	if (!h->gid) return sph_fail(h, SPH_ENOTBOUND, "sph_comm_init: bind SPH_F_FLUID_GID first");
 	int rc = nccl_load(h);
@@ -598,6 +597,8 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 	case MG_F4_T2: a = wa = h->a4[A4_T2]; break;
 	case MG_F4_VADV: a = wa = h->a4[A4_VADV]; break;
 	case MG_F4_T3: a = wa = h->a4[A4_T3]; break;
+	case MG_F4_T1W: a = wa = h->a4[A4_T1]; break;
+	case MG_F4_T2XYZ: a = wa = h->a4[A4_T2]; break;
 	default: break;
 	}
 	int ns = m->n_send[0] + m->n_send[1], nr = m->n_recv[0] + m->n_recv[1];

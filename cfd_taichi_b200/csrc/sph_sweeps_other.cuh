@@ -8,6 +8,8 @@ namespace SPH_NS {
 // shared non-pressure force pass: tension (SB:204-217) + viscosity (SB:170-202) for fluid neighbours.
 // posR.w = rho (written by k_build_lists).
 #define SPH_RIGID_ENTRY(j) (rg.active && ((j) & SPH_RIGID_BIT))
+// ghost copy of a neighbour rank's particle (multi-GPU slabs): never a centre particle (k_build_lists marks it)
+#define SPH_IS_GHOST(L, s) ((L).fcount[s] < 0)
 
 __device__ __forceinline__ void tension_viscosity(const SphConsts &c, const SphLists &L, const SphRigidArgs &rg, int s,
                                                   const float4 *__restrict__ posR, const float4 *__restrict__ svel,
@@ -194,7 +196,7 @@ k_pc_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restric
 	press[s] = 0.0f;                                 // PC:230
 	press_force[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); // PC:231
 	posT1[s] = make_float4(pi.x, pi.y, pi.z, 0.0f);  // payload of the force pass: press_iter
-	if (s >= c.N_owned) return;
+	if (SPH_IS_GHOST(L, s)) return;
 	f3 vi = xyz(svel[s]);
 	f3 tension, viscosity;
 	tension_viscosity(c, L, rg, s, posR, svel, rho, pi, vi, tension, viscosity);
@@ -213,11 +215,11 @@ __device__ __forceinline__ void pc_predict(const SphConsts &c, float dt, f3 x, f
 }
 
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_pc_predict(SphConsts c, const float4 *__restrict__ spos, const float4 *__restrict__ svel,
+k_pc_predict(SphConsts c, SphLists L, const float4 *__restrict__ spos, const float4 *__restrict__ svel,
              const float4 *__restrict__ ext_force, const float4 *__restrict__ press_force,
              float4 *__restrict__ pos_predict, float4 *__restrict__ vel_predict, const SphCtl *__restrict__ ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N_owned) return;
+	if (s >= c.N || SPH_IS_GHOST(L, s)) return;
 	pc_predict(c, ctl->dt, xyz(spos[s]), xyz(svel[s]), xyz(ext_force[s]), xyz(press_force[s]), pos_predict,
 	           vel_predict, s);
 }
@@ -234,7 +236,7 @@ k_pc_predict_rho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	double psum = 0.0;
 	int pcnt = 0;
-	if (s < c.N_owned) {
+	if (s < c.N && !SPH_IS_GHOST(L, s)) {
 		float4 pi = pos_predict[s];
 		float rp = 0.0f;
 		SPH_FOR_FLUID(L, c, s, j) {
@@ -273,11 +275,11 @@ k_pc_predict_rho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 
 // commits iter_press (PC:103-107) for every particle and publishes it as the .w payload
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_pc_commit_press(SphConsts c, const float *__restrict__ p_next, float *__restrict__ press,
+k_pc_commit_press(SphConsts c, SphLists L, const float *__restrict__ p_next, float *__restrict__ press,
                   float4 *__restrict__ posT1, const SphCtl *__restrict__ ctl) {
 	if (!ctl->pc_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N) return;
+	if (s >= c.N || SPH_IS_GHOST(L, s)) return; // ghosts receive posT1.w through the slab exchange
 	float p = p_next[s];
 	press[s] = p;
 	posT1[s].w = p;
@@ -292,7 +294,7 @@ k_pc_press_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
                  const SphCtl *__restrict__ ctl) {
 	if (!ctl->pc_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N_owned) return;
+	if (s >= c.N || SPH_IS_GHOST(L, s)) return;
 	float4 pi = posT1[s];
 	f3 pf = F3(0.0f, 0.0f, 0.0f);
 	float rho_i = rho[s];
@@ -329,11 +331,14 @@ __global__ void __launch_bounds__(256) k_pc_ctl(SphCtl *ctl, const SphPartial *p
 	double sum; int cnt; float mx;
 	reduce_partials(partials, n, sum, cnt, mx);
 	if (threadIdx.x != 0) return;
-	float avg = cnt > 0 ? (float)(sum / (double)cnt) : 0.0f; // PC:131-132
-	int it = mode == 0 ? 0 : ctl->pc_iters + 1;
-	ctl->pc_iters = it;
-	ctl->pc_err = avg;
-	ctl->pc_active = (((double)avg > 1000 * .1 * 0.01 || it < 1) && it < 80) ? 1 : 0; // PC:56
+	SphCtlArgs none = {};
+	sph_ctl_apply(mode == 0 ? SPH_CTL_PC_FIRST : SPH_CTL_PC_ITER, ctl, sum, cnt, mx, none); // PC:54-56, 68-69
+}
+// the loop decision after a residual sweep: one controller launch, or (slabs) part of the exchange
+static void pc_decide(SphHandle *h, int mode, int nb, cudaStream_t st) {
+	if (h->comm) { mg_exchange_reduce(h, MG_NONE, mode == 0 ? SPH_CTL_PC_FIRST : SPH_CTL_PC_ITER, nb, st); return; }
+	k_pc_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, mode);
+	h->launches++;
 }
 
 // PC:200-218 integration + write-back
@@ -389,36 +394,39 @@ void pc_set_delta(SphHandle *h, int target, cudaStream_t st) {
 
 static void pc_iteration(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N_owned, SPH_BLOCK), nba = cdiv(c.N, SPH_BLOCK);
+	int nba = cdiv(c.N, SPH_BLOCK);
 	float4 *pos_predict = h->a4[A4_T2], *vel_predict = h->a4[A4_VADV];
 	SphRigidArgs rg = rigid_args(h);
 	if (rg.active) rigid_lists(h, st);
 	sph_prof_begin(h, KC_PC_PREDICT, st);
-	k_pc_predict<<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA], h->a4[A4_FB], pos_predict,
-	                                       vel_predict, h->ctl);
+	k_pc_predict<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA], h->a4[A4_FB], pos_predict,
+	                                        vel_predict, h->ctl);
 	sph_prof_end(h, st);
+	mg_exchange(h, MG_F4_T2XYZ, st); // slabs: predicted positions of the ghost particles
 	sph_prof_begin(h, KC_PC_RHO, st);
-	k_pc_predict_rho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB], h->a1[A1_P],
-	                                           h->a1[A1_SC], h->ctl, h->partials, 0);
+	k_pc_predict_rho<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB], h->a1[A1_P],
+	                                            h->a1[A1_SC], h->ctl, h->partials, 0);
 	sph_prof_end(h, st);
-	k_pc_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0);
-	h->launches += 3;
+	pc_decide(h, 0, nba, st);
+	h->launches += 2;
 	int done = 0;
 	int chunk = h->last_den_chunk > 0 ? h->last_den_chunk : 4;
 	for (;;) {
 		for (int it = 0; it < chunk && done < 80; ++it, ++done) { // max_iteration (PC:21); gated on ctl->pc_active
-			k_pc_commit_press<<<nba, SPH_BLOCK, 0, st>>>(c, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+			k_pc_commit_press<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+			mg_exchange(h, MG_F4_T1W, st); // slabs: press_iter of the ghost particles
 			sph_prof_begin(h, KC_PC_FORCE, st);
-			k_pc_press_force<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
-			                                           h->a4[A4_FA], h->a4[A4_FB], pos_predict, vel_predict, h->ctl);
+			k_pc_press_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
+			                                            h->a4[A4_FA], h->a4[A4_FB], pos_predict, vel_predict, h->ctl);
 			sph_prof_end(h, st);
+			mg_exchange(h, MG_F4_T2XYZ, st);
 			if (rg.active) rigid_force(h, RF_PC, 1, st); // PC:186, gather form
 			sph_prof_begin(h, KC_PC_RHO, st);
-			k_pc_predict_rho<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB],
-			                                           h->a1[A1_P], h->a1[A1_SC], h->ctl, h->partials, 1);
+			k_pc_predict_rho<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB],
+			                                            h->a1[A1_P], h->a1[A1_SC], h->ctl, h->partials, 1);
 			sph_prof_end(h, st);
-			k_pc_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1);
-			h->launches += 4;
+			pc_decide(h, 1, nba, st);
+			h->launches += 3;
 		}
 		if (done >= 80) break;
 		// one look at the device flag per chunk (not per iteration)
@@ -436,6 +444,7 @@ void pc_phase(SphHandle *h, int phase, cudaStream_t st) {
 	int nba = cdiv(c.N, SPH_BLOCK);
 	if (phase == SPH_PH_PC_EXT_FORCE) {
 		build_lists(h, st);
+		mg_exchange(h, MG_F4_T1R, st); // slabs: rho of the ghost particles (posR.w)
 		sph_prof_begin(h, KC_PC_EXT, st);
 		k_pc_ext_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO],
 		                                          h->a4[A4_FA], h->a4[A4_FB], h->a1[A1_P], h->a4[A4_T1]);

@@ -32,12 +32,54 @@ class pcisph_solver(solver_base):
     def pre_compute(self):                                                           # PC:28-37
         ps = self.ps
         _lib.check(self._lib.sph_pcisph_precompute(ps._h, ps._stream()), ps._h)
-        max_index = ps.get_max_neighbor_particle_index()
-        if max_index >= 0:
-            _lib.check(self._lib.sph_pcisph_delta(ps._h, int(max_index), ps._stream()), ps._h)
+        if ps._slab is not None:
+            self._pre_compute_slab()
+        else:
+            max_index = ps.get_max_neighbor_particle_index()
+            if max_index >= 0:
+                _lib.check(self._lib.sph_pcisph_delta(ps._h, int(max_index), ps._stream()), ps._h)
         st = self.stats()
         self.delta[None] = st.pc_delta
         print('PCISPH parameter delta: {}, beta: {}'.format(self.delta[None], self.beta))
+
+    def _pre_compute_slab(self):
+        """x-slabs: the arg-max particle of the GLOBAL domain (PS:409-422 over all ranks' counts, by global
+        particle id) decides; its owner computes delta and every rank takes that value."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        ps = self.ps
+        world = dist.get_world_size()
+        n = ps.comm_info()['owned']
+        cnt = ps.neighbour_counts()[:n].to(torch.int32)
+        gid = ps._gid[:n]
+        sizes = [torch.zeros(1, dtype=torch.int64, device=cnt.device) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([n], dtype=torch.int64, device=cnt.device))
+        cap = int(max(int(s.item()) for s in sizes))
+        pad = torch.full((2, cap), -1, dtype=torch.int32, device=cnt.device)
+        pad[0, :n], pad[1, :n] = gid, cnt
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+        total = ps.particle_num
+        glob = np.zeros(total, dtype=np.int64)
+        owner = np.zeros(total, dtype=np.int64)
+        for r, (part, sz) in enumerate(zip(parts, sizes)):
+            k = int(sz.item())
+            g = part[0, :k].cpu().numpy()
+            glob[g] = part[1, :k].cpu().numpy()
+            owner[g] = r
+        run = np.maximum.accumulate(np.concatenate([[-1], glob[:-1]]))   # PS:409-422, one-thread semantics
+        hit = np.nonzero(run == glob)[0]
+        max_index = int(hit[-1]) if hit.size else -1
+        delta = torch.zeros(1, dtype=torch.float32, device=cnt.device)
+        if max_index >= 0:
+            src = int(owner[max_index])
+            if src == dist.get_rank():
+                local = int(torch.nonzero(gid == max_index)[0].item())
+                _lib.check(self._lib.sph_pcisph_delta(ps._h, local, ps._stream()), ps._h)
+                delta[0] = self.stats().pc_delta
+            dist.broadcast(delta, src=src)
+            _lib.check(self._lib.sph_pcisph_set_delta(ps._h, ctypes.c_float(float(delta.item())), max_index, ps._stream()), ps._h)
 
     def compute_ext_force(self):                                                     # PC:220-226
         self.ps.phase(_lib.PH_PC_EXT_FORCE)

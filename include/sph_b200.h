@@ -173,6 +173,9 @@ int sph_init_rigid(SphHandle *h, void *stream);
  * handed to sph_pcisph_delta, which evaluates pre_compute_delta (PC:39-45) for that particle. */
 int sph_pcisph_precompute(SphHandle *h, void *stream);
 int sph_pcisph_delta(SphHandle *h, int particle_index, void *stream);
+/* multi-GPU slabs: delta is computed by the rank that owns the arg-max particle (sph_pcisph_delta there) and
+ * handed to the other ranks as a value; particle_index is the GLOBAL id reported in SphStats.pc_max_index */
+int sph_pcisph_set_delta(SphHandle *h, float delta, int particle_index, void *stream);
 
 /* One full solver.step() (SB:136-143 + <name>_solver.step), n_substeps times. */
 int sph_step(SphHandle *h, int n_substeps, void *stream);

@@ -51,7 +51,7 @@ def main():
     st = sol.stats()
     gid, pos, v4 = ps.owned_state()
     rho = sol.rho.to_torch()[:len(gid)].cpu().numpy()
-    out = dict(rank=rank, gid=gid, pos=pos, vel=v4, rho=rho, hist=hist, div=st.div_iters, den=st.den_iters,
+    out = dict(rank=rank, gid=gid, pos=pos, vel=v4, rho=rho, hist=hist, div=st.div_iters, den=st.den_iters, pc=st.pc_iters, ii=st.ii_iters,
                dt=st.delta_time, flags=st.error_flags)
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(out, gathered, dst=0)
@@ -73,7 +73,8 @@ def main():
         order = np.argsort(gids)
         pos, vel4 = pos[order], vel4[order]
         moved = sum(abs(g["hist"][-1][0] - g["hist"][0][0]) for g in gathered)
-        iters_ok = all((g["div"], g["den"]) == (st1.div_iters, st1.den_iters) for g in gathered)
+        iters_ok = all((g["div"], g["den"], g["pc"], g["ii"]) == (st1.div_iters, st1.den_iters, st1.pc_iters, st1.ii_iters)
+                       for g in gathered)
         dpos = float(np.abs(pos - ref_pos).max())
         dvel = float(np.abs(vel4 - ref_vel).max())
         exact = np.array_equal(pos, ref_pos) and np.array_equal(vel4, ref_vel)

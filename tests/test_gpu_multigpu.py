@@ -29,9 +29,11 @@ def test_two_slabs_match_single_domain(built, mode):
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_slabs_wcsph_match_single_domain(built):
-    # WCSPH over slabs: one ghost-density exchange per step; bit-identical to the single-domain run
-    r = _run(2, ["25", "strict", "wcsph"])
+@pytest.mark.parametrize("solver", ["wcsph", "pcisph"])
+def test_two_slabs_other_solvers_match_single_domain(built, solver):
+    # WCSPH: one ghost-density exchange per step.  PCISPH: ghost density, then per pressure iteration the ghosts'
+    # pressure and predicted position plus the residual all-reduce.  Bit-identical to the single-domain run.
+    r = _run(2, ["25", "strict", solver])
     line = [l for l in r.stdout.splitlines() if l.startswith("MGRESULT")]
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
-    assert line and "perm_ok=True" in line[0] and "exact=True" in line[0]
+    assert line and "perm_ok=True" in line[0] and "iters_ok=True" in line[0] and "exact=True" in line[0]
