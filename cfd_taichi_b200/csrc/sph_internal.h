@@ -119,7 +119,8 @@ void sphg_visualize(SphHandle *h, int what, float *rgb, int stride, cudaStream_t
 // ---- sph_multigpu.cu: slab decomposition along x, NCCL halo exchange / migration / allreduce -------
 // Every call is a no-op (returns immediately) when h->comm is null.
 enum { MG_F4_T1R = 0 /* posT1.w + posR.w */, MG_F4_VEL, MG_F4_T2, MG_F4_VADV, MG_F4_T3,
-       MG_F4_T1W /* posT1.w */, MG_F4_T2XYZ /* xyz of A4_T2 (PCISPH pos_predict) */, MG_NONE = -1 };
+       MG_F4_T1W /* posT1.w */, MG_NONE = -1 };
+#define MG_XYZ(a4_index) (100 + (a4_index)) // xyz of the float4 work array a4[a4_index] (w is not carried)
 void mg_exchange(SphHandle *h, int what, cudaStream_t st);       // ghost values of one field, both neighbours
 // ghost values + the all-reduce of the sweep's n_blocks block partials + the loop decision `ctl_kind`
 // (sph_ctl.cuh) applied on every rank

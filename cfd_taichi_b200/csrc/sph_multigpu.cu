@@ -598,8 +598,9 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 	case MG_F4_VADV: a = wa = h->a4[A4_VADV]; break;
 	case MG_F4_T3: a = wa = h->a4[A4_T3]; break;
 	case MG_F4_T1W: a = wa = h->a4[A4_T1]; break;
-	case MG_F4_T2XYZ: a = wa = h->a4[A4_T2]; break;
-	default: break;
+	default:
+		if (what >= MG_XYZ(0) && what < MG_XYZ(A4_COUNT)) a = wa = h->a4[what - MG_XYZ(0)];
+		break;
 	}
 	int ns = m->n_send[0] + m->n_send[1], nr = m->n_recv[0] + m->n_recv[1];
 	if (m->p2p) {

@@ -402,7 +402,7 @@ static void pc_iteration(SphHandle *h, cudaStream_t st) {
 	k_pc_predict<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA], h->a4[A4_FB], pos_predict,
 	                                        vel_predict, h->ctl);
 	sph_prof_end(h, st);
-	mg_exchange(h, MG_F4_T2XYZ, st); // slabs: predicted positions of the ghost particles
+	mg_exchange(h, MG_XYZ(A4_T2), st); // slabs: predicted positions of the ghost particles
 	sph_prof_begin(h, KC_PC_RHO, st);
 	k_pc_predict_rho<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB], h->a1[A1_P],
 	                                            h->a1[A1_SC], h->ctl, h->partials, 0);
@@ -419,7 +419,7 @@ static void pc_iteration(SphHandle *h, cudaStream_t st) {
 			k_pc_press_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
 			                                            h->a4[A4_FA], h->a4[A4_FB], pos_predict, vel_predict, h->ctl);
 			sph_prof_end(h, st);
-			mg_exchange(h, MG_F4_T2XYZ, st);
+			mg_exchange(h, MG_XYZ(A4_T2), st);
 			if (rg.active) rigid_force(h, RF_PC, 1, st); // PC:186, gather form
 			sph_prof_begin(h, KC_PC_RHO, st);
 			k_pc_predict_rho<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB],
@@ -476,7 +476,7 @@ k_ii_advect(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__
             const float4 *__restrict__ svel, const float *__restrict__ rho, const float4 *__restrict__ bspos, float4 *__restrict__ f_adv, float4 *__restrict__ v_adv,
             float4 *__restrict__ d_ii, const SphCtl *__restrict__ ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N_owned) return;
+	if (s >= c.N || SPH_IS_GHOST(L, s)) return;
 	float dt = ctl->dt;
 	float4 pi = posR[s];
 	float rho_i = pi.w;
@@ -533,15 +533,15 @@ __global__ void __launch_bounds__(SPH_BLOCK)
 k_ii_rho_adv_aii(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posR,
                  const float4 *__restrict__ v_adv,
                  const float4 *__restrict__ bspos, const float4 *__restrict__ d_ii, const float4 *__restrict__ svel,
-                 float *__restrict__ rho_adv, float *__restrict__ a_ii, float *__restrict__ press,
+                 float *__restrict__ rho, float *__restrict__ rho_adv, float *__restrict__ a_ii, float *__restrict__ press,
                  float4 *__restrict__ posT1, const SphCtl *__restrict__ ctl) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N) return;
 	float4 pi = posR[s];
-	float p0 = 0.5f * svel[s].w; // II:67
+	float p0 = 0.5f * svel[s].w; // II:67 (ghost copies carry their p_past in vel.w as well)
 	press[s] = p0;
 	posT1[s] = make_float4(pi.x, pi.y, pi.z, p0);
-	if (s >= c.N_owned) return;
+	if (SPH_IS_GHOST(L, s)) { rho[s] = pi.w; return; } // slabs: k_ii_dij gathers rho[j] of ghosts too
 	float dt = ctl->dt;
 	float rho_i = pi.w;
 	f3 va = xyz(v_adv[s]);
@@ -617,7 +617,7 @@ k_ii_update_p(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	double psum = 0.0;
 	int pcnt = 0;
-	if (s < c.N_owned) {
+	if (s < c.N && !SPH_IS_GHOST(L, s)) {
 		float dt = ctl->dt;
 		float4 pi = posT1[s];
 		float rho_i = rho[s];
@@ -663,11 +663,11 @@ k_ii_update_p(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 }
 
 __global__ void __launch_bounds__(SPH_BLOCK)
-k_ii_commit(SphConsts c, const float *__restrict__ p_next, float *__restrict__ press, float4 *__restrict__ posT1,
+k_ii_commit(SphConsts c, SphLists L, const float *__restrict__ p_next, float *__restrict__ press, float4 *__restrict__ posT1,
             const SphCtl *__restrict__ ctl) {
 	if (!ctl->ii_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= c.N_owned) return;
+	if (s >= c.N || SPH_IS_GHOST(L, s)) return; // ghosts receive posT1.w through the slab exchange
 	float p = p_next[s];
 	press[s] = p;
 	posT1[s].w = p;
@@ -683,14 +683,8 @@ __global__ void __launch_bounds__(256) k_ii_ctl(SphCtl *ctl, const SphPartial *p
 	double sum; int cnt; float mx;
 	reduce_partials(partials, n, sum, cnt, mx);
 	if (threadIdx.x != 0) return;
-	float res = cnt > 0 ? (float)(sum / (double)cnt) : 0.0f; // II:111-112
-	int l = ctl->ii_iters + 1;                                // II:88
-	ctl->ii_iters = l;
-	ctl->ii_residual = res;
-	if (ctl->ii_have_last && (double)res - (double)ctl->ii_last > 0) { ctl->ii_active = 0; return; } // II:91-93
-	ctl->ii_last = res;
-	ctl->ii_have_last = 1;
-	ctl->ii_active = (((double)res > .1 * 1000 * 0.01 || l < 1) && l < 180) ? 1 : 0; // II:83
+	SphCtlArgs none = {};
+	sph_ctl_apply(SPH_CTL_II_ITER, ctl, sum, cnt, mx, none); // II:83-93, 102-113
 }
 
 // II:184-206 intergation (sic) + write-back
@@ -717,23 +711,29 @@ k_ii_integration(SphConsts c, const int *__restrict__ sorted_id, const float4 *_
 
 static void ii_pressure_solve(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N_owned, SPH_BLOCK);
-	k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 0);
+	int nba = cdiv(c.N, SPH_BLOCK);
+	k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nba, 0);
 	h->launches++;
 	int done = 0;
 	int chunk = h->last_den_chunk > 0 ? h->last_den_chunk : 4;
 	for (;;) {
 		for (int it = 0; it < chunk && done < 180; ++it, ++done) { // max_iter_cnt (II:27); gated on ctl->ii_active
 			sph_prof_begin(h, KC_II_DIJ, st);
-			k_ii_dij<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->ctl);
+			k_ii_dij<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->ctl);
 			sph_prof_end(h, st);
+			mg_exchange(h, MG_XYZ(A4_FB), st); // slabs: sum_j d_ij p_j of the ghost particles
 			sph_prof_begin(h, KC_II_UPDATE, st);
-			k_ii_update_p<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
-			                                        h->a4[A4_FC], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
-			                                        h->a1[A1_SC], h->ctl, h->partials);
+			k_ii_update_p<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
+			                                         h->a4[A4_FC], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
+			                                         h->a1[A1_SC], h->ctl, h->partials);
 			sph_prof_end(h, st);
-			k_ii_commit<<<nb, SPH_BLOCK, 0, st>>>(c, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
-			k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nb, 1);
+			k_ii_commit<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+			if (h->comm) {
+				mg_exchange(h, MG_F4_T1W, st); // slabs: the new pressure iterate of the ghost particles
+				mg_exchange_reduce(h, MG_NONE, SPH_CTL_II_ITER, nba, st);
+			} else {
+				k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nba, 1);
+			}
 			h->launches += 4;
 		}
 		if (done >= 180) break;
@@ -750,14 +750,17 @@ void ii_phase(SphHandle *h, int phase, cudaStream_t st) {
 	int nb = cdiv(c.N_owned, SPH_BLOCK), nba = cdiv(c.N, SPH_BLOCK);
 	if (phase == SPH_PH_II_PREDICT_ADVECTION) {
 		build_lists(h, st);
+		mg_exchange(h, MG_F4_T1R, st); // slabs: rho of the ghost particles (posR.w)
 		sph_prof_begin(h, KC_II_ADV, st);
 		SphRigidArgs rg = rigid_args(h);
-		k_ii_advect<<<nb, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->bspos, h->a4[A4_FA],
-		                                      h->a4[A4_VADV], h->a4[A4_FC], h->ctl);
+		k_ii_advect<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->bspos, h->a4[A4_FA],
+		                                       h->a4[A4_VADV], h->a4[A4_FC], h->ctl);
 		sph_prof_end(h, st);
+		mg_exchange(h, MG_F4_VADV, st);    // slabs: v_adv and d_ii of the ghost particles
+		mg_exchange(h, MG_XYZ(A4_FC), st);
 		sph_prof_begin(h, KC_II_AII, st);
 		k_ii_rho_adv_aii<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_PR], h->a4[A4_VADV], h->bspos, h->a4[A4_FC],
-		                                            h->a4[A4_VEL], h->a1[A1_RHOADV], h->a1[A1_SA], h->a1[A1_P],
+		                                            h->a4[A4_VEL], h->a1[A1_RHO], h->a1[A1_RHOADV], h->a1[A1_SA], h->a1[A1_P],
 		                                            h->a4[A4_T1], h->ctl);
 		sph_prof_end(h, st);
 		h->launches += 2;
