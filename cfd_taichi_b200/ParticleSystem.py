@@ -71,8 +71,6 @@ class ParticleSystem:
             self._owned_ids = ids
             self._n_owned_cap = owned_cap
             self._ghost_capacity = ghost_cap
-            if self.exist_rigid[None] == 1:
-                raise _lib.SphError("multi-GPU slabs do not carry a rigid body in this round")
 
         dev = self._device
         n, nb = self._n_owned_cap, self.boundary_particles_num

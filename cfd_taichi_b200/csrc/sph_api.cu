@@ -362,6 +362,7 @@ static int base_step(SphHandle *h, cudaStream_t st) {
 	if (h->c.Nr > 0 && h->c.active_rigid) { // PS:385-386, 399-407
 		sphg_build(h, h->rg, h->rpos, h->c.Nr, st);
 		sphg_gather_rigid(h, st);
+		mg_rigid_quirk_update(h, 0, st); // slabs: positions of the fluid particles the count quirk looks at
 	}
 	sph_prof_end(h, st);
 	h->grid_valid = true;

@@ -104,6 +104,9 @@ struct SphRigidArgs {
 	const SphRigidState *st;
 	const float4 *pos_orig;     // fluid positions in ORIGINAL order (neighbour-count quirk, PS:440-442)
 	const int *slot_of;         // fluid original index -> sorted slot (viscosity quirk, SB:199)
+	const int *gid;             // multi-GPU slabs only: global id of the fluid particle with local original index i; else null
+	const float4 *quirk;        // multi-GPU slabs only: (pos, rho) of the fluid particles with GLOBAL id < Nr, replicated
+	                            // on every rank (the two quirks index FLUID arrays with a rigid-local index); else null
 	int active;
 };
 

@@ -128,6 +128,10 @@ void mg_exchange_reduce(SphHandle *h, int what, int ctl_kind, int n_blocks, cuda
 int mg_begin_step(SphHandle *h, cudaStream_t st);                // migration + ghost exchange + counts
 void mg_after_grid(SphHandle *h, cudaStream_t st);               // sorted slots of the send / recv lists
 void mg_destroy(SphHandle *h);
+// rigid bodies over slabs (the body is replicated on every rank)
+void mg_allreduce_sum_f32(SphHandle *h, float *dev, size_t n, cudaStream_t st);   // no-op on one GPU
+const float4 *mg_rigid_quirk(const SphHandle *h);                                       // null on one GPU
+void mg_rigid_quirk_update(SphHandle *h, int with_rho, cudaStream_t st);          // no-op on one GPU
 
 // ---- sph_sweeps.cu, compiled twice (namespace sph_strict with -fmad=false, sph_fast) -------
 #define SPH_SWEEP_API(NS)                                                                   \

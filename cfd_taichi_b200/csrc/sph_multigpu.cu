@@ -85,6 +85,7 @@ struct SphComm {
 	size_t win_bytes;
 	int epoch;                   // exchanges issued so far (same sequence on every rank)
 	int *send_slot[2], *recv_slot; // sorted slots of the particles sent to each side / of the ghosts, per step
+	float4 *quirk;               // rigid scenes: (pos, rho) of the fluid particles with global id < Nr, replicated
 };
 
 // ---- window layout (identical on every rank) ----------------------------------------------------------
@@ -468,6 +469,10 @@ extern "C" int sph_comm_init(SphHandle *h, const char *id128, int rank, int nran
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->tmp_pos, sizeof(float4) * ncap));
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->tmp_vel, sizeof(float4) * ncap));
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->tmp_gid, sizeof(int) * ncap));
+	if (h->c.Nr > 0) {
+		SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->quirk, sizeof(float4) * (size_t)h->c.Nr));
+		SPH_CUDA_CHECK(h, cudaMemset(m->quirk, 0, sizeof(float4) * (size_t)h->c.Nr));
+	}
 	h->comm = m;
 	const char *tr = getenv("SPH_MG_TRANSPORT");
 	if (!(tr && strcmp(tr, "nccl") == 0)) {
@@ -489,7 +494,7 @@ void mg_destroy(SphHandle *h) {
 		for (int r = 0; r < m->nranks; ++r)
 			if (r != m->rank && m->peer_win[r]) cudaIpcCloseMemHandle(m->peer_win[r]);
 	}
-	cudaFree(m->win); cudaFree(m->send_slot[0]); cudaFree(m->send_slot[1]); cudaFree(m->recv_slot);
+	cudaFree(m->quirk); cudaFree(m->win); cudaFree(m->send_slot[0]); cudaFree(m->send_slot[1]); cudaFree(m->recv_slot);
 	if (m->comm) g_nccl.CommDestroy(m->comm);
 	delete m;
 	h->comm = nullptr;
@@ -656,6 +661,39 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 void mg_exchange(SphHandle *h, int what, cudaStream_t st) { mg_exchange_impl(h, what, SPH_CTL_NONE, 0, st); }
 void mg_exchange_reduce(SphHandle *h, int what, int ctl_kind, int n_blocks, cudaStream_t st) {
 	mg_exchange_impl(h, what, ctl_kind, n_blocks, st);
+}
+
+// ---- rigid bodies over slabs -------------------------------------------------------------------------------
+void mg_allreduce_sum_f32(SphHandle *h, float *dev, size_t n, cudaStream_t st) {
+	SphComm *m = h->comm;
+	if (!m || n == 0) return;
+	g_nccl.AllReduce(dev, dev, n, ncclFloat, ncclSum, m->comm, st);
+}
+
+// Two reference quirks index FLUID arrays with a rigid-local index k < Nr: the neighbour count measures the
+// distance to fluid particle k (PS:440-442, SURVEY B-7) and the viscosity uses its rho (SB:199, B-6).  With
+// slabs fluid particle k (a GLOBAL id) lives on some rank: its owner writes (pos, rho) into slot k of a zeroed
+// array and one all-reduce replicates the Nr records (x + 0 is exact, so every rank sees the owner's bits).
+__global__ void __launch_bounds__(256)
+k_mg_quirk_fill(const float4 *__restrict__ pos, const int *__restrict__ gid, const int *__restrict__ slot_of,
+                const float *__restrict__ rho, int n_owned, int nr, int with_rho, float4 *__restrict__ quirk) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_owned) return;
+	int g = gid[i];
+	if (g >= nr) return;
+	float4 p = pos[i];
+	quirk[g] = make_float4(p.x, p.y, p.z, with_rho ? rho[slot_of[i]] : 0.0f);
+}
+const float4 *mg_rigid_quirk(const SphHandle *h) { return (h->comm && h->c.Nr > 0) ? h->comm->quirk : nullptr; }
+void mg_rigid_quirk_update(SphHandle *h, int with_rho, cudaStream_t st) {
+	SphComm *m = h->comm;
+	if (!m || h->c.Nr <= 0) return;
+	cudaMemsetAsync(m->quirk, 0, sizeof(float4) * (size_t)h->c.Nr, st);
+	if (h->c.N_owned > 0)
+		k_mg_quirk_fill<<<cdiv(h->c.N_owned, 256), 256, 0, st>>>(h->pos, h->gid, h->fg.slot_of, h->a1[A1_RHO], h->c.N_owned,
+		                                                         h->c.Nr, with_rho, m->quirk);
+	g_nccl.AllReduce(m->quirk, m->quirk, 4 * (size_t)h->c.Nr, ncclFloat, ncclSum, m->comm, st);
+	h->launches++;
 }
 
 extern "C" int sph_comm_info(SphHandle *h, int32_t *out8) {

@@ -126,6 +126,7 @@ k_rigid_lists(SphConsts c, const float4 *__restrict__ rspos, const int *__restri
 	SPH_FOR_27(c, cx, cy, cz, c1) {
 		int a = cstart[c1], b = cstart[c1 + 1];
 		for (int e = a; e < b; ++e) {
+			if (sorted_id[e] >= c.N_owned) continue; // slabs: ghost copies push on their owner's rank
 			Pair p = make_pair(spos[e], pr);
 			if (culled(p, c)) continue;
 			if (n < cap) {
@@ -464,6 +465,9 @@ void rigid_step(SphHandle *h, cudaStream_t st) {
 		c.clamp_lo[k] = (float)(h->cfg.box_min[k] + h->cfg.particle_radius * 2);
 		c.clamp_hi[k] = (float)(h->cfg.box_max[k] - h->cfg.particle_radius * 2);
 	}
+	// slabs: every rank gathered the forces of its OWNED fluid particles; the body is replicated, so the sum over
+	// ranks goes to every rank and each integrates the identical state
+	mg_allreduce_sum_f32(h, (float *)h->rforce, 4 * (size_t)c.Nr, st);
 	sph_prof_begin(h, KC_RIGID, st);
 	k_rigid_step<<<1, RB_THREADS, 0, st>>>(c, h->rpos, h->rvel, h->rforce, h->rverts, (int)h->n_rverts, h->rstate, h->ctl);
 	sph_prof_end(h, st);

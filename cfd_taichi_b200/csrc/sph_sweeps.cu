@@ -60,6 +60,8 @@ static inline SphRigidArgs rigid_args(const SphHandle *h) {
 	a.st = h->rstate;
 	a.pos_orig = h->pos;
 	a.slot_of = h->fg.slot_of;
+	a.quirk = mg_rigid_quirk(h);
+	a.gid = a.quirk ? h->gid : nullptr;
 	a.active = (h->c.Nr > 0 && h->c.active_rigid && h->rigid_ready) ? 1 : 0;
 	return a;
 }
@@ -178,7 +180,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		// ---- phase 1: the 27-cell traversal only culls and appends (a 15 % hit rate would otherwise run
 		// ---- the kernel-function arithmetic at 15 % lane utilisation on every candidate) -----------------
 		int ncount = 0; // get_neighbour_count (PS:424-445)
-		int i_orig = RIGID ? sorted_id[s] : 0;
+		int i_orig = RIGID ? (rg.gid ? rg.gid[sorted_id[s]] : sorted_id[s]) : 0; // the reference compares GLOBAL indices
 		if (!RIGID) {
 			// append cursors: the word of entry n+1 is 1 further, 125 further after a quad (sph_list_word)
 			uint32_t *fcur = &SPH_FLW(0), *bcur = &SPH_BLW(0);
@@ -253,7 +255,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 					// distance to the FLUID particle with that index (SURVEY B-7)
 					int k = rg.rsorted_id[e];
 					if (k != i_orig) {
-						Pair q = make_pair(pi, rg.pos_orig[min(k, c.N_owned - 1)]);
+						Pair q = make_pair(pi, rg.quirk ? rg.quirk[k] : rg.pos_orig[min(k, c.N_owned - 1)]);
 						if (!culled(q, c)) ncount++;
 					}
 					Pair p = make_pair(pi, rg.rspos[e]);
@@ -372,6 +374,7 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 	sph_prof_end(h, st);
 	h->launches++;
 	h->lists_valid = true;
+	if (rg.active) mg_rigid_quirk_update(h, 1, st); // slabs: rho of the quirk particles is known now
 }
 
 // list walkers ---------------------------------------------------------------------------------
@@ -742,7 +745,8 @@ __device__ __forceinline__ void rigid_viscosity(const SphConsts &c, const SphRig
 		float q = sqrtf(p.r2);
 		float q2 = q * q;
 		int jr = min(rg.rsorted_id[r], c.N_owned - 1);
-		float nu = c.visc_num / (rho_i + rho[rg.slot_of[jr]]);
+		float rho_q = rg.quirk ? rg.quirk[rg.rsorted_id[r]].w : rho[rg.slot_of[jr]];
+		float nu = c.visc_num / (rho_i + rho_q);
 		float pi_ij = ((-nu) * shear) / (q2 + c.visc_eps_h2);
 		visc = visc + ((-SPH_RHO0 * pj.w) * pi_ij) * cubic_dw(p, c); // SB:201
 	}

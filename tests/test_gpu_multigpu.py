@@ -37,3 +37,15 @@ def test_two_slabs_other_solvers_match_single_domain(built, solver):
     line = [l for l in r.stdout.splitlines() if l.startswith("MGRESULT")]
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     assert line and "perm_ok=True" in line[0] and "iters_ok=True" in line[0] and "exact=True" in line[0]
+
+
+@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_slabs_with_rigid_body(built):
+    # replicated rigid body, fluid->rigid forces as partial sums + one all-reduce per rigid step:
+    # every rank integrates the identical body state; fluid and body agree with the single-domain run to tolerance
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "tests", "mg_worker_rigid.py"), "40"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    line = [l for l in r.stdout.splitlines() if l.startswith("MGRIGID")]
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    assert line and "perm_ok=True" in line[0] and "replicas_identical=True" in line[0]
