@@ -436,7 +436,6 @@ static int mg_open_windows(SphHandle *h, SphComm *m) {
 extern "C" int sph_comm_init(SphHandle *h, const char *id128, int rank, int nranks, int col_lo, int col_hi) {
 	if (!h || !id128) return SPH_EINVAL;
 	if (nranks < 2 || rank < 0 || rank >= nranks) return sph_fail(h, SPH_EINVAL, "sph_comm_init: bad rank %d / %d", rank, nranks);
-	if (h->c.solver == SPH_SOLVER_PBF) return sph_fail(h, SPH_EINVAL, "multi-GPU slabs are not built for the PBF solver");
 	if (h->cfg.n_ghost_capacity <= 0) return sph_fail(h, SPH_EINVAL, "sph_comm_init: create the handle with n_ghost_capacity > 0");
 	if (!h->gid) return sph_fail(h, SPH_ENOTBOUND, "sph_comm_init: bind SPH_F_FLUID_GID first");
 	int rc = nccl_load(h);

@@ -175,6 +175,8 @@ k_pbf_xsph(SphConsts c, const int *__restrict__ scell, const int *__restrict__ c
 	float4 pi = new_pos[s];
 	float4 vi4 = svel[s];
 	f3 vi = xyz(vi4);
+	int i = sorted_id[s];
+	if (i >= c.N_owned) return; // ghost copy (multi-GPU slabs): moved and corrected on its owner's rank
 	int cx, cy, cz;
 	cell_xyz(scell[s], c, cx, cy, cz);
 	f3 acc = F3(0.0f, 0.0f, 0.0f);
@@ -187,7 +189,6 @@ k_pbf_xsph(SphConsts c, const int *__restrict__ scell, const int *__restrict__ c
 			acc = acc + (xyz(svel[e]) - vi) * poly_w(sqrtf(p.r2), c.h); // PBF:99
 		}
 	}
-	int i = sorted_id[s];
 	pos[i] = make_float4(pi.x, pi.y, pi.z, 0.0f);   // PBF:84
 	vel[i] = F4(vi + PBF_C * acc, vi4.w);           // PBF:94-96 (the boundary sum PBF:91-92 is computed but unused)
 }
@@ -208,6 +209,7 @@ void pbf_phase(SphHandle *h, int phase, cudaStream_t st) {
 		                                       h->a4[A4_FA], h->a4[A4_T1]);
 		sph_prof_end(h, st);
 		h->launches++;
+		mg_exchange(h, MG_F4_T1W, st); // slabs: lambda of the ghost particles
 	} else if (phase == SPH_PH_PBF_DELTA_POS) {
 		float r_corr = (float)(0.3 * (4.0 * h->cfg.particle_radius)); // PBF:20, 166: s_corr_factor * kernel_h in Python scope
 		sph_prof_begin(h, KC_OTHER, st);
@@ -223,6 +225,8 @@ void pbf_phase(SphHandle *h, int phase, cudaStream_t st) {
 		sph_prof_begin(h, KC_OTHER, st);
 		k_pbf_move<<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], pos_predict, h->a4[A4_FB], new_pos, h->a4[A4_VEL], lo[0], lo[1],
 		                                     lo[2], hi[0], hi[1], hi[2], h->ctl);
+		mg_exchange(h, MG_XYZ(A4_T3), st); // slabs: moved positions and un-corrected velocities of the ghost particles
+		mg_exchange(h, MG_F4_VEL, st);
 		k_pbf_xsph<<<nb, SPH_BLOCK, 0, st>>>(c, h->fg.scell, h->fg.cell_start, h->fg.sorted_id, new_pos, h->a4[A4_VEL], h->pos,
 		                                     h->vel);
 		sph_prof_end(h, st);

@@ -29,7 +29,7 @@ def test_two_slabs_match_single_domain(built, mode):
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("solver", ["wcsph", "pcisph", "iisph"])
+@pytest.mark.parametrize("solver", ["wcsph", "pcisph", "iisph", "pbf"])
 def test_two_slabs_other_solvers_match_single_domain(built, solver):
     # WCSPH: one ghost-density exchange per step.  PCISPH: ghost density, then per pressure iteration the ghosts'
     # pressure and predicted position plus the residual all-reduce.  Bit-identical to the single-domain run.
