@@ -396,10 +396,7 @@ class ParticleSystem:
 
     def get_max_neighbor_particle_index(self):                                      # PS:409-422
         cnt = self.neighbour_counts().cpu().numpy()
-        # one-thread semantics of the racy arg-max: atomic_max returns the OLD maximum
-        run = np.maximum.accumulate(np.concatenate([[-1], cnt[:-1]]))
-        hit = np.nonzero(run == cnt)[0]
-        max_index = int(hit[-1]) if hit.size else -1
+        max_index = slab_plan.racy_argmax(cnt)      # one-thread semantics of the racy arg-max
         print('max_index is {}, length is {}'.format(max_index, int(cnt.max()) if cnt.size else -1))
         return max_index
 

@@ -45,7 +45,6 @@ class pcisph_solver(solver_base):
     def _pre_compute_slab(self):
         """x-slabs: the arg-max particle of the GLOBAL domain (PS:409-422 over all ranks' counts, by global
         particle id) decides; its owner computes delta and every rank takes that value."""
-        import numpy as np
         import torch
         import torch.distributed as dist
         ps = self.ps
@@ -60,20 +59,12 @@ class pcisph_solver(solver_base):
         pad[0, :n], pad[1, :n] = gid, cnt
         parts = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(parts, pad)
-        total = ps.particle_num
-        glob = np.zeros(total, dtype=np.int64)
-        owner = np.zeros(total, dtype=np.int64)
-        for r, (part, sz) in enumerate(zip(parts, sizes)):
-            k = int(sz.item())
-            g = part[0, :k].cpu().numpy()
-            glob[g] = part[1, :k].cpu().numpy()
-            owner[g] = r
-        run = np.maximum.accumulate(np.concatenate([[-1], glob[:-1]]))   # PS:409-422, one-thread semantics
-        hit = np.nonzero(run == glob)[0]
-        max_index = int(hit[-1]) if hit.size else -1
+        from . import slab as slab_plan
+        max_index, src = slab_plan.global_argmax(
+            ps.particle_num, [(part[0, :int(sz.item())].cpu().numpy(), part[1, :int(sz.item())].cpu().numpy())
+                              for part, sz in zip(parts, sizes)])
         delta = torch.zeros(1, dtype=torch.float32, device=cnt.device)
         if max_index >= 0:
-            src = int(owner[max_index])
             if src == dist.get_rank():
                 local = int(torch.nonzero(gid == max_index)[0].item())
                 _lib.check(self._lib.sph_pcisph_delta(ps._h, local, ps._stream()), ps._h)

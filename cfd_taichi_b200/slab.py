@@ -69,3 +69,27 @@ def capacities(config, cuts, rank):
     owned_cap = int(math.ceil(owned0 * 1.5)) + 4 * col_max + 65536
     ghost_cap = 2 * (3 * col_max + 16384)
     return owned0, owned_cap, ghost_cap
+
+
+def racy_argmax(counts):
+    """get_max_neighbor_particle_index (PS:409-422) with ti.cpu / one thread: atomic_max returns the OLD
+    maximum, so the winner is the LAST index whose count equals the running maximum of the counts before it."""
+    counts = np.asarray(counts, dtype=np.int64)
+    if counts.size == 0:
+        return -1
+    run = np.maximum.accumulate(np.concatenate([[-1], counts[:-1]]))
+    hit = np.nonzero(run == counts)[0]
+    return int(hit[-1]) if hit.size else -1
+
+
+def global_argmax(total, parts):
+    """The same decision for a slab-decomposed domain.  `parts` = one (gids, counts) pair per rank (owned
+    particles only).  Returns (global index of the winner, rank that owns it); (-1, -1) for an empty domain."""
+    glob = np.zeros(total, dtype=np.int64)
+    owner = np.full(total, -1, dtype=np.int64)
+    for r, (g, c) in enumerate(parts):
+        g = np.asarray(g, dtype=np.int64)
+        glob[g] = np.asarray(c, dtype=np.int64)
+        owner[g] = r
+    k = racy_argmax(glob)
+    return (k, int(owner[k])) if k >= 0 else (-1, -1)

@@ -146,3 +146,22 @@ def test_ghost_layer_protocol_world_size_2_gloo():
         p.join(timeout=180)
         assert p.exitcode == 0
     assert ret.get() is True
+
+
+def test_global_argmax_equals_single_domain():
+    # PCISPH picks its delta particle with the reference's racy arg-max (PS:409-422); over slabs the decision
+    # is taken on the merged counts and must name the same GLOBAL particle, whoever owns it
+    from cfd_taichi_b200 import slab
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        n = int(rng.integers(1, 400))
+        counts = rng.integers(0, 6, size=n)
+        want = slab.racy_argmax(counts)
+        perm = rng.permutation(n)
+        cut = sorted(rng.integers(0, n + 1, size=2))
+        ranks = [perm[:cut[0]], perm[cut[0]:cut[1]], perm[cut[1]:]]
+        k, owner = slab.global_argmax(n, [(g, counts[g]) for g in ranks])
+        assert k == want and (k == -1 or k in set(ranks[owner].tolist()))
+    assert slab.racy_argmax([]) == -1 and slab.global_argmax(0, []) == (-1, -1)
+    # one-thread semantics: atomic_max returns the old maximum, so only a REPEATED maximum registers
+    assert slab.racy_argmax([3, 1, 3, 2, 3]) == 4 and slab.racy_argmax([1, 2, 3]) == -1
