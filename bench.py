@@ -51,37 +51,73 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks and throttle reasons during the timed region: NVML in-process every 5 ms
+    (nvidia-ml-py), falling back to the nvidia-smi query of the profiling recipe (one sample per ~50 ms)."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []        # (sm_mhz, [bool x 4])
+        self.sm_max = None
+        self.source = None
         self.stop_flag = False
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as N
+        N.nvmlInit()
+        # CUDA_VISIBLE_DEVICES may renumber the devices: address the GPU by its PCI bus id
+        import torch
+        bus = torch.cuda.get_device_properties(self.index).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(self.index), "pci_bus_id") else None
+        hnd = None
+        if bus is not None:
+            for k in range(N.nvmlDeviceGetCount()):
+                h = N.nvmlDeviceGetHandleByIndex(k)
+                if int(N.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                    hnd = h
+                    break
+        if hnd is None:
+            hnd = N.nvmlDeviceGetHandleByIndex(self.index)
+        self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(hnd, N.NVML_CLOCK_SM))
+        bits = [N.nvmlClocksEventReasonHwSlowdown, N.nvmlClocksEventReasonHwThermalSlowdown,
+                N.nvmlClocksEventReasonSwThermalSlowdown, N.nvmlClocksEventReasonSwPowerCap]
+        self.source = "nvml"
+        while not self.stop_flag:
+            r = N.nvmlDeviceGetCurrentClocksEventReasons(hnd)
+            self.samples.append((float(N.nvmlDeviceGetClockInfo(hnd, N.NVML_CLOCK_SM)), [bool(r & b) for b in bits]))
+            time.sleep(0.005)
+
+    def _run_smi(self):
+        self.source = "nvidia-smi"
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [x.strip() for x in out.strip().split(",")]
                 if len(parts) >= 6:
-                    self.samples.append(parts)
+                    self.sm_max = float(parts[1])
+                    self.samples.append((float(parts[0]), [p.lower().startswith("active") for p in parts[2:6]]))
             except Exception:
                 pass
             time.sleep(0.05)
 
+    def run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
+
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [n for k, n in enumerate(self.NAMES) if any(s[1][k] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(self.samples), "source": self.source}
 
 
 def workload_name(n_side, n_gpus):
