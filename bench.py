@@ -7,11 +7,14 @@
 A "step" is one dfsph_solver.step() (grid build + neighbour lists + divergence-free solve +
 non-pressure forces + constant-density solve + advection) over the whole particle block.
 N = 1: BASELINE.json configs[1], 1 M particles (100^3) in a 15 x 8 x 5.2 box.
-N > 1: configs[4], the dam is slab-decomposed along x, 1 M... particles per GPU (weak scaling).
+N > 1: configs[4], the dam is slab-decomposed along x, --n-side^3 particles per GPU (weak scaling; default
+1 M per GPU, --n-side 200 = 8 M per GPU).
 
-Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
-synchronize on both sides, max over ranks.  Per-step working set (neighbour lists 128 MB + 11
-float4 arrays) exceeds the 126 MB L2, so no explicit flush is needed between steps.
+Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier + synchronize on both
+sides, max over ranks.  Three passes over the same K steps from one saved post-warm-up state: un-instrumented
+(value), with an event pair around every launch (kernel_ms, roofline), end to end with host buffers (e2e).
+Per-step working set (neighbour lists ~140 MB, gradient cache ~540 MB, 11 float4 arrays) exceeds the 126 MB
+L2, so no explicit flush is needed between steps.
 """
 import argparse
 import ctypes
@@ -315,10 +318,11 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.n_side, world), "particles_total": total_particles,
                        "kernels": "strict-fp32" if args.strict else "fast-fp32",
-                       "l2": "per-step working set ~300 MB > 126 MB L2, no flush",
+                       "l2": "per-step working set ~900 MB > 126 MB L2, no flush",
                        "iterations": {"divergence": st_timed.div_iters, "density": st_timed.den_iters, "of": "last timed step"},
                        "parallelism": "1 GPU" if world == 1 else
-                       "%d x-slabs, NCCL halo exchange + migration + loop all-reduces" % world},
+                       "%d x-slabs; per-sweep ghost values and loop partials over CUDA-IPC peer windows (NVLink), "
+                       "NCCL for migration / ghost particles" % world},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_dir, "d2h_bytes_per_step": bytes_dir,
                     "steps": e2e_steps},
