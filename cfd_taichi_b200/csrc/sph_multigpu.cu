@@ -294,6 +294,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ uint4 wait_slot(const void *p, int epoch, SphCtl *ctl) {
 	uint4 v = ld_slot(p);
 	if ((int)v.w == epoch) return v;
+	// a peer that already timed out once is gone: do not wait 10 s per slot and exchange for the rest of the run
+	if (*(volatile int *)&ctl->error_flags & SPH_ERR_COMM_TIMEOUT) return v;
 	unsigned long long t0 = global_ns();
 	for (;;) {
 		v = ld_slot(p);
@@ -550,6 +552,8 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 	sph_prof_end(h, st);
 	SPH_CUDA_CHECK(h, cudaStreamSynchronize(st));
 	const int *k = m->counters_host;
+	if (h->ctl_host && (h->ctl_host->error_flags & SPH_ERR_COMM_TIMEOUT))
+		return sph_fail(h, SPH_ESTATE, "multi-GPU: a peer rank stopped answering (exchange timed out after 10 s)");
 	if (k[MC_OVERFLOW]) return sph_fail(h, SPH_ESTATE, "multi-GPU: message or slab capacity exceeded (flags %d)", k[MC_OVERFLOW]);
 	h->c.N_owned = k[MC_OWNED];
 	h->c.N = k[MC_OWNED] + k[MC_GHOST_L] + k[MC_GHOST_R];
