@@ -604,6 +604,18 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
 	if (live) { pi = posT1[s]; vi = svel[s]; rho_i = rho[s]; }
 	float k_i = vi.w / dt; // DF:333, 342, 353
 	f3 va = F3(0.0f, 0.0f, 0.0f);
+#if SPH_STRICT
+	// strict kernels: IEEE sqrt / division make the gradient the costly part, so every DFSPH sweep reads it
+	// from the per-pair cache (bit-identical to a recomputation) and gathers only the neighbour's payload
+	walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * dw; // DF:345
+			return;
+		}
+		va = va + (c.m * (pi.w + __ldg(&posT1[j]).w)) * dw; // DF:337
+	});
+#else
 	SPH_FOR_FLUID_N(L, c, s, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
@@ -615,6 +627,7 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
 		Pair p = make_pair(pi, pj);
 		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:337
 	};
+#endif
 	f3 vb = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
 		SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
@@ -702,6 +715,17 @@ k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 	if (live) { pi = posT2[s]; da = drho[s] * alpha[s]; rho_i = rho[s]; }
 	float k_i = da / dt; // DF:363, 374, 388
 	f3 va = F3(0.0f, 0.0f, 0.0f);
+#if SPH_STRICT
+	walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * dw; // DF:377
+			return;
+		}
+		float f = pi.w + __ldg(&posT2[j]).w;
+		if (f > 1e-5f) va = va + (c.m * f) * dw; // DF:367-369
+	});
+#else
 	SPH_FOR_FLUID_N(L, c, s, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
@@ -715,6 +739,7 @@ k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 		f3 dw = cubic_dw(p, c);
 		if (f > 1e-5f) va = va + (c.m * f) * dw; // DF:367-369 (a select instead of the branch measured 4 us slower)
 	};
+#endif
 	f3 vb = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
 		SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
@@ -867,6 +892,16 @@ k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__rest
 		k_i = ((rho_adv[s] - SPH_RHO0) * alpha[s]) / dt2; // DF:199, 208, 217
 	}
 	f3 va = F3(0.0f, 0.0f, 0.0f);
+#if SPH_STRICT
+	walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+		if (SPH_IS_RIGID(j)) {
+			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
+			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * dw; // DF:211
+			return;
+		}
+		va = va + (c.m * (pi.w + __ldg(&posT3[j]).w)) * dw; // DF:203
+	});
+#else
 	SPH_FOR_FLUID_N(L, c, s, nf_, j) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
@@ -878,6 +913,7 @@ k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__rest
 		Pair p = make_pair(pi, pj);
 		va = va + (c.m * (pi.w + pj.w)) * cubic_dw(p, c); // DF:203
 	};
+#endif
 	f3 vb = F3(0.0f, 0.0f, 0.0f);
 	if (c.boundary_handle == 1) {
 		SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
