@@ -75,6 +75,10 @@ def lib():
         L.orc_cubic_kernel.restype = ctypes.c_float
         L.orc_cubic_kernel_derivative.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_float,
                                                   ctypes.POINTER(ctypes.c_float)]
+        L.orc_poly_kernel.argtypes = [ctypes.c_float, ctypes.c_float]
+        L.orc_poly_kernel.restype = ctypes.c_float
+        L.orc_spiky_kernel_derivative.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_float,
+                                                  ctypes.POINTER(ctypes.c_float)]
         L.orc_cull_threshold.argtypes = [ctypes.c_float]
         L.orc_cull_threshold.restype = ctypes.c_float
         _lib = L
@@ -188,6 +192,17 @@ def cubic_kernel_derivative(r, h):
     a = (ctypes.c_float * 3)(*[float(x) for x in r])
     o = (ctypes.c_float * 3)()
     lib().orc_cubic_kernel_derivative(a, float(h), o)
+    return np.array([o[0], o[1], o[2]], dtype=np.float32)
+
+
+def poly_kernel(r, h):
+    return lib().orc_poly_kernel(float(r), float(h))
+
+
+def spiky_kernel_derivative(r, h):
+    a = (ctypes.c_float * 3)(*[float(x) for x in r])
+    o = (ctypes.c_float * 3)()
+    lib().orc_spiky_kernel_derivative(a, float(h), o)
     return np.array([o[0], o[1], o[2]], dtype=np.float32)
 
 

@@ -201,6 +201,11 @@ static inline float poly_kernel(float r, float h) {
 }
 
 float orc_cubic_kernel(float r, float h) { return cubic_kernel(r, h); }
+float orc_poly_kernel(float r, float h) { return poly_kernel(r, h); }
+void orc_spiky_kernel_derivative(const float r[3], float h, float out[3]) {
+	v3 g = spiky_dw(V3(r[0], r[1], r[2]), h);
+	out[0] = g.x; out[1] = g.y; out[2] = g.z;
+}
 void orc_cubic_kernel_derivative(const float r[3], float h, float out[3]) {
 	st3(out, cubic_dw(ld3(r), h));
 }

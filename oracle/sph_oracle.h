@@ -70,6 +70,8 @@ void orc_set_scalar(OrcSim *s, const char *name, double v);
 /* Standalone kernel functions (known-answer tests). */
 float orc_cubic_kernel(float r, float h);
 void orc_cubic_kernel_derivative(const float r[3], float h, float out[3]);
+float orc_poly_kernel(float r, float h);                                        /* SB:122-129 */
+void orc_spiky_kernel_derivative(const float r[3], float h, float out[3]);      /* SB:113-120 */
 /* Largest float t such that sqrtf(t) <= h (the sqrt-free cull threshold). */
 float orc_cull_threshold(float h);
 

@@ -229,3 +229,20 @@ def test_pbf_update_order_modes():
     assert np.array_equal(out[0][0], out[1][0])                         # positions of one step: identical
     dv = np.abs(out[0][1] - out[1][1]).max()
     assert 0.0 < dv < 0.2 * np.abs(out[0][1]).max()
+
+
+def test_pbf_kernel_known_answers():
+    h = 0.1
+    # SB:122-129 poly6: W(0) = 315 / (64 pi h^3), W(h) = 0, unit integral over the support
+    assert abs(O.poly_kernel(0.0, h) - 315.0 / (64.0 * math.pi * h ** 3)) <= 1e-3
+    assert O.poly_kernel(h, h) == 0.0 and O.poly_kernel(1.5 * h, h) == 0.0
+    r = (np.arange(4000) + 0.5) * (h / 4000)
+    integral = sum(O.poly_kernel(x, h) * 4.0 * math.pi * x * x for x in r) * (h / 4000)
+    assert abs(integral - 1.0) <= 2e-3
+    # SB:113-120 spiky gradient: -45 (1 - q)^2 / (pi h^4) along r, zero at r = 0 and beyond the support
+    g = O.spiky_kernel_derivative([0.05, 0.0, 0.0], h)
+    assert abs(g[0] - (-45.0 * 0.25 / (math.pi * h ** 4))) <= 1e-3 * abs(g[0]) and g[1] == 0.0 and g[2] == 0.0
+    assert not O.spiky_kernel_derivative([0.0, 0.0, 0.0], h).any()
+    assert not O.spiky_kernel_derivative([0.0, 0.11, 0.0], h).any()
+    d = O.spiky_kernel_derivative([0.03, -0.04, 0.0], h)              # |r| = 0.05: same magnitude, direction r / |r|
+    assert abs(np.linalg.norm(d) - abs(g[0])) <= 1e-3 * abs(g[0]) and d[0] < 0 < d[1]
