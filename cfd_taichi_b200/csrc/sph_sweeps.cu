@@ -4,8 +4,9 @@
 // Design: positions are frozen inside a solver step (they change only in the
 // final integrate kernel: DF:238, PC:206, II:191, WC:52), so the 27-cell traversal with its exact
 // distance cull (PS:447-469, 337-366) is done ONCE per step by k_build_lists, which emits compact
-// per-particle neighbour lists in the reference's canonical visiting order.  Every later sweep
-// walks those lists: one coalesced index load and one float4 gather per neighbour.  Quantities a
+// per-particle neighbour lists (strict kernels: the reference's canonical visiting order; fast kernels:
+// address order) and, for DFSPH, the per-pair gradient cache.  Every later sweep walks those lists: one
+// coalesced 128-bit load of four indices and one float4 gather per neighbour.  Quantities a
 // neighbour contributes as a single scalar (k_j/rho_j, p_j/rho_j^2 ...) are pre-divided by their
 // producer kernel and ride in the .w lane of a position copy, so one 16-byte gather per pair
 // brings everything.  No per-pair atomics anywhere; reductions are warp-shuffle + one smem hop.
