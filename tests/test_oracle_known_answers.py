@@ -246,3 +246,58 @@ def test_pbf_kernel_known_answers():
     assert not O.spiky_kernel_derivative([0.0, 0.11, 0.0], h).any()
     d = O.spiky_kernel_derivative([0.03, -0.04, 0.0], h)              # |r| = 0.05: same magnitude, direction r / |r|
     assert abs(np.linalg.norm(d) - abs(g[0])) <= 1e-3 * abs(g[0]) and d[0] < 0 < d[1]
+
+
+def _cubic_dw64(r, h):
+    """SB:90-103 in float64, including the reference's extra factor 6."""
+    rn = np.linalg.norm(r, axis=-1, keepdims=True)
+    q = rn / h
+    k = 48.0 / (np.pi * h ** 3)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a = k * 6 * (3 * q * q - 2 * q) * r / (h * rn)
+        b = -k * 6 * (1 - q) ** 2 * r / (h * rn)
+    return np.where((q > 1e-5) & (q <= 0.5), a, np.where((q > 0.5) & (q <= 1.0), b, 0.0))
+
+
+def test_dfsph_alpha_and_drho_against_float64_brute_force():
+    # independent restatement of DF:32-89 (alpha) and DF:252-300 (D rho / D t) in numpy float64, all pairs,
+    # on a jittered block with random velocities; the fp32 oracle must agree to fp32 accuracy
+    cfg = scenes.shipped("small_block", "dfsph")
+    o = O.Oracle(cfg, solver="dfsph", threads=4)
+    rng = np.random.default_rng(2)
+    o.field("pos")[:] += rng.uniform(-0.006, 0.006, o.field("pos").shape).astype(np.float32)
+    o.field("vel")[:] = rng.normal(0, 1.0, o.field("vel").shape).astype(np.float32)
+    o.base_step()
+    o.phase("initialize")                      # rho, alpha
+    o.phase("derivative_iter_all_rho")         # rho_derivative (+ neighbour counts)
+    pos, vel = o.field("pos").astype(np.float64), o.field("vel").astype(np.float64)
+    bpos, bvol = o.field("bpos").astype(np.float64), o.field("bvol").astype(np.float64)
+    h, m = 0.1, 1000 * 0.025 ** 3 * 8
+    h32 = float(np.float32(h))
+    rho, alpha, drho, cnt = o.field("rho"), o.field("alpha"), o.field("rho_derivative"), o.field("nbr_count")
+    checked = 0
+    for i in rng.choice(len(pos), size=40, replace=False):
+        r = pos[i] - pos
+        d = np.linalg.norm(r, axis=1)
+        nb = (d <= h32 * (1 + 1e-6)) & (np.arange(len(pos)) != i)
+        if np.any(np.abs(d[nb] - h32) < 2e-6) or np.any(np.abs(np.linalg.norm(pos[i] - bpos, axis=1) - h32) < 2e-6):
+            continue                            # a pair on the cut-off shell: fp32 and fp64 may disagree on membership
+        g = m * _cubic_dw64(r[nb], h)
+        rb = pos[i] - bpos
+        nbb = np.linalg.norm(rb, axis=1) <= h32
+        gb = (bvol[nbb, None] * 1000.0) * _cubic_dw64(rb[nbb], h)
+        den = g.sum(0) @ g.sum(0) + (g * g).sum() + (gb * gb).sum() + gb.sum(0) @ gb.sum(0)      # DF:45
+        want_alpha = 0.0 if abs(den) < 1e-6 else rho[i] / den
+        assert abs(alpha[i] - want_alpha) <= 2e-4 * abs(want_alpha) + 1e-12, (i, alpha[i], want_alpha)
+        assert cnt[i] == nb.sum()
+        if cnt[i] >= 20:                                                                          # DF:258-261
+            dr = m * ((vel[i] - vel[nb]) * _cubic_dw64(r[nb], h)).sum() + 1000.0 * (
+                bvol[nbb] * (_cubic_dw64(rb[nbb], h) @ vel[i])).sum()                             # DF:287, 300, 267
+            want = max(dr, 0.0)
+            scale = m * np.abs((vel[i] - vel[nb]) * _cubic_dw64(r[nb], h)).sum() + 1.0
+            assert abs(drho[i] - want) <= 2e-5 * scale, (i, drho[i], want)
+        else:
+            assert drho[i] == 0.0
+        checked += 1
+    assert checked >= 25
+    o.close()
