@@ -301,3 +301,148 @@ def test_dfsph_alpha_and_drho_against_float64_brute_force():
         checked += 1
     assert checked >= 25
     o.close()
+
+
+def _cubic_w64(r, h):
+    """SB:74-88 in float64."""
+    q = r / h
+    k = 8.0 / (np.pi * h ** 3)
+    return np.where(q <= 0.5, k * (6 * (q ** 3 - q ** 2) + 1), np.where(q <= 1.0, 2 * k * (1 - q) ** 3, 0.0))
+
+
+def test_wcsph_pressure_phase_against_float64_brute_force():
+    # independent restatement of WC:65-129 (Tait pressure, symmetric pressure gradient, Akinci boundary term) and of
+    # SB:41-72 (density) in numpy float64 over all pairs, on a compressed block so that pressures are non-zero
+    cfg = scenes.shipped("small_block", "wcsph")
+    o = O.Oracle(cfg, solver="wcsph", threads=4)
+    rng = np.random.default_rng(4)
+    pos = o.field("pos").astype(np.float64)
+    c = pos.mean(axis=0, keepdims=True)
+    o.field("pos")[:] = (c + (pos - c) * 0.85 + rng.uniform(-0.003, 0.003, pos.shape)).astype(np.float32)   # rest rho is ~690
+    o.base_step()
+    o.phase("pressure_phase")
+    pos = o.field("pos").astype(np.float64)
+    bpos, bvol = o.field("bpos").astype(np.float64), o.field("bvol").astype(np.float64)
+    h, m = 0.1, 1000 * 0.025 ** 3 * 8
+    h32 = float(np.float32(h))
+    rho, p = o.field("rho").astype(np.float64), o.field("pressure").astype(np.float64)
+    pg, ba = o.field("pressure_gradient"), o.field("boundary_acc")
+    assert (p > 0).sum() > 1000
+    # Tait equation for every particle (WC:86-90)
+    want_p = 70000.0 * ((np.maximum(rho, 1000.0) / 1000.0) ** 7 - 1.0)
+    assert np.allclose(p, want_p, rtol=2e-5, atol=0.05)
+    checked = 0
+    for i in rng.choice(len(pos), size=40, replace=False):
+        r = pos[i] - pos
+        d = np.linalg.norm(r, axis=1)
+        nb = (d <= h32) & (np.arange(len(pos)) != i)
+        db = np.linalg.norm(pos[i] - bpos, axis=1)
+        if np.any(np.abs(d[nb] - h32) < 2e-6) or np.any(np.abs(db - h32) < 2e-6):
+            continue
+        nbb = db <= h32
+        want_rho = 0.001 + m * _cubic_w64(d[nb], h).sum() + 1000.0 * (bvol[nbb] * _cubic_w64(db[nbb], h)).sum()   # SB:44-49
+        assert abs(rho[i] - want_rho) <= 1e-5 * want_rho
+        dw = _cubic_dw64(r[nb], h)
+        want_pg = -(m * (p[i] / rho[i] ** 2 + p[nb] / rho[nb] ** 2)[:, None] * dw).sum(0)                          # WC:116
+        scale = np.abs(m * (p[i] / rho[i] ** 2 + p[nb] / rho[nb] ** 2)[:, None] * dw).sum() + 1e-3
+        assert np.abs(pg[i] - want_pg).max() <= 2e-5 * scale, (i, pg[i], want_pg)
+        want_ba = -1000.0 * ((bvol[nbb] * p[i] / rho[i] ** 2)[:, None] * _cubic_dw64((pos[i] - bpos)[nbb], h)).sum(0)  # WC:83, 99
+        assert np.abs(ba[i] - want_ba).max() <= 2e-5 * (np.abs(want_ba).max() + 1e-3)
+        checked += 1
+    assert checked >= 25
+    o.close()
+
+
+def test_iisph_predict_advection_against_float64_brute_force():
+    # independent restatement of II:35-75 + the tasks II:255-340 (d_ii, rho_adv, a_ii) in numpy float64, all pairs
+    cfg = scenes.shipped("small_block", "iisph")
+    o = O.Oracle(cfg, solver="iisph", threads=4)
+    rng = np.random.default_rng(6)
+    o.field("pos")[:] += rng.uniform(-0.006, 0.006, o.field("pos").shape).astype(np.float32)
+    o.field("vel")[:] = rng.normal(0, 0.5, o.field("vel").shape).astype(np.float32)
+    o.base_step()
+    o.phase("ii_predict_advection")
+    pos = o.field("pos").astype(np.float64)
+    bpos, bvol = o.field("bpos").astype(np.float64), o.field("bvol").astype(np.float64)
+    h, m, dt = 0.1, 1000 * 0.025 ** 3 * 8, float(np.float32(o.scalar("delta_time")))
+    h32 = float(np.float32(h))
+    rho, v_adv = o.field("rho").astype(np.float64), o.field("v_adv").astype(np.float64)
+    d_ii, a_ii, rho_adv = o.field("d_ii"), o.field("a_ii"), o.field("rho_adv")
+    checked = 0
+    for i in rng.choice(len(pos), size=40, replace=False):
+        r = pos[i] - pos
+        d = np.linalg.norm(r, axis=1)
+        nb = (d <= h32) & (np.arange(len(pos)) != i)
+        rb = pos[i] - bpos
+        db = np.linalg.norm(rb, axis=1)
+        if np.any(np.abs(d[nb] - h32) < 2e-6) or np.any(np.abs(db - h32) < 2e-6):
+            continue
+        nbb = db <= h32
+        dw, dwb = _cubic_dw64(r[nb], h), _cubic_dw64(rb[nbb], h)
+        want_dii = ((-m / rho[i] ** 2) * dw.sum(0) + 1000.0 * ((-bvol[nbb] / rho[i] ** 2)[:, None] * dwb).sum(0)) * dt * dt  # II:53
+        sc = (np.abs((m / rho[i] ** 2) * dw).sum() + 1000.0 * np.abs((bvol[nbb] / rho[i] ** 2)[:, None] * dwb).sum()) * dt * dt
+        assert np.abs(d_ii[i] - want_dii).max() <= 2e-5 * sc + 1e-20, (i, d_ii[i], want_dii)
+        want_ra = (m * ((v_adv[i] - v_adv[nb]) * dw).sum() + 1000.0 * (bvol[nbb] * (dwb @ v_adv[i])).sum()) * dt + rho[i]     # II:63
+        assert abs(rho_adv[i] - want_ra) <= 2e-5 * abs(want_ra)
+        dji = (-dt * dt * m / rho[i] ** 2) * _cubic_dw64(-r[nb], h)                                                       # II:283-284
+        djib = (-dt * dt * m / rho[i] ** 2) * _cubic_dw64(-rb[nbb], h)
+        dii = d_ii[i].astype(np.float64)
+        want_aii = m * ((dii - dji) * dw).sum() + 1000.0 * (bvol[nbb] * ((dii - djib) * dwb).sum(1)).sum()                # II:73, 285, 303
+        sca = m * np.abs((dii - dji) * dw).sum() + 1000.0 * np.abs(bvol[nbb][:, None] * (dii - djib) * dwb).sum()
+        assert abs(a_ii[i] - want_aii) <= 3e-5 * sca + 1e-20, (i, a_ii[i], want_aii)
+        checked += 1
+    assert checked >= 25
+    o.close()
+
+
+def test_pcisph_delta_predicted_density_and_force_against_float64_brute_force():
+    # independent restatement of PC:39-45 (delta), PC:89-101 (predicted density, neighbour set from the CURRENT
+    # positions, kernel on the PREDICTED ones) and PC:109-119 (pressure force) in numpy float64, all pairs
+    cfg = scenes.shipped("small_block", "pcisph")
+    o = O.Oracle(cfg, solver="pcisph", threads=4)
+    pos0 = o.field("pos").astype(np.float64)
+    h, m = 0.1, 1000 * 0.025 ** 3 * 8
+    h32 = float(np.float32(h))
+    dt = float(np.float32(cfg["solver"]["delta_time"]))
+    k = int(o.scalar("pc_max_index"))
+    r = pos0[k] - pos0
+    d = np.linalg.norm(r, axis=1)
+    nb = (d <= h32 * (1 + 2e-6)) & (np.arange(len(pos0)) != k)           # the lattice has pairs exactly on the shell (W' = 0 there)
+    g = _cubic_dw64(r[nb], h)
+    beta = dt * dt * m * m * 2 / 1000.0 ** 2                             # PC:23
+    want_delta = 1.0 / ((g.sum(0) @ g.sum(0) + (g * g).sum()) * beta)     # PC:45
+    assert abs(o.scalar("pc_delta") - want_delta) <= 2e-4 * want_delta
+    # a compressed, jittered state so that the pressure loop runs
+    rng = np.random.default_rng(8)
+    c = pos0.mean(axis=0, keepdims=True)
+    o.field("pos")[:] = (c + (pos0 - c) * 0.86 + rng.uniform(-0.003, 0.003, pos0.shape)).astype(np.float32)
+    o.base_step()
+    o.phase("pc_compute_ext_force")
+    o.phase("pc_iteration")
+    assert int(o.scalar("pc_iters")) >= 1
+    pos, pp = o.field("pos").astype(np.float64), o.field("pos_predict").astype(np.float64)
+    bpos, bvol = o.field("bpos").astype(np.float64), o.field("bvol").astype(np.float64)
+    rho, press = o.field("rho").astype(np.float64), o.field("press_iter").astype(np.float64)
+    rho_predict, pf = o.field("rho_predict"), o.field("press_force")
+    checked = 0
+    for i in rng.choice(len(pos), size=40, replace=False):
+        r = pos[i] - pos
+        d = np.linalg.norm(r, axis=1)
+        nb = (d <= h32) & (np.arange(len(pos)) != i)
+        db = np.linalg.norm(pos[i] - bpos, axis=1)
+        if np.any(np.abs(d[nb] - h32) < 2e-6) or np.any(np.abs(db - h32) < 2e-6):
+            continue
+        nbb = db <= h32
+        want_rp = m * _cubic_w64(np.linalg.norm(pp[i] - pp[nb], axis=1), h).sum() + 1000.0 * (
+            bvol[nbb] * _cubic_w64(np.linalg.norm(pp[i] - bpos[nbb], axis=1), h)).sum()            # PC:98, 141-153
+        assert abs(rho_predict[i] - want_rp) <= 2e-5 * want_rp
+        # press_force belongs to the last executed force pass; press_iter still holds the pressures it used
+        dw = _cubic_dw64(r[nb], h)
+        f = ((press[i] + press[nb])[:, None] * dw / 1000.0 ** 2 * m * m).sum(0)                    # PC:177
+        fb = -((bvol[nbb] * press[i] / rho[i] ** 2)[:, None] * _cubic_dw64((pos[i] - bpos)[nbb], h)).sum(0)   # PC:197
+        want_pf = -f + fb * 1000.0 * m                                                             # PC:117
+        sc = np.abs((press[i] + press[nb])[:, None] * dw / 1000.0 ** 2 * m * m).sum() + 1e-9
+        assert np.abs(pf[i] - want_pf).max() <= 3e-5 * sc + 1e-12, (i, pf[i], want_pf)
+        checked += 1
+    assert checked >= 25
+    o.close()
