@@ -446,3 +446,60 @@ def test_pcisph_delta_predicted_density_and_force_against_float64_brute_force():
         checked += 1
     assert checked >= 25
     o.close()
+
+
+def test_viscosity_tension_and_divergence_update_against_float64_brute_force():
+    # independent restatement of SB:170-217 (artificial viscosity, cohesion) and of one divergence iteration
+    # DF:302-312, 357-391 (velocity correction from kappa = D rho/D t * alpha / dt) in numpy float64, all pairs
+    cfg = scenes.shipped("small_block", "dfsph")
+    o = O.Oracle(cfg, solver="dfsph", threads=4)
+    rng = np.random.default_rng(12)
+    o.field("pos")[:] += rng.uniform(-0.006, 0.006, o.field("pos").shape).astype(np.float32)
+    o.field("vel")[:] = rng.normal(0, 1.0, o.field("vel").shape).astype(np.float32)
+    o.base_step()
+    o.phase("initialize")
+    o.phase("solve_all_viscosity")
+    o.phase("solve_all_tension")
+    o.phase("derivative_iter_all_rho")
+    vel0 = o.field("vel").astype(np.float64).copy()
+    o.phase("divergence_iter_all_vel_adv")
+    pos, vel1 = o.field("pos").astype(np.float64), o.field("vel").astype(np.float64)
+    bpos, bvol = o.field("bpos").astype(np.float64), o.field("bvol").astype(np.float64)
+    rho, alpha, drho = (o.field(k).astype(np.float64) for k in ("rho", "alpha", "rho_derivative"))
+    visc, ten = o.field("viscosity"), o.field("tension")
+    h, m, dt = 0.1, 1000 * 0.025 ** 3 * 8, float(np.float32(o.scalar("delta_time")))
+    h32 = float(np.float32(h))
+    kappa = drho * alpha / dt
+    checked = 0
+    for i in rng.choice(len(pos), size=40, replace=False):
+        r = pos[i] - pos
+        d = np.linalg.norm(r, axis=1)
+        nb = (d <= h32) & (np.arange(len(pos)) != i)
+        rb = pos[i] - bpos
+        db = np.linalg.norm(rb, axis=1)
+        if np.any(np.abs(d[nb] - h32) < 2e-6) or np.any(np.abs(db - h32) < 2e-6):
+            continue
+        nbb = db <= h32
+        dw = _cubic_dw64(r[nb], h)
+        # SB:204-217 tension = m * sum(-k_t / m * m * W * x_ij), k_t = 0.5
+        want_t = m * ((-0.5 / m * m) * _cubic_w64(d[nb], h)[:, None] * r[nb]).sum(0)
+        assert np.abs(ten[i] - want_t).max() <= 2e-5 * (np.abs(m * 0.5 * _cubic_w64(d[nb], h)[:, None] * r[nb]).sum() + 1e-9)
+        # SB:170-189 viscosity, alpha = 0.08, c_s = 13, eps = 0.01, only approaching pairs
+        shear = ((vel0[i] - vel0[nb]) * r[nb]).sum(1)
+        nu = (2 * 0.08 * h * 13) / (rho[i] + rho[nb])
+        pi_ij = -nu * shear / (d[nb] ** 2 + 0.01 * h * h)
+        terms = np.where((shear < 0)[:, None], -m * pi_ij[:, None] * dw, 0.0)
+        want_v = m * terms.sum(0)
+        assert np.abs(visc[i] - want_v).max() <= 3e-5 * (np.abs(m * terms).sum() + 1e-9), (i, visc[i], want_v)
+        # DF:302-312 one divergence iteration: v -= dt * (sum_j m (k_i/rho_i + k_j/rho_j) grad W [if > 1e-5] + rho0 * sum_b ...)
+        s = kappa[i] / rho[i] + kappa[nb] / rho[nb]
+        if np.any(np.abs(s - 1e-5) < 1e-6):
+            continue                              # a pair on the threshold of DF:367
+        acc = (m * np.where(s > 1e-5, s, 0.0)[:, None] * dw).sum(0) + 1000.0 * (
+            (bvol[nbb] * kappa[i] / rho[i])[:, None] * _cubic_dw64(rb[nbb], h)).sum(0)
+        want_vel = vel0[i] - acc * dt
+        sc = dt * (np.abs(m * s[:, None] * dw).sum() + 1e-9) + np.abs(vel0[i]).max() * 1e-2
+        assert np.abs(vel1[i] - want_vel).max() <= 3e-5 * sc, (i, vel1[i], want_vel)
+        checked += 1
+    assert checked >= 20
+    o.close()
