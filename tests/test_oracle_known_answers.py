@@ -503,3 +503,40 @@ def test_viscosity_tension_and_divergence_update_against_float64_brute_force():
         checked += 1
     assert checked >= 20
     o.close()
+
+
+def test_rigid_mass_properties_against_float64_brute_force():
+    # PS:249-307: V_r = 1 / sum_{r' != r} W, m_r = rho_r V_r, centroid, inertia tensor and its inverse, in float64
+    lo, hi, pitch = [0, 0, 0], [0.3, 0.4, 0.5], 0.05
+    ax = [np.arange(int(round(lo[k] / pitch)), int(round(hi[k] / pitch)) + 1) * pitch for k in range(3)]
+    pts = np.stack(np.meshgrid(*ax, indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    verts = np.array([[x, y, z] for x in (0.0, 0.3) for y in (0.0, 0.4) for z in (0.0, 0.5)], dtype=np.float32)
+    cfg = scenes.make_scene([2.0, 2.0, 1.0], [0.1, 0.1, 0.1], [0.6, 0.8, 0.8], "dfsph", 1e-4,
+                            solid={"mesh": "unused", "voxel_radius": 0.025, "rho_0": 2000, "scale": 1,
+                                   "pos_offset": [0.85, 0.0, 0.2], "attitude_offset": [0.0, 0.0, 0.0],
+                                   "fill": True, "active": True})
+    o = O.Oracle(cfg, solver="dfsph", rigid_points=pts, rigid_vertices=verts, threads=1)
+    rp = o.field("rpos").astype(np.float64)
+    assert np.allclose(rp, pts.astype(np.float64) + np.array([0.85, 0.0, 0.2]), atol=1e-6)       # PS:198-223, no rotation
+    d = np.linalg.norm(rp[:, None, :] - rp[None, :, :], axis=2)
+    w = _cubic_w64(d, 0.1)
+    w[(d > float(np.float32(0.1))) | np.eye(len(rp), dtype=bool)] = 0.0
+    vol = 1.0 / w.sum(1)
+    assert np.allclose(o.field("rvol"), vol, rtol=1e-5)
+    mass = 2000.0 * vol
+    assert np.allclose(o.field("rmass"), mass, rtol=1e-5)
+    cen = (rp * mass[:, None]).sum(0) / mass.sum()
+    assert np.allclose(o.field("centroid").reshape(-1), cen, atol=2e-6)
+    q = rp - cen
+    I = np.zeros((3, 3))
+    I[0, 0] = (mass * (q[:, 1] ** 2 + q[:, 2] ** 2)).sum()
+    I[1, 1] = (mass * (q[:, 0] ** 2 + q[:, 2] ** 2)).sum()
+    I[2, 2] = (mass * (q[:, 0] ** 2 + q[:, 1] ** 2)).sum()
+    I[0, 1] = I[1, 0] = -(mass * q[:, 0] * q[:, 1]).sum()
+    I[0, 2] = I[2, 0] = -(mass * q[:, 0] * q[:, 2]).sum()
+    I[1, 2] = I[2, 1] = -(mass * q[:, 2] * q[:, 1]).sum()
+    got = o.field("inertia").reshape(3, 3).astype(np.float64)
+    assert np.allclose(np.diag(got), np.diag(I), rtol=2e-5)
+    assert np.abs(got - I).max() <= 2e-5 * np.abs(np.diag(I)).max()
+    assert np.allclose(o.field("inertia_inv").reshape(3, 3) @ got, np.eye(3), atol=1e-4)
+    o.close()
