@@ -1236,6 +1236,8 @@ void orc_phase(OrcSim *s, const char *name) {
 	PH("ii_predict_advection", ii_predict_advection(s))
 	PH("ii_pressure_solve", ii_pressure_solve(s))
 	PH("ii_integration", ii_integration(s))
+	PH("ii_compute_all_d_ij", ii_compute_all_d_ij(s))
+	PH("ii_update_p", ii_update_p(s))
 	PH("pbf_externel_force_predict_pos", pbf_externel_force_predict_pos(s))
 	PH("pbf_compute_all_lambda", pbf_compute_all_lambda(s))
 	PH("pbf_compute_all_delta_pos", pbf_compute_all_delta_pos(s))

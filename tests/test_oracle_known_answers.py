@@ -540,3 +540,105 @@ def test_rigid_mass_properties_against_float64_brute_force():
     assert np.abs(got - I).max() <= 2e-5 * np.abs(np.diag(I)).max()
     assert np.allclose(o.field("inertia_inv").reshape(3, 3) @ got, np.eye(3), atol=1e-4)
     o.close()
+
+
+def test_dfsph_density_iteration_against_float64_brute_force():
+    # independent restatement of DF:124-152 (rho_adv = max(rho + dt * div, rho0)) and DF:178-219 (one constant-density
+    # iteration of v*) in numpy float64, all pairs, on a compressed block so that rho_adv > rho0 for many particles
+    cfg = scenes.shipped("small_block", "dfsph")
+    o = O.Oracle(cfg, solver="dfsph", threads=4)
+    rng = np.random.default_rng(14)
+    pos0 = o.field("pos").astype(np.float64)
+    c = pos0.mean(axis=0, keepdims=True)
+    o.field("pos")[:] = (c + (pos0 - c) * 0.86 + rng.uniform(-0.003, 0.003, pos0.shape)).astype(np.float32)
+    o.field("vel")[:] = rng.normal(0, 0.5, pos0.shape).astype(np.float32)
+    o.base_step()
+    o.phase("initialize")
+    o.phase("compute_all_ext_force")
+    o.phase("compute_all_vel_adv")
+    o.phase("compute_all_rho_adv")
+    va0 = o.field("vel_adv").astype(np.float64).copy()
+    o.phase("iter_all_vel_adv")
+    pos, va1 = o.field("pos").astype(np.float64), o.field("vel_adv").astype(np.float64)
+    bpos, bvol = o.field("bpos").astype(np.float64), o.field("bvol").astype(np.float64)
+    rho, alpha, rho_adv = (o.field(k).astype(np.float64) for k in ("rho", "alpha", "rho_adv"))
+    h, m = 0.1, 1000 * 0.025 ** 3 * 8
+    h32 = float(np.float32(h))
+    dt, dt2 = float(np.float32(o.scalar("delta_time"))), float(np.float32(o.scalar("delta_time_2")))
+    assert (rho_adv > 1000.0).sum() > 500
+    k = (rho_adv - 1000.0) * alpha / dt2
+    checked = 0
+    for i in rng.choice(len(pos), size=40, replace=False):
+        r = pos[i] - pos
+        d = np.linalg.norm(r, axis=1)
+        nb = (d <= h32) & (np.arange(len(pos)) != i)
+        rb = pos[i] - bpos
+        db = np.linalg.norm(rb, axis=1)
+        if np.any(np.abs(d[nb] - h32) < 2e-6) or np.any(np.abs(db - h32) < 2e-6):
+            continue
+        nbb = db <= h32
+        dw, dwb = _cubic_dw64(r[nb], h), _cubic_dw64(rb[nbb], h)
+        div = m * ((va0[i] - va0[nb]) * dw).sum() + 1000.0 * (bvol[nbb] * (dwb @ va0[i])).sum()
+        want_ra = max(rho[i] + dt * div, 1000.0)                                                    # DF:135
+        sc = dt * (m * np.abs((va0[i] - va0[nb]) * dw).sum() + 1.0)
+        assert abs(rho_adv[i] - want_ra) <= 2e-5 * (abs(want_ra) + sc), (i, rho_adv[i], want_ra)
+        delta = (m * (k[i] / rho[i] + k[nb] / rho[nb])[:, None] * dw).sum(0) + 1000.0 * (
+            (bvol[nbb] * k[i] / rho[i])[:, None] * dwb).sum(0)                                       # DF:187, 203, 219
+        want_va = va0[i] - delta * dt                                                               # DF:191
+        sc = dt * np.abs(m * (k[i] / rho[i] + k[nb] / rho[nb])[:, None] * dw).sum() + 1e-2 * np.abs(va0[i]).max() + 1e-9
+        assert np.abs(va1[i] - want_va).max() <= 3e-5 * sc, (i, va1[i], want_va)
+        checked += 1
+    assert checked >= 25
+    o.close()
+
+
+def test_iisph_relaxed_jacobi_update_against_float64_brute_force():
+    # independent restatement of II:121-147 + II:228-253 (sum_j d_ij p_j, the r_sum of the relaxed Jacobi update,
+    # omega = 0.5, clamp at 0) in numpy float64, all pairs, from a non-trivial pressure iterate
+    cfg = scenes.shipped("small_block", "iisph")
+    o = O.Oracle(cfg, solver="iisph", threads=4)
+    rng = np.random.default_rng(16)
+    pos0 = o.field("pos").astype(np.float64)
+    c = pos0.mean(axis=0, keepdims=True)
+    o.field("pos")[:] = (c + (pos0 - c) * 0.86 + rng.uniform(-0.003, 0.003, pos0.shape)).astype(np.float32)
+    o.field("p_past")[:] = rng.uniform(0.0, 4000.0, len(pos0)).astype(np.float32)
+    o.base_step()
+    o.phase("ii_predict_advection")            # p_iter = 0.5 p_past, d_ii, a_ii, rho_adv
+    p0 = o.field("p_iter").astype(np.float64).copy()
+    assert np.allclose(p0, 0.5 * o.field("p_past"))
+    o.phase("ii_compute_all_d_ij")
+    o.phase("ii_update_p")
+    pos = o.field("pos").astype(np.float64)
+    bpos, bvol = o.field("bpos").astype(np.float64), o.field("bvol").astype(np.float64)
+    rho, a_ii, rho_adv = (o.field(k).astype(np.float64) for k in ("rho", "a_ii", "rho_adv"))
+    d_ii, d_ij = o.field("d_ii").astype(np.float64), o.field("d_ij").astype(np.float64)
+    r_sum, p1 = o.field("r_sum"), o.field("p_iter")
+    h, m, dt = 0.1, 1000 * 0.025 ** 3 * 8, float(np.float32(o.scalar("delta_time")))
+    h32 = float(np.float32(h))
+    checked = 0
+    for i in rng.choice(len(pos), size=40, replace=False):
+        r = pos[i] - pos
+        d = np.linalg.norm(r, axis=1)
+        nb = (d <= h32) & (np.arange(len(pos)) != i)
+        rb = pos[i] - bpos
+        db = np.linalg.norm(rb, axis=1)
+        if np.any(np.abs(d[nb] - h32) < 2e-6) or np.any(np.abs(db - h32) < 2e-6):
+            continue
+        nbb = db <= h32
+        dw, dwb = _cubic_dw64(r[nb], h), _cubic_dw64(rb[nbb], h)
+        want_dij = (-m * (p0[nb] / rho[nb] ** 2)[:, None] * dw).sum(0) * dt * dt                     # II:126, 313
+        sc = np.abs(m * (p0[nb] / rho[nb] ** 2)[:, None] * dw).sum() * dt * dt + 1e-30
+        assert np.abs(d_ij[i] - want_dij).max() <= 2e-5 * sc, (i, d_ij[i], want_dij)
+        d_ji = (-dt * dt * m / rho[i] ** 2) * _cubic_dw64(-r[nb], h) * p0[i]                         # II:244-245
+        t = d_ij[i] - d_ii[nb] * p0[nb][:, None] - (d_ij[nb] - d_ji)                                 # II:246
+        want_rs = m * (t * dw).sum() + 1000.0 * (bvol[nbb] * (dwb @ d_ij[i])).sum()                  # II:136, 232
+        scr = m * np.abs(t * dw).sum() + 1000.0 * np.abs(bvol[nbb][:, None] * dwb * d_ij[i]).sum() + 1e-30
+        assert abs(r_sum[i] - want_rs) <= 5e-5 * scr, (i, r_sum[i], want_rs)
+        want_p = 0.0
+        if abs(a_ii[i]) > 1e-7:
+            want_p = 0.5 * p0[i] + 0.5 * (1000.0 - rho_adv[i] - float(r_sum[i])) / a_ii[i]           # II:140-142
+        want_p = max(want_p, 0.0)                                                                    # II:147
+        assert abs(p1[i] - want_p) <= 2e-5 * (abs(want_p) + abs(0.5 * (1000.0 - rho_adv[i]) / a_ii[i]) + 1.0)
+        checked += 1
+    assert checked >= 25
+    o.close()
