@@ -642,3 +642,30 @@ def test_iisph_relaxed_jacobi_update_against_float64_brute_force():
         checked += 1
     assert checked >= 25
     o.close()
+
+
+def test_rigid_free_flight_known_answer():
+    # RS:33-104, 216-234 with no fluid contact and no wall contact: acc = g (0, -1, 0), v += acc dt, every particle,
+    # vertex and the centroid move by v dt; no torque, so omega stays zero and the body does not rotate
+    lo, hi, pitch = [0, 0, 0], [0.2, 0.2, 0.2], 0.05
+    ax = [np.arange(int(round(lo[k] / pitch)), int(round(hi[k] / pitch)) + 1) * pitch for k in range(3)]
+    pts = np.stack(np.meshgrid(*ax, indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    verts = np.array([[x, y, z] for x in (0.0, 0.2) for y in (0.0, 0.2) for z in (0.0, 0.2)], dtype=np.float32)
+    dt, g = 1e-3, 9.8
+    cfg = scenes.make_scene([3.0, 3.0, 1.5], [0.1, 0.1, 0.1], [0.3, 0.3, 0.3], "wcsph", dt,
+                            solid={"mesh": "unused", "voxel_radius": 0.025, "rho_0": 2000, "scale": 1,
+                                   "pos_offset": [2.0, 2.0, 0.6], "attitude_offset": [0.0, 0.0, 0.0],
+                                   "fill": True, "active": True})
+    o = O.Oracle(cfg, solver="wcsph", rigid_points=pts, rigid_vertices=verts, threads=1)
+    p0, c0 = o.field("rpos").astype(np.float64).copy(), o.field("centroid").astype(np.float64).copy().reshape(-1)
+    v, y = 0.0, 0.0
+    for n in range(1, 6):
+        o.step(1)                                  # fluid step (far away) + rigid step
+        v -= g * dt
+        y += v * dt
+        assert np.allclose(o.field("rvel")[:, 1], v, rtol=1e-5) and not o.field("rvel")[:, [0, 2]].any()
+        assert np.allclose(o.field("rpos") - p0, [0.0, y, 0.0], atol=2e-6)
+        assert np.allclose(o.field("centroid").reshape(-1) - c0, [0.0, y, 0.0], atol=2e-6)
+        assert not o.field("rs_omega").any()
+    assert abs(o.scalar("rs_mass") - o.field("rmass").astype(np.float64).sum()) <= 1e-4 * o.scalar("rs_mass")   # RS:156-162
+    o.close()
