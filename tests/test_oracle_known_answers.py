@@ -669,3 +669,49 @@ def test_rigid_free_flight_known_answer():
         assert not o.field("rs_omega").any()
     assert abs(o.scalar("rs_mass") - o.field("rmass").astype(np.float64).sum()) <= 1e-4 * o.scalar("rs_mass")   # RS:156-162
     o.close()
+
+
+def test_fluid_to_rigid_force_against_float64_brute_force():
+    # DF:204-212: every fluid-rigid pair adds  m * V_r rho0 k_i / rho_i * grad W(x_i - x_r)  to the rigid particle's
+    # force during iter_all_vel_adv; restated per rigid particle in numpy float64 over all fluid particles
+    lo, hi, pitch = [0, 0, 0], [0.2, 0.3, 0.2], 0.05
+    ax = [np.arange(int(round(lo[k] / pitch)), int(round(hi[k] / pitch)) + 1) * pitch for k in range(3)]
+    pts = np.stack(np.meshgrid(*ax, indexing="ij"), axis=-1).reshape(-1, 3).astype(np.float32)
+    verts = np.array([[x, y, z] for x in (0.0, 0.2) for y in (0.0, 0.3) for z in (0.0, 0.2)], dtype=np.float32)
+    cfg = scenes.make_scene([2.0, 2.0, 1.0], [0.1, 0.1, 0.1], [0.6, 0.8, 0.8], "dfsph", 1e-4,
+                            solid={"mesh": "unused", "voxel_radius": 0.025, "rho_0": 2000, "scale": 1,
+                                   "pos_offset": [0.42, 0.3, 0.3], "attitude_offset": [0.0, 0.0, 0.0],   # inside the block: k_i > 0 around it
+                                   "fill": True, "active": True})
+    o = O.Oracle(cfg, solver="dfsph", rigid_points=pts, rigid_vertices=verts, threads=1)
+    rng = np.random.default_rng(18)
+    pos0 = o.field("pos").astype(np.float64)
+    c = pos0.mean(axis=0, keepdims=True)
+    o.field("pos")[:] = (c + (pos0 - c) * 0.86 + rng.uniform(-0.002, 0.002, pos0.shape)).astype(np.float32)
+    o.base_step()
+    for ph in ("initialize", "compute_all_ext_force", "compute_all_vel_adv", "compute_all_rho_adv"):
+        o.phase(ph)
+    assert not o.field("rforce").any()
+    o.phase("iter_all_vel_adv")
+    pos, rp, rvol = o.field("pos").astype(np.float64), o.field("rpos").astype(np.float64), o.field("rvol").astype(np.float64)
+    rho, alpha, rho_adv = (o.field(k).astype(np.float64) for k in ("rho", "alpha", "rho_adv"))
+    m, h = 1000 * 0.025 ** 3 * 8, 0.1
+    h32 = float(np.float32(h))
+    dt2 = float(np.float32(o.scalar("delta_time_2")))
+    k = (rho_adv - 1000.0) * alpha / dt2                                                        # DF:208
+    got = o.field("rforce").astype(np.float64)
+    assert np.abs(got).max() > 0
+    checked = 0
+    for r in range(len(rp)):
+        x = pos - rp[r]
+        d = np.linalg.norm(x, axis=1)
+        nb = d <= h32
+        if not nb.any():
+            assert not got[r].any()
+            continue
+        if np.any(np.abs(d[nb] - h32) < 2e-6):
+            continue
+        terms = m * (rvol[r] * 1000.0 * k[nb] / rho[nb])[:, None] * _cubic_dw64(x[nb], h)       # DF:211-212
+        assert np.abs(got[r] - terms.sum(0)).max() <= 3e-5 * (np.abs(terms).sum() + 1e-12), (r, got[r], terms.sum(0))
+        checked += 1
+    assert checked >= 20
+    o.close()
