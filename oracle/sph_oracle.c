@@ -347,7 +347,7 @@ static void build_boundary_grid(OrcSim *s) {
 		s->bcell_start[idx + 1]++;
 	}
 	for (long long c = 0; c < G; ++c) s->bcell_start[c + 1] += s->bcell_start[c];
-	int *fill = (int *)calloc(G, sizeof(int));
+	int *fill = (int *)calloc((size_t)(G > 0 ? G : 1), sizeof(int));
 	for (int i = 0; i < s->Nb; ++i) {
 		if (c1[i] < 0) continue;
 		s->bcell_items[s->bcell_start[c1[i]] + fill[c1[i]]++] = i;
@@ -387,7 +387,7 @@ static void reset_and_update_grid(OrcSim *s) {
 		}
 	}
 	for (long long c = 0; c < G; ++c) s->cell_start[c + 1] += s->cell_start[c];
-	int *fill = (int *)calloc(G, sizeof(int));
+	int *fill = (int *)calloc((size_t)(G > 0 ? G : 1), sizeof(int));
 	for (int i = 0; i < s->N; ++i) {
 		int c = s->cell1[i];
 		if (c < 0) continue;
