@@ -60,7 +60,24 @@ def save_state(path, ps, solver, rs=None):
     np.savez(path, **data)
 
 
-def run(config, max_frames=None, output_dir='./output', quiet=False):
+def load_state(path, ps, solver):
+    """Restart from a save_state dump: positions, velocities (with the solver-persistent scalar in .w: DFSPH
+    warm_start_k / IISPH p_past) and the time step the next step starts from.  Fluid-only scenes: the device-side
+    rigid-body state (pose, omega, rotated inertia) has no setter in this round."""
+    import torch
+    if ps.exist_rigid[None]:
+        raise NotImplementedError("load_state: scenes with a rigid body cannot be resumed in this round")
+    path = path if path.endswith('.npz') else path + '.npz'
+    with np.load(path) as d:
+        n = ps.particle_num
+        if d['pos4'].shape[0] != n:
+            raise ValueError("load_state: dump holds %d particles, the scene %d" % (d['pos4'].shape[0], n))
+        ps._pos4[:n].copy_(torch.from_numpy(d['pos4']).to(ps._device))
+        ps._vel4[:n].copy_(torch.from_numpy(d['vel4']).to(ps._device))
+        solver.delta_time[None] = float(d['delta_time'])
+
+
+def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None, save=None):
     scene_config = config.get('scene')
     solver_config = config.get('solver')
     print("Simulation Start!")
@@ -70,6 +87,8 @@ def run(config, max_frames=None, output_dir='./output', quiet=False):
     module = importlib.import_module('cfd_taichi_b200.' + solver_name + '_solver')     # main.py:65-68
     solver = getattr(module, solver_name + '_solver')(ps, config)
     rs = rigid_solver(ps, config) if config.get('solid', {}) else None                 # main.py:70-71
+    if resume:
+        load_state(resume, ps, solver)
 
     frame_cnt = 0
     iter_cnt = solver_config.get('iter_cnt')
@@ -102,6 +121,8 @@ def run(config, max_frames=None, output_dir='./output', quiet=False):
             ply_cnt += 1
         if t > 4.0:
             break
+    if save:
+        save_state(save, ps, solver, rs)
     print("Simulation time: {}".format(time.time() - start_time))
     return ps, solver, rs, t
 
@@ -111,9 +132,11 @@ def main(argv=None):
     parser.add_argument('--config', help="Please input a scene config json file.", type=str, default='default.json')
     parser.add_argument('--steps', help="stop after this many frames (default: run to t > 4.0)", type=int, default=None)
     parser.add_argument('--output-dir', type=str, default='./output')
+    parser.add_argument('--resume', help="restart from a state dump written with --save-state", type=str, default=None)
+    parser.add_argument('--save-state', help="write a restartable .npz dump when the run ends", type=str, default=None)
     args = parser.parse_args(argv)
     config = utils.read_config(args.config)
-    run(config, args.steps, args.output_dir)
+    run(config, args.steps, args.output_dir, resume=args.resume, save=args.save_state)
 
 
 if __name__ == "__main__":

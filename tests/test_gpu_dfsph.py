@@ -308,3 +308,28 @@ def test_state_transfer_xyz_round_trip(built):
     assert np.array_equal(ps.fluid_particles.vel.to_numpy(), hv2.numpy())
     assert torch.equal(ps._vel4[:n, 3], w_before)
     ps.close()
+
+
+def test_state_dump_and_restart_is_bit_exact(built, tmp_path):
+    # a run resumed from a dump continues exactly like the uninterrupted one (DFSPH carries
+    # warm_start_k in vel.w and the adaptive time step of the previous step)
+    from cfd_taichi_b200 import main as app
+    cfg = scenes.shipped("small_block", "dfsph")
+    ps = quiet_ps(cfg, strict=True)
+    sol = quiet_solver(dfsph_solver, ps, cfg)
+    ps._vel4[:ps.particle_num, 0] = 1.5          # fast enough for the CFL rule to shorten the time step
+    for _ in range(4):
+        sol.step()
+    app.save_state(str(tmp_path / "dump"), ps, sol)
+    for _ in range(4):
+        sol.step()
+    want_pos, want_vel = ps.fluid_particles.pos.to_numpy(), ps._vel4[:ps.particle_num].cpu().numpy()
+    ps.close()
+    ps2 = quiet_ps(cfg, strict=True)
+    sol2 = quiet_solver(dfsph_solver, ps2, cfg)
+    app.load_state(str(tmp_path / "dump"), ps2, sol2)
+    for _ in range(4):
+        sol2.step()
+    assert np.array_equal(ps2.fluid_particles.pos.to_numpy(), want_pos)
+    assert np.array_equal(ps2._vel4[:ps2.particle_num].cpu().numpy(), want_vel)
+    ps2.close()

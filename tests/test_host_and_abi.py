@@ -129,3 +129,17 @@ def test_no_cpu_fallback_in_product():
         from cfd_taichi_b200.ParticleSystem import ParticleSystem
         with pytest.raises(_lib.SphError):
             ParticleSystem(scenes.shipped("small_block"))
+
+
+def test_ply_and_obj_writers(tmp_path):
+    # main.py:189-201: ASCII PLY with the vertex layout of ti.tools.PLYWriter, OBJ with 1-based faces
+    from cfd_taichi_b200 import main as app
+    pos = np.array([[0.1, 0.2, 0.3], [1.0, 2.0, 3.0]], dtype=np.float32)
+    rgba = np.array([[0.0, 0.26, 0.68, 1.0]] * 2, dtype=np.float32)
+    app.write_ply(str(tmp_path / "a.ply"), pos, rgba)
+    lines = (tmp_path / "a.ply").read_text().splitlines()
+    assert lines[:3] == ["ply", "format ascii 1.0", "element vertex 2"]
+    assert [l.split()[-1] for l in lines[3:10]] == ["x", "y", "z", "red", "green", "blue", "alpha"] and lines[10] == "end_header"
+    assert np.allclose(np.loadtxt(lines[11:]), np.concatenate([pos, rgba], axis=1), atol=1e-6)
+    app.write_obj(str(tmp_path / "a.obj"), pos, np.array([[0, 1, 0]]))
+    assert (tmp_path / "a.obj").read_text().splitlines() == ["v 0.100000 0.200000 0.300000", "v 1.000000 2.000000 3.000000", "f 1 2 1"]
