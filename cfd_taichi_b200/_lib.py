@@ -94,7 +94,8 @@ class SphRigidInfo(ctypes.Structure):
                 ("vel", ctypes.c_float * 3), ("omega", ctypes.c_float * 3), ("alpha", ctypes.c_float * 3),
                 ("acc", ctypes.c_float * 3), ("attitude", ctypes.c_float * 3), ("force_sum", ctypes.c_float * 3),
                 ("torque", ctypes.c_float * 3), ("mass", ctypes.c_float), ("delta_time", ctypes.c_float),
-                ("collision_cnt", ctypes.c_int32), ("simulate_cnt", ctypes.c_int32)]
+                ("collision_cnt", ctypes.c_int32), ("simulate_cnt", ctypes.c_int32),
+                ("max_surface_vel", ctypes.c_float), ("reserved", ctypes.c_int32)]
 
 
 # every symbol include/sph_b200.h declares: (name, restype, argtypes)
@@ -108,6 +109,7 @@ PROTOTYPES = [
     ("sph_bind", _i, [_vp, _i, _vp, ctypes.c_size_t]),
     ("sph_init_boundary", _i, [_vp, _vp]),
     ("sph_init_rigid", _i, [_vp, _vp]),
+    ("sph_rigid_set_state", _i, [_vp, ctypes.POINTER(SphRigidInfo)]),
     ("sph_pcisph_precompute", _i, [_vp, _vp]),
     ("sph_pcisph_delta", _i, [_vp, _i, _vp]),
     ("sph_pcisph_set_delta", _i, [_vp, ctypes.c_float, _i, _vp]),

@@ -349,6 +349,33 @@ extern "C" int sph_rigid_state(SphHandle *h, SphRigidInfo *out) {
 	out->delta_time = s.rs_dt;
 	out->collision_cnt = s.collision_cnt;
 	out->simulate_cnt = s.simulate_cnt;
+	out->max_surface_vel = s.max_surface_vel;
+	return SPH_OK;
+}
+
+extern "C" int sph_rigid_set_state(SphHandle *h, const SphRigidInfo *in) {
+	if (!h || !in) return SPH_EINVAL;
+	if (!h->rstate || h->c.Nr <= 0) return sph_fail(h, SPH_ESTATE, "sph_rigid_set_state: the handle has no rigid body");
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	SphRigidState s;
+	SPH_CUDA_CHECK(h, cudaDeviceSynchronize());
+	SPH_CUDA_CHECK(h, cudaMemcpy(&s, h->rstate, sizeof(s), cudaMemcpyDeviceToHost));
+	memcpy(s.centroid, in->centroid, sizeof(s.centroid));
+	memcpy(s.inertia, in->inertia, sizeof(s.inertia));
+	memcpy(s.inertia_inv, in->inertia_inv, sizeof(s.inertia_inv));
+	memcpy(s.vel, in->vel, sizeof(s.vel));
+	memcpy(s.omega, in->omega, sizeof(s.omega));
+	memcpy(s.alpha, in->alpha, sizeof(s.alpha));
+	memcpy(s.acc, in->acc, sizeof(s.acc));
+	memcpy(s.attitude, in->attitude, sizeof(s.attitude));
+	memcpy(s.force_sum, in->force_sum, sizeof(s.force_sum));
+	memcpy(s.torque, in->torque, sizeof(s.torque));
+	s.mass = in->mass;
+	s.rs_dt = in->delta_time;
+	s.collision_cnt = in->collision_cnt;
+	s.simulate_cnt = in->simulate_cnt;
+	s.max_surface_vel = in->max_surface_vel;
+	SPH_CUDA_CHECK(h, cudaMemcpy(h->rstate, &s, sizeof(s), cudaMemcpyHostToDevice));
 	return SPH_OK;
 }
 

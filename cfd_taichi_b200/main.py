@@ -51,22 +51,25 @@ def write_obj(path, vertices, faces):
 
 def save_state(path, ps, solver, rs=None):
     """Restartable dump: everything a step depends on."""
+    import ctypes
     n = ps.particle_num
     data = dict(pos4=ps._pos4[:n].cpu().numpy(), vel4=ps._vel4[:n].cpu().numpy(), delta_time=solver.delta_time[None])
     if ps.exist_rigid[None]:
         info = ps.rigid_state()
         data.update(rpos4=ps._rpos4.cpu().numpy(), rvel4=ps._rvel4.cpu().numpy(), rforce4=ps._rforce4.cpu().numpy(),
+                    rverts4=ps._rverts4.cpu().numpy(),
+                    rigid_info=np.frombuffer(ctypes.string_at(ctypes.addressof(info), ctypes.sizeof(info)), dtype=np.uint8).copy(),
                     centroid=np.array(list(info.centroid)), omega=np.array(list(info.omega)))
     np.savez(path, **data)
 
 
 def load_state(path, ps, solver):
     """Restart from a save_state dump: positions, velocities (with the solver-persistent scalar in .w: DFSPH
-    warm_start_k / IISPH p_past) and the time step the next step starts from.  Fluid-only scenes: the device-side
-    rigid-body state (pose, omega, rotated inertia) has no setter in this round."""
+    warm_start_k / IISPH p_past), the time step the next step starts from and, for scenes with a rigid body, its
+    particles, mesh vertices and the device-side body state (sph_rigid_set_state)."""
+    import ctypes
     import torch
-    if ps.exist_rigid[None]:
-        raise NotImplementedError("load_state: scenes with a rigid body cannot be resumed in this round")
+    from cfd_taichi_b200 import _lib
     path = path if path.endswith('.npz') else path + '.npz'
     with np.load(path) as d:
         n = ps.particle_num
@@ -75,6 +78,13 @@ def load_state(path, ps, solver):
         ps._pos4[:n].copy_(torch.from_numpy(d['pos4']).to(ps._device))
         ps._vel4[:n].copy_(torch.from_numpy(d['vel4']).to(ps._device))
         solver.delta_time[None] = float(d['delta_time'])
+        if ps.exist_rigid[None]:
+            if 'rigid_info' not in d:
+                raise ValueError("load_state: the dump holds no rigid-body state")
+            for name, t in (('rpos4', ps._rpos4), ('rvel4', ps._rvel4), ('rforce4', ps._rforce4), ('rverts4', ps._rverts4)):
+                t.copy_(torch.from_numpy(d[name]).to(ps._device))
+            info = _lib.SphRigidInfo.from_buffer_copy(d['rigid_info'].tobytes())
+            _lib.check(ps._lib.sph_rigid_set_state(ps._h, ctypes.byref(info)), ps._h)
 
 
 def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None, save=None):

@@ -194,8 +194,13 @@ typedef struct SphRigidInfo {
 	float vel[3], omega[3], alpha[3], acc[3], attitude[3], force_sum[3], torque[3];
 	float mass, delta_time;
 	int32_t collision_cnt, simulate_cnt;
+	float max_surface_vel;   /* DF:104-110, feeds the adaptive time step of the next DFSPH step */
+	int32_t reserved;
 } SphRigidInfo;
 int sph_rigid_state(SphHandle *h, SphRigidInfo *out); /* synchronises */
+/* Restart: put a state read with sph_rigid_state back (the rigid particle arrays are caller-owned and are
+ * restored by the caller).  Synchronises. */
+int sph_rigid_set_state(SphHandle *h, const SphRigidInfo *in);
 
 int sph_set_delta_time(SphHandle *h, float dt, void *stream);
 

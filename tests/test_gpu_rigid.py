@@ -157,3 +157,36 @@ def test_other_solvers_coupled_strict_bit_exact(built, monkeypatch, solver):
         assert np.array_equal(ps.fluid_particles.vel.to_numpy(), o.field("vel")), "step %d fluid vel" % step
         assert np.array_equal(ps.rigid_particles.pos.to_numpy(), o.field("rpos")), "step %d rigid pos" % step
     ps.close(); o.close()
+
+
+def test_rigid_scene_restart_is_bit_exact(built, monkeypatch, tmp_path):
+    # a dam hitting the box, dumped in the middle of the contact and resumed in a fresh ParticleSystem
+    from cfd_taichi_b200 import main as app
+    cfg, pts, verts = rigid_scene()
+    cfg["solid"]["pos_offset"] = [0.72, 0.0, 0.2]      # touching the fluid block from the first step on
+    monkeypatch.setattr(scene, "rigid_points_from_config", lambda solid, base_dir=".": (pts, verts, None))
+
+    def fresh():
+        ps = quiet_ps(cfg, strict=True, solver_name="dfsph")
+        return ps, quiet_solver(dfsph_solver, ps, cfg), rigid_solver(ps, cfg)
+
+    ps, sol, rs = fresh()
+    for _ in range(6):
+        sol.step(); rs.step()
+    app.save_state(str(tmp_path / "dump"), ps, sol, rs)
+    for _ in range(6):
+        sol.step(); rs.step()
+    want = (ps.fluid_particles.pos.to_numpy(), ps._vel4[:ps.particle_num].cpu().numpy(), ps.rigid_particles.pos.to_numpy(),
+            list(ps.rigid_state().centroid), list(ps.rigid_state().omega))
+    assert any(abs(w) > 0 for w in want[4]) or np.abs(ps.rigid_particles.vel.to_numpy()).max() > 0
+    ps.close()
+    ps2, sol2, rs2 = fresh()
+    app.load_state(str(tmp_path / "dump"), ps2, sol2)
+    for _ in range(6):
+        sol2.step(); rs2.step()
+    got = (ps2.fluid_particles.pos.to_numpy(), ps2._vel4[:ps2.particle_num].cpu().numpy(), ps2.rigid_particles.pos.to_numpy(),
+           list(ps2.rigid_state().centroid), list(ps2.rigid_state().omega))
+    for a, b in zip(got[:3], want[:3]):
+        assert np.array_equal(a, b)
+    assert got[3] == want[3] and got[4] == want[4]
+    ps2.close()
