@@ -715,3 +715,68 @@ def test_fluid_to_rigid_force_against_float64_brute_force():
         checked += 1
     assert checked >= 20
     o.close()
+
+
+def _spiky_dw64(r, h):
+    rn = np.linalg.norm(r, axis=-1, keepdims=True)
+    q = rn / h
+    with np.errstate(divide="ignore", invalid="ignore"):
+        g = -(45.0 * (1 - q) ** 2) * r / (np.pi * h ** 4 * rn)
+    return np.where((q <= 1.0) & (q > 0.0), g, 0.0)
+
+
+def test_pbf_delta_pos_against_float64_brute_force():
+    # PBF:55-65 + 164-174: delta_p_i = (sum_j (lambda_i + lambda_j + s_corr) grad W_spiky + sum_b (lambda_i + s_corr) grad W) / rho0,
+    # s_corr = -k (W_poly6(r) / W_poly6(0.3 h))^4, restated in numpy float64 over all pairs
+    cfg = scenes.shipped("small_block", "pbf")
+    o = O.Oracle(cfg, solver="pbf", threads=4)
+    rng = np.random.default_rng(20)
+    pos0 = o.field("pos").astype(np.float64)
+    c = pos0.mean(axis=0, keepdims=True)
+    o.field("pos")[:] = (c + (pos0 - c) * 0.86 + rng.uniform(-0.002, 0.002, pos0.shape)).astype(np.float32)
+    o.base_step()
+    for ph in ("pbf_externel_force_predict_pos", "pbf_compute_all_lambda", "pbf_compute_all_delta_pos"):
+        o.phase(ph)
+    pos, lam = o.field("pos").astype(np.float64), o.field("pbf_lambda").astype(np.float64)
+    bpos = o.field("bpos").astype(np.float64)
+    dp = o.field("pbf_delta_pos")
+    h = 0.1
+    h32 = float(np.float32(h))
+    w03 = float(_poly6(np.float64(np.float32(0.3 * 0.1)), h))
+    checked = 0
+    for i in rng.choice(len(pos), size=40, replace=False):
+        r = pos[i] - pos
+        d = np.linalg.norm(r, axis=1)
+        nb = (d <= h32) & (np.arange(len(pos)) != i)
+        rb = pos[i] - bpos
+        db = np.linalg.norm(rb, axis=1)
+        if np.any(np.abs(d[nb] - h32) < 2e-6) or np.any(np.abs(db - h32) < 2e-6):
+            continue
+        nbb = db <= h32
+        sc = -1e-7 * (_poly6(d[nb], h) / w03) ** 4
+        scb = -1e-7 * (_poly6(db[nbb], h) / w03) ** 4
+        tf = (lam[i] + lam[nb] + sc)[:, None] * _spiky_dw64(r[nb], h)
+        tb = (lam[i] + scb)[:, None] * _spiky_dw64(rb[nbb], h)
+        want = (tf.sum(0) + tb.sum(0)) / 1000.0
+        scale = (np.abs(tf).sum() + np.abs(tb).sum()) / 1000.0 + 1e-30
+        assert np.abs(dp[i] - want).max() <= 3e-5 * scale, (i, dp[i], want)
+        checked += 1
+    assert checked >= 25
+    o.close()
+
+
+def test_dfsph_adaptive_time_step_known_answer():
+    # DF:98-122: v* = v + dt f / m, dt_new = clamp(0.4 * d / max|v*| * 0.2, 1e-5, 1e-3), delta_time_2 = dt_new^2
+    cfg = scenes.shipped("small_block", "dfsph")
+    o = O.Oracle(cfg, solver="dfsph", threads=4)
+    o.field("vel")[:, 0] = 3.0                   # 0.4 * 0.05 / 3 * 0.2 = 1.33e-3 -> clamped to 1e-3
+    o.base_step(); o.phase("initialize"); o.phase("compute_all_ext_force"); o.phase("compute_all_vel_adv")
+    assert np.float32(o.scalar("delta_time")) == np.float32(1e-3)
+    o.field("vel")[:, 0] = 8.0
+    o.base_step(); o.phase("initialize"); o.phase("compute_all_ext_force"); o.phase("compute_all_vel_adv")
+    vmax = np.linalg.norm(o.field("vel_adv").astype(np.float64), axis=1).max()
+    want = 0.4 * 0.05 / vmax * 0.2
+    assert abs(o.scalar("delta_time") - want) <= 1e-5 * want and 1e-5 < want < 1e-3
+    assert abs(o.scalar("delta_time_2") - want * want) <= 1e-5 * want * want
+    assert abs(o.scalar("ps_delta_time") - want) <= 1e-5 * want             # DF:119, read by the rigid solver
+    o.close()
