@@ -94,6 +94,7 @@ class ParticleSystem:
         if self.exist_rigid[None] == 1:
             pts, verts, faces = scene.rigid_points_from_config(solid_config, self._base_dir)
             self._rigid_points, self._rigid_faces = pts, faces
+            self._rigid_vertices_local = np.ascontiguousarray(verts, dtype=np.float32)   # before rotation / offset
             self.voxel_radius = solid_config.get('voxel_radius')
             self.rigid_pos_offset = solid_config.get('pos_offset')
             self.rigid_attitude_offset = [a / 180.0 * math.pi for a in solid_config.get('attitude_offset')]

@@ -22,9 +22,10 @@ F_CELL_START, F_SORTED_INDEX, F_BOUNDARY_CELL_START, F_BOUNDARY_SORTED_INDEX = r
 # enum SphPhase
 PH_BUILD_GRID = 0
 PH_DF_INITIALIZE, PH_DF_DIVERGENCE, PH_DF_EXT_FORCE_VEL_ADV, PH_DF_DENSITY, PH_DF_POSITION = range(10, 15)
+PH_DF_DIV_BEGIN, PH_DF_DIV_ONE, PH_DF_DEN_ONE = 15, 16, 17   # the two DFSPH loops one pass at a time
 PH_WC_PRESSURE, PH_WC_KINEMATIC = 20, 21
-PH_PC_EXT_FORCE, PH_PC_ITERATION, PH_PC_INTEGRATION = 30, 31, 32
-PH_II_PREDICT_ADVECTION, PH_II_PRESSURE_SOLVE, PH_II_INTEGRATION = 40, 41, 42
+PH_PC_EXT_FORCE, PH_PC_ITERATION, PH_PC_INTEGRATION, PH_PC_ITER_BEGIN, PH_PC_ITER_ONE = 30, 31, 32, 33, 34
+PH_II_PREDICT_ADVECTION, PH_II_PRESSURE_SOLVE, PH_II_INTEGRATION, PH_II_SOLVE_BEGIN, PH_II_SOLVE_ONE = 40, 41, 42, 43, 44
 PH_PBF_PREDICT, PH_PBF_LAMBDA, PH_PBF_DELTA_POS, PH_PBF_UPDATE_POS = 50, 51, 52, 53
 PH_WRITEBACK = 90
 
@@ -85,7 +86,9 @@ class SphStats(ctypes.Structure):
         ("pc_delta", ctypes.c_float),
         ("pc_max_index", ctypes.c_int32),
         ("kernel_launches", ctypes.c_int32),
-        ("reserved", ctypes.c_int32 * 3),
+        ("div_active", ctypes.c_int32),
+        ("den_active", ctypes.c_int32),
+        ("loop_active", ctypes.c_int32),
     ]
 
 
@@ -127,6 +130,7 @@ PROTOTYPES = [
     ("sph_download_state_xyz", _i, [_vp, _vp, _vp, _vp]),
     ("sph_download_state", _i, [_vp, _vp, _vp, _vp]),
     ("sph_read_stats", _i, [_vp, ctypes.POINTER(SphStats)]),
+    ("sph_copy_work_state", _i, [_vp, _vp, _vp]),
     ("sph_profile_begin", _i, [_vp]),
     ("sph_profile_end", _i, [_vp, _fp, ctypes.POINTER(ctypes.c_int32), _i]),
     ("sph_comm_unique_id", _i, [ctypes.c_char_p]),

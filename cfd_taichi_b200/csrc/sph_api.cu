@@ -423,16 +423,16 @@ extern "C" int sph_phase(SphHandle *h, int phase, void *stream) {
 	if (phase != SPH_PH_DF_INITIALIZE && phase != SPH_PH_WC_PRESSURE && phase != SPH_PH_PC_EXT_FORCE &&
 	    phase != SPH_PH_II_PREDICT_ADVECTION && phase != SPH_PH_PBF_PREDICT && phase != SPH_PH_PBF_LAMBDA && !h->lists_valid)
 		return sph_fail(h, SPH_ESTATE, "sph_phase: neighbour lists not built (run the solver's first phase)");
-	if (phase >= SPH_PH_DF_INITIALIZE && phase <= SPH_PH_DF_POSITION) {
+	if (phase >= SPH_PH_DF_INITIALIZE && phase <= SPH_PH_DF_DEN_ONE) {
 		if (h->c.solver != SPH_SOLVER_DFSPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a DFSPH solver");
 		if (strict) sph_strict::df_phase(h, phase, st); else sph_fast::df_phase(h, phase, st);
 	} else if (phase >= SPH_PH_WC_PRESSURE && phase <= SPH_PH_WC_KINEMATIC) {
 		if (h->c.solver != SPH_SOLVER_WCSPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a WCSPH solver");
 		if (strict) sph_strict::wc_phase(h, phase, st); else sph_fast::wc_phase(h, phase, st);
-	} else if (phase >= SPH_PH_PC_EXT_FORCE && phase <= SPH_PH_PC_INTEGRATION) {
+	} else if (phase >= SPH_PH_PC_EXT_FORCE && phase <= SPH_PH_PC_ITER_ONE) {
 		if (h->c.solver != SPH_SOLVER_PCISPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a PCISPH solver");
 		if (strict) sph_strict::pc_phase(h, phase, st); else sph_fast::pc_phase(h, phase, st);
-	} else if (phase >= SPH_PH_II_PREDICT_ADVECTION && phase <= SPH_PH_II_INTEGRATION) {
+	} else if (phase >= SPH_PH_II_PREDICT_ADVECTION && phase <= SPH_PH_II_SOLVE_ONE) {
 		if (h->c.solver != SPH_SOLVER_IISPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not an IISPH solver");
 		if (strict) sph_strict::ii_phase(h, phase, st); else sph_fast::ii_phase(h, phase, st);
 	} else if (phase >= SPH_PH_PBF_PREDICT && phase <= SPH_PH_PBF_UPDATE_POS) {
@@ -733,6 +733,34 @@ extern "C" int sph_read_stats(SphHandle *h, SphStats *out) {
 	out->max_neighbors_seen = k.max_nbr;
 	out->max_boundary_neighbors_seen = k.max_bnbr;
 	out->kernel_launches = h->launches;
+	out->div_active = k.div_active;
+	out->den_active = k.den_active;
+	out->loop_active = h->c.solver == SPH_SOLVER_PCISPH ? k.pc_active : h->c.solver == SPH_SOLVER_IISPH ? k.ii_active : 0;
+	return SPH_OK;
+}
+
+// Single-sweep parity tests: put handle `dst` into the in-step state of handle `src` (same scene, grids built
+// from the same positions, so the sorted order is identical): every sorted per-particle work array, the
+// neighbour counts, the control block and the rigid-body state.  The neighbour lists are NOT copied -- the
+// strict and the fast kernels keep them in different orders; each handle builds its own.
+extern "C" int sph_copy_work_state(SphHandle *dst, SphHandle *src, void *stream) {
+	if (!dst || !src) return SPH_EINVAL;
+	if (dst->c.N != src->c.N || dst->c.solver != src->c.solver || dst->c.Nr != src->c.Nr || dst->device != src->device)
+		return sph_fail(dst, SPH_EINVAL, "sph_copy_work_state: the two handles do not describe the same scene on one device");
+	if (!dst->grid_valid || !src->grid_valid) return sph_fail(dst, SPH_ESTATE, "sph_copy_work_state: build both grids first");
+	cudaStream_t st = (cudaStream_t)stream;
+	SPH_CUDA_CHECK(dst, cudaSetDevice(dst->device));
+	size_t n = (size_t)src->c.N;
+	for (int k = 0; k < A4_COUNT; ++k)
+		SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->a4[k], src->a4[k], sizeof(float4) * n, cudaMemcpyDeviceToDevice, st));
+	for (int k = 0; k < A1_COUNT; ++k)
+		SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->a1[k], src->a1[k], sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+	SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->nbr_count, src->nbr_count, sizeof(int) * n, cudaMemcpyDeviceToDevice, st));
+	SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->ctl, src->ctl, sizeof(SphCtl), cudaMemcpyDeviceToDevice, st));
+	SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->rstate, src->rstate, sizeof(SphRigidState), cudaMemcpyDeviceToDevice, st));
+	if (src->c.Nr > 0 && src->rforce && dst->rforce)
+		SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->rforce, src->rforce, sizeof(float4) * (size_t)src->c.Nr, cudaMemcpyDeviceToDevice, st));
+	dst->den_piece = src->den_piece;
 	return SPH_OK;
 }
 

@@ -81,6 +81,7 @@ struct SphHandle {
 	bool grid_valid, boundary_ready, lists_valid;
 	int sweep_blocks;
 	int last_den_chunk;
+	int den_piece;        // density iterations issued one at a time through SPH_PH_DF_DEN_ONE since the last v* pass
 	float *xyz_stage;     // 2 x 3 floats per fluid particle: staging of sph_upload_state_xyz / sph_download_state_xyz
 	SphProf *prof;
 	struct SphComm *comm; // multi-GPU slab state (sph_multigpu.cu); null on one GPU

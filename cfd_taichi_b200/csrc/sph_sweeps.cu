@@ -996,7 +996,8 @@ static void df_decide(SphHandle *h, int what, int kind, int nb, cudaStream_t st)
 void rigid_lists(SphHandle *h, cudaStream_t st);
 void rigid_force_df(SphHandle *h, int gated, cudaStream_t st);
 
-static void df_divergence(SphHandle *h, cudaStream_t st) {
+// DF:393-399: warm start, first D rho / D t evaluation and the decision whether the loop starts
+static void df_divergence_begin(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
@@ -1011,20 +1012,30 @@ static void df_divergence(SphHandle *h, cudaStream_t st) {
 	sph_prof_end(h, st);
 	df_decide(h, MG_F4_T2, SPH_CTL_DIV_FIRST, nb, st);
 	h->launches += 2;
-	for (int it = 0; it < 15; ++it) { // max_iteration_density_divergence (DF:24); gated on ctl->div_active
-		sph_prof_begin(h, KC_DF_DIV, st);
-		SPH_LAUNCH_R(k_df_div_iter, nb, c, h->L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-		             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
-		sph_prof_end(h, st);
-		mg_exchange(h, MG_F4_VEL, st);
-		sph_prof_begin(h, KC_DF_DRHO, st);
-		SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
+}
+
+// DF:400-414: one pass of the loop body, gated on ctl->div_active (a no-op once the loop has ended)
+static void df_divergence_one(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N, SPH_BLOCK);
+	SphRigidArgs rg = rigid_args(h);
+	sph_prof_begin(h, KC_DF_DIV, st);
+	SPH_LAUNCH_R(k_df_div_iter, nb, c, h->L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
+	             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
+	sph_prof_end(h, st);
+	mg_exchange(h, MG_F4_VEL, st);
+	sph_prof_begin(h, KC_DF_DRHO, st);
+	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
 	             h->a1[A1_RHO],
-		             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 1);
-		sph_prof_end(h, st);
-		df_decide(h, MG_F4_T2, SPH_CTL_DIV_ITER, nb, st);
-		h->launches += 2;
-	}
+	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 1);
+	sph_prof_end(h, st);
+	df_decide(h, MG_F4_T2, SPH_CTL_DIV_ITER, nb, st);
+	h->launches += 2;
+}
+
+static void df_divergence(SphHandle *h, cudaStream_t st) {
+	df_divergence_begin(h, st);
+	for (int it = 0; it < 15; ++it) df_divergence_one(h, st); // max_iteration_density_divergence (DF:24)
 }
 
 static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
@@ -1093,8 +1104,16 @@ void df_phase(SphHandle *h, int phase, cudaStream_t st) {
 	switch (phase) {
 	case SPH_PH_DF_INITIALIZE: build_lists(h, st); mg_exchange(h, MG_F4_T1R, st); break;
 	case SPH_PH_DF_DIVERGENCE: df_divergence(h, st); break;
-	case SPH_PH_DF_EXT_FORCE_VEL_ADV: df_ext_force_vel_adv(h, st); break;
+	case SPH_PH_DF_EXT_FORCE_VEL_ADV: df_ext_force_vel_adv(h, st); h->den_piece = 0; break;
 	case SPH_PH_DF_DENSITY: df_density(h, st); break;
+	// the same loops one pass at a time (single-sweep parity tests drive these; the loop decisions stay on the device)
+	case SPH_PH_DF_DIV_BEGIN: df_divergence_begin(h, st); break;
+	case SPH_PH_DF_DIV_ONE: df_divergence_one(h, st); break;
+	case SPH_PH_DF_DEN_ONE:
+		if (h->den_piece == 0 && rigid_args(h).active) rigid_lists(h, st);
+		df_density_iters(h, h->den_piece, 1, st);
+		h->den_piece++;
+		break;
 	case SPH_PH_DF_POSITION: df_position(h, st); break;
 	default: break;
 	}

@@ -392,7 +392,8 @@ void pc_set_delta(SphHandle *h, int target, cudaStream_t st) {
 	h->launches++;
 }
 
-static void pc_iteration(SphHandle *h, cudaStream_t st) {
+// PC:47-55: predicted state at zero pressure correction, its density error and the decision whether the loop starts
+static void pc_iteration_begin(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nba = cdiv(c.N, SPH_BLOCK);
 	float4 *pos_predict = h->a4[A4_T2], *vel_predict = h->a4[A4_VADV];
@@ -409,25 +410,40 @@ static void pc_iteration(SphHandle *h, cudaStream_t st) {
 	sph_prof_end(h, st);
 	pc_decide(h, 0, nba, st);
 	h->launches += 2;
+}
+
+// PC:56-70: `count` passes of the loop body, each gated on ctl->pc_active (a no-op once the loop has ended)
+static void pc_iteration_passes(SphHandle *h, int count, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nba = cdiv(c.N, SPH_BLOCK);
+	float4 *pos_predict = h->a4[A4_T2], *vel_predict = h->a4[A4_VADV];
+	SphRigidArgs rg = rigid_args(h);
+	for (int it = 0; it < count; ++it) {
+		k_pc_commit_press<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+		mg_exchange(h, MG_F4_T1W, st); // slabs: press_iter of the ghost particles
+		sph_prof_begin(h, KC_PC_FORCE, st);
+		k_pc_press_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
+		                                            h->a4[A4_FA], h->a4[A4_FB], pos_predict, vel_predict, h->ctl);
+		sph_prof_end(h, st);
+		mg_exchange(h, MG_XYZ(A4_T2), st);
+		if (rg.active) rigid_force(h, RF_PC, 1, st); // PC:186, gather form
+		sph_prof_begin(h, KC_PC_RHO, st);
+		k_pc_predict_rho<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB],
+		                                            h->a1[A1_P], h->a1[A1_SC], h->ctl, h->partials, 1);
+		sph_prof_end(h, st);
+		pc_decide(h, 1, nba, st);
+		h->launches += 3;
+	}
+}
+
+static void pc_iteration(SphHandle *h, cudaStream_t st) {
+	pc_iteration_begin(h, st);
 	int done = 0;
 	int chunk = h->last_den_chunk > 0 ? h->last_den_chunk : 4;
 	for (;;) {
-		for (int it = 0; it < chunk && done < 80; ++it, ++done) { // max_iteration (PC:21); gated on ctl->pc_active
-			k_pc_commit_press<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
-			mg_exchange(h, MG_F4_T1W, st); // slabs: press_iter of the ghost particles
-			sph_prof_begin(h, KC_PC_FORCE, st);
-			k_pc_press_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
-			                                            h->a4[A4_FA], h->a4[A4_FB], pos_predict, vel_predict, h->ctl);
-			sph_prof_end(h, st);
-			mg_exchange(h, MG_XYZ(A4_T2), st);
-			if (rg.active) rigid_force(h, RF_PC, 1, st); // PC:186, gather form
-			sph_prof_begin(h, KC_PC_RHO, st);
-			k_pc_predict_rho<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB],
-			                                            h->a1[A1_P], h->a1[A1_SC], h->ctl, h->partials, 1);
-			sph_prof_end(h, st);
-			pc_decide(h, 1, nba, st);
-			h->launches += 3;
-		}
+		int n = chunk < 80 - done ? chunk : 80 - done; // max_iteration (PC:21)
+		pc_iteration_passes(h, n, st);
+		done += n;
 		if (done >= 80) break;
 		// one look at the device flag per chunk (not per iteration)
 		cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SphCtl), cudaMemcpyDeviceToHost, st);
@@ -452,6 +468,10 @@ void pc_phase(SphHandle *h, int phase, cudaStream_t st) {
 		h->launches++;
 	} else if (phase == SPH_PH_PC_ITERATION) {
 		pc_iteration(h, st);
+	} else if (phase == SPH_PH_PC_ITER_BEGIN) { // the loop one pass at a time (single-sweep parity tests)
+		pc_iteration_begin(h, st);
+	} else if (phase == SPH_PH_PC_ITER_ONE) {
+		pc_iteration_passes(h, 1, st);
 	} else if (phase == SPH_PH_PC_INTEGRATION) {
 		sph_prof_begin(h, KC_PC_INT, st);
 		k_pc_integration<<<nba, SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA],
@@ -709,33 +729,45 @@ k_ii_integration(SphConsts c, const int *__restrict__ sorted_id, const float4 *_
 	vel[i] = F4(v, p);                     // II:206 p_past = p_iter
 }
 
-static void ii_pressure_solve(SphHandle *h, cudaStream_t st) {
+// II:78-82: residual of the start iterate and the decision whether the loop starts
+static void ii_pressure_solve_begin(SphHandle *h, cudaStream_t st) {
+	k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, cdiv(h->c.N, SPH_BLOCK), 0);
+	h->launches++;
+}
+
+// II:83-100: `count` relaxed Jacobi passes, each gated on ctl->ii_active
+static void ii_pressure_solve_passes(SphHandle *h, int count, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nba = cdiv(c.N, SPH_BLOCK);
-	k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nba, 0);
-	h->launches++;
+	for (int it = 0; it < count; ++it) {
+		sph_prof_begin(h, KC_II_DIJ, st);
+		k_ii_dij<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->ctl);
+		sph_prof_end(h, st);
+		mg_exchange(h, MG_XYZ(A4_FB), st); // slabs: sum_j d_ij p_j of the ghost particles
+		sph_prof_begin(h, KC_II_UPDATE, st);
+		k_ii_update_p<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
+		                                         h->a4[A4_FC], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
+		                                         h->a1[A1_SC], h->ctl, h->partials);
+		sph_prof_end(h, st);
+		k_ii_commit<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+		if (h->comm) {
+			mg_exchange(h, MG_F4_T1W, st); // slabs: the new pressure iterate of the ghost particles
+			mg_exchange_reduce(h, MG_NONE, SPH_CTL_II_ITER, nba, st);
+		} else {
+			k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nba, 1);
+		}
+		h->launches += 4;
+	}
+}
+
+static void ii_pressure_solve(SphHandle *h, cudaStream_t st) {
+	ii_pressure_solve_begin(h, st);
 	int done = 0;
 	int chunk = h->last_den_chunk > 0 ? h->last_den_chunk : 4;
 	for (;;) {
-		for (int it = 0; it < chunk && done < 180; ++it, ++done) { // max_iter_cnt (II:27); gated on ctl->ii_active
-			sph_prof_begin(h, KC_II_DIJ, st);
-			k_ii_dij<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->ctl);
-			sph_prof_end(h, st);
-			mg_exchange(h, MG_XYZ(A4_FB), st); // slabs: sum_j d_ij p_j of the ghost particles
-			sph_prof_begin(h, KC_II_UPDATE, st);
-			k_ii_update_p<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
-			                                         h->a4[A4_FC], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
-			                                         h->a1[A1_SC], h->ctl, h->partials);
-			sph_prof_end(h, st);
-			k_ii_commit<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
-			if (h->comm) {
-				mg_exchange(h, MG_F4_T1W, st); // slabs: the new pressure iterate of the ghost particles
-				mg_exchange_reduce(h, MG_NONE, SPH_CTL_II_ITER, nba, st);
-			} else {
-				k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nba, 1);
-			}
-			h->launches += 4;
-		}
+		int n = chunk < 180 - done ? chunk : 180 - done; // max_iter_cnt (II:27)
+		ii_pressure_solve_passes(h, n, st);
+		done += n;
 		if (done >= 180) break;
 		cudaMemcpyAsync(h->ctl_host, h->ctl, sizeof(SphCtl), cudaMemcpyDeviceToHost, st);
 		cudaStreamSynchronize(st);
@@ -766,6 +798,10 @@ void ii_phase(SphHandle *h, int phase, cudaStream_t st) {
 		h->launches += 2;
 	} else if (phase == SPH_PH_II_PRESSURE_SOLVE) {
 		ii_pressure_solve(h, st);
+	} else if (phase == SPH_PH_II_SOLVE_BEGIN) { // the loop one pass at a time (single-sweep parity tests)
+		ii_pressure_solve_begin(h, st);
+	} else if (phase == SPH_PH_II_SOLVE_ONE) {
+		ii_pressure_solve_passes(h, 1, st);
 	} else if (phase == SPH_PH_II_INTEGRATION) {
 		if (rigid_args(h).active) { rigid_lists(h, st); rigid_force(h, RF_II, 0, st); } // II:159, gather form
 		sph_prof_begin(h, KC_II_INT, st);

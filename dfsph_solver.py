@@ -1,0 +1,5 @@
+# coding=utf-8
+"""Top-level module name of the reference (`dfsph_solver.py`), so that `main.py:10-11, 65-68` of the reference
+(`from ParticleSystem import ParticleSystem`, `importlib.import_module(name + '_solver')`, `utils.read_config`)
+resolve unchanged.  The implementation lives in cfd_taichi_b200/dfsph_solver.py."""
+from cfd_taichi_b200.dfsph_solver import dfsph_solver  # noqa: F401

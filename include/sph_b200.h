@@ -106,6 +106,12 @@ enum SphPhase {
 	SPH_PH_DF_EXT_FORCE_VEL_ADV,  /* DF:91-122 compute_all_ext_force + compute_all_vel_adv */
 	SPH_PH_DF_DENSITY,            /* DF:221-233 correct_density_error */
 	SPH_PH_DF_POSITION,           /* DF:235-250 compute_all_position */
+	/* the two DFSPH loops one pass at a time (loop decisions still taken on the device; a pass after the loop
+	 * has ended is a no-op).  DIVERGENCE == DIV_BEGIN + 15 x DIV_ONE; DENSITY == DEN_ONE until
+	 * SphStats says the loop is over. */
+	SPH_PH_DF_DIV_BEGIN,          /* DF:396-399 warm start + first derivative_iter_all_rho */
+	SPH_PH_DF_DIV_ONE,            /* DF:400-414 one loop body: divergence_iter_all_vel_adv, sum_up_stiff, derivative_iter_all_rho */
+	SPH_PH_DF_DEN_ONE,            /* DF:225-231 one loop body: compute_all_rho_adv, iter_all_vel_adv */
 	/* WCSPH */
 	SPH_PH_WC_PRESSURE = 20,      /* WC:32-38 */
 	SPH_PH_WC_KINEMATIC,          /* WC:40-63 */
@@ -113,10 +119,14 @@ enum SphPhase {
 	SPH_PH_PC_EXT_FORCE = 30,     /* PC:220-226 */
 	SPH_PH_PC_ITERATION,          /* PC:47-70 */
 	SPH_PH_PC_INTEGRATION,        /* PC:200-218 */
+	SPH_PH_PC_ITER_BEGIN,         /* PC:47-55 the pressure loop one pass at a time: ITERATION == ITER_BEGIN + ITER_ONE while pc_active */
+	SPH_PH_PC_ITER_ONE,           /* PC:56-70 one loop body */
 	/* IISPH */
 	SPH_PH_II_PREDICT_ADVECTION = 40, /* II:35-75 */
 	SPH_PH_II_PRESSURE_SOLVE,         /* II:78-100 */
 	SPH_PH_II_INTEGRATION,            /* II:184-206 */
+	SPH_PH_II_SOLVE_BEGIN,            /* II:78-82 the Jacobi loop one pass at a time: PRESSURE_SOLVE == SOLVE_BEGIN + SOLVE_ONE while ii_active */
+	SPH_PH_II_SOLVE_ONE,              /* II:83-100 one relaxed Jacobi pass */
 	/* PBF (fetch: rho = SPH_F_RHO, constrain = SCALAR_A, pbf_lambda = SCALAR_B, constrain_derivative =
 	 * FORCE_A, delta_pos = FORCE_B, pos_predict = VEC_C) */
 	SPH_PH_PBF_PREDICT = 50,          /* PBF:26-30 externel_force_predict_pos */
@@ -149,7 +159,8 @@ typedef struct SphStats {
 	float pc_delta;            /* PC:45 */
 	int32_t pc_max_index;      /* PS:409-422 */
 	int32_t kernel_launches;   /* launches issued by the library since creation */
-	int32_t reserved[3];
+	int32_t div_active, den_active; /* DFSPH loop flags on the device (1 while the loop of DF:400 / DF:225 would continue) */
+	int32_t loop_active;            /* PCISPH / IISPH loop flag on the device (PC:56 / II:83) */
 } SphStats;
 
 typedef struct SphHandle SphHandle;
@@ -242,6 +253,12 @@ int sph_upload_state_xyz(SphHandle *h, const float *host_pos3, const float *host
 int sph_download_state_xyz(SphHandle *h, float *host_pos3, float *host_vel3, void *stream);
 
 int sph_read_stats(SphHandle *h, SphStats *out);
+
+/* Test support (single-sweep parity of the fast kernels against the strict ones, tests/test_gpu_fast_parity.py):
+ * copy the in-step work state -- every sorted per-particle array, the control block, the rigid-body state -- of
+ * `src` into `dst`.  Both handles must describe the same scene on the same device with their grids built from the
+ * same positions.  Neighbour lists are not copied (each arithmetic mode keeps its own order). */
+int sph_copy_work_state(SphHandle *dst, SphHandle *src, void *stream);
 
 /* Live per-kernel-class timing: CUDA events recorded on the launching stream around every launch
  * between sph_profile_begin and sph_profile_end (which synchronises).  Class ids are listed in
