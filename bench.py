@@ -15,6 +15,15 @@ sides, max over ranks.  Three passes over the same K steps from one saved post-w
 (value), with an event pair around every launch (kernel_ms, roofline), end to end with host buffers (e2e).
 Per-step working set (neighbour lists ~140 MB, gradient cache ~540 MB, 11 float4 arrays) exceeds the 126 MB
 L2, so no explicit flush is needed between steps.
+
+Besides the contract keys the line carries
+  parity  N = 1: strict kernels bit-exact against the oracle and the fast kernels (the ones timed) sweep by sweep
+          within 1e-5 of them, on the SAME 100^3 block, from the oracle's state after its warm-up steps;
+          N > 1: the slab-decomposed run against the single-domain run, bit for bit by global particle id.
+  step    whole-step algorithmic GB/s from SURVEY 8(d)'s B_step(D, C), neighbour_search_ms (grid build, lists)
+  also    the other BASELINE configs timed in the same process: DFSPH 8 M (north_star's target size), WCSPH 30 k,
+          PCISPH / IISPH 4 M (N = 1); DFSPH 8 M per GPU (N > 1, configs[4])
+  comm    N > 1: ms per step in the halo-exchange kernels and in migration + ghost-particle exchange
 """
 import argparse
 import ctypes
@@ -40,8 +49,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-side", type=int, default=100, help="particles per edge of the per-GPU block")
     ap.add_argument("--strict", action="store_true", help="strict-fp32 kernels (bit-exact vs the oracle)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-n-side", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline + parity leg (N = 1)")
+    ap.add_argument("--cpu-n-side", type=int, default=0, help="edge of the CPU arm's block (default: --n-side, the GPU arm's block)")
+    ap.add_argument("--no-also", action="store_true", help="skip the other BASELINE configs")
+    ap.add_argument("--no-parity", action="store_true")
     return ap.parse_args()
 
 
@@ -131,38 +142,44 @@ def workload_name(n_side, n_gpus):
 # ---------------------------------------------------------------------------------------------
 # reference arm: the restated reference (oracle port, OpenMP) on the box's host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_reference(n_side, steps, warmup, threads=None):
+def host_threads():
+    return len(os.sched_getaffinity(0))
+
+
+def run_reference(args):
+    """`--impl reference`: the restated reference (oracle port, OpenMP over particles) on ALL host cores, on the GPU
+    arm's own block (100^3 per GPU; for N > 1 one GPU's block -- CPU throughput does not depend on the block count)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
     from oracle import oracle as O          # bench.py's cpu_baseline / reference legs may use oracle/
     from cfd_taichi_b200 import scenes
-    threads = threads or len(os.sched_getaffinity(0))
+    n_side = args.cpu_n_side or args.n_side
+    threads = host_threads()
     cfg = scenes.breaking_dam(n_side)
     o = O.Oracle(cfg, solver="dfsph", threads=threads)
     n = int(o.scalar("particle_num"))
-    for _ in range(warmup):
+    # bounded: ~4 s per 1 M-particle step on 16 cores; K + W capped so that the arm ends within a few minutes
+    budget = max(3, int(30 * 1.0e6 / max(n, 1)))
+    warm = min(args.warmup, max(1, budget // 5))
+    steps = max(1, min(args.steps, budget - warm))
+    for _ in range(warm):
         o.step()
     t0 = time.perf_counter()
     for _ in range(steps):
         o.step()
     dt = time.perf_counter() - t0
-    info = {"div_iters": int(o.scalar("df_div_iters")), "den_iters": int(o.scalar("df_den_iters"))}
+    info = {"divergence": int(o.scalar("df_div_iters")), "density": int(o.scalar("df_den_iters")), "of": "last timed step"}
     o.close()
-    return n * steps / dt, dt / steps * 1e3, threads, n, info
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    # bounded sample: a smaller block of the same dam so that K + W steps end within minutes
-    n_side = min(args.cpu_n_side, args.n_side)
-    val, ms, threads, n, info = cpu_reference(n_side, args.steps, args.warmup)
-    sample = "%d^3 = %d-particle block of the same dam, %d timed + %d warm-up dfsph steps, %d OpenMP threads" % (
-        n_side, n, args.steps, args.warmup, threads)
+    val, ms = n * steps / dt, dt / steps * 1e3
+    sample = "%d^3 = %d-particle block (the GPU arm's per-GPU block), %d timed + %d warm-up dfsph steps, %d OpenMP threads" % (
+        n_side, n, steps, warm, threads)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.n_side, args.gpus), "sample": sample, "iterations": info},
+        "config": {"workload": workload_name(args.n_side, args.gpus), "sample": sample, "iterations": info,
+                   "same_block_as_gpu_arm": n_side == args.n_side, "host_cores": threads},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

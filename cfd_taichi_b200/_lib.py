@@ -16,24 +16,42 @@ SOLVER_IDS = {"wcsph": 0, "pcisph": 1, "iisph": 2, "dfsph": 3, "pbf": 4}
 F_FLUID_POS, F_FLUID_VEL, F_BOUNDARY_POS, F_RIGID_POS, F_RIGID_VEL, F_RIGID_FORCE, F_FLUID_ACC, F_RIGID_VERTICES, F_FLUID_GID = range(9)
 (F_RHO, F_ALPHA, F_RHO_DERIVATIVE, F_RHO_ADV, F_VEL_ADV, F_CELL1D, F_NEIGHBOR_COUNT,
  F_BOUNDARY_NEIGHBOR_COUNT, F_PRESSURE, F_FORCE_A, F_FORCE_B, F_SCALAR_A, F_SCALAR_B, F_SCALAR_C,
- F_VEC_A, F_VEC_B, F_VEC_C) = range(16, 33)
+ F_VEC_A, F_VEC_B, F_VEC_C, F_PAYLOAD_1, F_PAYLOAD_3, F_POS_RHO) = range(16, 36)
 F_CELL_START, F_SORTED_INDEX, F_BOUNDARY_CELL_START, F_BOUNDARY_SORTED_INDEX = range(64, 68)
 
 # enum SphPhase
 PH_BUILD_GRID = 0
 PH_DF_INITIALIZE, PH_DF_DIVERGENCE, PH_DF_EXT_FORCE_VEL_ADV, PH_DF_DENSITY, PH_DF_POSITION = range(10, 15)
-PH_DF_DIV_BEGIN, PH_DF_DIV_ONE, PH_DF_DEN_ONE = 15, 16, 17   # the two DFSPH loops one pass at a time
 PH_WC_PRESSURE, PH_WC_KINEMATIC = 20, 21
-PH_PC_EXT_FORCE, PH_PC_ITERATION, PH_PC_INTEGRATION, PH_PC_ITER_BEGIN, PH_PC_ITER_ONE = 30, 31, 32, 33, 34
-PH_II_PREDICT_ADVECTION, PH_II_PRESSURE_SOLVE, PH_II_INTEGRATION, PH_II_SOLVE_BEGIN, PH_II_SOLVE_ONE = 40, 41, 42, 43, 44
+PH_PC_EXT_FORCE, PH_PC_ITERATION, PH_PC_INTEGRATION = 30, 31, 32
+PH_II_PREDICT_ADVECTION, PH_II_PRESSURE_SOLVE, PH_II_INTEGRATION = 40, 41, 42
 PH_PBF_PREDICT, PH_PBF_LAMBDA, PH_PBF_DELTA_POS, PH_PBF_UPDATE_POS = 50, 51, 52, 53
 PH_WRITEBACK = 90
+# the same steps one sweep at a time (selfcheck.py)
+PH_BUILD_LISTS = 100
+PH_DF_WARM_START, PH_DF_DRHO_FIRST, PH_DF_DIV_VEL, PH_DF_DIV_DRHO, PH_DF_DEN_RHO, PH_DF_DEN_VEL = range(110, 116)
+PH_WC_EOS, PH_WC_FORCE = 120, 121
+PH_PC_PREDICT, PH_PC_RHO_FIRST, PH_PC_PRESS_FORCE, PH_PC_RHO = range(130, 134)
+PH_II_ADVECT, PH_II_AII, PH_II_SOLVE_BEGIN, PH_II_DIJ, PH_II_UPDATE = range(140, 145)
 
 # kernel classes of sph_profile_end (csrc/sph_internal.h)
 KERNEL_CLASSES = ["grid", "lists", "df_warm_start", "df_drho", "df_div_iter", "df_ext_force", "df_rho_adv",
                   "df_vel_adv_iter", "df_position", "ctl", "wc_force", "wc_kinematic", "pc_ext", "pc_predict",
                   "pc_rho", "pc_force", "pc_integrate", "ii_adv", "ii_aii", "ii_dij", "ii_update", "ii_integrate",
                   "rigid", "other", "mg_exchange", "mg_begin_step", "mg_wait"]
+
+
+# SphStats.error_flags (csrc/sph_common.cuh): conditions under which the run has left the reference's physics
+ERROR_BITS = {1: "a particle left the grid and was clamped into it (PS:393-395)",
+              2: "a fluid neighbour list overflowed max_neighbors (the reference has no cap): raise solver.max_neighbors",
+              4: "a boundary neighbour list overflowed its capacity",
+              8: "the DFSPH density loop hit the library's 1000-pass cap (the reference's loop has none, DF:225)",
+              16: "a non-finite value appeared in the solver state",
+              32: "a peer rank stopped answering a halo exchange (multi-GPU)"}
+
+
+def decode_error_flags(flags):
+    return [msg for bit, msg in ERROR_BITS.items() if flags & bit]
 
 
 class SphLattice(ctypes.Structure):

@@ -276,6 +276,7 @@ static int require_state(SphHandle *h) {
 }
 
 static int check_launch(SphHandle *h, const char *what) {
+	if (h->async_error) { int rc = h->async_error; h->async_error = 0; return rc; } // message already recorded by sph_fail
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return sph_fail(h, SPH_ECUDA, "%s: %s", what, cudaGetErrorString(e));
 	return SPH_OK;
@@ -394,6 +395,7 @@ static int base_step(SphHandle *h, cudaStream_t st) {
 	sph_prof_end(h, st);
 	h->grid_valid = true;
 	h->lists_valid = false;
+	h->lists_fresh = false;
 	return SPH_OK;
 }
 
@@ -420,19 +422,24 @@ extern "C" int sph_phase(SphHandle *h, int phase, void *stream) {
 		sphg_writeback(h, h->a4[A4_POS], h->a4[A4_VEL], st);
 		return check_launch(h, "sph_phase(writeback)");
 	}
-	if (phase != SPH_PH_DF_INITIALIZE && phase != SPH_PH_WC_PRESSURE && phase != SPH_PH_PC_EXT_FORCE &&
+	if (phase != SPH_PH_DF_INITIALIZE && phase != SPH_PH_WC_PRESSURE && phase != SPH_PH_PC_EXT_FORCE && phase != SPH_PH_BUILD_LISTS &&
 	    phase != SPH_PH_II_PREDICT_ADVECTION && phase != SPH_PH_PBF_PREDICT && phase != SPH_PH_PBF_LAMBDA && !h->lists_valid)
 		return sph_fail(h, SPH_ESTATE, "sph_phase: neighbour lists not built (run the solver's first phase)");
-	if (phase >= SPH_PH_DF_INITIALIZE && phase <= SPH_PH_DF_DEN_ONE) {
+	if (phase == SPH_PH_BUILD_LISTS) {
+		if (h->c.solver == SPH_SOLVER_PBF) return sph_fail(h, SPH_EINVAL, "sph_phase: PBF builds its lists on the predicted positions (SPH_PH_PBF_LAMBDA)");
+		h->lists_fresh = false;
+		if (strict) sph_strict::first_phase_lists(h, st); else sph_fast::first_phase_lists(h, st);
+		h->lists_fresh = true;
+	} else if ((phase >= SPH_PH_DF_INITIALIZE && phase <= SPH_PH_DF_POSITION) || (phase >= SPH_PH_DF_WARM_START && phase <= SPH_PH_DF_DEN_VEL)) {
 		if (h->c.solver != SPH_SOLVER_DFSPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a DFSPH solver");
 		if (strict) sph_strict::df_phase(h, phase, st); else sph_fast::df_phase(h, phase, st);
-	} else if (phase >= SPH_PH_WC_PRESSURE && phase <= SPH_PH_WC_KINEMATIC) {
+	} else if ((phase >= SPH_PH_WC_PRESSURE && phase <= SPH_PH_WC_KINEMATIC) || phase == SPH_PH_WC_EOS || phase == SPH_PH_WC_FORCE) {
 		if (h->c.solver != SPH_SOLVER_WCSPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a WCSPH solver");
 		if (strict) sph_strict::wc_phase(h, phase, st); else sph_fast::wc_phase(h, phase, st);
-	} else if (phase >= SPH_PH_PC_EXT_FORCE && phase <= SPH_PH_PC_ITER_ONE) {
+	} else if ((phase >= SPH_PH_PC_EXT_FORCE && phase <= SPH_PH_PC_INTEGRATION) || (phase >= SPH_PH_PC_PREDICT && phase <= SPH_PH_PC_RHO)) {
 		if (h->c.solver != SPH_SOLVER_PCISPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not a PCISPH solver");
 		if (strict) sph_strict::pc_phase(h, phase, st); else sph_fast::pc_phase(h, phase, st);
-	} else if (phase >= SPH_PH_II_PREDICT_ADVECTION && phase <= SPH_PH_II_SOLVE_ONE) {
+	} else if ((phase >= SPH_PH_II_PREDICT_ADVECTION && phase <= SPH_PH_II_INTEGRATION) || (phase >= SPH_PH_II_ADVECT && phase <= SPH_PH_II_UPDATE)) {
 		if (h->c.solver != SPH_SOLVER_IISPH) return sph_fail(h, SPH_EINVAL, "sph_phase: handle is not an IISPH solver");
 		if (strict) sph_strict::ii_phase(h, phase, st); else sph_fast::ii_phase(h, phase, st);
 	} else if (phase >= SPH_PH_PBF_PREDICT && phase <= SPH_PH_PBF_UPDATE_POS) {
@@ -585,6 +592,9 @@ extern "C" int sph_fetch(SphHandle *h, int field, void *dev_out, size_t n, void 
 	case SPH_F_VEC_A: rc = f4(h->a4[A4_FC]); break;
 	case SPH_F_VEC_B: rc = f4(h->a4[A4_FD]); break;
 	case SPH_F_VEC_C: rc = f4(h->a4[A4_T2]); break;
+	case SPH_F_PAYLOAD_1: rc = f4(h->a4[A4_T1]); break;
+	case SPH_F_PAYLOAD_3: rc = f4(h->a4[A4_T3]); break;
+	case SPH_F_POS_RHO: rc = f4(h->a4[A4_PR]); break;
 	case SPH_F_FLUID_VEL: rc = f4(h->a4[A4_VEL]); break;   // in-step (sorted) velocity, original order
 	case SPH_F_FLUID_POS: rc = f4(h->a4[A4_POS]); break;
 	case SPH_F_CELL1D: rc = raw(h->fg.cell_of, N, sizeof(int)); break;

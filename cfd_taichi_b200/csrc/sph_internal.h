@@ -79,6 +79,8 @@ struct SphHandle {
 	int n_partials;
 	double *red; // device: {sum, cnt, max} of the last reduction (all ranks)
 	bool grid_valid, boundary_ready, lists_valid;
+	int async_error;      // a library call inside a void helper failed (NCCL transport): the enclosing sph_* call returns it
+	bool lists_fresh;     // SPH_PH_BUILD_LISTS has built this step's lists: the solver's first phase skips its own build
 	int sweep_blocks;
 	int last_den_chunk;
 	int den_piece;        // density iterations issued one at a time through SPH_PH_DF_DEN_ONE since the last v* pass
@@ -141,6 +143,7 @@ void mg_rigid_quirk_update(SphHandle *h, int with_rho, cudaStream_t st);        
 	void build_lists(SphHandle *h, cudaStream_t st);                                        \
 	void df_step(SphHandle *h, cudaStream_t st);                                            \
 	void df_phase(SphHandle *h, int phase, cudaStream_t st);                                \
+	void first_phase_lists(SphHandle *h, cudaStream_t st);                                  \
 	void wc_phase(SphHandle *h, int phase, cudaStream_t st);                                \
 	void pc_phase(SphHandle *h, int phase, cudaStream_t st);                                \
 	void pc_precompute(SphHandle *h, cudaStream_t st);                                      \

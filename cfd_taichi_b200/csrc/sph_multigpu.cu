@@ -17,9 +17,9 @@
 // rank's window, polls all ranks' slots, sums them in rank order (deterministic, identical on every rank)
 // and takes the loop decision (sph_ctl.cuh).  Every 16-byte slot carries the exchange's epoch in its last
 // word and is written with one 128-bit store (the atomicity NCCL's LL protocols rely on), so there is no
-// fence, no flag, no host involvement and no proxy thread.  Windows are double-buffered by epoch parity: a
-// full handshake with both neighbours per exchange means a rank can be at most one exchange ahead of a
-// peer.  NCCL keeps the two variable-size particle messages per step (migration, ghost particles).
+// fence, no flag, no host involvement and no proxy thread.  Windows are double-buffered by epoch parity; every
+// exchange carries a tagged sync slot to and from both neighbours (whatever the halo counts), so a rank can be
+// at most one exchange ahead of a peer.  NCCL keeps the two variable-size particle messages per step (migration, ghost particles).
 // SPH_MG_TRANSPORT=nccl selects NCCL for everything (A/B measurements).
 #include <dlfcn.h>
 #include <nccl.h>
@@ -93,6 +93,7 @@ struct SphComm {
 //   [4096, ...)          float4 xr[2 parity][2 side][cap_halo], .w = epoch tag
 struct MgCtlWin {
 	double rslot[2][SPH_MG_MAX_RANKS][4]; // two tagged 16-byte slots per (parity, source rank)
+	uint4 sync[2][2];                     // [parity][side]: "my neighbour on that side has entered this exchange"
 };
 static_assert(sizeof(MgCtlWin) <= 4096, "window control block");
 __host__ __device__ static inline MgCtlWin *win_ctl(char *w) { return (MgCtlWin *)w; }
@@ -104,6 +105,14 @@ __host__ __device__ static inline float4 *win_xr(char *w, int cap, int parity, i
 	do {                                                                                                 \
 		ncclResult_t r_ = (expr);                                                                        \
 		if (r_ != ncclSuccess) return sph_fail((h), SPH_ECUDA, "NCCL: %s (%s)", g_nccl.GetErrorString(r_), #expr); \
+	} while (0)
+
+// inside the void exchange helpers: record the failure; the enclosing sph_step / sph_phase returns it (check_launch)
+#define NCCL_LATCH(h, expr)                                                                              \
+	do {                                                                                                 \
+		ncclResult_t r_ = (expr);                                                                        \
+		if (r_ != ncclSuccess && !(h)->async_error)                                                      \
+			(h)->async_error = sph_fail((h), SPH_ECUDA, "NCCL: %s (%s)", g_nccl.GetErrorString(r_), #expr); \
 	} while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -349,6 +358,17 @@ k_mg_exchange(int what, const int *__restrict__ send_slot_l, const int *__restri
 		return;
 	}
 	if (!src_a) return;
+	// Handshake with both neighbours on EVERY exchange, whatever the halo counts: a rank that sends to an empty
+	// neighbour column would otherwise never wait for that neighbour, run two epochs ahead and overwrite slots of
+	// the same parity before they were read.  With it a rank cannot leave exchange e before both neighbours have
+	// entered e, i.e. finished reading e-1: one epoch of slack, which is what the two parities cover.
+	if (blockIdx.x == 0 && threadIdx.x < 2) {
+		int side = threadIdx.x, peer = side == 0 ? rank - 1 : rank + 1;
+		if (peer >= 0 && peer < nranks) {
+			st_slot(&win_ctl(peers.w[peer])->sync[parity][1 - side], 0u, 0u, 0u, (uint32_t)epoch);
+			wait_slot(&win_ctl(win)->sync[parity][side], epoch, ctl);
+		}
+	}
 	const int nblk = (int)gridDim.x - (do_reduce ? 1 : 0);
 	const int stride = nblk * (int)blockDim.x;
 	const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -533,7 +553,7 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 	                                                        m->msg_send[1], m->cap_mig, m->counters);
 	k_mg_header<<<1, 32, 0, st>>>(m->msg_send[0], m->msg_send[1], m->counters, MC_MIG_L, MC_MIG_R, m->cap_mig);
 	int rc = exchange_bytes(h, m, m->msg_bytes_mig, st);
-	if (rc != SPH_OK) return rc;
+	if (rc != SPH_OK) { sph_prof_end(h, st); return rc; }
 	k_mg_rebuild<<<cdiv(capacity_owned, 256), 256, 0, st>>>(m->tmp_pos, m->tmp_vel, m->tmp_gid, m->msg_recv[0], m->msg_recv[1],
 	                                                        has_left, has_right, m->cap_mig, h->pos, h->vel, h->gid,
 	                                                        capacity_owned, m->counters);
@@ -543,12 +563,14 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 	                                                          m->send_orig[0], m->send_orig[1], m->counters);
 	k_mg_header<<<1, 32, 0, st>>>(m->msg_send[0], m->msg_send[1], m->counters, MC_HALO_L, MC_HALO_R, m->cap_halo);
 	rc = exchange_bytes(h, m, m->msg_bytes_halo, st);
-	if (rc != SPH_OK) return rc;
+	if (rc != SPH_OK) { sph_prof_end(h, st); return rc; }
 	k_mg_unpack_halo<<<cdiv(2 * m->cap_halo, 256), 256, 0, st>>>(m->msg_recv[0], m->msg_recv[1], has_left, has_right,
 	                                                             m->cap_halo, h->pos, h->vel, h->gid, capacity_all, m->counters);
 	h->launches += 6;
 	// (3) the one host read-back of the step
 	SPH_CUDA_CHECK(h, cudaMemcpyAsync(m->counters_host, m->counters, sizeof(int) * MC_COUNT, cudaMemcpyDeviceToHost, st));
+	// the flags latched by the previous step's exchanges travel with the counters (WCSPH / PBF have no other read-back)
+	SPH_CUDA_CHECK(h, cudaMemcpyAsync(&h->ctl_host->error_flags, &h->ctl->error_flags, sizeof(int), cudaMemcpyDeviceToHost, st));
 	sph_prof_end(h, st);
 	SPH_CUDA_CHECK(h, cudaStreamSynchronize(st));
 	const int *k = m->counters_host;
@@ -638,20 +660,20 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 	}
 	if (reduce_blocks > 0) sph_reduce_partials_launch(h, reduce_blocks, st);
 	int left = m->rank - 1, right = m->rank + 1;
-	g_nccl.GroupStart();
+	NCCL_LATCH(h, g_nccl.GroupStart());
 	if (a && left >= 0) {
-		if (m->n_send[0] > 0) g_nccl.Send(m->xsend[0], (size_t)m->n_send[0] * 4, ncclFloat, left, m->comm, st);
-		if (m->n_recv[0] > 0) g_nccl.Recv(m->xrecv[0], (size_t)m->n_recv[0] * 4, ncclFloat, left, m->comm, st);
+		if (m->n_send[0] > 0) NCCL_LATCH(h, g_nccl.Send(m->xsend[0], (size_t)m->n_send[0] * 4, ncclFloat, left, m->comm, st));
+		if (m->n_recv[0] > 0) NCCL_LATCH(h, g_nccl.Recv(m->xrecv[0], (size_t)m->n_recv[0] * 4, ncclFloat, left, m->comm, st));
 	}
 	if (a && right < m->nranks) {
-		if (m->n_send[1] > 0) g_nccl.Send(m->xsend[1], (size_t)m->n_send[1] * 4, ncclFloat, right, m->comm, st);
-		if (m->n_recv[1] > 0) g_nccl.Recv(m->xrecv[1], (size_t)m->n_recv[1] * 4, ncclFloat, right, m->comm, st);
+		if (m->n_send[1] > 0) NCCL_LATCH(h, g_nccl.Send(m->xsend[1], (size_t)m->n_send[1] * 4, ncclFloat, right, m->comm, st));
+		if (m->n_recv[1] > 0) NCCL_LATCH(h, g_nccl.Recv(m->xrecv[1], (size_t)m->n_recv[1] * 4, ncclFloat, right, m->comm, st));
 	}
 	if (reduce_blocks > 0) {
-		g_nccl.AllReduce(h->red, h->red, 2, ncclDouble, ncclSum, m->comm, st);
-		g_nccl.AllReduce(h->red + 2, h->red + 2, 1, ncclDouble, ncclMax, m->comm, st);
+		NCCL_LATCH(h, g_nccl.AllReduce(h->red, h->red, 2, ncclDouble, ncclSum, m->comm, st));
+		NCCL_LATCH(h, g_nccl.AllReduce(h->red + 2, h->red + 2, 1, ncclDouble, ncclMax, m->comm, st));
 	}
-	g_nccl.GroupEnd();
+	NCCL_LATCH(h, g_nccl.GroupEnd());
 	if (reduce_blocks > 0) { k_mg_ctl_apply<<<1, 1, 0, st>>>(ctl_kind, cargs, h->red, h->ctl); h->launches++; }
 	if (a && nr > 0) {
 		k_mg_unpack_values<<<cdiv(nr, 256), 256, 0, st>>>(what, h->fg.slot_of, h->c.N_owned, m->n_recv[0], m->n_recv[1],
@@ -670,7 +692,7 @@ void mg_exchange_reduce(SphHandle *h, int what, int ctl_kind, int n_blocks, cuda
 void mg_allreduce_sum_f32(SphHandle *h, float *dev, size_t n, cudaStream_t st) {
 	SphComm *m = h->comm;
 	if (!m || n == 0) return;
-	g_nccl.AllReduce(dev, dev, n, ncclFloat, ncclSum, m->comm, st);
+	NCCL_LATCH(h, g_nccl.AllReduce(dev, dev, n, ncclFloat, ncclSum, m->comm, st));
 }
 
 // Two reference quirks index FLUID arrays with a rigid-local index k < Nr: the neighbour count measures the
@@ -695,7 +717,7 @@ void mg_rigid_quirk_update(SphHandle *h, int with_rho, cudaStream_t st) {
 	if (h->c.N_owned > 0)
 		k_mg_quirk_fill<<<cdiv(h->c.N_owned, 256), 256, 0, st>>>(h->pos, h->gid, h->fg.slot_of, h->a1[A1_RHO], h->c.N_owned,
 		                                                         h->c.Nr, with_rho, m->quirk);
-	g_nccl.AllReduce(m->quirk, m->quirk, 4 * (size_t)h->c.Nr, ncclFloat, ncclSum, m->comm, st);
+	NCCL_LATCH(h, g_nccl.AllReduce(m->quirk, m->quirk, 4 * (size_t)h->c.Nr, ncclFloat, ncclSum, m->comm, st));
 	h->launches++;
 }
 

@@ -378,6 +378,16 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 	if (rg.active) mg_rigid_quirk_update(h, 1, st); // slabs: rho of the quirk particles is known now
 }
 
+// Every solver's first phase starts with the step's lists (and the ghosts' density on slabs); a caller that
+// drives single sweeps has already built them with SPH_PH_BUILD_LISTS.
+void first_phase_lists(SphHandle *h, cudaStream_t st) {
+	if (!h->lists_fresh) {
+		build_lists(h, st);
+		mg_exchange(h, MG_F4_T1R, st); // slabs: rho of the ghost particles (posR.w)
+	}
+	h->lists_fresh = false;
+}
+
 // list walkers ---------------------------------------------------------------------------------
 // Lists are quad-interleaved (sph_list_word): one 128-bit load brings four entries of a particle and a
 // warp reads 512 contiguous bytes.  The list stream comes from DRAM (it is larger than L2), so the
@@ -996,8 +1006,8 @@ static void df_decide(SphHandle *h, int what, int kind, int nb, cudaStream_t st)
 void rigid_lists(SphHandle *h, cudaStream_t st);
 void rigid_force_df(SphHandle *h, int gated, cudaStream_t st);
 
-// DF:393-399: warm start, first D rho / D t evaluation and the decision whether the loop starts
-static void df_divergence_begin(SphHandle *h, cudaStream_t st) {
+// DF:314-355 divergence_warm_start
+static void df_warm_start(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
@@ -1005,17 +1015,26 @@ static void df_divergence_begin(SphHandle *h, cudaStream_t st) {
 	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl);
 	sph_prof_end(h, st);
 	mg_exchange(h, MG_F4_VEL, st);
+	h->launches += 1;
+}
+
+// DF:252-280 derivative_iter_all_rho + the loop decision that follows it (DF:398-399 before the loop, DF:406-414
+// inside it, where the sweep is gated on ctl->div_active)
+static void df_drho(SphHandle *h, int in_loop, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N, SPH_BLOCK);
+	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_DRHO, st);
 	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
 	             h->a1[A1_RHO],
-	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 0);
+	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, in_loop);
 	sph_prof_end(h, st);
-	df_decide(h, MG_F4_T2, SPH_CTL_DIV_FIRST, nb, st);
-	h->launches += 2;
+	df_decide(h, MG_F4_T2, in_loop ? SPH_CTL_DIV_ITER : SPH_CTL_DIV_FIRST, nb, st);
+	h->launches += 1;
 }
 
-// DF:400-414: one pass of the loop body, gated on ctl->div_active (a no-op once the loop has ended)
-static void df_divergence_one(SphHandle *h, cudaStream_t st) {
+// DF:302-312 divergence_iter_all_vel_adv + DF:381-384 sum_up_stiff, gated on ctl->div_active
+static void df_div_vel(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
@@ -1024,18 +1043,18 @@ static void df_divergence_one(SphHandle *h, cudaStream_t st) {
 	             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
 	sph_prof_end(h, st);
 	mg_exchange(h, MG_F4_VEL, st);
-	sph_prof_begin(h, KC_DF_DRHO, st);
-	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
-	             h->a1[A1_RHO],
-	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, 1);
-	sph_prof_end(h, st);
-	df_decide(h, MG_F4_T2, SPH_CTL_DIV_ITER, nb, st);
-	h->launches += 2;
+	h->launches += 1;
 }
 
+// DF:393-416 correct_divergence_error: the 15 passes (max_iteration_density_divergence, DF:24) are enqueued
+// unconditionally and gate themselves on the device flag
 static void df_divergence(SphHandle *h, cudaStream_t st) {
-	df_divergence_begin(h, st);
-	for (int it = 0; it < 15; ++it) df_divergence_one(h, st); // max_iteration_density_divergence (DF:24)
+	df_warm_start(h, st);
+	df_drho(h, 0, st);
+	for (int it = 0; it < 15; ++it) {
+		df_div_vel(h, st);
+		df_drho(h, 1, st);
+	}
 }
 
 static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
@@ -1051,25 +1070,40 @@ static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	h->launches += 1;
 }
 
-static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st) {
+// DF:124-152 compute_all_rho_adv of pass `it` + the average the loop condition reads (DF:225)
+static void df_den_rho(SphHandle *h, int it, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
+	int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
+	sph_prof_begin(h, KC_DF_RHOADV, st);
+	SPH_LAUNCH_R(k_df_rho_adv, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
+	             h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated);
+	sph_prof_end(h, st);
+	df_decide(h, MG_F4_T3, SPH_CTL_DEN, nb, st);
+	h->launches += 1;
+}
+
+// DF:178-219 iter_all_vel_adv of pass `it` (+ the fluid -> rigid forces, DF:212) and the decision whether pass it+1 runs
+static void df_den_vel(SphHandle *h, int it, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nb = cdiv(c.N, SPH_BLOCK);
+	SphRigidArgs rg = rigid_args(h);
+	int gated = it >= 2 ? 1 : 0;
+	sph_prof_begin(h, KC_DF_VELADV, st);
+	SPH_LAUNCH_R(k_df_vel_adv_iter, nb, c, h->L, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
+	             h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
+	sph_prof_end(h, st);
+	mg_exchange(h, MG_F4_VADV, st);
+	if (rg.active) rigid_force_df(h, gated, st); // DF:212, gather form
+	k_df_ctl_den_next<<<1, 1, 0, st>>>(h->ctl);
+	h->launches += 2;
+}
+
+static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st) {
 	for (int it = first; it < first + count; ++it) {
-		int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
-		sph_prof_begin(h, KC_DF_RHOADV, st);
-		SPH_LAUNCH_R(k_df_rho_adv, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
-		             h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated);
-		sph_prof_end(h, st);
-		df_decide(h, MG_F4_T3, SPH_CTL_DEN, nb, st);
-		sph_prof_begin(h, KC_DF_VELADV, st);
-		SPH_LAUNCH_R(k_df_vel_adv_iter, nb, c, h->L, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-		             h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
-		sph_prof_end(h, st);
-		mg_exchange(h, MG_F4_VADV, st);
-		if (rg.active) rigid_force_df(h, gated, st); // DF:212, gather form
-		k_df_ctl_den_next<<<1, 1, 0, st>>>(h->ctl);
-		h->launches += 3;
+		df_den_rho(h, it, st);
+		df_den_vel(h, it, st);
 	}
 }
 
@@ -1102,26 +1136,27 @@ static void df_position(SphHandle *h, cudaStream_t st) {
 
 void df_phase(SphHandle *h, int phase, cudaStream_t st) {
 	switch (phase) {
-	case SPH_PH_DF_INITIALIZE: build_lists(h, st); mg_exchange(h, MG_F4_T1R, st); break;
+	case SPH_PH_DF_INITIALIZE: first_phase_lists(h, st); break;
 	case SPH_PH_DF_DIVERGENCE: df_divergence(h, st); break;
 	case SPH_PH_DF_EXT_FORCE_VEL_ADV: df_ext_force_vel_adv(h, st); h->den_piece = 0; break;
 	case SPH_PH_DF_DENSITY: df_density(h, st); break;
-	// the same loops one pass at a time (single-sweep parity tests drive these; the loop decisions stay on the device)
-	case SPH_PH_DF_DIV_BEGIN: df_divergence_begin(h, st); break;
-	case SPH_PH_DF_DIV_ONE: df_divergence_one(h, st); break;
-	case SPH_PH_DF_DEN_ONE:
-		if (h->den_piece == 0 && rigid_args(h).active) rigid_lists(h, st);
-		df_density_iters(h, h->den_piece, 1, st);
-		h->den_piece++;
-		break;
 	case SPH_PH_DF_POSITION: df_position(h, st); break;
+	// the same step one sweep at a time (single-sweep parity tests drive these; the loop decisions stay on the device)
+	case SPH_PH_DF_WARM_START: df_warm_start(h, st); break;
+	case SPH_PH_DF_DRHO_FIRST: df_drho(h, 0, st); break;
+	case SPH_PH_DF_DIV_VEL: df_div_vel(h, st); break;
+	case SPH_PH_DF_DIV_DRHO: df_drho(h, 1, st); break;
+	case SPH_PH_DF_DEN_RHO:
+		if (h->den_piece == 0 && rigid_args(h).active) rigid_lists(h, st);
+		df_den_rho(h, h->den_piece, st);
+		break;
+	case SPH_PH_DF_DEN_VEL: df_den_vel(h, h->den_piece, st); h->den_piece++; break;
 	default: break;
 	}
 }
 
 void df_step(SphHandle *h, cudaStream_t st) {
-	build_lists(h, st);
-	mg_exchange(h, MG_F4_T1R, st);
+	first_phase_lists(h, st);
 	df_divergence(h, st);
 	df_ext_force_vel_adv(h, st);
 	df_density(h, st);

@@ -157,20 +157,37 @@ k_wc_kinematic(SphConsts c, const int *__restrict__ sorted_id, const float4 *__r
 	if (acc_out) acc_out[i] = F4(a, 0.0f);
 }
 
+// WC:32-38 Tait pressure per particle (+ the payload copies the force sweep gathers)
+static void wc_eos(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	sph_prof_begin(h, KC_WC_FORCE, st);
+	k_wc_pressure<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_P], h->a4[A4_T1], h->a4[A4_VADV]);
+	sph_prof_end(h, st);
+	h->launches += 1;
+}
+// WC:65-144 pressure gradient + boundary term + viscosity + tension (+ fluid -> rigid forces, WC:126)
+static void wc_force(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	SphRigidArgs rg = rigid_args(h);
+	sph_prof_begin(h, KC_WC_FORCE, st);
+	k_wc_force<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->a4[A4_VADV], h->bspos, h->a1[A1_P],
+	                                                      h->a1[A1_RHO], h->a4[A4_FA], h->a4[A4_FB], h->a4[A4_FC], h->a4[A4_FD]);
+	sph_prof_end(h, st);
+	h->launches += 1;
+	if (rg.active) { rigid_lists(h, st); rigid_force(h, RF_WC, 0, st); } // WC:126, gather form
+}
+
 void wc_phase(SphHandle *h, int phase, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N_owned, SPH_BLOCK), nba = cdiv(c.N, SPH_BLOCK);
+	int nba = cdiv(c.N, SPH_BLOCK);
 	if (phase == SPH_PH_WC_PRESSURE) {
-		build_lists(h, st);
-		mg_exchange(h, MG_F4_T1R, st); // slabs: rho of the ghost particles (posR.w); p follows from it pointwise
-		sph_prof_begin(h, KC_WC_FORCE, st);
-		k_wc_pressure<<<nba, SPH_BLOCK, 0, st>>>(c, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_P], h->a4[A4_T1], h->a4[A4_VADV]);
-		SphRigidArgs rg = rigid_args(h);
-		k_wc_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->a4[A4_VADV], h->bspos, h->a1[A1_P],
-		                                     h->a1[A1_RHO], h->a4[A4_FA], h->a4[A4_FB], h->a4[A4_FC], h->a4[A4_FD]);
-		sph_prof_end(h, st);
-		h->launches += 2;
-		if (rg.active) { rigid_lists(h, st); rigid_force(h, RF_WC, 0, st); } // WC:126, gather form
+		first_phase_lists(h, st); // slabs: rho of the ghost particles travels here; p follows from it pointwise
+		wc_eos(h, st);
+		wc_force(h, st);
+	} else if (phase == SPH_PH_WC_EOS) {
+		wc_eos(h, st);
+	} else if (phase == SPH_PH_WC_FORCE) {
+		wc_force(h, st);
 	} else if (phase == SPH_PH_WC_KINEMATIC) {
 		sph_prof_begin(h, KC_WC_KIN, st);
 		k_wc_kinematic<<<nba, SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA],
@@ -392,47 +409,56 @@ void pc_set_delta(SphHandle *h, int target, cudaStream_t st) {
 	h->launches++;
 }
 
-// PC:47-55: predicted state at zero pressure correction, its density error and the decision whether the loop starts
-static void pc_iteration_begin(SphHandle *h, cudaStream_t st) {
+// PC:72-87 predict_vel_pos at the current pressure force (the first evaluation of a step; later ones are fused
+// into the pressure-force sweep)
+static void pc_predict(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nba = cdiv(c.N, SPH_BLOCK);
-	float4 *pos_predict = h->a4[A4_T2], *vel_predict = h->a4[A4_VADV];
-	SphRigidArgs rg = rigid_args(h);
-	if (rg.active) rigid_lists(h, st);
+	if (rigid_args(h).active) rigid_lists(h, st);
 	sph_prof_begin(h, KC_PC_PREDICT, st);
-	k_pc_predict<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA], h->a4[A4_FB], pos_predict,
-	                                        vel_predict, h->ctl);
+	k_pc_predict<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA], h->a4[A4_FB],
+	                                                        h->a4[A4_T2], h->a4[A4_VADV], h->ctl);
 	sph_prof_end(h, st);
 	mg_exchange(h, MG_XYZ(A4_T2), st); // slabs: predicted positions of the ghost particles
+	h->launches += 1;
+}
+// PC:89-100 predict_rho + PC:123-133 compute_residual + the loop decision (PC:54 before the loop, PC:56 inside it)
+static void pc_rho(SphHandle *h, int in_loop, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nba = cdiv(c.N, SPH_BLOCK);
 	sph_prof_begin(h, KC_PC_RHO, st);
-	k_pc_predict_rho<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB], h->a1[A1_P],
-	                                            h->a1[A1_SC], h->ctl, h->partials, 0);
+	k_pc_predict_rho<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_T2], h->bspos, h->a1[A1_SA], h->a1[A1_SB],
+	                                            h->a1[A1_P], h->a1[A1_SC], h->ctl, h->partials, in_loop);
 	sph_prof_end(h, st);
-	pc_decide(h, 0, nba, st);
+	pc_decide(h, in_loop, nba, st);
+	h->launches += 1;
+}
+// PC:102-121 iter_press + update_press_force (+ predict_vel_pos of the next evaluation, + fluid -> rigid forces PC:186)
+static void pc_press_force(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	int nba = cdiv(c.N, SPH_BLOCK);
+	SphRigidArgs rg = rigid_args(h);
+	k_pc_commit_press<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+	mg_exchange(h, MG_F4_T1W, st); // slabs: press_iter of the ghost particles
+	sph_prof_begin(h, KC_PC_FORCE, st);
+	k_pc_press_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
+	                                            h->a4[A4_FA], h->a4[A4_FB], h->a4[A4_T2], h->a4[A4_VADV], h->ctl);
+	sph_prof_end(h, st);
+	mg_exchange(h, MG_XYZ(A4_T2), st);
+	if (rg.active) rigid_force(h, RF_PC, 1, st); // PC:186, gather form
 	h->launches += 2;
+}
+
+// PC:47-55: predicted state at zero pressure correction, its density error and the decision whether the loop starts
+static void pc_iteration_begin(SphHandle *h, cudaStream_t st) {
+	pc_predict(h, st);
+	pc_rho(h, 0, st);
 }
 
 // PC:56-70: `count` passes of the loop body, each gated on ctl->pc_active (a no-op once the loop has ended)
 static void pc_iteration_passes(SphHandle *h, int count, cudaStream_t st) {
-	const SphConsts &c = h->c;
-	int nba = cdiv(c.N, SPH_BLOCK);
-	float4 *pos_predict = h->a4[A4_T2], *vel_predict = h->a4[A4_VADV];
-	SphRigidArgs rg = rigid_args(h);
 	for (int it = 0; it < count; ++it) {
-		k_pc_commit_press<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
-		mg_exchange(h, MG_F4_T1W, st); // slabs: press_iter of the ghost particles
-		sph_prof_begin(h, KC_PC_FORCE, st);
-		k_pc_press_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL],
-		                                            h->a4[A4_FA], h->a4[A4_FB], pos_predict, vel_predict, h->ctl);
-		sph_prof_end(h, st);
-		mg_exchange(h, MG_XYZ(A4_T2), st);
-		if (rg.active) rigid_force(h, RF_PC, 1, st); // PC:186, gather form
-		sph_prof_begin(h, KC_PC_RHO, st);
-		k_pc_predict_rho<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, pos_predict, h->bspos, h->a1[A1_SA], h->a1[A1_SB],
-		                                            h->a1[A1_P], h->a1[A1_SC], h->ctl, h->partials, 1);
-		sph_prof_end(h, st);
-		pc_decide(h, 1, nba, st);
-		h->launches += 3;
+		pc_press_force(h, st);
+		pc_rho(h, 1, st);
 	}
 }
 
@@ -459,8 +485,7 @@ void pc_phase(SphHandle *h, int phase, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nba = cdiv(c.N, SPH_BLOCK);
 	if (phase == SPH_PH_PC_EXT_FORCE) {
-		build_lists(h, st);
-		mg_exchange(h, MG_F4_T1R, st); // slabs: rho of the ghost particles (posR.w)
+		first_phase_lists(h, st);
 		sph_prof_begin(h, KC_PC_EXT, st);
 		k_pc_ext_force<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO],
 		                                          h->a4[A4_FA], h->a4[A4_FB], h->a1[A1_P], h->a4[A4_T1]);
@@ -468,10 +493,14 @@ void pc_phase(SphHandle *h, int phase, cudaStream_t st) {
 		h->launches++;
 	} else if (phase == SPH_PH_PC_ITERATION) {
 		pc_iteration(h, st);
-	} else if (phase == SPH_PH_PC_ITER_BEGIN) { // the loop one pass at a time (single-sweep parity tests)
-		pc_iteration_begin(h, st);
-	} else if (phase == SPH_PH_PC_ITER_ONE) {
-		pc_iteration_passes(h, 1, st);
+	} else if (phase == SPH_PH_PC_PREDICT) { // the loop one sweep at a time (single-sweep parity tests)
+		pc_predict(h, st);
+	} else if (phase == SPH_PH_PC_RHO_FIRST) {
+		pc_rho(h, 0, st);
+	} else if (phase == SPH_PH_PC_PRESS_FORCE) {
+		pc_press_force(h, st);
+	} else if (phase == SPH_PH_PC_RHO) {
+		pc_rho(h, 1, st);
 	} else if (phase == SPH_PH_PC_INTEGRATION) {
 		sph_prof_begin(h, KC_PC_INT, st);
 		k_pc_integration<<<nba, SPH_BLOCK, 0, st>>>(c, h->fg.sorted_id, h->a4[A4_POS], h->a4[A4_VEL], h->a4[A4_FA],
@@ -735,28 +764,39 @@ static void ii_pressure_solve_begin(SphHandle *h, cudaStream_t st) {
 	h->launches++;
 }
 
-// II:83-100: `count` relaxed Jacobi passes, each gated on ctl->ii_active
-static void ii_pressure_solve_passes(SphHandle *h, int count, cudaStream_t st) {
+// II:208-250 compute_all_d_ij: sum_j d_ij p_j, gated on ctl->ii_active
+static void ii_dij(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	sph_prof_begin(h, KC_II_DIJ, st);
+	k_ii_dij<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->ctl);
+	sph_prof_end(h, st);
+	mg_exchange(h, MG_XYZ(A4_FB), st); // slabs: sum_j d_ij p_j of the ghost particles
+	h->launches += 1;
+}
+// II:252-340 update_p (relaxed Jacobi, omega = 0.5) + II:102-113 compute_residual + the loop decision (II:83-93)
+static void ii_update(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nba = cdiv(c.N, SPH_BLOCK);
+	sph_prof_begin(h, KC_II_UPDATE, st);
+	k_ii_update_p<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
+	                                         h->a4[A4_FC], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
+	                                         h->a1[A1_SC], h->ctl, h->partials);
+	sph_prof_end(h, st);
+	k_ii_commit<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+	if (h->comm) {
+		mg_exchange(h, MG_F4_T1W, st); // slabs: the new pressure iterate of the ghost particles
+		mg_exchange_reduce(h, MG_NONE, SPH_CTL_II_ITER, nba, st);
+	} else {
+		k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nba, 1);
+	}
+	h->launches += 3;
+}
+
+// II:83-100: `count` relaxed Jacobi passes, each gated on ctl->ii_active
+static void ii_pressure_solve_passes(SphHandle *h, int count, cudaStream_t st) {
 	for (int it = 0; it < count; ++it) {
-		sph_prof_begin(h, KC_II_DIJ, st);
-		k_ii_dij<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->ctl);
-		sph_prof_end(h, st);
-		mg_exchange(h, MG_XYZ(A4_FB), st); // slabs: sum_j d_ij p_j of the ghost particles
-		sph_prof_begin(h, KC_II_UPDATE, st);
-		k_ii_update_p<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
-		                                         h->a4[A4_FC], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
-		                                         h->a1[A1_SC], h->ctl, h->partials);
-		sph_prof_end(h, st);
-		k_ii_commit<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);
-		if (h->comm) {
-			mg_exchange(h, MG_F4_T1W, st); // slabs: the new pressure iterate of the ghost particles
-			mg_exchange_reduce(h, MG_NONE, SPH_CTL_II_ITER, nba, st);
-		} else {
-			k_ii_ctl<<<1, 256, 0, st>>>(h->ctl, h->partials, nba, 1);
-		}
-		h->launches += 4;
+		ii_dij(h, st);
+		ii_update(h, st);
 	}
 }
 
@@ -777,31 +817,47 @@ static void ii_pressure_solve(SphHandle *h, cudaStream_t st) {
 	h->last_den_chunk = done < 180 ? h->ctl_host->ii_iters + 1 : 180;
 }
 
+// II:35-54 advection force, v_adv and d_ii in one pass
+static void ii_advect(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	sph_prof_begin(h, KC_II_ADV, st);
+	k_ii_advect<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO],
+	                                                       h->bspos, h->a4[A4_FA], h->a4[A4_VADV], h->a4[A4_FC], h->ctl);
+	sph_prof_end(h, st);
+	mg_exchange(h, MG_F4_VADV, st);    // slabs: v_adv and d_ii of the ghost particles
+	mg_exchange(h, MG_XYZ(A4_FC), st);
+	h->launches += 1;
+}
+// II:56-75 rho_adv, a_ii and the start iterate p = 0.5 p_past
+static void ii_aii(SphHandle *h, cudaStream_t st) {
+	const SphConsts &c = h->c;
+	sph_prof_begin(h, KC_II_AII, st);
+	k_ii_rho_adv_aii<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_PR], h->a4[A4_VADV], h->bspos,
+	                                                            h->a4[A4_FC], h->a4[A4_VEL], h->a1[A1_RHO], h->a1[A1_RHOADV],
+	                                                            h->a1[A1_SA], h->a1[A1_P], h->a4[A4_T1], h->ctl);
+	sph_prof_end(h, st);
+	h->launches += 1;
+}
+
 void ii_phase(SphHandle *h, int phase, cudaStream_t st) {
 	const SphConsts &c = h->c;
-	int nb = cdiv(c.N_owned, SPH_BLOCK), nba = cdiv(c.N, SPH_BLOCK);
+	int nba = cdiv(c.N, SPH_BLOCK);
 	if (phase == SPH_PH_II_PREDICT_ADVECTION) {
-		build_lists(h, st);
-		mg_exchange(h, MG_F4_T1R, st); // slabs: rho of the ghost particles (posR.w)
-		sph_prof_begin(h, KC_II_ADV, st);
-		SphRigidArgs rg = rigid_args(h);
-		k_ii_advect<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->bspos, h->a4[A4_FA],
-		                                       h->a4[A4_VADV], h->a4[A4_FC], h->ctl);
-		sph_prof_end(h, st);
-		mg_exchange(h, MG_F4_VADV, st);    // slabs: v_adv and d_ii of the ghost particles
-		mg_exchange(h, MG_XYZ(A4_FC), st);
-		sph_prof_begin(h, KC_II_AII, st);
-		k_ii_rho_adv_aii<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rg, h->a4[A4_PR], h->a4[A4_VADV], h->bspos, h->a4[A4_FC],
-		                                            h->a4[A4_VEL], h->a1[A1_RHO], h->a1[A1_RHOADV], h->a1[A1_SA], h->a1[A1_P],
-		                                            h->a4[A4_T1], h->ctl);
-		sph_prof_end(h, st);
-		h->launches += 2;
+		first_phase_lists(h, st);
+		ii_advect(h, st);
+		ii_aii(h, st);
 	} else if (phase == SPH_PH_II_PRESSURE_SOLVE) {
 		ii_pressure_solve(h, st);
-	} else if (phase == SPH_PH_II_SOLVE_BEGIN) { // the loop one pass at a time (single-sweep parity tests)
+	} else if (phase == SPH_PH_II_ADVECT) { // the step one sweep at a time (single-sweep parity tests)
+		ii_advect(h, st);
+	} else if (phase == SPH_PH_II_AII) {
+		ii_aii(h, st);
+	} else if (phase == SPH_PH_II_SOLVE_BEGIN) {
 		ii_pressure_solve_begin(h, st);
-	} else if (phase == SPH_PH_II_SOLVE_ONE) {
-		ii_pressure_solve_passes(h, 1, st);
+	} else if (phase == SPH_PH_II_DIJ) {
+		ii_dij(h, st);
+	} else if (phase == SPH_PH_II_UPDATE) {
+		ii_update(h, st);
 	} else if (phase == SPH_PH_II_INTEGRATION) {
 		if (rigid_args(h).active) { rigid_lists(h, st); rigid_force(h, RF_II, 0, st); } // II:159, gather form
 		sph_prof_begin(h, KC_II_INT, st);

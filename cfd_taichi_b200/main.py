@@ -49,11 +49,16 @@ def write_obj(path, vertices, faces):
                 f.write('f %d %d %d\n' % (t[0] + 1, t[1] + 1, t[2] + 1))
 
 
-def save_state(path, ps, solver, rs=None):
-    """Restartable dump: everything a step depends on."""
+def save_state(path, ps, solver, rs=None, t=0.0, frame_cnt=0, ply_cnt=0):
+    """Restartable dump: everything a step depends on, plus the driver's own clock (simulated
+    time, frame and output counters) so that a resumed run stops at the original end time and continues the
+    output numbering."""
     import ctypes
+    if ps._slab is not None:
+        raise ValueError("save_state: a slab ParticleSystem holds one x-slab; dump from a single-domain run")
     n = ps.particle_num
-    data = dict(pos4=ps._pos4[:n].cpu().numpy(), vel4=ps._vel4[:n].cpu().numpy(), delta_time=solver.delta_time[None])
+    data = dict(pos4=ps._pos4[:n].cpu().numpy(), vel4=ps._vel4[:n].cpu().numpy(), delta_time=solver.delta_time[None],
+                t=float(t), frame_cnt=int(frame_cnt), ply_cnt=int(ply_cnt))
     if ps.exist_rigid[None]:
         info = ps.rigid_state()
         data.update(rpos4=ps._rpos4.cpu().numpy(), rvel4=ps._rvel4.cpu().numpy(), rforce4=ps._rforce4.cpu().numpy(),
@@ -70,8 +75,14 @@ def load_state(path, ps, solver):
     import ctypes
     import torch
     from cfd_taichi_b200 import _lib
+    if ps._slab is not None:
+        raise ValueError("load_state: a slab ParticleSystem holds one x-slab; restart from a single-domain run")
     path = path if path.endswith('.npz') else path + '.npz'
+    clock = dict(t=0.0, frame_cnt=0, ply_cnt=0)
     with np.load(path) as d:
+        for k in clock:
+            if k in d:
+                clock[k] = d[k].item()
         n = ps.particle_num
         if d['pos4'].shape[0] != n:
             raise ValueError("load_state: dump holds %d particles, the scene %d" % (d['pos4'].shape[0], n))
@@ -85,6 +96,16 @@ def load_state(path, ps, solver):
                 t.copy_(torch.from_numpy(d[name]).to(ps._device))
             info = _lib.SphRigidInfo.from_buffer_copy(d['rigid_info'].tobytes())
             _lib.check(ps._lib.sph_rigid_set_state(ps._h, ctypes.byref(info)), ps._h)
+    return clock
+
+
+def check_error_flags(ps, frame_cnt):
+    """The flags the library latches on the device mean the run has left the reference's physics (a truncated
+    neighbour list, a clamped particle, the density-loop cap, a non-finite value, a dead peer): fail loudly."""
+    from cfd_taichi_b200 import _lib
+    flags = ps.read_stats().error_flags
+    if flags:
+        raise _lib.SphError("frame %d: device error flags 0x%x: %s" % (frame_cnt, flags, "; ".join(_lib.decode_error_flags(flags))))
 
 
 def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None, save=None):
@@ -97,21 +118,21 @@ def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None
     module = importlib.import_module('cfd_taichi_b200.' + solver_name + '_solver')     # main.py:65-68
     solver = getattr(module, solver_name + '_solver')(ps, config)
     rs = rigid_solver(ps, config) if config.get('solid', {}) else None                 # main.py:70-71
-    if resume:
-        load_state(resume, ps, solver)
+    clock = load_state(resume, ps, solver) if resume else dict(t=0.0, frame_cnt=0, ply_cnt=0)
 
-    frame_cnt = 0
+    frame_cnt = int(clock['frame_cnt'])
+    first_frame = frame_cnt
     iter_cnt = solver_config.get('iter_cnt')
     np_rgba = np.reshape(ps.rgba.to_numpy(), (ps.particle_num, 4))
     is_output_ply = scene_config.get('is_output_ply', False)
     output_fps = scene_config.get('output_fps', 60)
     frame_time = 1.0 / output_fps
-    ply_cnt = 0
-    t = 0.0
+    ply_cnt = int(clock['ply_cnt'])
+    t = float(clock['t'])
     if is_output_ply:
         os.makedirs(output_dir, exist_ok=True)
     while True:
-        if frame_cnt > 100000 or (max_frames is not None and frame_cnt >= max_frames):
+        if frame_cnt > 100000 or (max_frames is not None and frame_cnt - first_frame >= max_frames):
             break
         for _ in range(iter_cnt):
             solver.step()
@@ -119,6 +140,7 @@ def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None
             if rs and ps.active_rigid[None] == 1:
                 rs.step()
         frame_cnt += 1
+        check_error_flags(ps, frame_cnt)   # the same synchronising read the next line needs
         t += iter_cnt * solver.delta_time[None]
         if not quiet and frame_cnt % 50 == 0:
             print("time: {:.4f}  frame_cnt: {}  delta time: {:.5f}".format(t, frame_cnt, solver.delta_time[None]))
@@ -132,7 +154,7 @@ def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None
         if t > 4.0:
             break
     if save:
-        save_state(save, ps, solver, rs)
+        save_state(save, ps, solver, rs, t=t, frame_cnt=frame_cnt, ply_cnt=ply_cnt)
     print("Simulation time: {}".format(time.time() - start_time))
     return ps, solver, rs, t
 

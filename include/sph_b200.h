@@ -90,6 +90,8 @@ enum SphField {
 	SPH_F_PRESSURE, SPH_F_FORCE_A /*float4 generic force/acc buffer*/, SPH_F_FORCE_B /*float4*/,
 	SPH_F_SCALAR_A, SPH_F_SCALAR_B, SPH_F_SCALAR_C, SPH_F_VEC_A /*float4*/, SPH_F_VEC_B /*float4*/,
 	SPH_F_VEC_C /*float4*/,
+	/* the payload copies the sweeps gather (xyz = sorted position, w = the scalar the next sweep reads of a neighbour) */
+	SPH_F_PAYLOAD_1 /*float4*/, SPH_F_PAYLOAD_3 /*float4*/, SPH_F_POS_RHO /*float4: xyz, rho*/,
 	/* grid arrays (int32), fetched verbatim */
 	SPH_F_CELL_START = 64,   /* G+1 exclusive prefix sums == per-cell list offsets */
 	SPH_F_SORTED_INDEX,      /* N: original index of the particle in sorted slot s */
@@ -106,12 +108,6 @@ enum SphPhase {
 	SPH_PH_DF_EXT_FORCE_VEL_ADV,  /* DF:91-122 compute_all_ext_force + compute_all_vel_adv */
 	SPH_PH_DF_DENSITY,            /* DF:221-233 correct_density_error */
 	SPH_PH_DF_POSITION,           /* DF:235-250 compute_all_position */
-	/* the two DFSPH loops one pass at a time (loop decisions still taken on the device; a pass after the loop
-	 * has ended is a no-op).  DIVERGENCE == DIV_BEGIN + 15 x DIV_ONE; DENSITY == DEN_ONE until
-	 * SphStats says the loop is over. */
-	SPH_PH_DF_DIV_BEGIN,          /* DF:396-399 warm start + first derivative_iter_all_rho */
-	SPH_PH_DF_DIV_ONE,            /* DF:400-414 one loop body: divergence_iter_all_vel_adv, sum_up_stiff, derivative_iter_all_rho */
-	SPH_PH_DF_DEN_ONE,            /* DF:225-231 one loop body: compute_all_rho_adv, iter_all_vel_adv */
 	/* WCSPH */
 	SPH_PH_WC_PRESSURE = 20,      /* WC:32-38 */
 	SPH_PH_WC_KINEMATIC,          /* WC:40-63 */
@@ -119,14 +115,10 @@ enum SphPhase {
 	SPH_PH_PC_EXT_FORCE = 30,     /* PC:220-226 */
 	SPH_PH_PC_ITERATION,          /* PC:47-70 */
 	SPH_PH_PC_INTEGRATION,        /* PC:200-218 */
-	SPH_PH_PC_ITER_BEGIN,         /* PC:47-55 the pressure loop one pass at a time: ITERATION == ITER_BEGIN + ITER_ONE while pc_active */
-	SPH_PH_PC_ITER_ONE,           /* PC:56-70 one loop body */
 	/* IISPH */
 	SPH_PH_II_PREDICT_ADVECTION = 40, /* II:35-75 */
 	SPH_PH_II_PRESSURE_SOLVE,         /* II:78-100 */
 	SPH_PH_II_INTEGRATION,            /* II:184-206 */
-	SPH_PH_II_SOLVE_BEGIN,            /* II:78-82 the Jacobi loop one pass at a time: PRESSURE_SOLVE == SOLVE_BEGIN + SOLVE_ONE while ii_active */
-	SPH_PH_II_SOLVE_ONE,              /* II:83-100 one relaxed Jacobi pass */
 	/* PBF (fetch: rho = SPH_F_RHO, constrain = SCALAR_A, pbf_lambda = SCALAR_B, constrain_derivative =
 	 * FORCE_A, delta_pos = FORCE_B, pos_predict = VEC_C) */
 	SPH_PH_PBF_PREDICT = 50,          /* PBF:26-30 externel_force_predict_pos */
@@ -134,7 +126,34 @@ enum SphPhase {
 	SPH_PH_PBF_DELTA_POS,             /* PBF:55-65 compute_all_delta_pos */
 	SPH_PH_PBF_UPDATE_POS,            /* PBF:67-96 update_all_pos (move all, then XSPH) */
 	/* commit the sorted work buffers back into the bound original-order state */
-	SPH_PH_WRITEBACK = 90
+	SPH_PH_WRITEBACK = 90,
+
+	/* The same steps ONE SWEEP AT A TIME (cfd_taichi_b200/selfcheck.py, tests/test_gpu_fast_parity.py: every sweep
+	 * of the fast kernels is fed the strict kernels' inputs through sph_copy_work_state).  The loop decisions stay
+	 * on the device; a sweep of a loop that has ended is a no-op; SphStats reports the loop flags.
+	 *   DF_DIVERGENCE    == WARM_START, DRHO_FIRST, 15 x (DIV_VEL, DIV_DRHO)
+	 *   DF_DENSITY       == (DEN_RHO, DEN_VEL) while den_active
+	 *   WC_PRESSURE      == BUILD_LISTS, WC_EOS, WC_FORCE
+	 *   PC_EXT_FORCE     == BUILD_LISTS, PC_EXT_FORCE;   PC_ITERATION == PC_PREDICT, PC_RHO_FIRST, (PC_PRESS_FORCE, PC_RHO) while loop_active
+	 *   II_PREDICT_ADVECTION == BUILD_LISTS, II_ADVECT, II_AII;   II_PRESSURE_SOLVE == II_SOLVE_BEGIN, (II_DIJ, II_UPDATE) while loop_active */
+	SPH_PH_BUILD_LISTS = 100,     /* PS:447-469 the step's neighbour lists (+ rho SB:41-72, + alpha DF:32-89); the solver's first phase then skips its own build */
+	SPH_PH_DF_WARM_START = 110,   /* DF:314-355 */
+	SPH_PH_DF_DRHO_FIRST,         /* DF:252-280 + the decision of DF:398-399 */
+	SPH_PH_DF_DIV_VEL,            /* DF:302-312 divergence_iter_all_vel_adv + DF:381-384 sum_up_stiff */
+	SPH_PH_DF_DIV_DRHO,           /* DF:252-280 + the decision of DF:406-414 */
+	SPH_PH_DF_DEN_RHO,            /* DF:124-152 compute_all_rho_adv + the average DF:225 reads */
+	SPH_PH_DF_DEN_VEL,            /* DF:178-219 iter_all_vel_adv (+ DF:212 rigid forces) + the decision of DF:225 */
+	SPH_PH_WC_EOS = 120,          /* WC:32-38 Tait pressure */
+	SPH_PH_WC_FORCE,              /* WC:65-144 pressure gradient, boundary term, viscosity, tension (+ WC:126) */
+	SPH_PH_PC_PREDICT = 130,      /* PC:72-87 predict_vel_pos */
+	SPH_PH_PC_RHO_FIRST,          /* PC:89-100 predict_rho + PC:123-133 compute_residual + PC:54 */
+	SPH_PH_PC_PRESS_FORCE,        /* PC:102-121 iter_press + update_press_force (+ predict_vel_pos, + PC:186) */
+	SPH_PH_PC_RHO,                /* PC:89-100 + PC:123-133 + the decision of PC:56 */
+	SPH_PH_II_ADVECT = 140,       /* II:35-54 f_adv, v_adv, d_ii */
+	SPH_PH_II_AII,                /* II:56-75 rho_adv, a_ii, start iterate */
+	SPH_PH_II_SOLVE_BEGIN,        /* II:78-82 */
+	SPH_PH_II_DIJ,                /* II:208-250 sum_j d_ij p_j */
+	SPH_PH_II_UPDATE              /* II:252-340 update_p + II:102-113 compute_residual + the decision of II:83-93 */
 };
 
 /* Read by sph_read_stats (the only synchronising query; replaces the kernel return values

@@ -68,7 +68,7 @@ def _inject_random_state(ps, o, seed):
     ps._vel4[:ps.particle_num, 3] = __import__("torch").from_numpy(k).to(ps._device)
 
 
-@pytest.mark.parametrize("strict", [True, False])
+@pytest.mark.parametrize("strict", [True])
 @pytest.mark.parametrize("seed", [0, 1])
 def test_single_substep_phases_on_random_state(built, strict, seed):
     """Phase by phase (the reference's public methods DF:423-438) from a randomised state."""
@@ -117,26 +117,27 @@ def test_single_substep_phases_on_random_state(built, strict, seed):
     ps.close(); o.close()
 
 
-def test_fast_single_sweeps_within_tolerance(built):
-    """Each sweep in isolation: feed the FAST kernels the oracle's exact inputs and compare outputs."""
-    import torch
+def test_fast_sweeps_on_random_state(built):
+    """Every sweep of the fast kernels in isolation (strict inputs, 1e-5 on every work array) from a RANDOMISED
+    state -- jittered positions, random velocities and warm-start scalars -- with the strict walk bit-exact on the
+    oracle at the end.  The dam states are covered in tests/test_gpu_fast_parity.py."""
+    from cfd_taichi_b200 import selfcheck
     cfg = scenes.shipped("small_block", "dfsph")
-    ps, sol, o = make(cfg, False)
-    _inject_random_state(ps, o, 3)
-    ps.update_grid(); o.base_step()
-    sol.initialize(); o.phase("initialize")
-    assert relinf(sol.rho.to_numpy(), o.field("rho")) <= RTOL
-    assert relinf(sol.alpha.to_numpy(), o.field("alpha")) <= RTOL
-    # one full fast step vs oracle from identical state: positions/velocities after ONE substep
-    ps2, sol2, o2 = make(cfg, False)
-    _inject_random_state(ps2, o2, 4)
-    sol2.step(); o2.step()
-    st = sol2.stats()
-    if (st.div_iters, st.den_iters) == (int(o2.scalar("df_div_iters")), int(o2.scalar("df_den_iters"))):
-        assert relinf(ps2.fluid_particles.pos.to_numpy(), o2.field("pos")) <= RTOL
-        assert relinf(sol2.rho.to_numpy(), o2.field("rho")) <= RTOL
-        assert relinf(ps2.fluid_particles.vel.to_numpy(), o2.field("vel")) <= 1e-3  # after up to 15+2 solver sweeps
-    ps.close(); o.close(); ps2.close(); o2.close()
+    for seed in (3, 4):
+        ps_s, sol_s, o = make(cfg, True)
+        ps_f, sol_f, o_unused = make(cfg, False)
+        o_unused.close()
+        _inject_random_state(ps_s, o, seed)
+        selfcheck.copy_caller_state(ps_f, sol_f, ps_s, sol_s)
+        err, info = selfcheck.sweeps("dfsph", ps_s, sol_s, ps_f, sol_f)
+        o.step()
+        assert np.array_equal(ps_s.fluid_particles.pos.to_numpy(), o.field("pos"))
+        assert np.array_equal(ps_s.fluid_particles.vel.to_numpy(), o.field("vel"))
+        assert info["loop_flags_equal"] and info["neighbour_counts_equal"] and info["error_flags"] == (0, 0)
+        assert info["iters"]["fast"] == info["iters"]["strict"] == (int(o.scalar("df_div_iters")), int(o.scalar("df_den_iters")))
+        w, where = selfcheck.worst(err)
+        assert w <= RTOL, "seed %d: %s off by %.3e" % (seed, where, w)
+        ps_s.close(); ps_f.close(); o.close()
 
 
 def test_clamp_boundary_mode(built):

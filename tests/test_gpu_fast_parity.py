@@ -45,8 +45,7 @@ def oracle_iters(solver, o):
     return 0
 
 
-def gpu_iters(solver, st):
-    return {"dfsph": (st.div_iters, st.den_iters), "pcisph": st.pc_iters, "iisph": st.ii_iters, "wcsph": 0}[solver]
+gpu_iters = selfcheck.iters_of
 
 
 class Trio:
@@ -69,6 +68,9 @@ class Trio:
             verts = self.ps_s._rigid_vertices_local
         self.o = O.Oracle(cfg, solver=solver, rigid_points=pts, rigid_vertices=verts, threads=1 if rigid else 8)
         self.done = 0
+        if solver == "pcisph":     # PC:28-45: delta from the arg-max particle's neighbourhood
+            assert relinf([self.sol_f.delta[None]], [self.sol_s.delta[None]]) <= RTOL
+            assert self.sol_s.delta[None] == np.float32(self.o.scalar("pc_delta"))
 
     def advance_to(self, n):
         while self.done < n:
@@ -93,7 +95,7 @@ class Trio:
 def check_sweeps(t, tag):
     """Layer 1 at the current state; advances strict, fast and the oracle by one step."""
     t.fast_takes_strict_state()
-    err, info = selfcheck.SWEEPS[t.solver](t.ps_s, t.sol_s, t.ps_f, t.sol_f, rigid=t.rigid)
+    err, info = selfcheck.sweeps(t.solver, t.ps_s, t.sol_s, t.ps_f, t.sol_f, rigid=t.rigid)
     O.lib().orc_step(t.o._h)
     if t.rigid:
         assert np.array_equal(t.ps_s.rigid_particles.force.to_numpy(), t.o.field("rforce")), tag + ": strict rigid force"
@@ -108,8 +110,11 @@ def check_sweeps(t, tag):
     assert info["error_flags"] == (0, 0), tag
     assert info["neighbour_counts_equal"], tag + ": fast and strict neighbour counts differ"
     assert info["loop_flags_equal"], tag + ": a device-side loop decision of the fast kernels differs from the strict one"
+    assert info["iters"]["fast"] == info["iters"]["strict"], tag
     w, where = selfcheck.worst(err)
-    assert w <= RTOL, "%s: fast sweep %s off by %.3e (> %g)\n%s" % (tag, where, w, RTOL, err)
+    assert w <= RTOL, "%s: fast sweep [%s] off by %.3e (> %g)\n%s" % (
+        tag, where, w, RTOL, "\n".join("  %-44s %s" % (k, {n: ("%.1e" % x if not isinstance(x, dict) else x) for n, x in v.items()})
+                                     for k, v in err.items()))
     return err, info
 
 
@@ -125,8 +130,8 @@ def test_dfsph_every_sweep_within_1e5(built, scene_name, warms, rigid):
     for warm in warms:
         t.advance_to(warm)
         err, info = check_sweeps(t, "%s/dfsph step %d" % (scene_name, warm))
-        seen_div = max(seen_div, info["div_iters"][0])
-        seen_den = max(seen_den, info["den_iters"][0])
+        seen_div = max(seen_div, info["iters"]["strict"][0])
+        seen_den = max(seen_den, info["iters"]["strict"][1])
     assert seen_div == 15 and seen_den >= 2      # the loops really ran in the states tested
     t.close()
 
@@ -227,10 +232,16 @@ def test_whole_substep_against_the_references_own_conditioning(built, scene_name
     out, a, b = whole_step_errors(t)
     assert a == b, "%s iterations on the GPU, %s in the oracle" % (a, b)
     assert gpu_iters(solver, ps_u.read_stats()) == b
+    ulp_press = relinf(sol_u.p_iter.to_numpy(), t.o.field("p_iter")) if solver == "iisph" else 0.0
     ulp_vel = relinf(ps_u.fluid_particles.vel.to_numpy(), t.o.field("vel"))
     ulp_pos = relinf(ps_u.fluid_particles.pos.to_numpy(), t.o.field("pos"))
     print("\n%s/%s step %d: iterations %s; fast vs oracle %s; strict with 1-ulp inputs vs oracle: vel %.3e pos %.3e"
           % (scene_name, solver, warm, a, {k: "%.2e" % v for k, v in out.items()}, ulp_vel, ulp_pos))
     assert out["rho"] <= RTOL and out["pos"] <= RTOL
     assert out["vel"] <= max(RTOL, 8.0 * ulp_vel), "fast velocity deviation %.3e vs one-ulp conditioning %.3e" % (out["vel"], ulp_vel)
+    if solver == "iisph":
+        print("   pressure: fast %.3e, strict with 1-ulp inputs %.3e" % (out["pressure"], ulp_press))
+        assert out["pressure"] <= max(RTOL, 8.0 * ulp_press)
+    else:
+        assert ulp_vel > RTOL      # the premise of this test: the reference's own loop is above 1e-5 per ulp here
     ps_u.close(); t.close()

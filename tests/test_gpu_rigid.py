@@ -92,25 +92,29 @@ def o_force_after_fluid(o):
 
 
 def test_coupled_steps_fast_within_tolerance(built, monkeypatch):
+    """Fast kernels on the coupled scene, every sweep in isolation (rigid forces included) at 1e-5 and identical loop
+    decisions; the strict walk it is compared with must end bit-exact on the oracle.  The shipped dam_flush_cube
+    scene gets the same treatment in tests/test_gpu_fast_parity.py."""
+    from cfd_taichi_b200 import selfcheck
     cfg, pts, verts = rigid_scene()
-    ps, sol, rs, o = make(cfg, pts, verts, False, monkeypatch)
+    ps_s, sol_s, rs_s, o = make(cfg, pts, verts, True, monkeypatch)
+    ps_f, sol_f, rs_f, o2 = make(cfg, pts, verts, False, monkeypatch)
+    o2.close()
     for step in range(3):
-        # restart every substep from the oracle's fluid state so that one substep of error is measured
-        ps.fluid_particles.pos.from_numpy(o.field("pos"))
-        ps.fluid_particles.vel.from_numpy(o.field("vel"))
-        import torch
-        ps._vel4[:ps.particle_num, 3] = torch.from_numpy(o.field("warm_start_k").copy()).to(ps._device)
-        sol.step()
+        selfcheck.copy_caller_state(ps_f, sol_f, ps_s, sol_s)
+        err, info = selfcheck.sweeps("dfsph", ps_s, sol_s, ps_f, sol_f, rigid=True)
         f_ref = o_force_after_fluid(o)
-        f_gpu = ps.rigid_particles.force.to_numpy()
-        rs.step()
-        st = sol.stats()
-        if (st.div_iters, st.den_iters) == (int(o.scalar("df_div_iters")), int(o.scalar("df_den_iters"))):
-            assert np.abs(f_gpu - f_ref).max() <= 1e-4 * (np.abs(f_ref).max() + 1e-30)
-            assert np.abs(ps.fluid_particles.pos.to_numpy() - o.field("pos")).max() <= 1e-5 * np.abs(o.field("pos")).max()
-        info = ps.rigid_state()
-        assert np.allclose(np.array(list(info.centroid)), o.field("centroid").reshape(-1), rtol=1e-4, atol=1e-6)
-    ps.close(); o.close()
+        assert np.array_equal(ps_s.rigid_particles.force.to_numpy(), f_ref)
+        assert selfcheck.relinf(ps_f.rigid_particles.force.to_numpy(), f_ref) <= 1e-5
+        rs_s.step(); rs_f.step()
+        assert np.array_equal(ps_s.fluid_particles.pos.to_numpy(), o.field("pos")), "step %d" % step
+        assert info["loop_flags_equal"] and info["neighbour_counts_equal"] and info["error_flags"] == (0, 0)
+        assert info["iters"]["fast"] == info["iters"]["strict"] == (int(o.scalar("df_div_iters")), int(o.scalar("df_den_iters")))
+        w, where = selfcheck.worst(err)
+        assert w <= 1e-5, "step %d: %s off by %.3e" % (step, where, w)
+        cf, cs = np.array(list(ps_f.rigid_state().centroid)), o.field("centroid").reshape(-1)
+        assert selfcheck.relinf(cf, cs) <= 1e-5
+    ps_s.close(); ps_f.close(); o.close()
 
 
 def test_dam_flush_cube_scene(built, monkeypatch):
