@@ -22,7 +22,8 @@ class ParticleSystem:
 
     def __init__(self, config, device=None, strict=None, solver_name=None, ghost_capacity=0,
                  max_neighbors=None, base_dir=None, slab=None):
-        """`slab=(rank, nranks)`: this process holds one x-slab of the domain (multi-GPU, SURVEY 8(e));
+        """`slab=(rank, nranks[, cuts])`: this process holds one x-slab of the domain (multi-GPU, SURVEY 8(e));
+        `cuts` overrides the histogram-balanced column cuts (nranks + 1 increasing x-cell columns);
         torch.distributed must be initialised (it carries the NCCL id; the exchange itself is in the library)."""
         if not torch.cuda.is_available():
             raise _lib.SphError("ParticleSystem needs a CUDA device: the B200 SPH path has no CPU fallback")
@@ -63,7 +64,9 @@ class ParticleSystem:
         if slab is not None and slab[1] > 1:
             rank, nranks = int(slab[0]), int(slab[1])
             hist, _ = slab_plan.column_histogram(config)
-            cuts = slab_plan.plan_cuts(hist, nranks)
+            cuts = list(slab[2]) if len(slab) > 2 and slab[2] is not None else slab_plan.plan_cuts(hist, nranks)
+            if len(cuts) != nranks + 1 or cuts[0] != 0 or cuts[-1] != len(hist) or any(b <= a for a, b in zip(cuts, cuts[1:])):
+                raise ValueError("slab cuts must be %d increasing x-cell columns from 0 to %d: %r" % (nranks + 1, len(hist), cuts))
             ids, _, _ = slab_plan.owned_lattice_ids(config, cuts[rank], cuts[rank + 1])
             owned0, owned_cap, ghost_cap = slab_plan.capacities(config, cuts, rank)
             assert owned0 == len(ids)

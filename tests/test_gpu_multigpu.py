@@ -1,5 +1,6 @@
-"""GPU parity of the multi-GPU slab path (BASELINE.json configs[4]): 2 ranks over NCCL vs the
-single-domain run, compared by global particle id.  Needs 2 GPUs; skipped otherwise."""
+"""GPU parity of the multi-GPU slab path (BASELINE.json configs[4]): 2 / 4 / 8 ranks vs the single-domain run,
+compared by global particle id.  Needs that many GPUs; skipped otherwise (the driver's test box has one GPU:
+bench.py --gpus N runs the same check -- selfcheck.slab_vs_single -- and reports it in its `parity` block)."""
 import os
 import subprocess
 import sys
@@ -49,3 +50,32 @@ def test_two_slabs_with_rigid_body(built):
     line = [l for l in r.stdout.splitlines() if l.startswith("MGRIGID")]
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     assert line and "perm_ok=True" in line[0] and "replicas_identical=True" in line[0]
+
+
+def _need(n):
+    return pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < n, reason="needs %d GPUs" % n)
+
+
+@_need(2)
+@pytest.mark.parametrize("solver", ["wcsph", "dfsph"])
+def test_two_slabs_with_an_empty_edge_column(built, solver):
+    """asymmetric halo counts.  The last rank starts empty, so its neighbour sends to it without ever
+    receiving from it; every exchange must still handshake with it (WCSPH has no all-rank reduce at all), or the
+    sender runs two epochs ahead and overwrites unread slots."""
+    r = _run(2, ["40", "strict", solver, "empty-edge"])
+    line = [l for l in r.stdout.splitlines() if l.startswith("MGRESULT")]
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    assert line and "perm_ok=True" in line[0] and "iters_ok=True" in line[0] and "exact=True" in line[0]
+
+
+@pytest.mark.parametrize("nranks", [4, 8])
+def test_many_slabs_match_single_domain(built, nranks):
+    """4 and 8 slabs of the 14-column block: one or two columns per rank, particles crossing two cuts."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < nranks:
+        pytest.skip("needs %d GPUs" % nranks)
+    r = _run(nranks, ["40", "strict", "dfsph"])
+    line = [l for l in r.stdout.splitlines() if l.startswith("MGRESULT")]
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    assert line and "perm_ok=True" in line[0] and "iters_ok=True" in line[0] and "exact=True" in line[0]
+    two_cuts = int(line[0].split("two_cuts=")[1].split()[0])
+    assert two_cuts > 0, line[0]
