@@ -58,6 +58,13 @@ static void fill_consts(const SphConfig &cfg, SphConsts &c) {
 	c.nkDW6 = (-c.kDW) * 6.0f;    // SB:100
 	c.dwA = (float)((double)c.kDW6 / (h_d * h_d));
 	c.dwB = (float)((double)c.nkDW6 / h_d);
+	{
+		// |grad W| <= kDW6 / (3 h) (at q = 1/3; the outer branch stays below kDW6 / (4 h)): 21-bit fixed point over
+		// [-S, S] with S 0.1 % above the bound, step S / (2^20 - 1)
+		double S = (double)c.kDW6 / (3.0 * h_d) * 1.001;
+		c.gq_scale = (float)(S / 1048575.0);
+		c.gq_inv = (float)(1048575.0 / S);
+	}
 	c.gravity = (float)cfg.gravity;
 	c.visc_num = (float)(2 * 0.08 * h_d * c_s);   // SB:187
 	c.visc_eps_h2 = (float)(0.01 * h_d * h_d);    // SB:188
@@ -175,7 +182,12 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	SPH_CUDA_CHECK(h, dalloc(&h->L.flist, nwarps * 32 * (size_t)c.kstride));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.blist, nwarps * 32 * (size_t)c.kbstride));
 	h->L.gw = nullptr;
-	if (c.solver == SPH_SOLVER_DFSPH) SPH_CUDA_CHECK(h, dalloc(&h->L.gw, nwarps * 32 * (size_t)c.kstride));
+	h->L.gq = nullptr;
+	if (c.solver == SPH_SOLVER_DFSPH) {
+		// per-pair gradient stream of the step: strict kernels keep the exact float4 records, fast kernels 8 bytes per pair
+		if (cfg->strict) SPH_CUDA_CHECK(h, dalloc(&h->L.gw, nwarps * 32 * (size_t)c.kstride));
+		else SPH_CUDA_CHECK(h, dalloc(&h->L.gq, nwarps * 32 * (size_t)(c.kstride >> 1)));
+	}
 	SPH_CUDA_CHECK(h, dalloc(&h->L.fcount, ncap));
 	SPH_CUDA_CHECK(h, dalloc(&h->L.bcount, ncap));
 	SPH_CUDA_CHECK(h, cudaMemset(h->L.fcount, 0, sizeof(int) * (ncap ? ncap : 1)));
@@ -213,7 +225,7 @@ extern "C" int sph_destroy(SphHandle *h) {
 	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rstate); cudaFree(h->rl_list); cudaFree(h->rl_count);
 	for (int k = 0; k < A4_COUNT; ++k) cudaFree(h->a4[k]);
 	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
-	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.gw);
+	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.gw); cudaFree(h->L.gq);
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount);
 	mg_destroy(h);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);

@@ -32,6 +32,7 @@ struct SphConsts {
 	float kDW;          // 48 / (pi h^3)  (SB:95)
 	float kDW6, nkDW6;  // (k*6) and ((-k)*6) of SB:98,100
 	float dwA, dwB;     // fast kernels: kDW6 / h^2 and nkDW6 / h
+	float gq_inv, gq_scale; // fast kernels: fixed-point step of the quantised gradient stream (sph_sweeps.cu) and its inverse
 	float gravity;
 	float visc_num;     // 2 * alpha * h * c_s  (SB:187)
 	float visc_eps_h2;  // eps * h * h          (SB:188)
@@ -125,6 +126,9 @@ struct SphLists {
 	// DFSPH only (null otherwise): per-pair cache [index | grad W_ij] of the fluid list, one float4 per entry,
 	// entry k of sorted particle s at gw[((s >> 5) * cap + k) * 32 + (s & 31)] (a warp reads 512 contiguous bytes)
 	float4 *gw;
+	// fast DFSPH kernels instead: grad W_ij as 3 x 21-bit fixed point in 8 bytes (the index comes from flist);
+	// entries 2p, 2p+1 of sorted particle s in the uint4 at gq[((s >> 5) * (cap / 2) + p) * 32 + (s & 31)]
+	uint4 *gq;
 };
 
 __host__ __device__ inline size_t sph_list_base(int s, int cap) {

@@ -32,6 +32,28 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t sph_gw_index(int s, int cap, int k) {
 	return ((size_t)(s >> 5) * (size_t)cap + (size_t)k) * 32u + (size_t)(s & 31);
 }
+// The two streaming sweeps are HBM-bound on this stream (ncu: 19x their algorithmic bytes, 77 % of the HBM peak),
+// so the FAST kernels shrink it: the index is already in the neighbour list (4 bytes), and the gradient is stored
+// as three 21-bit fixed-point numbers over [-S, S], S = max |grad W| = kDW6 / (3 h) (8 bytes): 12 bytes per pair
+// instead of 16, and k_build_lists writes 8 instead of 16.  Quantisation error <= S 2^-21 per component, i.e.
+// 5e-7 of the largest gradient; measured per-sweep error against the strict kernels ~1e-6 (tolerance 1e-5).
+#if !SPH_STRICT
+__device__ __forceinline__ uint2 gq_pack(f3 g, const SphConsts &c) {
+	const int B = 1 << 20;
+	uint32_t mx = (uint32_t)min(max(__float2int_rn(g.x * c.gq_inv) + B, 0), 2 * B - 1);
+	uint32_t my = (uint32_t)min(max(__float2int_rn(g.y * c.gq_inv) + B, 0), 2 * B - 1);
+	uint32_t mz = (uint32_t)min(max(__float2int_rn(g.z * c.gq_inv) + B, 0), 2 * B - 1);
+	return make_uint2(mx | (my << 21), (my >> 11) | (mz << 10)); // bits 0-20 x, 21-41 y, 42-62 z
+}
+__device__ __forceinline__ f3 gq_unpack(uint32_t lo, uint32_t hi, float scale, float bias) {
+	uint32_t mx = lo & 0x1FFFFFu, my = __funnelshift_r(lo, hi, 21) & 0x1FFFFFu, mz = (hi >> 10) & 0x1FFFFFu;
+	return F3(fmaf((float)mx, scale, bias), fmaf((float)my, scale, bias), fmaf((float)mz, scale, bias));
+}
+__device__ __forceinline__ void gq_store(uint4 *gq, int s, int cap, int k, uint2 w) {
+	uint2 *p = reinterpret_cast<uint2 *>(gq) + ((((size_t)(s >> 5) * (size_t)(cap >> 1) + (size_t)(k >> 1)) * 32u + (size_t)(s & 31)) << 1) + (size_t)(k & 1);
+	*p = w;
+}
+#endif
 
 
 // decode the 1-D cell id (PS:102) back into (x, y, z)
@@ -283,6 +305,11 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 			}
 		}
 		int nfl = min(nf, c.kmax), nbl = min(nb, c.kbmax);
+#if SPH_STRICT
+#define SPH_GRAD_STORE(k, j, dw) if (L.gw) L.gw[sph_gw_index(s, c.kstride, k)] = make_float4(__uint_as_float(j), (dw).x, (dw).y, (dw).z)
+#else
+#define SPH_GRAD_STORE(k, j, dw) if (L.gq) gq_store(L.gq, s, c.kstride, k, gq_pack(dw, c))
+#endif
 		// ---- phase 2: walk the fresh lists (canonical order, every lane busy): rho (SB:41-72), alpha (DF:32-89)
 		float rho_f = 0.001f; // SB:44
 		f3 ss = F3(0.0f, 0.0f, 0.0f);
@@ -295,7 +322,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 				rho_f += (pj.w * cubic_w(p, c)) * SPH_RHO0; // SB:65
 				if (ALPHA) {
 					f3 dw = cubic_dw(p, c);
-					if (L.gw) L.gw[sph_gw_index(s, c.kstride, k)] = make_float4(__uint_as_float(j), dw.x, dw.y, dw.z);
+					SPH_GRAD_STORE(k, j, dw);
 					f3 g = (pj.w * SPH_RHO0) * dw; // DF:62, 75
 					ss = ss + g;
 					sq += dot(g, g);
@@ -306,7 +333,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 			rho_f += c.m * cubic_w(p, c); // SB:62
 			if (ALPHA) {
 				f3 dw = cubic_dw(p, c);
-				if (L.gw) L.gw[sph_gw_index(s, c.kstride, k)] = make_float4(__uint_as_float(j), dw.x, dw.y, dw.z);
+				SPH_GRAD_STORE(k, j, dw);
 				f3 g = c.m * dw; // DF:58, 70
 				ss = ss + g;
 				sq += dot(g, g);
@@ -345,6 +372,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		}
 #undef SPH_FLW
 #undef SPH_BLW
+#undef SPH_GRAD_STORE
 	}
 	int mf = warp_max_i(nf), mb = warp_max_i(nb);
 	if ((threadIdx.x & 31) == 0) {
@@ -501,88 +529,60 @@ __device__ __forceinline__ void walk_gw(const float4 *__restrict__ gw, int cap, 
 	}
 }
 
-// ---- the same walk with the records staged through shared memory by TMA bulk copies ------------------------
-// The cache rows of a warp are contiguous (512 bytes per entry row), so a stage of four rows is one 2 KB
-// cp.async.bulk (global -> shared, completion on an mbarrier).  Each warp owns a private ring of GW_STAGES
-// stages: lane 0 issues the copies, every lane waits on the stage's barrier parity and reads its own record
-// with one conflict-free LDS.128.  The bytes in flight no longer live in registers (64 instead of 80).
-// Measured on B200 (profiles/r1d_experiments.md section 9): k_df_drho 111 us with two stages, 124 us with three,
-// against 107 us for the register-prefetched walk_gw -- the ring's shared memory is taken from the L1 that
-// the velocity gathers live in.  Compile-time opt-in, off by default.
-#ifndef SPH_GW_BULK
-#define SPH_GW_BULK 0
-#endif
-#ifndef GW_STAGES
-#define GW_STAGES 3
-#endif
-#define GW_STAGE_F4 128 // four rows of 32 records
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bulk_stage(float4 *dst, const float4 *src, uint64_t *bar) {
-	const uint32_t bytes = GW_STAGE_F4 * sizeof(float4);
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
-	             : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
-	asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(
-	                 smem_u32(bar)),
-	             "r"(parity)
-	             : "memory");
-}
-// every lane of the warp must call (dead lanes with n <= 0); ring / bars are the warp's private slices
+// (A variant that staged the float4 records through shared memory with TMA bulk copies -- cp.async.bulk + mbarrier,
+// a per-warp ring of 2 KB stages -- was measured slower on B200, 111-124 us against 107 us: the ring takes L1 away
+// from the velocity gathers.  profiles/r1d_experiments.md section 9; removed in round 2.)
+
+#if !SPH_STRICT
+// fast kernels: f(j, grad W_ij) from the neighbour list (index) + the quantised gradient stream; per quad of
+// entries three coalesced 128-bit loads (one of indices, two of gradients), two quads in flight ahead of the one
+// in use, L1 no-allocate, L2 evict-first
+struct GqQuad {
+	uint4 j, a, b;
+};
 template <class F>
-__device__ __forceinline__ void walk_gw_bulk(const float4 *__restrict__ gw, int cap, int s, int n, float4 *ring, uint64_t *bars,
-                                             F &&f) {
-	const int lane = threadIdx.x & 31;
-	int nmax = max(n, 0);
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
-	if (nmax == 0) return;
-	const float4 *src = gw + ((size_t)(s >> 5) * (size_t)cap) * 32u; // row 0 of this warp (s >> 5 is warp-uniform)
-	const int nst = (nmax + 3) >> 2;
-	if (lane == 0) {
-#pragma unroll
-		for (int k = 0; k < GW_STAGES; ++k) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[k])));
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		for (int k = 0; k < GW_STAGES && k < nst; ++k) bulk_stage(ring + k * GW_STAGE_F4, src + (size_t)k * GW_STAGE_F4, &bars[k]);
+__device__ __forceinline__ void walk_gq(const SphLists &L, const SphConsts &c, int s, int n, F &&f) {
+	if (n <= 0) return;
+	const uint64_t pol = list_policy();
+	const uint4 *pl = reinterpret_cast<const uint4 *>(L.flist) + ((size_t)(s >> 5) * (size_t)(c.kstride >> 2)) * 32u + (size_t)(s & 31);
+	const uint4 *pg = L.gq + ((size_t)(s >> 5) * (size_t)(c.kstride >> 1)) * 32u + (size_t)(s & 31);
+	const float scale = c.gq_scale, bias = -1048576.0f * c.gq_scale;
+	const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+	auto load = [&](const uint4 *l, const uint4 *g) {
+		GqQuad r;
+		r.j = ld_list(l, pol);
+		r.a = ld_list(g, pol);
+		r.b = ld_list(g + 32, pol);
+		return r;
+	};
+	GqQuad cur = load(pl, pg), nx1;
+	if (n > 4) nx1 = load(pl + 32, pg + 64);
+	else { nx1.j = z; nx1.a = z; nx1.b = z; }
+	int k = 0;
+	for (; k + 4 <= n; k += 4) {
+		GqQuad nx2;
+		if (k + 8 < n) nx2 = load(pl + 64, pg + 128);
+		else { nx2.j = z; nx2.a = z; nx2.b = z; }
+		pl += 32;
+		pg += 64;
+		f(cur.j.x, gq_unpack(cur.a.x, cur.a.y, scale, bias));
+		f(cur.j.y, gq_unpack(cur.a.z, cur.a.w, scale, bias));
+		f(cur.j.z, gq_unpack(cur.b.x, cur.b.y, scale, bias));
+		f(cur.j.w, gq_unpack(cur.b.z, cur.b.w, scale, bias));
+		cur = nx1;
+		nx1 = nx2;
 	}
-	__syncwarp();
-	for (int st = 0; st < nst; ++st) {
-		const int slot = st % GW_STAGES;
-		bar_wait(&bars[slot], (uint32_t)((st / GW_STAGES) & 1));
-		const float4 *r = ring + slot * GW_STAGE_F4 + lane;
-		float4 c0 = r[0], c1 = r[32], c2 = r[64], c3 = r[96];
-		__syncwarp();
-		if (lane == 0 && st + GW_STAGES < nst) {
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			bulk_stage(ring + slot * GW_STAGE_F4, src + (size_t)(st + GW_STAGES) * GW_STAGE_F4, &bars[slot]);
-		}
-		const int k = st * 4;
-		if (k + 4 <= n) {
-			f(__float_as_uint(c0.x), F3(c0.y, c0.z, c0.w));
-			f(__float_as_uint(c1.x), F3(c1.y, c1.z, c1.w));
-			f(__float_as_uint(c2.x), F3(c2.y, c2.z, c2.w));
-			f(__float_as_uint(c3.x), F3(c3.y, c3.z, c3.w));
-		} else if (k < n) {
-			f(__float_as_uint(c0.x), F3(c0.y, c0.z, c0.w));
-			if (k + 1 < n) {
-				f(__float_as_uint(c1.x), F3(c1.y, c1.z, c1.w));
-				if (k + 2 < n) f(__float_as_uint(c2.x), F3(c2.y, c2.z, c2.w));
-			}
+	int m = n - k;
+	if (m > 0) {
+		f(cur.j.x, gq_unpack(cur.a.x, cur.a.y, scale, bias));
+		if (m > 1) {
+			f(cur.j.y, gq_unpack(cur.a.z, cur.a.w, scale, bias));
+			if (m > 2) f(cur.j.z, gq_unpack(cur.b.x, cur.b.y, scale, bias));
 		}
 	}
 }
-#if SPH_GW_BULK
-#define SPH_GW_RING()                                                                              \
-	__shared__ __align__(128) float4 gw_ring_[(SPH_BLOCK / 32) * GW_STAGES * GW_STAGE_F4];         \
-	__shared__ __align__(8) uint64_t gw_bars_[(SPH_BLOCK / 32) * GW_STAGES]
-#define SPH_WALK_GW(L, c, s, n, ...)                                                               \
-	walk_gw_bulk((L).gw, (c).kstride, s, n, gw_ring_ + (threadIdx.x >> 5) * GW_STAGES * GW_STAGE_F4, \
-	             gw_bars_ + (threadIdx.x >> 5) * GW_STAGES, __VA_ARGS__)
+#define SPH_WALK_GW(L, c, s, n, ...) walk_gq(L, c, s, n, __VA_ARGS__)
 #else
-#define SPH_GW_RING() (void)0
 #define SPH_WALK_GW(L, c, s, n, ...) walk_gw((L).gw, (c).kstride, s, n, __VA_ARGS__)
 #endif
 
@@ -665,7 +665,6 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
           float4 *__restrict__ posT2, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
 	if (gated && !ctl->div_active) return;
 	SPH_DF_THREAD();
-	SPH_GW_RING();
 	double psum = 0.0;
 	int pcnt = 0;
 	float dt = ctl->dt;
@@ -678,14 +677,8 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 		enough = nbr_count[s] >= 20; // DF:258-261
 	}
 	float rd = 0.0f, rdb = 0.0f;
-#if SPH_GW_BULK
-	const int nwalk = enough ? nf_ : 0; // the staged walker needs every lane of the warp: the others walk an empty list
-	{
-#else
-	const int nwalk = nf_;
 	if (enough) {
-#endif
-		SPH_WALK_GW(L, c, s, nwalk, [&](uint32_t j, f3 dw) {
+		SPH_WALK_GW(L, c, s, nf_, [&](uint32_t j, f3 dw) {
 			if (SPH_IS_RIGID(j)) {
 				float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 				f3 v_j = rigid_velocity(rg.st, xyz(pj), dt, false);             // DF:292-293
@@ -694,7 +687,7 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 			}
 			rd += c.m * dot(vi - xyz(__ldg(&svel[j])), dw); // DF:287
 		});
-		if (enough && c.boundary_handle == 1) {
+		if (c.boundary_handle == 1) {
 			SPH_FOR_BOUNDARY_N(L, c, s, nb_, j) {
 				float4 pj = __ldg(&bspos[j]);
 				Pair p = make_pair(pi, pj);
@@ -848,7 +841,6 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
              const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
 	if (gated && !ctl->den_active) return;
 	SPH_DF_THREAD();
-	SPH_GW_RING();
 	double psum = 0.0;
 	int pcnt = 0;
 	float dt = ctl->dt, dt2 = ctl->dt2;

@@ -28,9 +28,9 @@ def main():
     cuts = None
     if variant == "empty-edge":
         # asymmetric halo counts.  The small block occupies the x-cell columns 3 .. 10 of 16; with the cut
-        # after column 11 the last rank starts EMPTY and its edge column stays empty for a while: its neighbour
-        # sends nothing, receives nothing, but must still be waited for on every exchange.
-        cuts = [0] + [3 + (8 * k) // (world - 1) for k in range(1, world - 1)] + [12, 16]
+        # after column 9 the last rank starts EMPTY while its neighbour's edge column is full: that neighbour sends,
+        # receives nothing, and must still wait for the empty rank on every exchange.
+        cuts = [0] + [3 + (8 * k) // (world - 1) for k in range(1, world - 1)] + [10, 16]
     res = selfcheck.slab_vs_single(solver=solver, steps=steps, strict=strict, cuts=cuts)
     ok = True
     if rank == 0:
