@@ -533,6 +533,12 @@ __device__ __forceinline__ void walk_gw(const float4 *__restrict__ gw, int cap, 
 // a per-warp ring of 2 KB stages -- was measured slower on B200, 111-124 us against 107 us: the ring takes L1 away
 // from the velocity gathers.  profiles/r1d_experiments.md section 9; removed in round 2.)
 
+#ifndef SPH_GQ_AHEAD
+#define SPH_GQ_AHEAD 2 // quads of (indices, gradients) in flight ahead of the one in use
+#endif
+#ifndef SPH_MINB_STREAM
+#define SPH_MINB_STREAM SPH_MINB // minimum resident blocks per SM of the two streaming sweeps (k_df_drho, k_df_rho_adv)
+#endif
 #if !SPH_STRICT
 // fast kernels: f(j, grad W_ij) from the neighbour list (index) + the quantised gradient stream; per quad of
 // entries three coalesced 128-bit loads (one of indices, two of gradients), two quads in flight ahead of the one
@@ -560,9 +566,11 @@ __device__ __forceinline__ void walk_gq(const SphLists &L, const SphConsts &c, i
 	else { nx1.j = z; nx1.a = z; nx1.b = z; }
 	int k = 0;
 	for (; k + 4 <= n; k += 4) {
+#if SPH_GQ_AHEAD == 2
 		GqQuad nx2;
 		if (k + 8 < n) nx2 = load(pl + 64, pg + 128);
 		else { nx2.j = z; nx2.a = z; nx2.b = z; }
+#endif
 		pl += 32;
 		pg += 64;
 		f(cur.j.x, gq_unpack(cur.a.x, cur.a.y, scale, bias));
@@ -570,7 +578,11 @@ __device__ __forceinline__ void walk_gq(const SphLists &L, const SphConsts &c, i
 		f(cur.j.z, gq_unpack(cur.b.x, cur.b.y, scale, bias));
 		f(cur.j.w, gq_unpack(cur.b.z, cur.b.w, scale, bias));
 		cur = nx1;
+#if SPH_GQ_AHEAD == 2
 		nx1 = nx2;
+#else
+		if (k + 8 < n) nx1 = load(pl + 32, pg + 64);
+#endif
 	}
 	int m = n - k;
 	if (m > 0) {
@@ -657,7 +669,7 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
 // DF:252-300 derivative_iter_all_rho.  Writes drho and the payload t2 = ((drho*alpha)/dt)/rho of
 // the following divergence iteration (DF:363-367); block partials feed the device-side average.
 template <bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB_STREAM)
 k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ spos,
           const float4 *__restrict__ svel, const float4 *__restrict__ bspos,
           const int *__restrict__ nbr_count,
@@ -834,7 +846,7 @@ k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restric
 // DF:124-176 compute_all_rho_adv.  Writes rho_adv and the payload t3 = (((rho_adv-rho0)*alpha)/dt2)/rho
 // of iter_all_vel_adv (DF:199-203).
 template <bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB_STREAM)
 k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ spos,
              const float4 *__restrict__ svadv, const float4 *__restrict__ bspos, const float *__restrict__ rho,
              const float *__restrict__ alpha, float *__restrict__ rho_adv, float4 *__restrict__ posT3,

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for v in main "$@"; do
   if [ "$v" = main ]; then unset SPH_B200_LIB; else export SPH_B200_LIB=$PWD/scratch/variants/$v/libsph_b200.so; fi
-  python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
+  python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-also > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err
   python - "$v" <<'PY'
 import json,sys
 v=sys.argv[1]
