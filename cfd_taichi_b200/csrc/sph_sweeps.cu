@@ -39,10 +39,12 @@ __host__ __device__ inline size_t sph_gw_index(int s, int cap, int k) {
 // 5e-7 of the largest gradient; measured per-sweep error against the strict kernels ~1e-6 (tolerance 1e-5).
 #if !SPH_STRICT
 __device__ __forceinline__ uint2 gq_pack(f3 g, const SphConsts &c) {
-	const int B = 1 << 20;
-	uint32_t mx = (uint32_t)min(max(__float2int_rn(g.x * c.gq_inv) + B, 0), 2 * B - 1);
-	uint32_t my = (uint32_t)min(max(__float2int_rn(g.y * c.gq_inv) + B, 0), 2 * B - 1);
-	uint32_t mz = (uint32_t)min(max(__float2int_rn(g.z * c.gq_inv) + B, 0), 2 * B - 1);
+	// |g| <= S / 1.001 analytically, so the biased values stay inside 21 bits without a clamp (the mask only keeps a
+	// non-finite gradient -- flagged elsewhere -- from spilling into its neighbours' bits)
+	const float B = 1048576.0f;
+	uint32_t mx = (uint32_t)__float2int_rn(fmaf(g.x, c.gq_inv, B)) & 0x1FFFFFu;
+	uint32_t my = (uint32_t)__float2int_rn(fmaf(g.y, c.gq_inv, B)) & 0x1FFFFFu;
+	uint32_t mz = (uint32_t)__float2int_rn(fmaf(g.z, c.gq_inv, B)) & 0x1FFFFFu;
 	return make_uint2(mx | (my << 21), (my >> 11) | (mz << 10)); // bits 0-20 x, 21-41 y, 42-62 z
 }
 __device__ __forceinline__ f3 gq_unpack(uint32_t lo, uint32_t hi, float scale, float bias) {
@@ -537,7 +539,14 @@ __device__ __forceinline__ void walk_gw(const float4 *__restrict__ gw, int cap, 
 #define SPH_GQ_AHEAD 2 // quads of (indices, gradients) in flight ahead of the one in use
 #endif
 #ifndef SPH_MINB_STREAM
-#define SPH_MINB_STREAM SPH_MINB // minimum resident blocks per SM of the two streaming sweeps (k_df_drho, k_df_rho_adv)
+// minimum resident blocks per SM of the two streaming sweeps (k_df_drho, k_df_rho_adv).  They are latency-bound on the
+// stream: measured on B200 at 10^6 particles (profiles/r2_experiments.md) k_df_drho 108 us at 110 registers (4 blocks),
+// 99 us at 96 (5), 90 us at 80 (6), 89 us at 72 (7), 107 us at 64 (8: spills).  Strict kernels keep ptxas' choice.
+#if SPH_STRICT
+#define SPH_MINB_STREAM SPH_MINB
+#else
+#define SPH_MINB_STREAM 7
+#endif
 #endif
 #if !SPH_STRICT
 // fast kernels: f(j, grad W_ij) from the neighbour list (index) + the quantised gradient stream; per quad of

@@ -9,9 +9,13 @@
  * Conventions
  *   - every function returns 0 on success, a negative SPH_E* code on failure; the message is
  *     available from sph_last_error().  No exceptions cross the boundary.
- *   - all work is asynchronous on the `stream` argument (a cudaStream_t passed as void*);
- *     only sph_read_stats, sph_upload_* / sph_download_* with host buffers, and sph_create /
- *     sph_destroy synchronise.
+ *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*).  Host synchronisation:
+ *     sph_create / sph_destroy, sph_read_stats, sph_rigid_state / sph_rigid_set_state, sph_profile_end and the
+ *     sph_download_* calls synchronise by contract.  sph_step / sph_phase of the three iterative solvers
+ *     synchronise ONCE per step (never per solver iteration): the uncapped DFSPH density loop (DF:225) and the
+ *     PCISPH / IISPH pressure loops are enqueued in chunks gated by a device flag, and the host reads that flag
+ *     once per chunk (one chunk per step in steady state).  WCSPH, PBF and every single-sweep phase are fully
+ *     asynchronous.  On several GPUs each step additionally reads the migration / ghost counts back once.
  *   - one host thread per handle (as in the reference: one Python thread drives main.py:95-206).
  *   - the caller (Python/torch) owns the particle state buffers bound with sph_bind; the
  *     library owns scratch only (cell arrays, neighbour lists, sorted work buffers).
@@ -237,7 +241,6 @@ int sph_set_delta_time(SphHandle *h, float dt, void *stream);
 /* Copy a result field into caller device memory, original particle order. */
 int sph_fetch(SphHandle *h, int field, void *dev_out, size_t n, void *stream);
 
-/* Host-buffer entry points (the e2e path): pinned or pageable host memory, float4 * n. */
 /* Device-side scene initialisation (init_particle_pos, PS:139-195): the fluid lattice and the one-layer
  * boundary shell written straight into caller-owned float4 arrays, with the reference's f32 arithmetic.
  * Stateless: no handle is needed (the reference fills the positions before anything else, PS:119).
@@ -263,6 +266,7 @@ int sph_init_boundary_shell(const SphLattice *lat, size_t nb, void *dev_bpos4, i
 #define SPH_VIS_NEIGHBOUR 1
 int sph_visualize(SphHandle *h, int what, void *dev_rgb, int stride_floats, size_t n, void *stream);
 
+/* Host-buffer entry points (the e2e path): pinned or pageable host memory, float4 * n_fluid. */
 int sph_upload_state(SphHandle *h, const float *host_pos4, const float *host_vel4, void *stream);
 int sph_download_state(SphHandle *h, float *host_pos4, float *host_vel4, void *stream);
 /* The same with the host arrays the reference's callers hold (pos / vel as N x 3 floats, main.py:190):
@@ -291,8 +295,10 @@ int sph_profile_end(SphHandle *h, float *ms_by_class, int32_t *launches_by_class
  * sets the initial owned count with sph_set_counts and joins the NCCL communicator:
  *   rank 0: sph_comm_unique_id(id) -> broadcast the 128 bytes (torch.distributed plumbing) -> every
  *   rank: sph_comm_init(h, id, rank, nranks, col_lo, col_hi).
- * sph_step then performs, per step: particle migration, one-column ghost exchange, per-sweep ghost
- * value exchange and the loop-decision all-reduces, all over NCCL on the caller's stream. */
+ * sph_step then performs, per step, on the caller's stream: particle migration and the one-column ghost-particle
+ * exchange (two NCCL send/recv groups + one count read-back), and -- per sweep -- the ghost-value exchange and the
+ * loop-decision reduction as ONE kernel that stores into the neighbours' CUDA-IPC peer windows over NVLink and
+ * polls its own (no NCCL, no host; SPH_MG_TRANSPORT=nccl selects NCCL for these too, for A/B runs). */
 int sph_comm_unique_id(char *out128);
 int sph_comm_init(SphHandle *h, const char *id128, int rank, int nranks, int col_lo, int col_hi);
 int sph_comm_info(SphHandle *h, int32_t *out8); /* owned, ghosts, sent L/R, received L/R, rank, nranks */
