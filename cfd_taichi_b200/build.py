@@ -44,12 +44,13 @@ def build(force=False, verbose=False):
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     hdrs.append(os.path.join(HERE, "..", "include", "sph_b200.h"))
     extra = os.environ.get("SPH_EXTRA_NVCC", "").split()
+    fast_extra = os.environ.get("SPH_FAST_NVCC", "").split()     # A/B knob: extra flags of the fast sweep unit only
     units = [
         ("sph_grid.cu", "sph_grid.o", extra),
         ("sph_api.cu", "sph_api.o", extra),
         ("sph_multigpu.cu", "sph_multigpu.o", ["-I", NCCL_INC] + extra),
         ("sph_sweeps.cu", "sph_sweeps_strict.o", ["-DSPH_STRICT=1", "-fmad=false"] + extra),
-        ("sph_sweeps.cu", "sph_sweeps_fast.o", ["-DSPH_STRICT=0", "-fmad=true"] + extra),
+        ("sph_sweeps.cu", "sph_sweeps_fast.o", ["-DSPH_STRICT=0", "-fmad=true"] + fast_extra + extra),
     ]
     objs = []
     procs = []

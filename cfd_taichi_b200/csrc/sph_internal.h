@@ -124,6 +124,8 @@ void sphg_visualize(SphHandle *h, int what, float *rgb, int stride, cudaStream_t
 enum { MG_F4_T1R = 0 /* posT1.w + posR.w */, MG_F4_VEL, MG_F4_T2, MG_F4_VADV, MG_F4_T3,
        MG_F4_T1W /* posT1.w */, MG_NONE = -1 };
 #define MG_XYZ(a4_index) (100 + (a4_index)) // xyz of the float4 work array a4[a4_index] (w is not carried)
+struct SphMgPush;
+SphMgPush mg_push_args(SphHandle *h);                            // the next sweep pushes its edge values itself (sph_mgwin.cuh)
 void mg_exchange(SphHandle *h, int what, cudaStream_t st);       // ghost values of one field, both neighbours
 // ghost values + the all-reduce of the sweep's n_blocks block partials + the loop decision `ctl_kind`
 // (sph_ctl.cuh) applied on every rank
@@ -140,7 +142,7 @@ void mg_rigid_quirk_update(SphHandle *h, int with_rho, cudaStream_t st);        
 #define SPH_SWEEP_API(NS)                                                                   \
 	namespace NS {                                                                          \
 	void boundary_volume(SphHandle *h, cudaStream_t st);                                    \
-	void build_lists(SphHandle *h, cudaStream_t st);                                        \
+	void build_lists(SphHandle *h, cudaStream_t st, bool push_lists = false);               \
 	void df_step(SphHandle *h, cudaStream_t st);                                            \
 	void df_phase(SphHandle *h, int phase, cudaStream_t st);                                \
 	void first_phase_lists(SphHandle *h, cudaStream_t st);                                  \

@@ -30,8 +30,7 @@
 
 #include "sph_internal.h"
 #include "sph_ctl.cuh"
-
-#define SPH_MG_MAX_RANKS 16
+#include "sph_mgwin.cuh"
 
 struct NcclApi {
 	void *lib;
@@ -85,21 +84,11 @@ struct SphComm {
 	size_t win_bytes;
 	int epoch;                   // exchanges issued so far (same sequence on every rank)
 	int *send_slot[2], *recv_slot; // sorted slots of the particles sent to each side / of the ghosts, per step
+	int2 *push_tag;              // per sorted slot: where the particle's value goes in each neighbour's receive block (-1: nowhere)
+	int *pushed_epoch;           // device word written by a producing sweep that pushed its own edge values
+	int push_pending;            // host: epoch handed to a producer with mg_push_args, consumed by the next exchange
 	float4 *quirk;               // rigid scenes: (pos, rho) of the fluid particles with global id < Nr, replicated
 };
-
-// ---- window layout (identical on every rank) ----------------------------------------------------------
-//   [0, 4096)            loop partials: rslot[2 parity][MAX_RANKS] = {sum | tag}, {count, max | tag}
-//   [4096, ...)          float4 xr[2 parity][2 side][cap_halo], .w = epoch tag
-struct MgCtlWin {
-	double rslot[2][SPH_MG_MAX_RANKS][4]; // two tagged 16-byte slots per (parity, source rank)
-	uint4 sync[2][2];                     // [parity][side]: "my neighbour on that side has entered this exchange"
-};
-static_assert(sizeof(MgCtlWin) <= 4096, "window control block");
-__host__ __device__ static inline MgCtlWin *win_ctl(char *w) { return (MgCtlWin *)w; }
-__host__ __device__ static inline float4 *win_xr(char *w, int cap, int parity, int side) {
-	return (float4 *)(w + 4096) + ((size_t)parity * 2 + (size_t)side) * (size_t)cap;
-}
 
 #define NCCL_OK(h, expr)                                                                                 \
 	do {                                                                                                 \
@@ -285,14 +274,6 @@ k_mg_unpack_values(int what, const int *__restrict__ slot_of, int first_orig, in
 struct MgPeers {
 	char *w[SPH_MG_MAX_RANKS];
 };
-__device__ __forceinline__ void st_slot(void *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
-	asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
-}
-__device__ __forceinline__ uint4 ld_slot(const void *p) {
-	uint4 r;
-	asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
-	return r;
-}
 __device__ __forceinline__ unsigned long long global_ns() {
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -325,7 +306,7 @@ k_mg_exchange(int what, const int *__restrict__ send_slot_l, const int *__restri
               const float4 *src_a, const float4 *src_b, float4 *dst_a, float4 *dst_b, const float4 *__restrict__ spos,
               MgPeers peers, char *win, int cap, int rank, int nranks, int epoch, int do_reduce,
               const SphPartial *__restrict__ partials, int n_partials, int ctl_kind, SphCtlArgs cargs,
-              double *__restrict__ red, SphCtl *ctl) {
+              double *__restrict__ red, SphCtl *ctl, const int *__restrict__ pushed_epoch) {
 	const int parity = epoch & 1;
 	if (do_reduce && blockIdx.x == gridDim.x - 1) {
 		double sum; int cnt; float mx;
@@ -373,7 +354,10 @@ k_mg_exchange(int what, const int *__restrict__ send_slot_l, const int *__restri
 	const int stride = nblk * (int)blockDim.x;
 	const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
 	// phase 1: push.  My left neighbour receives on its right side (1), my right neighbour on its left side (0).
-	for (int k = t0; k < nsl + nsr; k += stride) {
+	// Skipped when the producing sweep pushed these values from its own epilogue (it recorded the epoch; a producer
+	// that was gated off by its loop flag did not, and the -- unchanged -- values are pushed here as before).
+	const bool pushed = pushed_epoch && *pushed_epoch == epoch;
+	for (int k = t0; !pushed && k < nsl + nsr; k += stride) {
 		bool left = k < nsl;
 		int kk = left ? k : k - nsl;
 		int s = (left ? send_slot_l : send_slot_r)[kk];
@@ -429,6 +413,13 @@ static int mg_open_windows(SphHandle *h, SphComm *m) {
 	m->win_bytes = 4096 + sizeof(float4) * 4 * (size_t)m->cap_halo;
 	for (int d = 0; d < 2; ++d) SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->send_slot[d], sizeof(int) * (size_t)m->cap_halo));
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->recv_slot, sizeof(int) * 2 * (size_t)m->cap_halo));
+	{
+		size_t ncap = (size_t)h->cfg.n_fluid + (size_t)h->cfg.n_ghost_capacity;
+		SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->push_tag, sizeof(int2) * ncap));
+		SPH_CUDA_CHECK(h, cudaMemset(m->push_tag, 0xff, sizeof(int2) * ncap));
+		SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->pushed_epoch, sizeof(int)));
+		SPH_CUDA_CHECK(h, cudaMemset(m->pushed_epoch, 0, sizeof(int)));
+	}
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->win, m->win_bytes));
 	SPH_CUDA_CHECK(h, cudaMemset(m->win, 0, m->win_bytes));
 	cudaIpcMemHandle_t mine;
@@ -515,7 +506,7 @@ void mg_destroy(SphHandle *h) {
 		for (int r = 0; r < m->nranks; ++r)
 			if (r != m->rank && m->peer_win[r]) cudaIpcCloseMemHandle(m->peer_win[r]);
 	}
-	cudaFree(m->quirk); cudaFree(m->win); cudaFree(m->send_slot[0]); cudaFree(m->send_slot[1]); cudaFree(m->recv_slot);
+	cudaFree(m->quirk); cudaFree(m->win); cudaFree(m->send_slot[0]); cudaFree(m->send_slot[1]); cudaFree(m->recv_slot); cudaFree(m->push_tag); cudaFree(m->pushed_epoch);
 	if (m->comm) g_nccl.CommDestroy(m->comm);
 	delete m;
 	h->comm = nullptr;
@@ -590,10 +581,11 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 k_mg_slots(const int *__restrict__ send_orig_l, const int *__restrict__ send_orig_r, const int *__restrict__ slot_of,
            int nsl, int nsr, int first_orig, int nr, int *__restrict__ send_slot_l, int *__restrict__ send_slot_r,
-           int *__restrict__ recv_slot) {
+           int *__restrict__ recv_slot, int2 *__restrict__ push_tag) {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
-	if (k < nsl) send_slot_l[k] = slot_of[send_orig_l[k]];
-	if (k < nsr) send_slot_r[k] = slot_of[send_orig_r[k]];
+	// push_tag was filled with (-1, -1); a particle of a one-column slab is sent to both sides (two different threads)
+	if (k < nsl) { int s = slot_of[send_orig_l[k]]; send_slot_l[k] = s; push_tag[s].x = k; }
+	if (k < nsr) { int s = slot_of[send_orig_r[k]]; send_slot_r[k] = s; push_tag[s].y = k; }
 	if (k < nr) recv_slot[k] = slot_of[first_orig + k];
 }
 void mg_after_grid(SphHandle *h, cudaStream_t st) {
@@ -602,9 +594,10 @@ void mg_after_grid(SphHandle *h, cudaStream_t st) {
 	int nr = m->n_recv[0] + m->n_recv[1];
 	int work = nr > m->n_send[0] ? nr : m->n_send[0];
 	if (m->n_send[1] > work) work = m->n_send[1];
+	if (h->c.N > 0) cudaMemsetAsync(m->push_tag, 0xff, sizeof(int2) * (size_t)h->c.N, st); // (-1, -1): not sent
 	if (work <= 0) return;
 	k_mg_slots<<<cdiv(work, 256), 256, 0, st>>>(m->send_orig[0], m->send_orig[1], h->fg.slot_of, m->n_send[0], m->n_send[1],
-	                                            h->c.N_owned, nr, m->send_slot[0], m->send_slot[1], m->recv_slot);
+	                                            h->c.N_owned, nr, m->send_slot[0], m->send_slot[1], m->recv_slot, m->push_tag);
 	h->launches++;
 }
 
@@ -635,7 +628,8 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 	int ns = m->n_send[0] + m->n_send[1], nr = m->n_recv[0] + m->n_recv[1];
 	if (m->p2p) {
 		sph_prof_begin(h, KC_MG_EXCHANGE, st);
-		int epoch = ++m->epoch;
+		int epoch = m->push_pending ? m->push_pending : ++m->epoch; // a producer already holds this exchange's epoch
+		m->push_pending = 0;
 		MgPeers peers;
 		for (int r = 0; r < SPH_MG_MAX_RANKS; ++r) peers.w[r] = r < m->nranks ? m->peer_win[r] : nullptr;
 		int work = ns > nr ? ns : nr;
@@ -646,7 +640,7 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 			k_mg_exchange<<<blocks, 256, 0, st>>>(what, m->send_slot[0], m->send_slot[1], m->recv_slot, m->n_send[0], m->n_send[1],
 			                                      m->n_recv[0], m->n_recv[1], a, b, wa, wb, h->a4[A4_POS], peers,
 			                                      m->win, m->cap_halo, m->rank, m->nranks, epoch, reduce_blocks > 0 ? 1 : 0,
-			                                      h->partials, reduce_blocks, ctl_kind, cargs, h->red, h->ctl);
+			                                      h->partials, reduce_blocks, ctl_kind, cargs, h->red, h->ctl, m->pushed_epoch);
 			h->launches += 1;
 		}
 		sph_prof_end(h, st);
@@ -681,6 +675,27 @@ static void mg_exchange_impl(SphHandle *h, int what, int ctl_kind, int reduce_bl
 		h->launches++;
 	}
 	sph_prof_end(h, st);
+}
+
+// The sweep about to be launched produces the values of the NEXT exchange: hand it that exchange's epoch and the
+// neighbours' windows so that it stores its edge values itself (sph_mgwin.cuh); the exchange kernel then only polls
+// and unpacks.  Must be followed by exactly one mg_exchange / mg_exchange_reduce of those values.
+// MEASURED on 2 x B200, 10^6 particles per GPU (profiles/r2_experiments.md): the exchange kernels get shorter
+// (0.63 -> 0.52 ms per step) but every sweep pays for the tag load and the peer stores: 4.30 ms per step against
+// 4.14 ms.  Hence OPT-IN (SPH_MG_EPILOGUE_PUSH=1); by default tag == nullptr and the exchange kernel pushes.
+SphMgPush mg_push_args(SphHandle *h) {
+	SphMgPush pu;
+	memset(&pu, 0, sizeof(pu));
+	SphComm *m = h->comm;
+	static const bool enabled = getenv("SPH_MG_EPILOGUE_PUSH") != nullptr;
+	if (!m || !m->p2p || !enabled) return pu;
+	pu.tag = m->push_tag;
+	pu.peer_l = m->rank > 0 ? m->peer_win[m->rank - 1] : nullptr;
+	pu.peer_r = m->rank + 1 < m->nranks ? m->peer_win[m->rank + 1] : nullptr;
+	pu.pushed_epoch = m->pushed_epoch;
+	pu.cap = m->cap_halo;
+	pu.epoch = m->push_pending = ++m->epoch;
+	return pu;
 }
 
 void mg_exchange(SphHandle *h, int what, cudaStream_t st) { mg_exchange_impl(h, what, SPH_CTL_NONE, 0, st); }

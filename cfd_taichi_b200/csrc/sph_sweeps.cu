@@ -13,6 +13,7 @@
 #include "sph_math.cuh"
 #include "sph_internal.h"
 #include "sph_ctl.cuh"
+#include "sph_mgwin.cuh"
 
 #ifndef SPH_MINB
 #define SPH_MINB 1 // minimum resident blocks per SM requested from ptxas for the list-walking sweeps
@@ -183,9 +184,10 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
               const int *__restrict__ scell, const int *__restrict__ cstart, const int *__restrict__ sorted_id,
               const float4 *__restrict__ bspos, const int *__restrict__ bstart, SphLists L, SphRigidArgs rg,
               int *__restrict__ nbr_count, float *__restrict__ rho, float *__restrict__ alpha,
-              float4 *__restrict__ posR, float4 *__restrict__ posT1, SphCtl *ctl) {
+              float4 *__restrict__ posR, float4 *__restrict__ posT1, SphCtl *ctl, SphMgPush pu) {
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	int nf = 0, nb = 0;
+	mg_push_mark(pu);
 	if (s < c.N && c.N != c.N_owned && sorted_id[s] >= c.N_owned) {
 		// ghost copy of a neighbour rank's particle (multi-GPU): never a centre particle; its rho / alpha /
 		// payloads arrive through the halo exchange.  fcount < 0 is the ownership flag every sweep tests.
@@ -370,7 +372,9 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 			alpha[s] = al;
 			// payload of the warm start (DF:333-337): (k / dt) / rho
 			float k = svel[s].w;
-			posT1[s] = make_float4(pi.x, pi.y, pi.z, (k / ctl->dt) / rho_i);
+			float t1 = (k / ctl->dt) / rho_i;
+			posT1[s] = make_float4(pi.x, pi.y, pi.z, t1);
+			mg_push(pu, s, t1, rho_i, 0.0f); // slabs: (warm-start payload, rho) of an edge particle, MG_F4_T1R
 		}
 #undef SPH_FLW
 #undef SPH_BLW
@@ -385,18 +389,23 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 	}
 }
 
-void build_lists(SphHandle *h, cudaStream_t st) {
+void build_lists(SphHandle *h, cudaStream_t st, bool push_lists) {
 	const SphConsts &c = h->c;
 	if (c.N <= 0) return;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	bool al = c.solver == SPH_SOLVER_DFSPH;
+	// DFSPH: the kernel pushes (payload, rho) of its edge particles itself; the other solvers' T1R exchange carries
+	// a payload this kernel does not write, so their exchange kernel pushes as before
+	SphMgPush pu;
+	if (al && push_lists) pu = mg_push_args(h);
+	else memset(&pu, 0, sizeof(pu));
 	sph_prof_begin(h, KC_LISTS, st);
 #define SPH_BL(A, R)                                                                                              \
 	k_build_lists<A, R><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,  \
 	                                              h->fg.sorted_id, h->bspos, h->bg.cell_start, h->L, rg,           \
 	                                              h->nbr_count, h->a1[A1_RHO], h->a1[A1_ALPHA], h->a4[A4_PR],      \
-	                                              h->a4[A4_T1], h->ctl)
+	                                              h->a4[A4_T1], h->ctl, pu)
 	if (al && rg.active) SPH_BL(true, true);
 	else if (al) SPH_BL(true, false);
 	else if (rg.active) SPH_BL(false, true);
@@ -412,7 +421,7 @@ void build_lists(SphHandle *h, cudaStream_t st) {
 // drives single sweeps has already built them with SPH_PH_BUILD_LISTS.
 void first_phase_lists(SphHandle *h, cudaStream_t st) {
 	if (!h->lists_fresh) {
-		build_lists(h, st);
+		build_lists(h, st, true);
 		mg_exchange(h, MG_F4_T1R, st); // slabs: rho of the ghost particles (posR.w)
 	}
 	h->lists_fresh = false;
@@ -628,8 +637,9 @@ template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
 k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT1,
                 const float4 *__restrict__ bspos, const float *__restrict__ rho, float4 *__restrict__ svel,
-                const SphCtl *__restrict__ ctl) {
+                const SphCtl *__restrict__ ctl, SphMgPush pu) {
 	SPH_DF_THREAD();
+	mg_push_mark(pu);
 	float dt = ctl->dt;
 	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vi = pi;
 	float rho_i = 1.0f;
@@ -673,6 +683,7 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
 	if (c.boundary_handle == 1) v = v - (va + vb * SPH_RHO0) * dt; // DF:322
 	else v = v - va * dt;                                          // DF:324
 	svel[s] = F4(v, 0.0f); // DF:325 warm_start_k.fill(0)
+	mg_push(pu, s, v.x, v.y, v.z);
 }
 
 // DF:252-300 derivative_iter_all_rho.  Writes drho and the payload t2 = ((drho*alpha)/dt)/rho of
@@ -683,9 +694,11 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
           const float4 *__restrict__ svel, const float4 *__restrict__ bspos,
           const int *__restrict__ nbr_count,
           const float *__restrict__ rho, const float *__restrict__ alpha, float *__restrict__ drho,
-          float4 *__restrict__ posT2, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
+          float4 *__restrict__ posT2, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated,
+          SphMgPush pu) {
 	if (gated && !ctl->div_active) return;
 	SPH_DF_THREAD();
+	mg_push_mark(pu);
 	double psum = 0.0;
 	int pcnt = 0;
 	float dt = ctl->dt;
@@ -720,7 +733,9 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 		float out = 0.0f;
 		if (enough) out = c.boundary_handle == 1 ? fmaxf(rd + rdb * SPH_RHO0, 0.0f) : fmaxf(rd, 0.0f); // DF:267
 		drho[s] = out;
-		posT2[s] = make_float4(pi.x, pi.y, pi.z, ((out * alpha[s]) / dt) / rho[s]);
+		float t2 = ((out * alpha[s]) / dt) / rho[s];
+		posT2[s] = make_float4(pi.x, pi.y, pi.z, t2);
+		mg_push(pu, s, t2, 0.0f, 0.0f);
 		if (out > 0.0f) { psum = (double)out; pcnt = 1; } // DF:275-277
 	}
 	block_partial(psum, pcnt, 0.0f, partials);
@@ -731,9 +746,10 @@ template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
 k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT2,
               const float4 *__restrict__ bspos, const float *__restrict__ rho, const float *__restrict__ alpha,
-              const float *__restrict__ drho, float4 *__restrict__ svel, const SphCtl *__restrict__ ctl) {
+              const float *__restrict__ drho, float4 *__restrict__ svel, const SphCtl *__restrict__ ctl, SphMgPush pu) {
 	if (!ctl->div_active) return;
 	SPH_DF_THREAD();
+	mg_push_mark(pu);
 	float dt = ctl->dt;
 	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	float da = 0.0f, rho_i = 1.0f;
@@ -779,6 +795,7 @@ k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 	if (c.boundary_handle == 1) v = v - (va + vb * SPH_RHO0) * dt; // DF:310
 	else v = v - va * dt;
 	svel[s] = F4(v, vi.w + da); // DF:384
+	mg_push(pu, s, v.x, v.y, v.z);
 }
 
 // SB:190-201: viscosity contribution of a rigid neighbour (uses rho[particle_j.index], SURVEY B-6)
@@ -808,8 +825,9 @@ template <bool RIGID>
 __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
 k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posR,
                const float4 *__restrict__ svel, const float *__restrict__ rho, float4 *__restrict__ svadv,
-               float4 *__restrict__ fext, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials) {
+               float4 *__restrict__ fext, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, SphMgPush pu) {
 	SPH_DF_THREAD();
+	mg_push_mark(pu);
 	float vmax = -INFINITY;
 	float dt = ctl->dt;
 	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 1.0f);
@@ -847,6 +865,7 @@ k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restric
 		f3 va = vi + (dt * f) / c.m;       // DF:102
 		fext[s] = F4(f, 0.0f);
 		svadv[s] = F4(va, 0.0f);
+		mg_push(pu, s, va.x, va.y, va.z);
 		vmax = sqrtf(dot(va, va)); // DF:103
 	}
 	block_partial(0.0, 0, vmax, partials);
@@ -859,9 +878,10 @@ __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB_STREAM)
 k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ spos,
              const float4 *__restrict__ svadv, const float4 *__restrict__ bspos, const float *__restrict__ rho,
              const float *__restrict__ alpha, float *__restrict__ rho_adv, float4 *__restrict__ posT3,
-             const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated) {
+             const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials, int gated, SphMgPush pu) {
 	if (gated && !ctl->den_active) return;
 	SPH_DF_THREAD();
+	mg_push_mark(pu);
 	double psum = 0.0;
 	int pcnt = 0;
 	float dt = ctl->dt, dt2 = ctl->dt2;
@@ -891,7 +911,9 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
 		if (c.boundary_handle == 1) ra = fmaxf(rho_i + dt * (delta + db * SPH_RHO0), SPH_RHO0); // DF:135
 		else ra = fmaxf(rho_i + dt * delta, SPH_RHO0);                                          // DF:137
 		rho_adv[s] = ra;
-		posT3[s] = make_float4(pi.x, pi.y, pi.z, (((ra - SPH_RHO0) * alpha[s]) / dt2) / rho_i);
+		float t3 = (((ra - SPH_RHO0) * alpha[s]) / dt2) / rho_i;
+		posT3[s] = make_float4(pi.x, pi.y, pi.z, t3);
+		mg_push(pu, s, t3, 0.0f, 0.0f);
 		if (!(ra == SPH_RHO0)) { psum = (double)ra; pcnt = 1; } // DF:139-141
 	}
 	block_partial(psum, pcnt, 0.0f, partials);
@@ -904,9 +926,10 @@ __global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB)
 k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT3,
                   const float4 *__restrict__ bspos, const float *__restrict__ rho, const float *__restrict__ alpha,
                   const float *__restrict__ rho_adv, float4 *__restrict__ svadv, const SphCtl *__restrict__ ctl,
-                  int gated) {
+                  int gated, SphMgPush pu) {
 	if (gated && !ctl->den_active) return;
 	SPH_DF_THREAD();
+	mg_push_mark(pu);
 	float dt = ctl->dt, dt2 = ctl->dt2;
 	float4 pi = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 	float rho_i = 1.0f, k_i = 0.0f;
@@ -948,8 +971,9 @@ k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__rest
 	}
 	if (!live) return;
 	f3 delta = c.boundary_handle == 1 ? va + vb * SPH_RHO0 : va; // DF:187
-	float4 v = svadv[s];
-	svadv[s] = F4(xyz(v) - delta * dt, 0.0f); // DF:191
+	f3 v = xyz(svadv[s]) - delta * dt; // DF:191
+	svadv[s] = F4(v, 0.0f);
+	mg_push(pu, s, v.x, v.y, v.z);
 }
 
 // DF:235-250 compute_all_position, fused with the write-back into the caller's original-order state
@@ -1025,7 +1049,7 @@ static void df_warm_start(SphHandle *h, cudaStream_t st) {
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_WARM, st);
-	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl);
+	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl, mg_push_args(h));
 	sph_prof_end(h, st);
 	mg_exchange(h, MG_F4_VEL, st);
 	h->launches += 1;
@@ -1040,7 +1064,7 @@ static void df_drho(SphHandle *h, int in_loop, cudaStream_t st) {
 	sph_prof_begin(h, KC_DF_DRHO, st);
 	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
 	             h->a1[A1_RHO],
-	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, in_loop);
+	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, in_loop, mg_push_args(h));
 	sph_prof_end(h, st);
 	df_decide(h, MG_F4_T2, in_loop ? SPH_CTL_DIV_ITER : SPH_CTL_DIV_FIRST, nb, st);
 	h->launches += 1;
@@ -1053,7 +1077,7 @@ static void df_div_vel(SphHandle *h, cudaStream_t st) {
 	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_DIV, st);
 	SPH_LAUNCH_R(k_df_div_iter, nb, c, h->L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-	             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl);
+	             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl, mg_push_args(h));
 	sph_prof_end(h, st);
 	mg_exchange(h, MG_F4_VEL, st);
 	h->launches += 1;
@@ -1076,7 +1100,7 @@ static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	SphRigidArgs rg = rigid_args(h);
 	sph_prof_begin(h, KC_DF_EXT, st);
 	SPH_LAUNCH_R(k_df_ext_force, nb, c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->a4[A4_VADV],
-	             h->a4[A4_FA], h->ctl, h->partials);
+	             h->a4[A4_FA], h->ctl, h->partials, mg_push_args(h));
 	sph_prof_end(h, st);
 	// DF:105-110 loops over all rigid particles whenever a rigid body exists, active or not
 	df_decide(h, MG_F4_VADV, SPH_CTL_DT, nb, st);
@@ -1091,7 +1115,7 @@ static void df_den_rho(SphHandle *h, int it, cudaStream_t st) {
 	int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
 	sph_prof_begin(h, KC_DF_RHOADV, st);
 	SPH_LAUNCH_R(k_df_rho_adv, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
-	             h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated);
+	             h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated, mg_push_args(h));
 	sph_prof_end(h, st);
 	df_decide(h, MG_F4_T3, SPH_CTL_DEN, nb, st);
 	h->launches += 1;
@@ -1105,7 +1129,7 @@ static void df_den_vel(SphHandle *h, int it, cudaStream_t st) {
 	int gated = it >= 2 ? 1 : 0;
 	sph_prof_begin(h, KC_DF_VELADV, st);
 	SPH_LAUNCH_R(k_df_vel_adv_iter, nb, c, h->L, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-	             h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated);
+	             h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated, mg_push_args(h));
 	sph_prof_end(h, st);
 	mg_exchange(h, MG_F4_VADV, st);
 	if (rg.active) rigid_force_df(h, gated, st); // DF:212, gather form

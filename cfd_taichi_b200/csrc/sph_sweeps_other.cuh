@@ -313,7 +313,8 @@ k_pc_press_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N || SPH_IS_GHOST(L, s)) return;
 	float4 pi = posT1[s];
-	f3 pf = F3(0.0f, 0.0f, 0.0f);
+	f3 pf = F3(0.0f, 0.0f, 0.0f), pf_fluid = pf;
+	(void)pf_fluid;
 	float rho_i = rho[s];
 	float rho_i_2 = rho_i * rho_i;
 	SPH_FOR_FLUID(L, c, s, j) {
@@ -326,15 +327,28 @@ k_pc_press_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 		}
 		float4 pj = __ldg(&posT1[j]);
 		Pair p = make_pair(pi, pj);
+#if SPH_STRICT
 		pf = pf + ((((pi.w + pj.w) * cubic_dw(p, c)) / 1000000.0f) * c.m) * c.m; // PC:177
+#else
+		pf_fluid = pf_fluid + (pi.w + pj.w) * cubic_dw(p, c); // the constant factor m^2 / rho_0^2 is applied once below
+#endif
 	};
+#if !SPH_STRICT
+	pf = pf + pf_fluid * ((c.m * c.m) / 1000000.0f);
+#endif
 	f3 out = neg(pf);
 	if (c.boundary_handle == 1) {
 		f3 bacc = F3(0.0f, 0.0f, 0.0f);
+		const float p_over_rho2 = pi.w / rho_i_2;
+		(void)p_over_rho2;
 		SPH_FOR_BOUNDARY(L, c, s, j) {
 			float4 pj = __ldg(&bspos[j]);
 			Pair p = make_pair(pi, pj);
+#if SPH_STRICT
 			bacc = bacc - ((pj.w * pi.w) / rho_i_2) * cubic_dw(p, c); // PC:197
+#else
+			bacc = bacc - (pj.w * p_over_rho2) * cubic_dw(p, c);
+#endif
 		};
 		out = neg(pf) + (bacc * SPH_RHO0) * c.m; // PC:117
 	}
@@ -637,7 +651,8 @@ k_ii_rho_adv_aii(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restr
 // II:121-126, 305-314 compute_all_d_ij.  posT1.w = p_iter of the neighbour.
 __global__ void __launch_bounds__(SPH_BLOCK)
 k_ii_dij(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float *__restrict__ rho,
-         float4 *__restrict__ d_ij, const SphCtl *__restrict__ ctl) {
+         float4 *__restrict__ d_ij, const float4 *__restrict__ d_ii, float4 *__restrict__ q_out,
+         const SphCtl *__restrict__ ctl) {
 	if (!ctl->ii_active) return;
 	int s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= c.N || L.fcount[s] < 0) return;
@@ -649,9 +664,18 @@ k_ii_dij(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float 
 		float4 pj = __ldg(&posT1[j]);
 		float rho_j = __ldg(&rho[j]);
 		Pair p = make_pair(pi, pj);
+#if SPH_STRICT
 		dij = dij + (((-c.m) * pj.w) * cubic_dw(p, c)) / (rho_j * rho_j); // II:313
+#else
+		dij = dij + sdiv((-c.m) * pj.w, rho_j * rho_j) * cubic_dw(p, c); // one approximate reciprocal instead of three divisions
+#endif
 	};
-	d_ij[s] = F4((dij * dt) * dt, 0.0f); // II:126
+	f3 d = (dij * dt) * dt; // II:126
+	d_ij[s] = F4(d, 0.0f);
+#if !SPH_STRICT
+	// what update_p needs of a NEIGHBOUR j is d_ii_j p_j + sum_k d_jk p_k (II:246): one vector instead of two gathers
+	q_out[s] = F4(xyz(d_ii[s]) * pi.w + d, 0.0f);
+#endif
 }
 
 // II:128-147 update_p (sum_factor II:228-253) + residual partials (II:102-113); p_next is committed
@@ -660,6 +684,7 @@ __global__ void __launch_bounds__(SPH_BLOCK)
 k_ii_update_p(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ posT1,
               const float4 *__restrict__ bspos,
               const float *__restrict__ rho, const float4 *__restrict__ d_ij, const float4 *__restrict__ d_ii,
+              const float4 *__restrict__ q_in,
               const float *__restrict__ a_ii, const float *__restrict__ rho_adv, float *__restrict__ r_sum,
               float *__restrict__ p_next, const SphCtl *__restrict__ ctl, SphPartial *__restrict__ partials) {
 	if (!ctl->ii_active) return;
@@ -681,12 +706,16 @@ k_ii_update_p(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 				return;
 			}
 			float4 pj = __ldg(&posT1[j]);
-			f3 dij_j = xyz(__ldg(&d_ij[j]));
-			f3 dii_j = xyz(__ldg(&d_ii[j]));
 			Pair p = make_pair(pi, pj);
 			f3 w_ij = cubic_dw(p, c);
 			f3 d_ji = (coef * neg(w_ij)) * pi.w;                       // II:244-245
+#if SPH_STRICT
+			f3 dij_j = xyz(__ldg(&d_ij[j]));
+			f3 dii_j = xyz(__ldg(&d_ii[j]));
 			f3 t = (dij_i - dii_j * pj.w) - (dij_j - d_ji);            // II:246
+#else
+			f3 t = (dij_i + d_ji) - xyz(__ldg(&q_in[j]));              // the same terms, the neighbour's two in one gather
+#endif
 			sum += c.m * dot(t, w_ij);
 		};
 		float rs = sum;
@@ -768,9 +797,14 @@ static void ii_pressure_solve_begin(SphHandle *h, cudaStream_t st) {
 static void ii_dij(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	sph_prof_begin(h, KC_II_DIJ, st);
-	k_ii_dij<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->ctl);
+	k_ii_dij<<<cdiv(c.N, SPH_BLOCK), SPH_BLOCK, 0, st>>>(c, h->L, h->a4[A4_T1], h->a1[A1_RHO], h->a4[A4_FB], h->a4[A4_FC],
+	                                                     h->a4[A4_T2], h->ctl);
 	sph_prof_end(h, st);
+#if SPH_STRICT
 	mg_exchange(h, MG_XYZ(A4_FB), st); // slabs: sum_j d_ij p_j of the ghost particles
+#else
+	mg_exchange(h, MG_XYZ(A4_T2), st); // slabs: d_ii p + sum_j d_ij p_j of the ghost particles
+#endif
 	h->launches += 1;
 }
 // II:252-340 update_p (relaxed Jacobi, omega = 0.5) + II:102-113 compute_residual + the loop decision (II:83-93)
@@ -779,7 +813,7 @@ static void ii_update(SphHandle *h, cudaStream_t st) {
 	int nba = cdiv(c.N, SPH_BLOCK);
 	sph_prof_begin(h, KC_II_UPDATE, st);
 	k_ii_update_p<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, rigid_args(h), h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_FB],
-	                                         h->a4[A4_FC], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
+	                                         h->a4[A4_FC], h->a4[A4_T2], h->a1[A1_SA], h->a1[A1_RHOADV], h->a1[A1_SB],
 	                                         h->a1[A1_SC], h->ctl, h->partials);
 	sph_prof_end(h, st);
 	k_ii_commit<<<nba, SPH_BLOCK, 0, st>>>(c, h->L, h->a1[A1_SC], h->a1[A1_P], h->a4[A4_T1], h->ctl);

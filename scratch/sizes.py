@@ -26,5 +26,5 @@ def run(solver, n_side, steps, warm=3):
           'mem GB %.1f' % (torch.cuda.mem_get_info()[1] / 1e9 - torch.cuda.mem_get_info()[0] / 1e9), flush=True)
     ps.close()
 for a in sys.argv[1:]:
-    s, n, k = a.split(':')
-    run(s, int(n), int(k))
+    f = a.split(':')       # solver:n_side:steps[:warm-up steps]
+    run(f[0], int(f[1]), int(f[2]), int(f[3]) if len(f) > 3 else 3)
