@@ -672,10 +672,9 @@ k_ii_dij(SphConsts c, SphLists L, const float4 *__restrict__ posT1, const float 
 	};
 	f3 d = (dij * dt) * dt; // II:126
 	d_ij[s] = F4(d, 0.0f);
-#if !SPH_STRICT
-	// what update_p needs of a NEIGHBOUR j is d_ii_j p_j + sum_k d_jk p_k (II:246): one vector instead of two gathers
+	// what update_p needs of a NEIGHBOUR j is d_ii_j p_j + sum_k d_jk p_k (II:246): the fast kernels gather this one
+	// vector instead of the two (the strict kernels write it too, so that both modes keep the same set of work arrays)
 	q_out[s] = F4(xyz(d_ii[s]) * pi.w + d, 0.0f);
-#endif
 }
 
 // II:128-147 update_p (sum_factor II:228-253) + residual partials (II:102-113); p_next is committed

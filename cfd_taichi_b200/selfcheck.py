@@ -111,21 +111,41 @@ def snapshot(ps):
 
 # Residual fields: sums that the solver loop drives towards zero while their TERMS keep their size (D rho / D t =
 # sum_j m (v_i - v_j) . grad W_ij: max |.| falls from ~50 to < 1 within the 15 passes).  fp32 summation error is
-# eps * sum |terms| whatever the result, so for these fields -- and the payload derived from them -- the error is
-# measured on the un-cancelled scale: the largest max |field| the strict run has seen in this step (the first
-# evaluation).  The raw ratio against the current max |field| is reported next to it ("... (vs current max)").
-#
-# The density loop's stiffness payload kappa_j / rho_j = (rho*_j - rho_0) alpha_j / (dt^2 rho_j) (DF:178-196) is the
-# same situation by subtraction: rho* is accurate to fp32 rounding of rho_0 (2e-7 relative, compared as `rho_adv`),
-# the residual rho* - rho_0 is ~1e-3 rho_0, so rounding alone is 1e-4 of the payload's own magnitude.  It is
-# measured on the scale the payload would have at rho* - rho_0 = rho_0.
-RESIDUAL_FIELDS = {"dfsph": ("rho_derivative", "payload_2.w")}
+# eps * sum |terms| whatever the result, so for these fields the error is measured on the un-cancelled scale: the
+# largest max |field| the strict run has seen in this step (the first evaluation).  The raw ratio against the
+# current max |field| is reported next to it ("... (vs current max)").
+RESIDUAL_FIELDS = {"dfsph": ("rho_derivative",)}
+# Derived payloads: the stiffness scalars a neighbour contributes, pre-divided by the sweep that produces them --
+# kappa_j / rho_j = ((D rho/D t)_j alpha_j / dt) / rho_j (DF:363-367) and ((rho*_j - rho_0) alpha_j / dt^2) / rho_j
+# (DF:199-203).  They are pointwise functions of fields that ARE compared between the modes, so comparing them
+# between the modes again would only re-measure those inputs, amplified by a particle's alpha or by the cancellation
+# in rho* - rho_0.  Each handle's payload is instead checked against its definition, evaluated in float64 from the
+# same handle's fields: that pins the production arithmetic (the pre-division) of both modes.
+DERIVED_PAYLOADS = {"dfsph": ("payload_2.w", "payload_3.w")}
+
+
+def _derived_check(err, piece, snaps, stats):
+    """dfsph: payload_2.w after a D rho / D t sweep, payload_3.w after a rho* sweep, against their definitions"""
+    rec = err.setdefault(piece, {})
+    for tag, snap, st in zip(_MODES, snaps, stats):
+        rho, alpha = _t(snap["rho"]), _t(snap["alpha"])
+        dt = float(np.float32(st.delta_time))
+        if "derivative" in piece:
+            want = (_t(snap["rho_derivative"]) * alpha / dt) / rho
+            got, name = _t(snap["payload_2.w"]), "kappa_j/rho_j == (drho alpha / dt) / rho, " + tag
+        else:
+            dt2 = float(np.float32(np.float32(dt) * np.float32(dt)))
+            want = ((_t(snap["rho_adv"]) - 1000.0) * alpha / dt2) / rho
+            got, name = _t(snap["payload_3.w"]), "kappa_j/rho_j == ((rho* - rho_0) alpha / dt^2) / rho, " + tag
+        rec[name] = max(rec.get(name, 0.0), relinf(got, want))
 
 
 def _record(err, piece, solver, snap_f, snap_s, extra=(), scales=None):
     rec = err.setdefault(piece, {})
     al = ALIASES.get(solver, {})
     for k in snap_s:
+        if k in DERIVED_PAYLOADS.get(solver, ()):
+            continue
         name = al.get(k, k)
         if scales is not None and k in scales:
             raw = relinf(snap_f[k], snap_s[k])
@@ -212,14 +232,12 @@ def sweeps(solver, ps_s, sol_s, ps_f, sol_f, rigid=False, max_passes=200):
             extra.append(("rigid_force", ps_f.rigid_particles.force.to_numpy(), ps_s.rigid_particles.force.to_numpy()))
         for k in RESIDUAL_FIELDS.get(solver, ()):
             state["scales"][k] = max(state["scales"][k], absmax(snaps[0][k]))
-        if solver == "dfsph":
-            resid = absmax(_t(snaps[0]["rho_adv"]) - 1000.0)
-            if resid > 0.0:
-                state["scales"]["payload_3.w"] = absmax(snaps[0]["payload_3.w"]) * 1000.0 / resid
         _record(err, piece, solver, snaps[1], snaps[0], extra, state["scales"])
         stats = (ps_s.read_stats(), ps_f.read_stats())
         if stat is not None:
             stat(err, piece, snaps, stats, **kw)
+            if solver == "dfsph":
+                _derived_check(err, piece, snaps, stats)
         for f in ("div_active", "den_active", "loop_active", "div_iters", "den_iters", "pc_iters", "ii_iters"):
             if getattr(stats[0], f) != getattr(stats[1], f):
                 state["flags_equal"] = False
