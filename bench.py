@@ -379,6 +379,19 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one process per GPU: bind it to the CPUs next to its GPU, so that its pinned e2e buffers (first touch) and the
+        # copy engine's host side stay on the GPU's NUMA node instead of all ranks sharing one
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            bus = int(torch.cuda.get_device_properties(local_rank).pci_bus_id)
+            for k in range(N.nvmlDeviceGetCount()):
+                hnd = N.nvmlDeviceGetHandleByIndex(k)
+                if int(N.nvmlDeviceGetPciInfo(hnd).bus) == bus:
+                    N.nvmlDeviceSetCpuAffinity(hnd)
+                    break
+        except Exception:
+            pass
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():

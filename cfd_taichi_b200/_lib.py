@@ -54,6 +54,15 @@ def decode_error_flags(flags):
     return [msg for bit, msg in ERROR_BITS.items() if flags & bit]
 
 
+class SphCamera(ctypes.Structure):
+    _fields_ = [("pos", ctypes.c_double * 3), ("look_at", ctypes.c_double * 3), ("up", ctypes.c_double * 3),
+                ("fov_y_deg", ctypes.c_double), ("light_pos", ctypes.c_double * 3), ("ambient", ctypes.c_double),
+                ("background", ctypes.c_uint8 * 4)]
+
+
+RENDER_FLUID, RENDER_RIGID = 1, 2
+
+
 class SphLattice(ctypes.Structure):
     _fields_ = [("particle_radius", ctypes.c_double), ("start_pos", ctypes.c_double * 3),
                 ("water_size", ctypes.c_double * 3), ("box_min", ctypes.c_double * 3), ("box_max", ctypes.c_double * 3)]
@@ -149,6 +158,7 @@ PROTOTYPES = [
     ("sph_download_state", _i, [_vp, _vp, _vp, _vp]),
     ("sph_read_stats", _i, [_vp, ctypes.POINTER(SphStats)]),
     ("sph_copy_work_state", _i, [_vp, _vp, _vp]),
+    ("sph_render", _i, [_vp, ctypes.POINTER(SphCamera), _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp]),
     ("sph_profile_begin", _i, [_vp]),
     ("sph_profile_end", _i, [_vp, _fp, ctypes.POINTER(ctypes.c_int32), _i]),
     ("sph_comm_unique_id", _i, [ctypes.c_char_p]),

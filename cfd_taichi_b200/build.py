@@ -48,6 +48,7 @@ def build(force=False, verbose=False):
     units = [
         ("sph_grid.cu", "sph_grid.o", extra),
         ("sph_api.cu", "sph_api.o", extra),
+        ("sph_render.cu", "sph_render.o", extra),
         ("sph_multigpu.cu", "sph_multigpu.o", ["-I", NCCL_INC] + extra),
         ("sph_sweeps.cu", "sph_sweeps_strict.o", ["-DSPH_STRICT=1", "-fmad=false"] + extra),
         # fast kernels: FMA contraction, approximate division / square root (2 ulp: inside the 1e-5 budget, asserted

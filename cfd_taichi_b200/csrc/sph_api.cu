@@ -225,7 +225,7 @@ extern "C" int sph_destroy(SphHandle *h) {
 	cudaFree(h->scan_sums); cudaFree(h->bspos); cudaFree(h->rspos); cudaFree(h->rstate); cudaFree(h->rl_list); cudaFree(h->rl_count);
 	for (int k = 0; k < A4_COUNT; ++k) cudaFree(h->a4[k]);
 	for (int k = 0; k < A1_COUNT; ++k) cudaFree(h->a1[k]);
-	cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.gw); cudaFree(h->L.gq);
+	cudaFree(h->render_zbuf); cudaFree(h->L.flist); cudaFree(h->L.blist); cudaFree(h->L.gw); cudaFree(h->L.gq);
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount);
 	mg_destroy(h);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);

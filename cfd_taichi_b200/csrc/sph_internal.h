@@ -79,6 +79,8 @@ struct SphHandle {
 	int n_partials;
 	double *red; // device: {sum, cnt, max} of the last reduction (all ranks)
 	bool grid_valid, boundary_ready, lists_valid;
+	unsigned long long *render_zbuf; // sph_render: (depth | colour) per pixel
+	size_t render_cap;
 	int async_error;      // a library call inside a void helper failed (NCCL transport): the enclosing sph_* call returns it
 	bool lists_fresh;     // SPH_PH_BUILD_LISTS has built this step's lists: the solver's first phase skips its own build
 	int sweep_blocks;

@@ -267,6 +267,25 @@ int sph_init_boundary_shell(const SphLattice *lat, size_t nb, void *dev_bpos4, i
 int sph_visualize(SphHandle *h, int what, void *dev_rgb, int stride_floats, size_t n, void *stream);
 
 /* Host-buffer entry points (the e2e path): pinned or pageable host memory, float4 * n_fluid. */
+/* Headless replacement of the GGUI draw calls of main.py:153-161 (scene.ambient_light, scene.point_light,
+ * scene.particles for the fluid and the rigid body with per-vertex colours) with the scene file's camera
+ * (cam_pos / cam_look_at / cam_up, main.py:60-62): shaded sphere splats, depth-tested, into a caller-owned device
+ * image of width * height RGBA8 pixels (row 0 = top).  dev_*_rgb: per-particle colours, `stride` floats per particle
+ * (ps.fluid_particles.rgb / ps.rigid_particles.rgb); dev_depth (optional): float depth along the view direction,
+ * +inf where nothing was drawn.  Asynchronous on `stream`. */
+typedef struct SphCamera {
+	double pos[3], look_at[3], up[3];
+	double fov_y_deg;       /* <= 0: GGUI's default, 45 */
+	double light_pos[3];    /* main.py:154: (0.5, 1.5, 1.5) */
+	double ambient;         /* main.py:153: 0.8 */
+	uint8_t background[4];  /* r, g, b, unused */
+} SphCamera;
+#define SPH_RENDER_FLUID 1  /* key 'f' / 'g' of main.py:134-137 */
+#define SPH_RENDER_RIGID 2  /* key 'r' / 't' of main.py:138-141 */
+int sph_render(SphHandle *h, const SphCamera *camera, int width, int height, int what, const void *dev_fluid_rgb,
+               int fluid_rgb_stride, const void *dev_rigid_rgb, int rigid_rgb_stride, void *dev_rgba8, void *dev_depth,
+               void *stream);
+
 int sph_upload_state(SphHandle *h, const float *host_pos4, const float *host_vel4, void *stream);
 int sph_download_state(SphHandle *h, float *host_pos4, float *host_vel4, void *stream);
 /* The same with the host arrays the reference's callers hold (pos / vel as N x 3 floats, main.py:190):

@@ -9,8 +9,11 @@ tail -c 600 gpurun_out/bench_$TAG.json; echo
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-also > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo "launch list rc=$?"
+# the .ncu-rep files stay on the box (gpurun merges at most 64 MiB back): the summaries are written there
+REP=/tmp/ncu_$TAG
+mkdir -p $REP
 full() { # name regex count solver what warm steps
-  ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"$2" -c $3 -o gpurun_out/prof_${TAG}_$1 -f \
+  ncu --set full --clock-control none --profile-from-start off -k regex:"$2" -c $3 -o $REP/prof_${TAG}_$1 -f \
       python scratch/t_prof_solver.py $4 $5 $6 $7 > gpurun_out/ncu_full_${TAG}_$1.log 2>&1
   echo "full $1 rc=$? $(tail -1 gpurun_out/ncu_full_${TAG}_$1.log)"
 }
@@ -20,3 +23,6 @@ full pcisph 'k_pc_' 40 pcisph 100 400 1
 full iisph 'k_ii_' 40 iisph 100 250 1
 full wcsph 'k_wc_|k_build_lists' 8 wcsph 100 20 1
 full rigid 'k_rigid' 30 dfsph dam_flush_cube 20 1
+mkdir -p gpurun_out/profiles_$TAG
+python scratch/prof_summary_r2.py $TAG $REP gpurun_out/profiles_$TAG
+ls -la gpurun_out/profiles_$TAG

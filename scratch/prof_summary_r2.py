@@ -1,8 +1,10 @@
 """gpurun_out/launches_<TAG>.csv + gpurun_out/prof_<TAG>_<group>.ncu-rep  ->  profiles/<TAG>_launch_shares_1M.md,
 profiles/<TAG>_ncu_<group>.md and profiles/traffic.json (DRAM bytes per launch of every profiled kernel).
-usage: python scratch/prof_summary_r2.py TAG"""
+usage: python scratch/prof_summary_r2.py TAG [directory of the .ncu-rep files] [output directory]"""
 import collections, csv, glob, io, json, os, re, subprocess, sys
 tag = sys.argv[1]
+REP = sys.argv[2] if len(sys.argv) > 2 else 'gpurun_out'
+OUT = sys.argv[3] if len(sys.argv) > 3 else 'profiles'
 SHORT = {'k_df_drho': 'df_drho', 'k_df_div_iter': 'df_div_iter', 'k_df_ext_force': 'df_ext_force', 'k_df_rho_adv': 'df_rho_adv',
          'k_df_vel_adv_iter': 'df_vel_adv_iter', 'k_df_warm_start': 'df_warm_start', 'k_build_lists': 'lists', 'k_df_position': 'df_position',
          'k_pc_ext_force': 'pc_ext', 'k_pc_predict_rho': 'pc_rho', 'k_pc_press_force': 'pc_force', 'k_ii_advect': 'ii_adv',
@@ -19,13 +21,13 @@ if os.path.exists(lp):
         us = v / 1000.0 if u in ('ns', 'nsecond') else (v if u in ('us', 'usecond') else v * 1000.0)
         a = agg.setdefault(clean(r[ki]), [0, 0.0]); a[0] += 1; a[1] += us
     tot = sum(a[1] for a in agg.values())
-    with open('profiles/%s_launch_shares_1M.md' % tag, 'w') as f:
+    with open(OUT + '/%s_launch_shares_1M.md' % tag, 'w') as f:
         f.write('# %s: ncu launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-also` (DFSPH, 10^6 particles, fast kernels)\n\n' % tag)
         f.write('`ncu --metrics gpu__time_duration.sum --clock-control none -c 1200` (cold-cache, serialised: compare SHARES, not absolute times). Raw list: %s_launches_bench_1M.csv\n\n' % tag)
         f.write('| kernel | launches | total us | avg us | share |\n|---|---|---|---|---|\n')
         for n, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write('| %s | %d | %.1f | %.1f | %.1f %% |\n' % (n[:90], c, us, us / c, 100 * us / tot))
-    subprocess.run(['cp', lp, 'profiles/%s_launches_bench_1M.csv' % tag])
+    subprocess.run(['cp', lp, OUT + '/%s_launches_bench_1M.csv' % tag])
 # ---- full captures ------------------------------------------------------------------------------------
 KEYS = [('gpu__time_duration.sum', 'duration'), ('dram__bytes_read.sum', 'DRAM read'), ('dram__bytes_write.sum', 'DRAM write'),
         ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'DRAM throughput % of peak'),
@@ -39,10 +41,10 @@ KEYS = [('gpu__time_duration.sum', 'duration'), ('dram__bytes_read.sum', 'DRAM r
         ('smsp__thread_inst_executed_per_inst_executed.ratio', 'active lanes per instruction'),
         ('smsp__inst_executed.sum', 'warp instructions'),
         ('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'long-scoreboard stalls per issue')]
-tpath = 'profiles/traffic.json'
-traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
+tpath = OUT + '/traffic.json'
+traffic = json.load(open('profiles/traffic.json')) if os.path.exists('profiles/traffic.json') else {}
 traffic.setdefault('kernels', {})
-for rep in sorted(glob.glob('gpurun_out/prof_%s_*.ncu-rep' % tag)):
+for rep in sorted(glob.glob(REP + '/prof_%s_*.ncu-rep' % tag)):
     group = re.sub(r'.*prof_%s_(.*)\.ncu-rep' % tag, r'\1', rep)
     out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -55,7 +57,7 @@ for rep in sorted(glob.glob('gpurun_out/prof_%s_*.ncu-rep' % tag)):
         if n not in best or float(r[ti].replace(',', '')) > float(best[n][ti].replace(',', '')): best[n] = r
     log = 'gpurun_out/ncu_full_%s_%s.log' % (tag, group)
     run = [l for l in open(log).read().splitlines() if ' N ' in l and 'iters' in l] if os.path.exists(log) else []
-    with open('profiles/%s_ncu_%s.md' % (tag, group), 'w') as f:
+    with open(OUT + '/%s_ncu_%s.md' % (tag, group), 'w') as f:
         f.write('# %s: `ncu --set full --clock-control none --import-source on --profile-from-start off`, group `%s`\n\n' % (tag, group))
         f.write('One step after the warm-up (scratch/prof_r2.sh, scratch/t_prof_solver.py); fast kernels; per kernel the longest captured launch.\n')
         if run: f.write('Run: `%s` (solver, block, N, iterations div / den / pcisph / iisph of the profiled step, error flags)\n' % run[-1])
@@ -76,4 +78,4 @@ for rep in sorted(glob.glob('gpurun_out/prof_%s_*.ncu-rep' % tag)):
                                          'particles': npart, 'source': 'profiles/%s_ncu_%s.md' % (tag, group)}
 traffic['source'] = 'ncu --set full captures of round %s (per kernel: see "source"); dram__bytes_read.sum + dram__bytes_write.sum per launch' % tag
 json.dump(traffic, open(tpath, 'w'), indent=1)
-for p in sorted(glob.glob('profiles/%s_*.md' % tag)): print(p)
+for p in sorted(glob.glob(OUT + '/%s_*.md' % tag)): print(p)
