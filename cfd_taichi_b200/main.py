@@ -108,7 +108,7 @@ def check_error_flags(ps, frame_cnt):
         raise _lib.SphError("frame %d: device error flags 0x%x: %s" % (frame_cnt, flags, "; ".join(_lib.decode_error_flags(flags))))
 
 
-def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None, save=None):
+def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None, save=None, render_dir=None):
     scene_config = config.get('scene')
     solver_config = config.get('solver')
     print("Simulation Start!")
@@ -128,9 +128,15 @@ def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None
     output_fps = scene_config.get('output_fps', 60)
     frame_time = 1.0 / output_fps
     ply_cnt = int(clock['ply_cnt'])
+    renderer_cnt = int(clock['ply_cnt'])
     t = float(clock['t'])
     if is_output_ply:
         os.makedirs(output_dir, exist_ok=True)
+    renderer = None
+    if render_dir:                                  # what window.show() / video_manager.write_frame show (main.py:175-188)
+        from cfd_taichi_b200.render import Renderer
+        os.makedirs(render_dir, exist_ok=True)
+        renderer = Renderer(ps, config)
     while True:
         if frame_cnt > 100000 or (max_frames is not None and frame_cnt - first_frame >= max_frames):
             break
@@ -151,6 +157,9 @@ def run(config, max_frames=None, output_dir='./output', quiet=False, resume=None
                 ps.update_mesh_vextics()
                 write_obj(os.path.join(output_dir, 'obj_%06d.obj' % ply_cnt), ps.mesh_vertices, ps._rigid_faces)
             ply_cnt += 1
+        if renderer is not None and (t / frame_time) > renderer_cnt:
+            renderer.save_png(os.path.join(render_dir, 'frame_%06d.png' % renderer_cnt))
+            renderer_cnt += 1
         if t > 4.0:
             break
     if save:
@@ -166,9 +175,11 @@ def main(argv=None):
     parser.add_argument('--output-dir', type=str, default='./output')
     parser.add_argument('--resume', help="restart from a state dump written with --save-state", type=str, default=None)
     parser.add_argument('--save-state', help="write a restartable .npz dump when the run ends", type=str, default=None)
+    parser.add_argument('--render-dir', help="write a rendered frame (PNG, the scene file's camera) every 1 / output_fps of "
+                        "simulated time: the headless stand-in for the reference's window", type=str, default=None)
     args = parser.parse_args(argv)
     config = utils.read_config(args.config)
-    run(config, args.steps, args.output_dir, resume=args.resume, save=args.save_state)
+    run(config, args.steps, args.output_dir, resume=args.resume, save=args.save_state, render_dir=args.render_dir)
 
 
 if __name__ == "__main__":
