@@ -22,6 +22,14 @@ __host__ __device__ static inline float4 *win_xr(char *w, int cap, int parity, i
 	return (float4 *)(w + 4096) + ((size_t)parity * 2 + (size_t)side) * (size_t)cap;
 }
 
+// particle messages (migration = kind 0, ghost particles = kind 1), one area per (kind, receiving side), behind the
+// value slots: [count slot | cap x {pos.xyz | tag} | cap x {vel.xyz | tag} | cap x {vel.w, gid, - | tag}]
+__host__ __device__ static inline size_t win_pm_bytes(int cap) { return 64 + (size_t)48 * (size_t)cap; }
+__host__ __device__ static inline char *win_pm(char *w, int cap, int kind, int side) {
+	return w + 4096 + (size_t)64 * (size_t)cap + ((size_t)kind * 2 + (size_t)side) * win_pm_bytes(cap);
+}
+__host__ __device__ static inline size_t win_total_bytes(int cap) { return 4096 + (size_t)64 * (size_t)cap + 4 * win_pm_bytes(cap); }
+
 __device__ __forceinline__ void st_slot(void *p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 	asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }

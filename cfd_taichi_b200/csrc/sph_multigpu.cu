@@ -381,6 +381,59 @@ k_mg_exchange(int what, const int *__restrict__ send_slot_l, const int *__restri
 	}
 }
 
+// Particle messages over the peer windows (migration, ghost particles): the packed message of each side
+// (msg_send: count known on the device) goes straight into the neighbour's window, count in the first slot; the
+// slots the neighbours fill are polled and copied into msg_recv in the layout k_mg_rebuild / k_mg_unpack_halo read.
+// The count slot doubles as the handshake with both neighbours (every rank pushes one, empty or not).
+__global__ void __launch_bounds__(256)
+k_mg_xfer(int kind, const char *__restrict__ send_l, const char *__restrict__ send_r, char *recv_l, char *recv_r,
+          const int *__restrict__ counters, int idx_l, int idx_r, int cap_msg, MgPeers peers, char *win, int cap, int rank,
+          int nranks, int epoch, SphCtl *ctl) {
+	const bool has_l = rank > 0, has_r = rank + 1 < nranks;
+	const int nsl = has_l ? min(counters[idx_l], cap_msg) : 0, nsr = has_r ? min(counters[idx_r], cap_msg) : 0;
+	const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+	// push: my left neighbour receives on its right side (1), my right neighbour on its left side (0)
+	for (int k = t0; k < nsl + nsr; k += stride) {
+		bool left = k < nsl;
+		int kk = left ? k : k - nsl;
+		const char *msg = left ? send_l : send_r;
+		char *area = left ? win_pm(peers.w[rank - 1], cap, kind, 1) : win_pm(peers.w[rank + 1], cap, kind, 0);
+		float4 p = msg_pos((char *)msg)[kk], v = msg_vel((char *)msg, cap_msg)[kk];
+		int g = msg_gid((char *)msg, cap_msg)[kk];
+		uint4 *slots = (uint4 *)(area + 64);
+		st_slot(&slots[kk], __float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), (uint32_t)epoch);
+		st_slot(&slots[(size_t)cap + kk], __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), (uint32_t)epoch);
+		st_slot(&slots[(size_t)2 * cap + kk], __float_as_uint(v.w), (uint32_t)g, 0u, (uint32_t)epoch);
+	}
+	if (t0 == 0) {
+		if (has_l) st_slot(win_pm(peers.w[rank - 1], cap, kind, 1), (uint32_t)nsl, 0u, 0u, (uint32_t)epoch);
+		if (has_r) st_slot(win_pm(peers.w[rank + 1], cap, kind, 0), (uint32_t)nsr, 0u, 0u, (uint32_t)epoch);
+	}
+	// poll: the counts first (every block for itself), then the particles
+	__shared__ int s_n[2];
+	if (threadIdx.x < 2) {
+		bool ex = threadIdx.x == 0 ? has_l : has_r;
+		s_n[threadIdx.x] = ex ? (int)wait_slot(win_pm(win, cap, kind, threadIdx.x), epoch, ctl).x : 0;
+	}
+	__syncthreads();
+	const int nrl = min(s_n[0], cap_msg), nrr = min(s_n[1], cap_msg);
+	if (t0 == 0) {
+		if (has_l) ((int *)recv_l)[0] = nrl;
+		if (has_r) ((int *)recv_r)[0] = nrr;
+	}
+	for (int k = t0; k < nrl + nrr; k += stride) {
+		bool left = k < nrl;
+		int kk = left ? k : k - nrl;
+		const uint4 *slots = (const uint4 *)(win_pm(win, cap, kind, left ? 0 : 1) + 64);
+		uint4 a = wait_slot(&slots[kk], epoch, ctl), b = wait_slot(&slots[(size_t)cap + kk], epoch, ctl),
+		      c3 = wait_slot(&slots[(size_t)2 * cap + kk], epoch, ctl);
+		char *msg = left ? recv_l : recv_r;
+		msg_pos(msg)[kk] = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), 0.0f);
+		msg_vel(msg, cap_msg)[kk] = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(c3.x));
+		msg_gid(msg, cap_msg)[kk] = (int)c3.y;
+	}
+}
+
 // NCCL transport: this rank's partial before, and the decision after, the all-reduce
 __global__ void __launch_bounds__(256) k_mg_reduce_partials(const SphPartial *partials, int n, double *red) {
 	double sum; int cnt; float mx;
@@ -410,7 +463,7 @@ extern "C" int sph_comm_unique_id(char *out128) {
 // Allocate this rank's window, exchange the IPC handles (one NCCL all-gather at start-up) and map the peers'.
 static int mg_open_windows(SphHandle *h, SphComm *m) {
 	if (m->nranks > SPH_MG_MAX_RANKS) return sph_fail(h, SPH_EINVAL, "multi-GPU: at most %d ranks", SPH_MG_MAX_RANKS);
-	m->win_bytes = 4096 + sizeof(float4) * 4 * (size_t)m->cap_halo;
+	m->win_bytes = win_total_bytes(m->cap_halo);
 	for (int d = 0; d < 2; ++d) SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->send_slot[d], sizeof(int) * (size_t)m->cap_halo));
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->recv_slot, sizeof(int) * 2 * (size_t)m->cap_halo));
 	{
@@ -527,6 +580,18 @@ static int exchange_bytes(SphHandle *h, SphComm *m, size_t bytes, cudaStream_t s
 	return SPH_OK;
 }
 
+// one particle message per side over the peer windows (kind 0 = migration, 1 = ghost particles)
+static void xfer_particles(SphHandle *h, SphComm *m, int kind, int idx_l, int idx_r, int cap_msg, int expect, cudaStream_t st) {
+	MgPeers peers;
+	for (int r = 0; r < SPH_MG_MAX_RANKS; ++r) peers.w[r] = r < m->nranks ? m->peer_win[r] : nullptr;
+	int blocks = cdiv(expect > 0 ? expect : 1, 256);
+	if (blocks > 296) blocks = 296; // one resident wave: pushing blocks are never queued behind polling ones
+	int epoch = ++m->epoch;
+	k_mg_xfer<<<blocks, 256, 0, st>>>(kind, m->msg_send[0], m->msg_send[1], m->msg_recv[0], m->msg_recv[1], m->counters, idx_l,
+	                                  idx_r, cap_msg, peers, m->win, m->cap_halo, m->rank, m->nranks, epoch, h->ctl);
+	h->launches++;
+}
+
 // migration + ghost particle exchange + one read-back of the new counts (sets c.N_owned / c.N)
 int mg_begin_step(SphHandle *h, cudaStream_t st) {
 	SphComm *m = h->comm;
@@ -542,9 +607,14 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 	k_mg_classify<<<cdiv(n > 0 ? n : 1, 256), 256, 0, st>>>(h->pos, h->vel, h->gid, n, c.h, m->col_lo, m->col_hi, has_left,
 	                                                        has_right, m->tmp_pos, m->tmp_vel, m->tmp_gid, m->msg_send[0],
 	                                                        m->msg_send[1], m->cap_mig, m->counters);
-	k_mg_header<<<1, 32, 0, st>>>(m->msg_send[0], m->msg_send[1], m->counters, MC_MIG_L, MC_MIG_R, m->cap_mig);
-	int rc = exchange_bytes(h, m, m->msg_bytes_mig, st);
-	if (rc != SPH_OK) { sph_prof_end(h, st); return rc; }
+	int rc = SPH_OK;
+	if (m->p2p) {
+		xfer_particles(h, m, 0, MC_MIG_L, MC_MIG_R, m->cap_mig, m->n_send[0] / 8 + 256, st); // a few particles per step
+	} else {
+		k_mg_header<<<1, 32, 0, st>>>(m->msg_send[0], m->msg_send[1], m->counters, MC_MIG_L, MC_MIG_R, m->cap_mig);
+		rc = exchange_bytes(h, m, m->msg_bytes_mig, st);
+		if (rc != SPH_OK) { sph_prof_end(h, st); return rc; }
+	}
 	k_mg_rebuild<<<cdiv(capacity_owned, 256), 256, 0, st>>>(m->tmp_pos, m->tmp_vel, m->tmp_gid, m->msg_recv[0], m->msg_recv[1],
 	                                                        has_left, has_right, m->cap_mig, h->pos, h->vel, h->gid,
 	                                                        capacity_owned, m->counters);
@@ -552,9 +622,15 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 	k_mg_pack_halo<<<cdiv(capacity_owned, 256), 256, 0, st>>>(h->pos, h->vel, h->gid, c.h, m->col_lo, m->col_hi, has_left,
 	                                                          has_right, m->msg_send[0], m->msg_send[1], m->cap_halo,
 	                                                          m->send_orig[0], m->send_orig[1], m->counters);
-	k_mg_header<<<1, 32, 0, st>>>(m->msg_send[0], m->msg_send[1], m->counters, MC_HALO_L, MC_HALO_R, m->cap_halo);
-	rc = exchange_bytes(h, m, m->msg_bytes_halo, st);
-	if (rc != SPH_OK) { sph_prof_end(h, st); return rc; }
+	if (m->p2p) {
+		// grid sized from the previous step's ghost counts (the kernel strides; the true counts are on the device)
+		int expect = m->n_send[0] + m->n_send[1] > m->n_recv[0] + m->n_recv[1] ? m->n_send[0] + m->n_send[1] : m->n_recv[0] + m->n_recv[1];
+		xfer_particles(h, m, 1, MC_HALO_L, MC_HALO_R, m->cap_halo, expect > 0 ? expect : 4 * m->cap_halo / 8, st);
+	} else {
+		k_mg_header<<<1, 32, 0, st>>>(m->msg_send[0], m->msg_send[1], m->counters, MC_HALO_L, MC_HALO_R, m->cap_halo);
+		rc = exchange_bytes(h, m, m->msg_bytes_halo, st);
+		if (rc != SPH_OK) { sph_prof_end(h, st); return rc; }
+	}
 	k_mg_unpack_halo<<<cdiv(2 * m->cap_halo, 256), 256, 0, st>>>(m->msg_recv[0], m->msg_recv[1], has_left, has_right,
 	                                                             m->cap_halo, h->pos, h->vel, h->gid, capacity_all, m->counters);
 	h->launches += 6;

@@ -17,7 +17,7 @@ full() { # name regex count solver what warm steps
       python scratch/t_prof_solver.py $4 $5 $6 $7 > gpurun_out/ncu_full_${TAG}_$1.log 2>&1
   echo "full $1 rc=$? $(tail -1 gpurun_out/ncu_full_${TAG}_$1.log)"
 }
-full dfsph 'k_df_|k_build_lists' 45 dfsph 100 6 1
+full dfsph 'k_df_|k_build_lists' 95 dfsph 100 6 1
 full grid 'k_hash|k_scan|k_scatter|k_cell_fix|k_gather|k_reorder' 16 dfsph 100 6 1
 full pcisph 'k_pc_' 40 pcisph 100 400 1
 full iisph 'k_ii_' 40 iisph 100 250 1

@@ -58,7 +58,7 @@ for rep in sorted(glob.glob(REP + '/prof_%s_*.ncu-rep' % tag)):
     log = 'gpurun_out/ncu_full_%s_%s.log' % (tag, group)
     run = [l for l in open(log).read().splitlines() if ' N ' in l and 'iters' in l] if os.path.exists(log) else []
     with open(OUT + '/%s_ncu_%s.md' % (tag, group), 'w') as f:
-        f.write('# %s: `ncu --set full --clock-control none --import-source on --profile-from-start off`, group `%s`\n\n' % (tag, group))
+        f.write('# %s: `ncu --set full --clock-control none --profile-from-start off`, group `%s`\n\n' % (tag, group))
         f.write('One step after the warm-up (scratch/prof_r2.sh, scratch/t_prof_solver.py); fast kernels; per kernel the longest captured launch.\n')
         if run: f.write('Run: `%s` (solver, block, N, iterations div / den / pcisph / iisph of the profiled step, error flags)\n' % run[-1])
         f.write('\n| metric | ' + ' | '.join(best) + ' |\n|---|' + '---|' * len(best) + '\n')
