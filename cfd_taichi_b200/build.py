@@ -53,8 +53,8 @@ def build(force=False, verbose=False):
         ("sph_sweeps.cu", "sph_sweeps_strict.o", ["-DSPH_STRICT=1", "-fmad=false"] + extra),
         # fast kernels: FMA contraction, approximate division / square root (2 ulp: inside the 1e-5 budget, asserted
         # sweep by sweep in tests/test_gpu_fast_parity.py); the cull and the cell hash use explicit IEEE intrinsics
-        ("sph_sweeps.cu", "sph_sweeps_fast.o", ["-DSPH_STRICT=0", "-fmad=true", "-prec-div=false", "-prec-sqrt=false"]
-         + fast_extra + extra),
+        ("sph_sweeps.cu", "sph_sweeps_fast.o", ["-DSPH_STRICT=0", "-fmad=true"] + (
+            [] if os.environ.get("SPH_FAST_IEEE_DIV") else ["-prec-div=false", "-prec-sqrt=false"]) + fast_extra + extra),
     ]
     objs = []
     procs = []

@@ -46,7 +46,9 @@ __device__ __forceinline__ void sph_ctl_apply(int kind, SphCtl *ctl, double sum,
 	case SPH_CTL_DT: { // DF:100-119: max |v*| (+ rigid surface speed) -> adaptive dt on the device
 		float max_rigid_vel = a.rigid_exists ? a.rs->max_surface_vel : 0.0f; // DF:104-110 (loops over ALL rigid particles)
 		float max_vel = mx + max_rigid_vel;              // DF:111
-		float max_dt = (a.dt_cfl_c1 / max_vel) * 0.2f;   // DF:112
+		// explicit IEEE division: this header is compiled into translation units with and without -prec-div=false,
+		// and the time step must not depend on which of them decides (single GPU: the sweep unit, slabs: the exchange unit)
+		float max_dt = __fmul_rn(__fdiv_rn(a.dt_cfl_c1, max_vel), 0.2f);   // DF:112
 		float dt;
 		if (max_dt > 1e-3f) dt = 1e-3f;                  // DF:114-115
 		else dt = fmaxf(max_dt, 1e-5f);                  // DF:117
