@@ -47,7 +47,8 @@ ERROR_BITS = {1: "a particle left the grid and was clamped into it (PS:393-395)"
               4: "a boundary neighbour list overflowed its capacity",
               8: "the DFSPH density loop hit the library's 1000-pass cap (the reference's loop has none, DF:225)",
               16: "a non-finite value appeared in the solver state",
-              32: "a peer rank stopped answering a halo exchange (multi-GPU)"}
+              32: "a peer rank stopped answering a halo exchange (multi-GPU)",
+              64: "an index check of the bounds-checked build failed (internal error)"}
 
 
 def decode_error_flags(flags):

@@ -39,6 +39,28 @@ def _newer(src_list, target):
     return any(os.path.getmtime(s) > t for s in src_list)
 
 
+DEBUG_OUT = os.path.join(HERE, "_build_debug")
+DEBUG_LIB = os.path.join(DEBUG_OUT, "libsph_b200.so")
+
+
+def build_debug(force=False):
+    """The same library with -DSPH_DEBUG_BOUNDS=1 (every neighbour-list entry, list length and candidate segment is
+    validated before use, SPH_ERR_BOUNDS latched): what tests/test_gpu_bounds.py runs instead of compute-sanitizer,
+    which is closed on this GPU pool.  Loaded through SPH_B200_LIB; never the default."""
+    global OUT, LIB
+    saved = (OUT, LIB, os.environ.get("SPH_EXTRA_NVCC"))
+    OUT, LIB = DEBUG_OUT, DEBUG_LIB
+    os.environ["SPH_EXTRA_NVCC"] = ((saved[2] or "") + " -DSPH_DEBUG_BOUNDS=1").strip()
+    try:
+        return build(force=force)
+    finally:
+        OUT, LIB = saved[0], saved[1]
+        if saved[2] is None:
+            os.environ.pop("SPH_EXTRA_NVCC", None)
+        else:
+            os.environ["SPH_EXTRA_NVCC"] = saved[2]
+
+
 def build(force=False, verbose=False):
     os.makedirs(OUT, exist_ok=True)
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]

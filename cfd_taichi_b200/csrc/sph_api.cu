@@ -194,6 +194,8 @@ extern "C" int sph_create(const SphConfig *cfg, int device, SphHandle **out) {
 	SPH_CUDA_CHECK(h, cudaMemset(h->L.bcount, 0, sizeof(int) * (ncap ? ncap : 1)));
 	SPH_CUDA_CHECK(h, dalloc(&h->nbr_count, ncap));
 	SPH_CUDA_CHECK(h, dalloc(&h->ctl, 1));
+	h->L.err = &h->ctl->error_flags;
+	h->L.n_fluid = c.N; h->L.n_rigid = c.Nr; h->L.n_boundary = c.Nb; h->L.cap_f = c.kstride; h->L.cap_b = c.kbstride;
 	SPH_CUDA_CHECK(h, cudaMallocHost((void **)&h->ctl_host, sizeof(SphCtl)));
 	h->n_partials = cdiv((int)(ncap ? ncap : 1), SPH_BLOCK) + 1;
 	SPH_CUDA_CHECK(h, dalloc(&h->partials, (size_t)h->n_partials));
@@ -395,6 +397,7 @@ extern "C" int sph_rigid_set_state(SphHandle *h, const SphRigidInfo *in) {
 static int base_step(SphHandle *h, cudaStream_t st) {
 	// SB:136-143: simulate_cnt += 1 ; reset_grid ; update_grid ; reset()
 	h->simulate_cnt += 1;
+	h->L.n_fluid = h->c.N; // slabs: owned + ghost particles of this step
 	sph_prof_begin(h, KC_GRID, st);
 	sphg_build(h, h->fg, h->pos, h->c.N, st, h->comm ? h->gid : nullptr);
 	sphg_gather_fluid(h, st);
@@ -760,6 +763,18 @@ extern "C" int sph_read_stats(SphHandle *h, SphStats *out) {
 	out->loop_active = h->c.solver == SPH_SOLVER_PCISPH ? k.pc_active : h->c.solver == SPH_SOLVER_IISPH ? k.ii_active : 0;
 	return SPH_OK;
 }
+
+#if SPH_DEBUG_BOUNDS
+// bounds-checked build only (not part of the ABI): overwrite entry `entry` of sorted particle `slot`'s fluid list, so
+// that tests/test_gpu_bounds.py can show the index checks are live
+extern "C" int sph_debug_poke_list(SphHandle *h, int slot, int entry, unsigned int value) {
+	if (!h || slot < 0 || slot >= h->c.N || entry < 0 || entry >= h->c.kstride) return SPH_EINVAL;
+	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	SPH_CUDA_CHECK(h, cudaDeviceSynchronize());
+	SPH_CUDA_CHECK(h, cudaMemcpy(h->L.flist + sph_list_word(slot, h->c.kstride, entry), &value, sizeof(value), cudaMemcpyHostToDevice));
+	return SPH_OK;
+}
+#endif
 
 // Single-sweep parity tests: put handle `dst` into the in-step state of handle `src` (same scene, grids built
 // from the same positions, so the sorted order is identical): every sorted per-particle work array, the

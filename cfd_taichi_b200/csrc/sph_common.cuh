@@ -19,6 +19,20 @@
 #define SPH_ERR_DENSITY_CAP 8
 #define SPH_ERR_NONFINITE 16
 #define SPH_ERR_COMM_TIMEOUT 32 // a peer did not raise its exchange flag within 10 s (multi-GPU windows)
+#define SPH_ERR_BOUNDS 64       // an index check of the bounds-checked build (-DSPH_DEBUG_BOUNDS=1) failed
+
+// compute-sanitizer is closed on the GPU pool this is developed on, so the library carries its own index checks:
+// a build with -DSPH_DEBUG_BOUNDS=1 (cfd_taichi_b200/build.py: _build_debug/) validates every neighbour-list entry,
+// list length and candidate segment before it is used and latches SPH_ERR_BOUNDS; tests/test_gpu_bounds.py runs every
+// solver, the coupled rigid scene and restart on small scenes under it.
+#ifndef SPH_DEBUG_BOUNDS
+#define SPH_DEBUG_BOUNDS 0
+#endif
+#if SPH_DEBUG_BOUNDS
+#define SPH_BOUNDS_OK(cond, errptr) do { if (!(cond)) atomicOr((errptr), SPH_ERR_BOUNDS); } while (0)
+#else
+#define SPH_BOUNDS_OK(cond, errptr) ((void)0)
+#endif
 
 // Constants the reference evaluates in Python scope (fp64) and then casts to f32 where they meet
 // an f32 expression.  Filled once on the host in sph_api.cu.
@@ -129,6 +143,8 @@ struct SphLists {
 	// fast DFSPH kernels instead: grad W_ij as 3 x 21-bit fixed point in 8 bytes (the index comes from flist);
 	// entries 2p, 2p+1 of sorted particle s in the uint4 at gq[((s >> 5) * (cap / 2) + p) * 32 + (s & 31)]
 	uint4 *gq;
+	int *err;       // &ctl->error_flags (bounds-checked build)
+	int n_fluid, n_rigid, n_boundary, cap_f, cap_b; // limits the bounds-checked build validates list entries against
 };
 
 __host__ __device__ inline size_t sph_list_base(int s, int cap) {

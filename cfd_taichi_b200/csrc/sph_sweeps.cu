@@ -155,7 +155,11 @@ void boundary_volume(SphHandle *h, cudaStream_t st) {
 #define NO_SELF (-0x40000000)
 template <class Emit>
 __device__ __forceinline__ void scan_segment(const SphConsts &c, const float4 &pi, const float4 *__restrict__ arr, int a,
-                                             int b, int self, Emit &&emit) {
+                                             int b, int self, Emit &&emit, int limit = 0x7fffffff, int *err = nullptr) {
+	SPH_BOUNDS_OK(a >= 0 && a <= b && b <= limit, err);
+#if SPH_DEBUG_BOUNDS
+	if (!(a >= 0 && a <= b && b <= limit)) return;
+#endif
 	for (int base = a; base < b; base += 32) {
 		int len = min(32, b - base);
 		uint32_t mask = 0;
@@ -223,9 +227,9 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 			};
 #if SPH_STRICT
 			// canonical order of the reference: cell by cell, (dx, dy, dz) with dz fastest
-			SPH_FOR_27(c, cx, cy, cz, c1) { scan_segment(c, pi, spos, cstart[c1], cstart[c1 + 1], s, emit_f); }
+			SPH_FOR_27(c, cx, cy, cz, c1) { scan_segment(c, pi, spos, cstart[c1], cstart[c1 + 1], s, emit_f, c.N, L.err); }
 			if (c.boundary_handle == 1)
-				SPH_FOR_27(c, cx, cy, cz, c1) { scan_segment(c, pi, bspos, bstart[c1], bstart[c1 + 1], NO_SELF, emit_b); }
+				SPH_FOR_27(c, cx, cy, cz, c1) { scan_segment(c, pi, bspos, bstart[c1], bstart[c1 + 1], NO_SELF, emit_b, c.Nb, L.err); }
 #else
 			// The 27 cells are 9 runs of up to three x-adjacent cells, contiguous in the sorted arrays (cell id =
 			// x + gx z + gx gz y).  The 18 run bounds of a grid are fetched up front (independent loads instead of
@@ -242,7 +246,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 					rb[r] = ok ? cstart[c0 + xw] : 0;
 				}
 #pragma unroll
-				for (int r = 0; r < 9; ++r) scan_segment(c, pi, spos, ra[r], rb[r], s, emit_f);
+				for (int r = 0; r < 9; ++r) scan_segment(c, pi, spos, ra[r], rb[r], s, emit_f, c.N, L.err);
 			}
 			if (c.boundary_handle == 1) {
 				int qa[9], qb[9];
@@ -255,7 +259,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 					qb[r] = ok ? bstart[c0 + xw] : 0;
 				}
 #pragma unroll
-				for (int r = 0; r < 9; ++r) scan_segment(c, pi, bspos, qa[r], qb[r], NO_SELF, emit_b);
+				for (int r = 0; r < 9; ++r) scan_segment(c, pi, bspos, qa[r], qb[r], NO_SELF, emit_b, c.Nb, L.err);
 			}
 #endif
 			ncount = nf; // no rigid entries: get_neighbour_count (PS:424-445) equals the fluid hits
@@ -460,11 +464,27 @@ __device__ __forceinline__ uint4 ld_list(const uint4 *p, uint64_t pol) {
 struct ListRange {
 	const uint4 *p; // quad 0 of this lane
 	int n;          // entries of this lane
+#if SPH_DEBUG_BOUNDS
+	int lim, lim_rigid, *err;
+#endif
 };
-__device__ __forceinline__ ListRange list_range(const uint32_t *list, int cap, int s, int n) {
+// bounds-checked build: entry j of a list must address an existing particle of the array it indexes
+#if SPH_DEBUG_BOUNDS
+#define SPH_CHECK_ENTRY(j, lim, lim_rigid, err) \
+	SPH_BOUNDS_OK(((j) & SPH_RIGID_BIT) ? (int)((j) & ~SPH_RIGID_BIT) < (lim_rigid) : (int)(j) < (lim), err)
+#else
+#define SPH_CHECK_ENTRY(j, lim, lim_rigid, err) ((void)0)
+#endif
+__device__ __forceinline__ ListRange list_range(const SphLists &L, bool boundary, int cap, int s, int n) {
 	ListRange r;
-	r.p = reinterpret_cast<const uint4 *>(list) + ((size_t)(s >> 5) * (size_t)(cap >> 2)) * 32u + (size_t)(s & 31);
+	r.p = reinterpret_cast<const uint4 *>(boundary ? L.blist : L.flist) + ((size_t)(s >> 5) * (size_t)(cap >> 2)) * 32u + (size_t)(s & 31);
 	r.n = n;
+#if SPH_DEBUG_BOUNDS
+	r.lim = boundary ? L.n_boundary : L.n_fluid;
+	r.lim_rigid = boundary ? 0 : L.n_rigid;
+	r.err = L.err;
+	SPH_BOUNDS_OK(n <= (boundary ? L.cap_b : L.cap_f) && cap == (boundary ? L.cap_b : L.cap_f), L.err);
+#endif
 	return r;
 }
 template <class F>
@@ -476,28 +496,37 @@ __device__ __forceinline__ void operator<<(ListRange r, F &&f) {
 	uint4 cur = ld_list(p, pol);
 	uint4 nx1 = r.n > 4 ? ld_list(p + 32, pol) : zero;
 	int k = 0;
+#if SPH_DEBUG_BOUNDS
+#define SPH_CHK(j) SPH_CHECK_ENTRY(j, r.lim, r.lim_rigid, r.err)
+#else
+#define SPH_CHK(j) ((void)0)
+#endif
 	for (; k + 4 <= r.n; k += 4) {
 		uint4 nx2 = k + 8 < r.n ? ld_list(p + 64, pol) : zero;
 		p += 32;
+		SPH_CHK(cur.x); SPH_CHK(cur.y); SPH_CHK(cur.z); SPH_CHK(cur.w);
 		f(cur.x); f(cur.y); f(cur.z); f(cur.w);
 		cur = nx1;
 		nx1 = nx2;
 	}
 	int m = r.n - k;
 	if (m > 0) {
+		SPH_CHK(cur.x);
 		f(cur.x);
 		if (m > 1) {
+			SPH_CHK(cur.y);
 			f(cur.y);
-			if (m > 2) f(cur.z);
+			if (m > 2) { SPH_CHK(cur.z); f(cur.z); }
 		}
 	}
+#undef SPH_CHK
 }
 // usage:  SPH_FOR_FLUID(L, c, s, j) { ...body, `return` skips to the next neighbour... };
-#define SPH_FOR_FLUID(L, c, s, J) list_range((L).flist, (c).kstride, s, (L).fcount[s]) << [&](uint32_t J)
-#define SPH_FOR_BOUNDARY(L, c, s, J) list_range((L).blist, (c).kbstride, s, (L).bcount[s]) << [&](uint32_t J)
+#define SPH_FOR_FLUID(L, c, s, J) list_range(L, false, (c).kstride, s, (L).fcount[s]) << [&](uint32_t J)
+#define SPH_FOR_BOUNDARY(L, c, s, J) list_range(L, true, (c).kbstride, s, (L).bcount[s]) << [&](uint32_t J)
 // the same with the count already in a register
-#define SPH_FOR_FLUID_N(L, c, s, n, J) list_range((L).flist, (c).kstride, s, n) << [&](uint32_t J)
-#define SPH_FOR_BOUNDARY_N(L, c, s, n, J) list_range((L).blist, (c).kbstride, s, n) << [&](uint32_t J)
+#define SPH_FOR_FLUID_N(L, c, s, n, J) list_range(L, false, (c).kstride, s, n) << [&](uint32_t J)
+#define SPH_FOR_BOUNDARY_N(L, c, s, n, J) list_range(L, true, (c).kbstride, s, n) << [&](uint32_t J)
 
 __device__ __forceinline__ float4 ld_gw(const float4 *p, uint64_t pol) {
 	float4 r;
@@ -512,8 +541,14 @@ __device__ __forceinline__ float4 ld_gw(const float4 *p, uint64_t pol) {
 }
 // f(j, grad W_ij) for the n entries of sorted particle s; four records in flight ahead of the four in use
 template <class F>
-__device__ __forceinline__ void walk_gw(const float4 *__restrict__ gw, int cap, int s, int n, F &&f) {
+__device__ __forceinline__ void walk_gw(const SphLists &L, const float4 *__restrict__ gw, int cap, int s, int n, F &&f_) {
 	if (n <= 0) return;
+#if SPH_DEBUG_BOUNDS
+	if (n > L.cap_f || cap != L.cap_f) { atomicOr(L.err, SPH_ERR_BOUNDS); return; }
+	auto f = [&](uint32_t j, f3 dw) { SPH_CHECK_ENTRY(j, L.n_fluid, L.n_rigid, L.err); f_(j, dw); };
+#else
+	F &f = f_;
+#endif
 	const uint64_t pol = list_policy();
 	const float4 *p = gw + sph_gw_index(s, cap, 0);
 	const float4 z = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -565,8 +600,14 @@ struct GqQuad {
 	uint4 j, a, b;
 };
 template <class F>
-__device__ __forceinline__ void walk_gq(const SphLists &L, const SphConsts &c, int s, int n, F &&f) {
+__device__ __forceinline__ void walk_gq(const SphLists &L, const SphConsts &c, int s, int n, F &&f_) {
 	if (n <= 0) return;
+#if SPH_DEBUG_BOUNDS
+	if (n > L.cap_f || c.kstride != L.cap_f) { atomicOr(L.err, SPH_ERR_BOUNDS); return; }
+	auto f = [&](uint32_t j, f3 dw) { SPH_CHECK_ENTRY(j, L.n_fluid, L.n_rigid, L.err); f_(j, dw); };
+#else
+	F &f = f_;
+#endif
 	const uint64_t pol = list_policy();
 	const uint4 *pl = reinterpret_cast<const uint4 *>(L.flist) + ((size_t)(s >> 5) * (size_t)(c.kstride >> 2)) * 32u + (size_t)(s & 31);
 	const uint4 *pg = L.gq + ((size_t)(s >> 5) * (size_t)(c.kstride >> 1)) * 32u + (size_t)(s & 31);
@@ -613,7 +654,7 @@ __device__ __forceinline__ void walk_gq(const SphLists &L, const SphConsts &c, i
 }
 #define SPH_WALK_GW(L, c, s, n, ...) walk_gq(L, c, s, n, __VA_ARGS__)
 #else
-#define SPH_WALK_GW(L, c, s, n, ...) walk_gw((L).gw, (c).kstride, s, n, __VA_ARGS__)
+#define SPH_WALK_GW(L, c, s, n, ...) walk_gw(L, (L).gw, (c).kstride, s, n, __VA_ARGS__)
 #endif
 
 // =============================================================================================
@@ -649,7 +690,7 @@ k_df_warm_start(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restri
 #if SPH_STRICT
 	// strict kernels: IEEE sqrt / division make the gradient the costly part, so every DFSPH sweep reads it
 	// from the per-pair cache (bit-identical to a recomputation) and gathers only the neighbour's payload
-	walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+	walk_gw(L, L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * dw; // DF:345
@@ -757,7 +798,7 @@ k_df_div_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict
 	float k_i = da / dt; // DF:363, 374, 388
 	f3 va = F3(0.0f, 0.0f, 0.0f);
 #if SPH_STRICT
-	walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+	walk_gw(L, L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * dw; // DF:377
@@ -940,7 +981,7 @@ k_df_vel_adv_iter(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__rest
 	}
 	f3 va = F3(0.0f, 0.0f, 0.0f);
 #if SPH_STRICT
-	walk_gw(L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
+	walk_gw(L, L.gw, c.kstride, s, nf_, [&](uint32_t j, f3 dw) {
 		if (SPH_IS_RIGID(j)) {
 			float4 pj = __ldg(&rg.rspos[SPH_RIGID_SLOT(j)]);
 			va = va + (((pj.w * SPH_RHO0) * k_i) / rho_i) * dw; // DF:211

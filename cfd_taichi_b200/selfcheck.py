@@ -411,7 +411,7 @@ def slab_vs_single(solver="dfsph", steps=3, strict=True, scene_name="small_block
                    crossed_two_cuts=int((np.abs(owner0 - owner1) >= 2).sum()),
                    max_abs_dpos=dpos, max_abs_dvel=dvel, error_flags=[int(g["flags"]) for g in gathered],
                    owned_ghosts_last_step=[list(g["hist"][-1]) for g in gathered])
-        res["ok"] = bool(perm_ok and res["iters_ok"] and (exact if strict else dpos <= 1e-3) and not any(res["error_flags"]))
+        res["ok"] = bool(perm_ok and res["iters_ok"] and exact and not any(res["error_flags"]))   # both modes: bit for bit
     ps.close()
     dist.barrier()
     return res

@@ -169,7 +169,7 @@ typedef struct SphStats {
 	int32_t error_flags;       /* bit0 particle outside grid (PS:393-395), bit1 neighbour list overflow,
 	                              bit2 boundary list overflow, bit3 density loop hit the safety cap,
 	                              bit4 non-finite value, bit5 a peer rank did not answer a slab exchange
-	                              within 10 s (multi-GPU) */
+	                              within 10 s (multi-GPU), bit6 an index check failed (bounds-checked build only) */
 	int32_t div_iters;         /* DF:416 */
 	float div_first_err, div_err;
 	int32_t den_iters;         /* DF:233 */

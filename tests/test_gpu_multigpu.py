@@ -25,8 +25,10 @@ def test_two_slabs_match_single_domain(built, mode):
     line = [l for l in r.stdout.splitlines() if l.startswith("MGRESULT")]
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
     assert line and "perm_ok=True" in line[0] and "iters_ok=True" in line[0]
-    if mode == "strict":
-        assert "exact=True" in line[0]          # bit-identical to the single-GPU run, migration included
+    # bit-identical to the single-GPU run of the same arithmetic mode, migration included -- strict AND fast: the
+    # sort tie-break is the global id, the sums run in the same order, and the control arithmetic (adaptive dt)
+    # uses explicit IEEE intrinsics in whichever translation unit decides
+    assert "exact=True" in line[0]
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
