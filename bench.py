@@ -547,8 +547,8 @@ def run_ours(args):
                        "l2": "per-step working set ~900 MB > 126 MB L2, no flush",
                        "iterations": {"divergence": st_timed.div_iters, "density": st_timed.den_iters, "of": "last timed step"},
                        "parallelism": "1 GPU" if world == 1 else
-                       "%d x-slabs; per-sweep ghost values and loop partials over CUDA-IPC peer windows (NVLink), "
-                       "NCCL for migration / ghost particles" % world},
+                       "%d x-slabs; ghost values, loop partials, migration and ghost particles over CUDA-IPC peer windows "
+                       "(NVLink)" % world},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_dir, "d2h_bytes_per_step": bytes_dir,
                     "steps": e2e_steps},
@@ -570,8 +570,8 @@ def run_ours(args):
         if world > 1:
             line["comm"] = {"exchange_ms_per_step": per_step("mg_exchange"), "begin_step_ms_per_step": per_step("mg_begin_step"),
                             "exchange_launches_per_step": prof.get("mg_exchange", {}).get("launches", 0) / args.steps,
-                            "transport": "one kernel per exchange over CUDA-IPC peer windows (NVLink); NCCL send/recv for "
-                                         "migration + ghost particles"}
+                            "transport": "one kernel per exchange over CUDA-IPC peer windows (NVLink), migration and ghost "
+                                         "particles included; no NCCL on the step path"}
             if slab_parity is not None:
                 line["parity"] = slab_parity
         if world == 1 and not args.no_cpu_baseline:

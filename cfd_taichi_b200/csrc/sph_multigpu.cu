@@ -1,15 +1,16 @@
 // sph_multigpu.cu -- x-slab domain decomposition over the GPUs of one box.
 //
 // Rank p owns the x-cell columns [col_lo, col_hi) of the GLOBAL grid (cell ids stay the reference's,
-// PS:102, so integer outputs equal the single-domain run).  NCCL over NVLink is used for exactly three
-// things: (1) particle migration after advection, (2) the one-column ghost (halo) layer -- particle
+// PS:102, so integer outputs equal the single-domain run).  Exactly three things cross GPUs over NVLink:
+// (1) particle migration after advection, (2) the one-column ghost (halo) layer -- particle
 // copies once per step, then one float4 per ghost after every sweep that produces a quantity a
 // neighbour reads, (3) the (sum, count) / max all-reduce behind each solver-loop decision, so that every
 // rank executes the single-domain iteration counts.  Nothing here synchronises the host except the one
-// count read-back per step in mg_begin_step.  NCCL is bound at run time with dlopen (the torch-bundled
+// count read-back per step in mg_begin_step.  NCCL (start-up all-gather of the IPC handles, the rigid-body
+// all-reduce, and the optional SPH_MG_TRANSPORT=nccl transport) is bound at run time with dlopen (the torch-bundled
 // libnccl.so.2 that the process already maps); a missing library is an error, never a fallback.
 //
-// Transport of (2) and (3) inside a step: the ~40 exchanges per DFSPH step are 0.3 MB each, i.e. pure
+// Transport of (1), (2) and (3) inside a step: the ~40 exchanges per DFSPH step are 0.3 MB each, i.e. pure
 // latency, so they do not go through NCCL.  Every rank owns a "window" of device memory that its peers
 // map with CUDA IPC.  One kernel per exchange (k_mg_exchange): each block stores this rank's ghost values
 // straight into the neighbours' windows over NVLink, then polls the slots its neighbours fill and scatters
@@ -19,8 +20,8 @@
 // word and is written with one 128-bit store (the atomicity NCCL's LL protocols rely on), so there is no
 // fence, no flag, no host involvement and no proxy thread.  Windows are double-buffered by epoch parity; every
 // exchange carries a tagged sync slot to and from both neighbours (whatever the halo counts), so a rank can be
-// at most one exchange ahead of a peer.  NCCL keeps the two variable-size particle messages per step (migration, ghost particles).
-// SPH_MG_TRANSPORT=nccl selects NCCL for everything (A/B measurements).
+// at most one exchange ahead of a peer.  The two variable-size particle messages per step (migration, ghost particles)
+// use the same windows (k_mg_xfer).  SPH_MG_TRANSPORT=nccl selects NCCL for everything (A/B measurements).
 #include <dlfcn.h>
 #include <nccl.h>
 

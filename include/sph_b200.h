@@ -315,9 +315,9 @@ int sph_profile_end(SphHandle *h, float *ms_by_class, int32_t *launches_by_class
  *   rank 0: sph_comm_unique_id(id) -> broadcast the 128 bytes (torch.distributed plumbing) -> every
  *   rank: sph_comm_init(h, id, rank, nranks, col_lo, col_hi).
  * sph_step then performs, per step, on the caller's stream: particle migration and the one-column ghost-particle
- * exchange (two NCCL send/recv groups + one count read-back), and -- per sweep -- the ghost-value exchange and the
- * loop-decision reduction as ONE kernel that stores into the neighbours' CUDA-IPC peer windows over NVLink and
- * polls its own (no NCCL, no host; SPH_MG_TRANSPORT=nccl selects NCCL for these too, for A/B runs). */
+ * exchange (one kernel each + one count read-back), and -- per sweep -- the ghost-value exchange and the
+ * loop-decision reduction as ONE kernel; all of them store into the neighbours' CUDA-IPC peer windows over NVLink
+ * and poll their own (no NCCL, no host; SPH_MG_TRANSPORT=nccl selects NCCL instead, for A/B runs). */
 int sph_comm_unique_id(char *out128);
 int sph_comm_init(SphHandle *h, const char *id128, int rank, int nranks, int col_lo, int col_hi);
 int sph_comm_info(SphHandle *h, int32_t *out8); /* owned, ghosts, sent L/R, received L/R, rank, nranks */

@@ -71,7 +71,8 @@ for strict in (True, False):
     L = ps._lib
     L.sph_debug_poke_list.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
     assert L.sph_debug_poke_list(ps._h, 1000, 0, 0x00ffffff) == 0
-    ps.phase(_lib.PH_DF_WARM_START); ps.phase(_lib.PH_DF_DRHO_FIRST)
+    # (the strict DFSPH solve sweeps take j from the gradient records; the force sweep walks the list in both modes)
+    ps.phase(_lib.PH_DF_WARM_START); ps.phase(_lib.PH_DF_DRHO_FIRST); ps.phase(_lib.PH_DF_EXT_FORCE_VEL_ADV)
     f = ps.read_stats().error_flags
     print('poked', 'strict' if strict else 'fast', 'flags', f, flush=True)
     assert f & 64, f
