@@ -470,10 +470,11 @@ struct ListRange {
 };
 // bounds-checked build: entry j of a list must address an existing particle of the array it indexes
 #if SPH_DEBUG_BOUNDS
-#define SPH_CHECK_ENTRY(j, lim, lim_rigid, err) \
-	SPH_BOUNDS_OK(((j) & SPH_RIGID_BIT) ? (int)((j) & ~SPH_RIGID_BIT) < (lim_rigid) : (int)(j) < (lim), err)
-#else
-#define SPH_CHECK_ENTRY(j, lim, lim_rigid, err) ((void)0)
+__device__ __forceinline__ bool sph_entry_ok(uint32_t j, int lim, int lim_rigid, int *err) {
+	bool ok = (j & SPH_RIGID_BIT) ? (int)(j & ~SPH_RIGID_BIT) < lim_rigid : (int)j < lim;
+	if (!ok) atomicOr(err, SPH_ERR_BOUNDS);
+	return ok; // an invalid entry is reported and skipped, never dereferenced
+}
 #endif
 __device__ __forceinline__ ListRange list_range(const SphLists &L, bool boundary, int cap, int s, int n) {
 	ListRange r;
@@ -497,29 +498,26 @@ __device__ __forceinline__ void operator<<(ListRange r, F &&f) {
 	uint4 nx1 = r.n > 4 ? ld_list(p + 32, pol) : zero;
 	int k = 0;
 #if SPH_DEBUG_BOUNDS
-#define SPH_CHK(j) SPH_CHECK_ENTRY(j, r.lim, r.lim_rigid, r.err)
+#define SPH_CALL(j) do { if (sph_entry_ok(j, r.lim, r.lim_rigid, r.err)) f(j); } while (0)
 #else
-#define SPH_CHK(j) ((void)0)
+#define SPH_CALL(j) f(j)
 #endif
 	for (; k + 4 <= r.n; k += 4) {
 		uint4 nx2 = k + 8 < r.n ? ld_list(p + 64, pol) : zero;
 		p += 32;
-		SPH_CHK(cur.x); SPH_CHK(cur.y); SPH_CHK(cur.z); SPH_CHK(cur.w);
-		f(cur.x); f(cur.y); f(cur.z); f(cur.w);
+		SPH_CALL(cur.x); SPH_CALL(cur.y); SPH_CALL(cur.z); SPH_CALL(cur.w);
 		cur = nx1;
 		nx1 = nx2;
 	}
 	int m = r.n - k;
 	if (m > 0) {
-		SPH_CHK(cur.x);
-		f(cur.x);
+		SPH_CALL(cur.x);
 		if (m > 1) {
-			SPH_CHK(cur.y);
-			f(cur.y);
-			if (m > 2) { SPH_CHK(cur.z); f(cur.z); }
+			SPH_CALL(cur.y);
+			if (m > 2) SPH_CALL(cur.z);
 		}
 	}
-#undef SPH_CHK
+#undef SPH_CALL
 }
 // usage:  SPH_FOR_FLUID(L, c, s, j) { ...body, `return` skips to the next neighbour... };
 #define SPH_FOR_FLUID(L, c, s, J) list_range(L, false, (c).kstride, s, (L).fcount[s]) << [&](uint32_t J)
@@ -545,7 +543,7 @@ __device__ __forceinline__ void walk_gw(const SphLists &L, const float4 *__restr
 	if (n <= 0) return;
 #if SPH_DEBUG_BOUNDS
 	if (n > L.cap_f || cap != L.cap_f) { atomicOr(L.err, SPH_ERR_BOUNDS); return; }
-	auto f = [&](uint32_t j, f3 dw) { SPH_CHECK_ENTRY(j, L.n_fluid, L.n_rigid, L.err); f_(j, dw); };
+	auto f = [&](uint32_t j, f3 dw) { if (sph_entry_ok(j, L.n_fluid, L.n_rigid, L.err)) f_(j, dw); };
 #else
 	F &f = f_;
 #endif
@@ -604,7 +602,7 @@ __device__ __forceinline__ void walk_gq(const SphLists &L, const SphConsts &c, i
 	if (n <= 0) return;
 #if SPH_DEBUG_BOUNDS
 	if (n > L.cap_f || c.kstride != L.cap_f) { atomicOr(L.err, SPH_ERR_BOUNDS); return; }
-	auto f = [&](uint32_t j, f3 dw) { SPH_CHECK_ENTRY(j, L.n_fluid, L.n_rigid, L.err); f_(j, dw); };
+	auto f = [&](uint32_t j, f3 dw) { if (sph_entry_ok(j, L.n_fluid, L.n_rigid, L.err)) f_(j, dw); };
 #else
 	F &f = f_;
 #endif

@@ -87,5 +87,5 @@ def test_bounds_checked_build_is_clean_and_live(built):
     assert os.path.exists(lib), "bounds-checked library missing: __graft_entry__.build() builds it"
     env = dict(os.environ, SPH_B200_LIB=lib)
     r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert r.returncode == 0, "stdout:\n%s\nstderr:\n%s" % (r.stdout[-2500:], r.stderr[-2500:])
     assert "CLEAN" in r.stdout and "LIVE" in r.stdout, r.stdout[-3000:]
