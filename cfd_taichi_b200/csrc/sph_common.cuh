@@ -143,6 +143,14 @@ struct SphLists {
 	// fast DFSPH kernels instead: grad W_ij as 3 x 21-bit fixed point in 8 bytes (the index comes from flist);
 	// entries 2p, 2p+1 of sorted particle s in the uint4 at gq[((s >> 5) * (cap / 2) + p) * 32 + (s & 31)]
 	uint4 *gq;
+	// multi-GPU overlap (sph_multigpu.cu: mg_split): a sweep is launched twice -- split_mode 1 over the edge particles
+	// (edge_list: the sorted slots of the particles a neighbour rank holds a ghost copy of), split_mode 2 over all
+	// particles except those (edge_mask: one bit per sorted slot) -- so that the halo exchange of the edge values runs
+	// behind the interior launch.  split_mode 0: one launch over everything (one GPU, and the default on slabs).
+	const int *edge_list;
+	const uint32_t *edge_mask;
+	int n_edge, split_mode, partial_offset;
+	int skip_ghost_fill; // the exchange that runs beside this launch fills the ghosts' records: the list build must not touch them
 	int *err;       // &ctl->error_flags (bounds-checked build)
 	int n_fluid, n_rigid, n_boundary, cap_f, cap_b; // limits the bounds-checked build validates list entries against
 };

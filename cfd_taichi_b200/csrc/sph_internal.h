@@ -127,7 +127,19 @@ enum { MG_F4_T1R = 0 /* posT1.w + posR.w */, MG_F4_VEL, MG_F4_T2, MG_F4_VADV, MG
        MG_F4_T1W /* posT1.w */, MG_NONE = -1 };
 #define MG_XYZ(a4_index) (100 + (a4_index)) // xyz of the float4 work array a4[a4_index] (w is not carried)
 struct SphMgPush;
-SphMgPush mg_push_args(SphHandle *h);                            // the next sweep pushes its edge values itself (sph_mgwin.cuh)
+SphMgPush mg_push_args(SphHandle *h);
+// overlap of the halo exchange with interior compute (sph_sweeps.cu: sweep()): edge particles first on the exchange
+// stream `xs`, the interior concurrently on the main stream; on == false: one launch over everything
+struct MgSplit {
+	bool on;
+	cudaStream_t xs;
+	const int *edge_list;
+	const uint32_t *edge_mask;
+	int n_edge;
+};
+MgSplit mg_split(SphHandle *h);
+void mg_fork(SphHandle *h, cudaStream_t main_stream);   // the exchange stream waits for everything enqueued on the main stream
+void mg_join(SphHandle *h, cudaStream_t main_stream);   // the main stream waits for the exchange stream                            // the next sweep pushes its edge values itself (sph_mgwin.cuh)
 void mg_exchange(SphHandle *h, int what, cudaStream_t st);       // ghost values of one field, both neighbours
 // ghost values + the all-reduce of the sweep's n_blocks block partials + the loop decision `ctl_kind`
 // (sph_ctl.cuh) applied on every rank

@@ -85,6 +85,12 @@ struct SphComm {
 	size_t win_bytes;
 	int epoch;                   // exchanges issued so far (same sequence on every rank)
 	int *send_slot[2], *recv_slot; // sorted slots of the particles sent to each side / of the ghosts, per step
+	// overlap: edge particles (= every particle sent to a neighbour) as a list and as a bit mask over the sorted slots
+	int overlap;                 // SPH_MG_OVERLAP and a slab at least two columns wide (no particle is sent to both sides)
+	cudaStream_t xs;             // exchange stream (highest priority)
+	cudaEvent_t ev_fork, ev_join;
+	int *edge_list;
+	uint32_t *edge_mask;
 	int2 *push_tag;              // per sorted slot: where the particle's value goes in each neighbour's receive block (-1: nowhere)
 	int *pushed_epoch;           // device word written by a producing sweep that pushed its own edge values
 	int push_pending;            // host: epoch handed to a producer with mg_push_args, consumed by the next exchange
@@ -473,6 +479,16 @@ static int mg_open_windows(SphHandle *h, SphComm *m) {
 		SPH_CUDA_CHECK(h, cudaMemset(m->push_tag, 0xff, sizeof(int2) * ncap));
 		SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->pushed_epoch, sizeof(int)));
 		SPH_CUDA_CHECK(h, cudaMemset(m->pushed_epoch, 0, sizeof(int)));
+		SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->edge_list, sizeof(int) * 2 * (size_t)m->cap_halo));
+		SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->edge_mask, sizeof(uint32_t) * ((ncap + 31) / 32 + 1)));
+		SPH_CUDA_CHECK(h, cudaMemset(m->edge_mask, 0, sizeof(uint32_t) * ((ncap + 31) / 32 + 1)));
+		int lo = 0, hi = 0;
+		SPH_CUDA_CHECK(h, cudaDeviceGetStreamPriorityRange(&lo, &hi)); // hi = numerically lowest = highest priority
+		SPH_CUDA_CHECK(h, cudaStreamCreateWithPriority(&m->xs, cudaStreamNonBlocking, hi));
+		SPH_CUDA_CHECK(h, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+		SPH_CUDA_CHECK(h, cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+		// a particle of a one-column slab is sent to both sides and would be swept twice by the edge launch
+		m->overlap = (getenv("SPH_MG_OVERLAP") != nullptr && atoi(getenv("SPH_MG_OVERLAP")) != 0 && m->col_hi - m->col_lo >= 2) ? 1 : 0;
 	}
 	SPH_CUDA_CHECK(h, cudaMalloc((void **)&m->win, m->win_bytes));
 	SPH_CUDA_CHECK(h, cudaMemset(m->win, 0, m->win_bytes));
@@ -560,7 +576,8 @@ void mg_destroy(SphHandle *h) {
 		for (int r = 0; r < m->nranks; ++r)
 			if (r != m->rank && m->peer_win[r]) cudaIpcCloseMemHandle(m->peer_win[r]);
 	}
-	cudaFree(m->quirk); cudaFree(m->win); cudaFree(m->send_slot[0]); cudaFree(m->send_slot[1]); cudaFree(m->recv_slot); cudaFree(m->push_tag); cudaFree(m->pushed_epoch);
+	cudaFree(m->quirk); cudaFree(m->win); cudaFree(m->send_slot[0]); cudaFree(m->send_slot[1]); cudaFree(m->recv_slot); cudaFree(m->push_tag); cudaFree(m->pushed_epoch); cudaFree(m->edge_list); cudaFree(m->edge_mask);
+	if (m->xs) { cudaStreamDestroy(m->xs); cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join); }
 	if (m->comm) g_nccl.CommDestroy(m->comm);
 	delete m;
 	h->comm = nullptr;
@@ -658,11 +675,19 @@ int mg_begin_step(SphHandle *h, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 k_mg_slots(const int *__restrict__ send_orig_l, const int *__restrict__ send_orig_r, const int *__restrict__ slot_of,
            int nsl, int nsr, int first_orig, int nr, int *__restrict__ send_slot_l, int *__restrict__ send_slot_r,
-           int *__restrict__ recv_slot, int2 *__restrict__ push_tag) {
+           int *__restrict__ recv_slot, int2 *__restrict__ push_tag, int *__restrict__ edge_list, uint32_t *__restrict__ edge_mask) {
 	int k = blockIdx.x * blockDim.x + threadIdx.x;
 	// push_tag was filled with (-1, -1); a particle of a one-column slab is sent to both sides (two different threads)
-	if (k < nsl) { int s = slot_of[send_orig_l[k]]; send_slot_l[k] = s; push_tag[s].x = k; }
-	if (k < nsr) { int s = slot_of[send_orig_r[k]]; send_slot_r[k] = s; push_tag[s].y = k; }
+	if (k < nsl) {
+		int s = slot_of[send_orig_l[k]];
+		send_slot_l[k] = s; push_tag[s].x = k;
+		edge_list[k] = s; atomicOr(&edge_mask[s >> 5], 1u << (s & 31));
+	}
+	if (k < nsr) {
+		int s = slot_of[send_orig_r[k]];
+		send_slot_r[k] = s; push_tag[s].y = k;
+		edge_list[nsl + k] = s; atomicOr(&edge_mask[s >> 5], 1u << (s & 31));
+	}
 	if (k < nr) recv_slot[k] = slot_of[first_orig + k];
 }
 void mg_after_grid(SphHandle *h, cudaStream_t st) {
@@ -671,10 +696,14 @@ void mg_after_grid(SphHandle *h, cudaStream_t st) {
 	int nr = m->n_recv[0] + m->n_recv[1];
 	int work = nr > m->n_send[0] ? nr : m->n_send[0];
 	if (m->n_send[1] > work) work = m->n_send[1];
-	if (h->c.N > 0) cudaMemsetAsync(m->push_tag, 0xff, sizeof(int2) * (size_t)h->c.N, st); // (-1, -1): not sent
+	if (h->c.N > 0) {
+		cudaMemsetAsync(m->push_tag, 0xff, sizeof(int2) * (size_t)h->c.N, st); // (-1, -1): not sent
+		cudaMemsetAsync(m->edge_mask, 0, sizeof(uint32_t) * (size_t)((h->c.N + 31) / 32), st);
+	}
 	if (work <= 0) return;
 	k_mg_slots<<<cdiv(work, 256), 256, 0, st>>>(m->send_orig[0], m->send_orig[1], h->fg.slot_of, m->n_send[0], m->n_send[1],
-	                                            h->c.N_owned, nr, m->send_slot[0], m->send_slot[1], m->recv_slot, m->push_tag);
+	                                            h->c.N_owned, nr, m->send_slot[0], m->send_slot[1], m->recv_slot, m->push_tag,
+	                                            m->edge_list, m->edge_mask);
 	h->launches++;
 }
 
@@ -773,6 +802,29 @@ SphMgPush mg_push_args(SphHandle *h) {
 	pu.cap = m->cap_halo;
 	pu.epoch = m->push_pending = ++m->epoch;
 	return pu;
+}
+
+MgSplit mg_split(SphHandle *h) {
+	MgSplit sp;
+	memset(&sp, 0, sizeof(sp));
+	SphComm *m = h->comm;
+	if (!m || !m->p2p || !m->overlap) return sp;
+	sp.on = true;
+	sp.xs = m->xs;
+	sp.edge_list = m->edge_list;
+	sp.edge_mask = m->edge_mask;
+	sp.n_edge = m->n_send[0] + m->n_send[1];
+	return sp;
+}
+void mg_fork(SphHandle *h, cudaStream_t main_stream) {
+	SphComm *m = h->comm;
+	cudaEventRecord(m->ev_fork, main_stream);
+	cudaStreamWaitEvent(m->xs, m->ev_fork, 0);
+}
+void mg_join(SphHandle *h, cudaStream_t main_stream) {
+	SphComm *m = h->comm;
+	cudaEventRecord(m->ev_join, m->xs);
+	cudaStreamWaitEvent(main_stream, m->ev_join, 0);
 }
 
 void mg_exchange(SphHandle *h, int what, cudaStream_t st) { mg_exchange_impl(h, what, SPH_CTL_NONE, 0, st); }

@@ -59,6 +59,15 @@ __device__ __forceinline__ void gq_store(uint4 *gq, int s, int cap, int k, uint2
 #endif
 
 
+// One thread per sorted particle.  (Slabs with overlap: the edge launch maps its threads through the edge list, the interior launch skips those
+// particles; a skipped thread behaves like one past the end)
+__device__ __forceinline__ int sph_split_slot(const SphLists &L, int n) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (L.split_mode == 1) s = s < L.n_edge ? L.edge_list[s] : n;
+	else if (L.split_mode == 2 && s < n && ((L.edge_mask[s >> 5] >> (s & 31)) & 1u)) s = n;
+	return s;
+}
+
 // decode the 1-D cell id (PS:102) back into (x, y, z)
 __device__ __forceinline__ void cell_xyz(int cid, const SphConsts &c, int &cx, int &cy, int &cz) {
 	cy = cid / c.gxz;
@@ -189,7 +198,7 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
               const float4 *__restrict__ bspos, const int *__restrict__ bstart, SphLists L, SphRigidArgs rg,
               int *__restrict__ nbr_count, float *__restrict__ rho, float *__restrict__ alpha,
               float4 *__restrict__ posR, float4 *__restrict__ posT1, SphCtl *ctl, SphMgPush pu) {
-	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	int s = sph_split_slot(L, c.N);
 	int nf = 0, nb = 0;
 	mg_push_mark(pu);
 	if (s < c.N && c.N != c.N_owned && sorted_id[s] >= c.N_owned) {
@@ -199,8 +208,10 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 		L.fcount[s] = -1;
 		L.bcount[s] = 0;
 		nbr_count[s] = 0;
-		posR[s] = make_float4(pi.x, pi.y, pi.z, 0.0f);
-		if (ALPHA) posT1[s] = make_float4(pi.x, pi.y, pi.z, 0.0f);
+		if (!L.skip_ghost_fill) { // (overlap: the exchange beside this launch writes the complete records)
+			posR[s] = make_float4(pi.x, pi.y, pi.z, 0.0f);
+			if (ALPHA) posT1[s] = make_float4(pi.x, pi.y, pi.z, 0.0f);
+		}
 	} else if (s < c.N) {
 		float4 pi = spos[s];
 		int cx, cy, cz;
@@ -393,30 +404,67 @@ k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__rest
 	}
 }
 
-void build_lists(SphHandle *h, cudaStream_t st, bool push_lists) {
+// One sweep + the exchange of the values it produces for the neighbour ranks (`what`, MG_NONE: none).
+// `launch(grid, stream, lists, push)` issues the kernel.  Classic: one launch over all particles, then the exchange.
+// Slabs with overlap (mg_split): the edge particles first, on the exchange stream, with the exchange right behind
+// them, while the interior runs on the main stream; the main stream joins before anything reads the ghost values.
+// Returns the number of block partials the sweep wrote (interior blocks, then edge blocks); *exchanged tells the
+// caller whether the data exchange is done (a sweep with a loop decision still owes the reduction).
+template <class Launch>
+static int sweep(SphHandle *h, int what, int kc, cudaStream_t st, bool exchange_here, bool *exchanged, Launch &&launch) {
+	const int nb = cdiv(h->c.N, SPH_BLOCK);
+	MgSplit sp = mg_split(h);
+	SphMgPush nopush;
+	memset(&nopush, 0, sizeof(nopush));
+	if (!sp.on) {
+		sph_prof_begin(h, kc, st);
+		launch(nb, st, h->L, what == MG_NONE ? nopush : mg_push_args(h));
+		sph_prof_end(h, st);
+		h->launches += 1;
+		if (exchange_here && what != MG_NONE) mg_exchange(h, what, st);
+		if (exchanged) *exchanged = exchange_here;
+		return nb;
+	}
+	SphLists Le = h->L, Li = h->L;
+	Le.split_mode = 1; Le.edge_list = sp.edge_list; Le.n_edge = sp.n_edge; Le.partial_offset = nb;
+	Li.split_mode = 2; Li.edge_mask = sp.edge_mask; Li.skip_ghost_fill = what != MG_NONE ? 1 : 0;
+	const int nbe = cdiv(sp.n_edge, SPH_BLOCK);
+	mg_fork(h, st);
+	if (nbe > 0) launch(nbe, sp.xs, Le, nopush);
+	if (what != MG_NONE) mg_exchange(h, what, sp.xs);
+	sph_prof_begin(h, kc, st);
+	launch(nb, st, Li, nopush);
+	sph_prof_end(h, st);
+	mg_join(h, st);
+	h->launches += 1 + (nbe > 0 ? 1 : 0);
+	if (exchanged) *exchanged = true;
+	return nb + nbe;
+}
+void build_lists(SphHandle *h, cudaStream_t st, bool exchange) {
 	const SphConsts &c = h->c;
-	if (c.N <= 0) return;
-	int nb = cdiv(c.N, SPH_BLOCK);
+	if (c.N <= 0) { // an empty slab still takes part in the exchange (its neighbours wait for its handshake)
+		if (exchange) mg_exchange(h, MG_F4_T1R, st);
+		return;
+	}
 	SphRigidArgs rg = rigid_args(h);
 	bool al = c.solver == SPH_SOLVER_DFSPH;
-	// DFSPH: the kernel pushes (payload, rho) of its edge particles itself; the other solvers' T1R exchange carries
-	// a payload this kernel does not write, so their exchange kernel pushes as before
-	SphMgPush pu;
-	if (al && push_lists) pu = mg_push_args(h);
-	else memset(&pu, 0, sizeof(pu));
-	sph_prof_begin(h, KC_LISTS, st);
+	// `exchange`: the first phase of a step follows the build with the exchange of (payload, rho) of the edge
+	// particles (MG_F4_T1R); on slabs with overlap that exchange runs behind the interior part of the build
+	sweep(h, exchange ? MG_F4_T1R : MG_NONE, KC_LISTS, st, true, nullptr,
+	      [&](int grid, cudaStream_t s, const SphLists &L, const SphMgPush &pu_) {
+		SphMgPush pu = pu_;
+		if (!al) memset(&pu, 0, sizeof(pu)); // the other solvers' T1R payload is not written by this kernel
 #define SPH_BL(A, R)                                                                                              \
-	k_build_lists<A, R><<<nb, SPH_BLOCK, 0, st>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start,  \
-	                                              h->fg.sorted_id, h->bspos, h->bg.cell_start, h->L, rg,           \
-	                                              h->nbr_count, h->a1[A1_RHO], h->a1[A1_ALPHA], h->a4[A4_PR],      \
-	                                              h->a4[A4_T1], h->ctl, pu)
-	if (al && rg.active) SPH_BL(true, true);
-	else if (al) SPH_BL(true, false);
-	else if (rg.active) SPH_BL(false, true);
-	else SPH_BL(false, false);
+	k_build_lists<A, R><<<grid, SPH_BLOCK, 0, s>>>(c, h->a4[A4_POS], h->a4[A4_VEL], h->fg.scell, h->fg.cell_start, \
+	                                               h->fg.sorted_id, h->bspos, h->bg.cell_start, L, rg,             \
+	                                               h->nbr_count, h->a1[A1_RHO], h->a1[A1_ALPHA], h->a4[A4_PR],     \
+	                                               h->a4[A4_T1], h->ctl, pu)
+		if (al && rg.active) SPH_BL(true, true);
+		else if (al) SPH_BL(true, false);
+		else if (rg.active) SPH_BL(false, true);
+		else SPH_BL(false, false);
 #undef SPH_BL
-	sph_prof_end(h, st);
-	h->launches++;
+	});
 	h->lists_valid = true;
 	if (rg.active) mg_rigid_quirk_update(h, 1, st); // slabs: rho of the quirk particles is known now
 }
@@ -424,10 +472,7 @@ void build_lists(SphHandle *h, cudaStream_t st, bool push_lists) {
 // Every solver's first phase starts with the step's lists (and the ghosts' density on slabs); a caller that
 // drives single sweeps has already built them with SPH_PH_BUILD_LISTS.
 void first_phase_lists(SphHandle *h, cudaStream_t st) {
-	if (!h->lists_fresh) {
-		build_lists(h, st, true);
-		mg_exchange(h, MG_F4_T1R, st); // slabs: rho of the ghost particles (posR.w)
-	}
+	if (!h->lists_fresh) build_lists(h, st, true); // slabs: + rho (posR.w) and the payload of the ghost particles
 	h->lists_fresh = false;
 }
 
@@ -665,7 +710,7 @@ __device__ __forceinline__ void walk_gq(const SphLists &L, const SphConsts &c, i
 
 // ---- DFSPH sweeps: one thread per sorted particle; ghost copies (multi-GPU) carry fcount < 0 -------------
 #define SPH_DF_THREAD()                                        \
-	const int s = blockIdx.x * blockDim.x + threadIdx.x;       \
+	const int s = sph_split_slot(L, c.N);                      \
 	const int nf_ = s < c.N ? L.fcount[s] : -1;                \
 	const bool live = nf_ >= 0;                                \
 	const int nb_ = live ? L.bcount[s] : 0;                    \
@@ -777,7 +822,7 @@ k_df_drho(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict__ s
 		mg_push(pu, s, t2, 0.0f, 0.0f);
 		if (out > 0.0f) { psum = (double)out; pcnt = 1; } // DF:275-277
 	}
-	block_partial(psum, pcnt, 0.0f, partials);
+	block_partial(psum, pcnt, 0.0f, partials + L.partial_offset);
 }
 
 // DF:302-312, 357-391 divergence_iter_all_vel_adv fused with DF:381-384 sum_up_stiff
@@ -907,7 +952,7 @@ k_df_ext_force(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restric
 		mg_push(pu, s, va.x, va.y, va.z);
 		vmax = sqrtf(dot(va, va)); // DF:103
 	}
-	block_partial(0.0, 0, vmax, partials);
+	block_partial(0.0, 0, vmax, partials + L.partial_offset);
 }
 
 // DF:124-176 compute_all_rho_adv.  Writes rho_adv and the payload t3 = (((rho_adv-rho0)*alpha)/dt2)/rho
@@ -955,7 +1000,7 @@ k_df_rho_adv(SphConsts c, SphLists L, SphRigidArgs rg, const float4 *__restrict_
 		mg_push(pu, s, t3, 0.0f, 0.0f);
 		if (!(ra == SPH_RHO0)) { psum = (double)ra; pcnt = 1; } // DF:139-141
 	}
-	block_partial(psum, pcnt, 0.0f, partials);
+	block_partial(psum, pcnt, 0.0f, partials + L.partial_offset);
 }
 
 // DF:178-219 iter_all_vel_adv (fluid + boundary part; the rigid force scatter DF:212 is the gather
@@ -1073,25 +1118,29 @@ static void df_decide(SphHandle *h, int what, int kind, int nb, cudaStream_t st)
 
 // ---- DFSPH drivers -----------------------------------------------------------------------------
 // launch a kernel templated on RIGID with the instantiation the scene needs
-#define SPH_LAUNCH_R(K, GRID, ...)                                                        \
+#define SPH_LAUNCH_R(K, GRID, STREAM, ...)                                                \
 	do {                                                                                  \
-		if (rg.active) K<true><<<GRID, SPH_BLOCK, 0, st>>>(__VA_ARGS__);                  \
-		else K<false><<<GRID, SPH_BLOCK, 0, st>>>(__VA_ARGS__);                           \
+		if (rg.active) K<true><<<GRID, SPH_BLOCK, 0, STREAM>>>(__VA_ARGS__);              \
+		else K<false><<<GRID, SPH_BLOCK, 0, STREAM>>>(__VA_ARGS__);                       \
 	} while (0)
 
 void rigid_lists(SphHandle *h, cudaStream_t st);
 void rigid_force_df(SphHandle *h, int gated, cudaStream_t st);
+
+// the loop decision after a sweep that wrote `n_partials` block partials; `what` still has to travel unless `exchanged`
+static void df_decide_after(SphHandle *h, int what, bool exchanged, int kind, int n_partials, cudaStream_t st) {
+	df_decide(h, exchanged ? MG_NONE : what, kind, n_partials, st);
+}
 
 // DF:314-355 divergence_warm_start
 static void df_warm_start(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
-	sph_prof_begin(h, KC_DF_WARM, st);
-	SPH_LAUNCH_R(k_df_warm_start, nb, c, h->L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl, mg_push_args(h));
-	sph_prof_end(h, st);
-	mg_exchange(h, MG_F4_VEL, st);
-	h->launches += 1;
+	(void)nb;
+	sweep(h, MG_F4_VEL, KC_DF_WARM, st, true, nullptr, [&](int grid, cudaStream_t s, const SphLists &L, const SphMgPush &pu) {
+		SPH_LAUNCH_R(k_df_warm_start, grid, s, c, L, rg, h->a4[A4_T1], h->bspos, h->a1[A1_RHO], h->a4[A4_VEL], h->ctl, pu);
+	});
 }
 
 // DF:252-280 derivative_iter_all_rho + the loop decision that follows it (DF:398-399 before the loop, DF:406-414
@@ -1100,13 +1149,13 @@ static void df_drho(SphHandle *h, int in_loop, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
-	sph_prof_begin(h, KC_DF_DRHO, st);
-	SPH_LAUNCH_R(k_df_drho, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count,
-	             h->a1[A1_RHO],
-	             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, in_loop, mg_push_args(h));
-	sph_prof_end(h, st);
-	df_decide(h, MG_F4_T2, in_loop ? SPH_CTL_DIV_ITER : SPH_CTL_DIV_FIRST, nb, st);
-	h->launches += 1;
+	(void)nb;
+	bool done = false;
+	int np = sweep(h, MG_F4_T2, KC_DF_DRHO, st, false, &done, [&](int grid, cudaStream_t s, const SphLists &L, const SphMgPush &pu) {
+		SPH_LAUNCH_R(k_df_drho, grid, s, c, L, rg, h->a4[A4_POS], h->a4[A4_VEL], h->bspos, h->nbr_count, h->a1[A1_RHO],
+		             h->a1[A1_ALPHA], h->a1[A1_DRHO], h->a4[A4_T2], h->ctl, h->partials, in_loop, pu);
+	});
+	df_decide_after(h, MG_F4_T2, done, in_loop ? SPH_CTL_DIV_ITER : SPH_CTL_DIV_FIRST, np, st);
 }
 
 // DF:302-312 divergence_iter_all_vel_adv + DF:381-384 sum_up_stiff, gated on ctl->div_active
@@ -1114,12 +1163,11 @@ static void df_div_vel(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
-	sph_prof_begin(h, KC_DF_DIV, st);
-	SPH_LAUNCH_R(k_df_div_iter, nb, c, h->L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-	             h->a1[A1_DRHO], h->a4[A4_VEL], h->ctl, mg_push_args(h));
-	sph_prof_end(h, st);
-	mg_exchange(h, MG_F4_VEL, st);
-	h->launches += 1;
+	(void)nb;
+	sweep(h, MG_F4_VEL, KC_DF_DIV, st, true, nullptr, [&](int grid, cudaStream_t s, const SphLists &L, const SphMgPush &pu) {
+		SPH_LAUNCH_R(k_df_div_iter, grid, s, c, L, rg, h->a4[A4_T2], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA], h->a1[A1_DRHO],
+		             h->a4[A4_VEL], h->ctl, pu);
+	});
 }
 
 // DF:393-416 correct_divergence_error: the 15 passes (max_iteration_density_divergence, DF:24) are enqueued
@@ -1137,13 +1185,14 @@ static void df_ext_force_vel_adv(SphHandle *h, cudaStream_t st) {
 	const SphConsts &c = h->c;
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
-	sph_prof_begin(h, KC_DF_EXT, st);
-	SPH_LAUNCH_R(k_df_ext_force, nb, c, h->L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->a4[A4_VADV],
-	             h->a4[A4_FA], h->ctl, h->partials, mg_push_args(h));
-	sph_prof_end(h, st);
+	(void)nb;
+	bool done = false;
+	int np = sweep(h, MG_F4_VADV, KC_DF_EXT, st, false, &done, [&](int grid, cudaStream_t s, const SphLists &L, const SphMgPush &pu) {
+		SPH_LAUNCH_R(k_df_ext_force, grid, s, c, L, rg, h->a4[A4_PR], h->a4[A4_VEL], h->a1[A1_RHO], h->a4[A4_VADV], h->a4[A4_FA],
+		             h->ctl, h->partials, pu);
+	});
 	// DF:105-110 loops over all rigid particles whenever a rigid body exists, active or not
-	df_decide(h, MG_F4_VADV, SPH_CTL_DT, nb, st);
-	h->launches += 1;
+	df_decide_after(h, MG_F4_VADV, done, SPH_CTL_DT, np, st);
 }
 
 // DF:124-152 compute_all_rho_adv of pass `it` + the average the loop condition reads (DF:225)
@@ -1152,12 +1201,13 @@ static void df_den_rho(SphHandle *h, int it, cudaStream_t st) {
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	int gated = it >= 2 ? 1 : 0; // min_iteration_density (DF:21)
-	sph_prof_begin(h, KC_DF_RHOADV, st);
-	SPH_LAUNCH_R(k_df_rho_adv, nb, c, h->L, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO],
-	             h->a1[A1_ALPHA], h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated, mg_push_args(h));
-	sph_prof_end(h, st);
-	df_decide(h, MG_F4_T3, SPH_CTL_DEN, nb, st);
-	h->launches += 1;
+	(void)nb;
+	bool done = false;
+	int np = sweep(h, MG_F4_T3, KC_DF_RHOADV, st, false, &done, [&](int grid, cudaStream_t s, const SphLists &L, const SphMgPush &pu) {
+		SPH_LAUNCH_R(k_df_rho_adv, grid, s, c, L, rg, h->a4[A4_POS], h->a4[A4_VADV], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
+		             h->a1[A1_RHOADV], h->a4[A4_T3], h->ctl, h->partials, gated, pu);
+	});
+	df_decide_after(h, MG_F4_T3, done, SPH_CTL_DEN, np, st);
 }
 
 // DF:178-219 iter_all_vel_adv of pass `it` (+ the fluid -> rigid forces, DF:212) and the decision whether pass it+1 runs
@@ -1166,14 +1216,14 @@ static void df_den_vel(SphHandle *h, int it, cudaStream_t st) {
 	int nb = cdiv(c.N, SPH_BLOCK);
 	SphRigidArgs rg = rigid_args(h);
 	int gated = it >= 2 ? 1 : 0;
-	sph_prof_begin(h, KC_DF_VELADV, st);
-	SPH_LAUNCH_R(k_df_vel_adv_iter, nb, c, h->L, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA],
-	             h->a1[A1_RHOADV], h->a4[A4_VADV], h->ctl, gated, mg_push_args(h));
-	sph_prof_end(h, st);
-	mg_exchange(h, MG_F4_VADV, st);
+	(void)nb;
+	sweep(h, MG_F4_VADV, KC_DF_VELADV, st, true, nullptr, [&](int grid, cudaStream_t s, const SphLists &L, const SphMgPush &pu) {
+		SPH_LAUNCH_R(k_df_vel_adv_iter, grid, s, c, L, rg, h->a4[A4_T3], h->bspos, h->a1[A1_RHO], h->a1[A1_ALPHA], h->a1[A1_RHOADV],
+		             h->a4[A4_VADV], h->ctl, gated, pu);
+	});
 	if (rg.active) rigid_force_df(h, gated, st); // DF:212, gather form
 	k_df_ctl_den_next<<<1, 1, 0, st>>>(h->ctl);
-	h->launches += 2;
+	h->launches += 1;
 }
 
 static void df_density_iters(SphHandle *h, int first, int count, cudaStream_t st) {
