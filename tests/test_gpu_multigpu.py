@@ -12,10 +12,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(nproc, args):
+def _run(nproc, args, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
            "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tests", "mg_worker.py")] + args
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, **(env or {})))
 
 
 @pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -81,3 +81,15 @@ def test_many_slabs_match_single_domain(built, nranks):
     assert line and "perm_ok=True" in line[0] and "iters_ok=True" in line[0] and "exact=True" in line[0]
     two_cuts = int(line[0].split("two_cuts=")[1].split()[0])
     assert two_cuts > 0, line[0]
+
+
+@_need(2)
+@pytest.mark.parametrize("knob", ["SPH_MG_OVERLAP", "SPH_MG_EPILOGUE_PUSH", "SPH_MG_TRANSPORT"])
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_two_slabs_opt_in_paths_stay_bit_identical(built, knob, mode):
+    """The measured-and-not-adopted variants (exchange behind the interior launch, edge values
+    pushed from the sweeps' epilogue) and the NCCL transport kept for A/B runs must stay correct while they exist."""
+    r = _run(2, ["25", mode], env={knob: "nccl" if knob == "SPH_MG_TRANSPORT" else "1"})
+    line = [l for l in r.stdout.splitlines() if l.startswith("MGRESULT")]
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    assert line and "perm_ok=True" in line[0] and "iters_ok=True" in line[0] and "exact=True" in line[0]
