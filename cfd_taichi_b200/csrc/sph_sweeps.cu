@@ -192,7 +192,10 @@ __device__ __forceinline__ void scan_segment(const SphConsts &c, const float4 &p
 // (SB:41-72) and, for DFSPH, alpha (DF:32-89) -- all of which depend on positions only.
 // ---------------------------------------------------------------------------------------------
 template <bool ALPHA, bool RIGID>
-__global__ void __launch_bounds__(SPH_BLOCK, 8) // 64 registers: this kernel is issue-bound and wants the warps
+#ifndef SPH_MINB_LISTS
+#define SPH_MINB_LISTS 8
+#endif
+__global__ void __launch_bounds__(SPH_BLOCK, SPH_MINB_LISTS) // 64 registers: this kernel is issue-bound and wants the warps
 k_build_lists(SphConsts c, const float4 *__restrict__ spos, const float4 *__restrict__ svel,
               const int *__restrict__ scell, const int *__restrict__ cstart, const int *__restrict__ sorted_id,
               const float4 *__restrict__ bspos, const int *__restrict__ bstart, SphLists L, SphRigidArgs rg,
