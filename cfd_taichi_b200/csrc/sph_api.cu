@@ -232,6 +232,7 @@ extern "C" int sph_destroy(SphHandle *h) {
 	mg_destroy(h);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);
 	cudaFree(h->xyz_stage);
+	if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_vel_ready); cudaEventDestroy(h->ev_mark); }
 	if (h->ctl_host) cudaFreeHost(h->ctl_host);
 	if (h->prof) {
 		if (h->prof->created)
@@ -339,6 +340,7 @@ extern "C" int sph_rigid_step(SphHandle *h, void *stream) {
 	if (!h->rigid_ready) return sph_fail(h, SPH_ESTATE, "sph_rigid_step: call sph_init_rigid first");
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	sph_finish_deferred_vel(h, (cudaStream_t)stream);
 	if (h->cfg.strict) sph_strict::rigid_step(h, st); else sph_fast::rigid_step(h, st);
 	return check_launch(h, "sph_rigid_step");
 }
@@ -394,13 +396,32 @@ extern "C" int sph_rigid_set_state(SphHandle *h, const SphRigidInfo *in) {
 	return SPH_OK;
 }
 
+// Deferred velocity upload (e2e path).  sph_upload_state_xyz puts the velocities on a copy stream; the step that follows
+// builds its grid and neighbour lists from the positions while they travel (0.45 ms of PCIe at 10^6 particles behind
+// 0.51 ms of kernels) and joins here, right before the first sweep that reads a velocity.
+void sph_finish_deferred_vel(SphHandle *h, cudaStream_t st) {
+	if (h->vel_in_flight) {
+		cudaStreamWaitEvent(st, h->ev_vel_ready, 0);
+		h->vel_in_flight = false;
+	}
+	if (h->vel_gather_pending) {
+		sphg_gather_vel(h, st);
+		h->vel_gather_pending = false;
+	}
+}
+
 static int base_step(SphHandle *h, cudaStream_t st) {
 	// SB:136-143: simulate_cnt += 1 ; reset_grid ; update_grid ; reset()
 	h->simulate_cnt += 1;
 	h->L.n_fluid = h->c.N; // slabs: owned + ghost particles of this step
 	sph_prof_begin(h, KC_GRID, st);
 	sphg_build(h, h->fg, h->pos, h->c.N, st, h->comm ? h->gid : nullptr);
-	sphg_gather_fluid(h, st);
+	if (h->vel_in_flight) { // the velocities are still on the copy stream: positions and vel.w now, the rest later
+		sphg_gather_fluid_pos(h, st);
+		h->vel_gather_pending = true;
+	} else {
+		sphg_gather_fluid(h, st);
+	}
 	mg_after_grid(h, st); // multi-GPU: sorted slots of the sent / received particles of this step
 	if (h->c.Nr > 0 && h->c.active_rigid) { // PS:385-386, 399-407
 		sphg_build(h, h->rg, h->rpos, h->c.Nr, st);
@@ -432,6 +453,11 @@ extern "C" int sph_phase(SphHandle *h, int phase, void *stream) {
 		return check_launch(h, "sph_phase(build_grid)");
 	}
 	if (!h->grid_valid) return sph_fail(h, SPH_ESTATE, "sph_phase: grid not built (SPH_PH_BUILD_GRID first)");
+	// a deferred velocity upload is joined by the first phase that reads a velocity: the list-building first phases
+	// do it themselves after the build (first_phase_lists), every other phase here
+	if (phase != SPH_PH_BUILD_LISTS && phase != SPH_PH_DF_INITIALIZE && phase != SPH_PH_WC_PRESSURE && phase != SPH_PH_PC_EXT_FORCE &&
+	    phase != SPH_PH_II_PREDICT_ADVECTION)
+		sph_finish_deferred_vel(h, st);
 	bool strict = h->cfg.strict != 0;
 	if (phase == SPH_PH_WRITEBACK) {
 		sphg_writeback(h, h->a4[A4_POS], h->a4[A4_VEL], st);
@@ -478,10 +504,12 @@ extern "C" int sph_step(SphHandle *h, int n_substeps, void *stream) {
 	}
 	for (int k = 0; k < n_substeps; ++k) {
 		if (h->comm) { // multi-GPU slab: migration + ghost particles first (positions moved last step)
+			sph_finish_deferred_vel(h, st);
 			rc = mg_begin_step(h, st);
 			if (rc != SPH_OK) return rc;
 		}
 		base_step(h, st);
+		if (h->c.solver == SPH_SOLVER_PBF) sph_finish_deferred_vel(h, st); // its first phase integrates the velocities
 		switch (h->c.solver) {
 		case SPH_SOLVER_DFSPH:
 			if (strict) sph_strict::df_step(h, st); else sph_fast::df_step(h, st);
@@ -515,6 +543,7 @@ extern "C" int sph_pcisph_precompute(SphHandle *h, void *stream) {
 	if (rc != SPH_OK) return rc;
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	sph_finish_deferred_vel(h, (cudaStream_t)stream);
 	if (h->comm) { // slabs: the ghost layer must be in place for the neighbour counts of the edge columns
 		rc = mg_begin_step(h, st);
 		if (rc != SPH_OK) return rc;
@@ -569,6 +598,7 @@ extern "C" int sph_fetch(SphHandle *h, int field, void *dev_out, size_t n, void 
 	if (!h || !dev_out) return SPH_EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	sph_finish_deferred_vel(h, (cudaStream_t)stream);
 	const SphConsts &c = h->c;
 	size_t N = (size_t)c.N;
 	auto f1 = [&](const float *src) -> int {
@@ -642,6 +672,7 @@ extern "C" int sph_upload_state(SphHandle *h, const float *host_pos4, const floa
 	if (!h || !h->pos || !h->vel) return h ? sph_fail(h, SPH_ENOTBOUND, "sph_upload_state: state not bound") : SPH_EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	sph_finish_deferred_vel(h, (cudaStream_t)stream);
 	size_t bytes = sizeof(float4) * (size_t)h->c.N_owned;
 	if (host_pos4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(h->pos, host_pos4, bytes, cudaMemcpyHostToDevice, st));
 	if (host_vel4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(h->vel, host_vel4, bytes, cudaMemcpyHostToDevice, st));
@@ -652,6 +683,7 @@ extern "C" int sph_download_state(SphHandle *h, float *host_pos4, float *host_ve
 	if (!h || !h->pos || !h->vel) return h ? sph_fail(h, SPH_ENOTBOUND, "sph_download_state: state not bound") : SPH_EINVAL;
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	sph_finish_deferred_vel(h, (cudaStream_t)stream);
 	size_t bytes = sizeof(float4) * (size_t)h->c.N_owned;
 	if (host_pos4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_pos4, h->pos, bytes, cudaMemcpyDeviceToHost, st));
 	if (host_vel4) SPH_CUDA_CHECK(h, cudaMemcpyAsync(host_vel4, h->vel, bytes, cudaMemcpyDeviceToHost, st));
@@ -674,9 +706,30 @@ extern "C" int sph_upload_state_xyz(SphHandle *h, const float *host_pos3, const 
 	if ((rc = xyz_stage(h)) != SPH_OK) return rc;
 	size_t n = (size_t)h->c.N_owned, bytes = sizeof(float) * 3 * n;
 	float *p3 = h->xyz_stage, *v3 = h->xyz_stage + 3 * (size_t)h->cfg.n_fluid;
+	sph_finish_deferred_vel(h, st); // an earlier deferred upload must have landed before its staging buffer is reused
+	// One GPU, positions and velocities together: the positions go first on the caller's stream -- the grid and the
+	// neighbour lists of the next step need nothing else -- and the velocities follow on a copy stream; the step joins
+	// them right before its first sweep that reads a velocity (sph_finish_deferred_vel).  SPH_E2E_NO_DEFER: A/B knob.
+	static const bool no_defer = getenv("SPH_E2E_NO_DEFER") != nullptr;
+	bool defer = host_pos3 && host_vel3 && !h->comm && !no_defer;
+	if (defer && !h->copy_stream) {
+		SPH_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+		SPH_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_vel_ready, cudaEventDisableTiming));
+		SPH_CUDA_CHECK(h, cudaEventCreateWithFlags(&h->ev_mark, cudaEventDisableTiming));
+	}
 	if (host_pos3) SPH_CUDA_CHECK(h, cudaMemcpyAsync(p3, host_pos3, bytes, cudaMemcpyHostToDevice, st));
-	if (host_vel3) SPH_CUDA_CHECK(h, cudaMemcpyAsync(v3, host_vel3, bytes, cudaMemcpyHostToDevice, st));
-	sphg_unpack_xyz(h, host_pos3 ? p3 : nullptr, host_vel3 ? v3 : nullptr, (int)n, st);
+	if (defer) {
+		sphg_unpack_xyz(h, p3, nullptr, (int)n, st);
+		SPH_CUDA_CHECK(h, cudaEventRecord(h->ev_mark, st));              // everything the caller enqueued before this call ...
+		SPH_CUDA_CHECK(h, cudaStreamWaitEvent(h->copy_stream, h->ev_mark, 0)); // ... has finished with h->vel and the staging buffer
+		SPH_CUDA_CHECK(h, cudaMemcpyAsync(v3, host_vel3, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+		sphg_unpack_xyz(h, nullptr, v3, (int)n, h->copy_stream);
+		SPH_CUDA_CHECK(h, cudaEventRecord(h->ev_vel_ready, h->copy_stream));
+		h->vel_in_flight = true;
+	} else {
+		if (host_vel3) SPH_CUDA_CHECK(h, cudaMemcpyAsync(v3, host_vel3, bytes, cudaMemcpyHostToDevice, st));
+		sphg_unpack_xyz(h, host_pos3 ? p3 : nullptr, host_vel3 ? v3 : nullptr, (int)n, st);
+	}
 	return check_launch(h, "sph_upload_state_xyz");
 }
 
@@ -685,6 +738,7 @@ extern "C" int sph_download_state_xyz(SphHandle *h, float *host_pos3, float *hos
 	if (rc != SPH_OK) return rc;
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(h, cudaSetDevice(h->device));
+	sph_finish_deferred_vel(h, (cudaStream_t)stream);
 	if ((rc = xyz_stage(h)) != SPH_OK) return rc;
 	size_t n = (size_t)h->c.N_owned, bytes = sizeof(float) * 3 * n;
 	float *p3 = h->xyz_stage, *v3 = h->xyz_stage + 3 * (size_t)h->cfg.n_fluid;
@@ -787,6 +841,8 @@ extern "C" int sph_copy_work_state(SphHandle *dst, SphHandle *src, void *stream)
 	if (!dst->grid_valid || !src->grid_valid) return sph_fail(dst, SPH_ESTATE, "sph_copy_work_state: build both grids first");
 	cudaStream_t st = (cudaStream_t)stream;
 	SPH_CUDA_CHECK(dst, cudaSetDevice(dst->device));
+	sph_finish_deferred_vel(dst, st);
+	sph_finish_deferred_vel(src, st);
 	size_t n = (size_t)src->c.N;
 	for (int k = 0; k < A4_COUNT; ++k)
 		SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->a4[k], src->a4[k], sizeof(float4) * n, cudaMemcpyDeviceToDevice, st));

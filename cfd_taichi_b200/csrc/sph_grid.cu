@@ -283,6 +283,42 @@ void sphg_gather_fluid(SphHandle *h, cudaStream_t st) {
 	h->launches++;
 }
 
+// The same in two parts, for a step whose velocities are still on their way from the host (sph_upload_state_xyz
+// defers them behind the grid and list build): positions + the solver-persistent scalar vel.w now (it never leaves
+// the device; the concurrent unpack kernel rewrites it with the same value), velocities when they have arrived.
+__global__ void __launch_bounds__(256) k_gather_fluid_pos(const int *__restrict__ sorted_id, const int *__restrict__ cell_of, int n,
+                                                           const float4 *__restrict__ pos, const float4 *vel,
+                                                           float4 *__restrict__ spos, float4 *__restrict__ svel,
+                                                           int *__restrict__ scell, int *__restrict__ slot_of) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	int i = sorted_id[s];
+	float4 p = pos[i];
+	p.w = 0.0f;
+	spos[s] = p;
+	svel[s] = make_float4(0.0f, 0.0f, 0.0f, reinterpret_cast<const volatile float *>(vel + i)[3]);
+	scell[s] = cell_of[i];
+	slot_of[i] = s;
+}
+__global__ void __launch_bounds__(256) k_gather_vel(const int *__restrict__ sorted_id, int n, const float4 *__restrict__ vel,
+                                                     float4 *__restrict__ svel) {
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s < n) svel[s] = vel[sorted_id[s]];
+}
+void sphg_gather_fluid_pos(SphHandle *h, cudaStream_t st) {
+	int n = h->fg.n;
+	if (n <= 0) return;
+	k_gather_fluid_pos<<<cdiv(n, 256), 256, 0, st>>>(h->fg.sorted_id, h->fg.cell_of, n, h->pos, h->vel, h->a4[A4_POS],
+	                                                  h->a4[A4_VEL], h->fg.scell, h->fg.slot_of);
+	h->launches++;
+}
+void sphg_gather_vel(SphHandle *h, cudaStream_t st) {
+	int n = h->fg.n;
+	if (n <= 0) return;
+	k_gather_vel<<<cdiv(n, 256), 256, 0, st>>>(h->fg.sorted_id, n, h->vel, h->a4[A4_VEL]);
+	h->launches++;
+}
+
 void sphg_gather_boundary(SphHandle *h, cudaStream_t st) {
 	int n = h->bg.n;
 	if (n <= 0) return;

@@ -79,6 +79,10 @@ struct SphHandle {
 	int n_partials;
 	double *red; // device: {sum, cnt, max} of the last reduction (all ranks)
 	bool grid_valid, boundary_ready, lists_valid;
+	cudaStream_t copy_stream;  // deferred velocity upload (sph_upload_state_xyz)
+	cudaEvent_t ev_vel_ready, ev_mark;
+	bool vel_in_flight;        // a velocity upload is on the copy stream: h->vel is not complete yet
+	bool vel_gather_pending;   // the grid of this step was built without the sorted velocities
 	unsigned long long *render_zbuf; // sph_render: (depth | colour) per pixel
 	size_t render_cap;
 	int async_error;      // a library call inside a void helper failed (NCCL transport): the enclosing sph_* call returns it
@@ -111,6 +115,11 @@ int sph_fail_cuda(SphHandle *h, cudaError_t e, const char *expr, const char *fil
 // ---- sph_grid.cu (mode independent) -------------------------------------------------------
 void sphg_build(SphHandle *h, SphGrid &g, const float4 *pos, int n, cudaStream_t st, const int *gid = nullptr);
 void sphg_gather_fluid(SphHandle *h, cudaStream_t st);
+void sphg_gather_fluid_pos(SphHandle *h, cudaStream_t st);   // deferred velocity upload: positions + vel.w now ...
+void sphg_gather_vel(SphHandle *h, cudaStream_t st);         // ... the velocities when they have arrived
+// sph_api.cu: velocities uploaded by sph_upload_state_xyz travel on a copy stream behind the grid and list build;
+// whoever reads the velocity arrays first calls this (waits for the copy, gathers the sorted velocities)
+void sph_finish_deferred_vel(SphHandle *h, cudaStream_t st);
 void sphg_gather_boundary(SphHandle *h, cudaStream_t st);
 void sphg_gather_rigid(SphHandle *h, cudaStream_t st);
 void sphg_unsort_f1(SphHandle *h, const SphGrid &g, const float *in, float *out, int n, cudaStream_t st);

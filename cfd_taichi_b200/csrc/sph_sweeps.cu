@@ -477,6 +477,7 @@ void build_lists(SphHandle *h, cudaStream_t st, bool exchange) {
 void first_phase_lists(SphHandle *h, cudaStream_t st) {
 	if (!h->lists_fresh) build_lists(h, st, true); // slabs: + rho (posR.w) and the payload of the ghost particles
 	h->lists_fresh = false;
+	sph_finish_deferred_vel(h, st); // e2e path: the velocities travelled behind the grid and list build (sph_api.cu)
 }
 
 // list walkers ---------------------------------------------------------------------------------

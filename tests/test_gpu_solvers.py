@@ -154,3 +154,39 @@ def test_headless_main_runs_and_exports(built, tmp_path):
     head = files[0].read_text().splitlines()
     assert head[0] == "ply" and head[2] == "element vertex 5879"
     ps.close()
+
+
+@pytest.mark.parametrize("solver", ["dfsph", "wcsph", "pcisph", "iisph"])
+def test_e2e_xyz_path_with_deferred_velocity_upload(built, solver):
+    """The e2e path bench.py times: sph_upload_state_xyz (velocities deferred onto a copy stream behind the grid and
+    list build) / sph_step / sph_download_state_xyz with N x 3 host arrays, every step, against the oracle --
+    bit-exact with the strict kernels, including a velocity-only and a position-only upload in between."""
+    import torch
+    from cfd_taichi_b200 import _lib
+    cfg = scenes.shipped("small_block", solver)
+    ps, sol, o = make(cfg, solver, True)
+    n = ps.particle_num
+    hp = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
+    hv = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
+    L, h, s = ps._lib, ps._h, ps._stream()
+    _lib.check(L.sph_download_state_xyz(h, hp.data_ptr(), hv.data_ptr(), s), h)
+    rng = np.random.default_rng(5)
+    for step in range(6):
+        if step == 2:   # the host changes the velocities between steps: the deferred copy must carry them
+            hv += torch.from_numpy(rng.normal(0, 0.2, size=(n, 3)).astype(np.float32))
+            o.field("vel")[:] = hv.numpy()
+        if step == 3:   # separate calls: nothing is deferred, same result
+            _lib.check(L.sph_upload_state_xyz(h, None, hv.data_ptr(), s), h)
+            _lib.check(L.sph_upload_state_xyz(h, hp.data_ptr(), None, s), h)
+        else:
+            _lib.check(L.sph_upload_state_xyz(h, hp.data_ptr(), hv.data_ptr(), s), h)
+        if step == 4:   # a fetch between upload and step must see the uploaded velocities (join on the copy stream)
+            v4 = ps._fetch(_lib.F_FLUID_POS, 4, torch.float32)   # any fetch joins; the caller array then holds the upload
+            assert np.array_equal(ps._vel4[:n, :3].cpu().numpy(), hv.numpy())
+        _lib.check(L.sph_step(h, 1, s), h)
+        _lib.check(L.sph_download_state_xyz(h, hp.data_ptr(), hv.data_ptr(), s), h)
+        o.step()
+        assert np.array_equal(hp.numpy(), o.field("pos")), "step %d pos" % step
+        assert np.array_equal(hv.numpy(), o.field("vel")), "step %d vel" % step
+    assert ps.read_stats().error_flags == 0
+    ps.close(); o.close()
