@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 from cfd_taichi_b200 import _lib, scenes
+from cfd_taichi_b200.dfsph_solver import dfsph_solver
 from cfd_taichi_b200.iisph_solver import iisph_solver
 from cfd_taichi_b200.pcisph_solver import pcisph_solver
 from cfd_taichi_b200.wcsph_solver import wcsph_solver
@@ -12,7 +13,8 @@ from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
-CLS = {"wcsph": wcsph_solver, "pcisph": pcisph_solver, "iisph": iisph_solver}
+
+CLS = {"wcsph": wcsph_solver, "pcisph": pcisph_solver, "iisph": iisph_solver, "dfsph": dfsph_solver}
 
 
 def relinf(a, b):
