@@ -231,6 +231,8 @@ extern "C" int sph_destroy(SphHandle *h) {
 	cudaFree(h->L.fcount); cudaFree(h->L.bcount);
 	mg_destroy(h);
 	cudaFree(h->nbr_count); cudaFree(h->ctl); cudaFree(h->partials); cudaFree(h->red);
+	if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+	if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
 	cudaFree(h->xyz_stage);
 	if (h->copy_stream) { cudaStreamDestroy(h->copy_stream); cudaEventDestroy(h->ev_vel_ready); cudaEventDestroy(h->ev_mark); }
 	if (h->ctl_host) cudaFreeHost(h->ctl_host);
@@ -248,6 +250,7 @@ extern "C" int sph_bind(SphHandle *h, int field, void *dev_ptr, size_t n) {
 	if (!dev_ptr && n > 0) return sph_fail(h, SPH_EINVAL, "sph_bind: null pointer for field %d", field);
 	if (((uintptr_t)dev_ptr & 15u) != 0 && field != SPH_F_FLUID_GID) return sph_fail(h, SPH_EINVAL, "sph_bind: field %d is not 16-byte aligned", field);
 	size_t ncap = (size_t)h->cfg.n_fluid + (size_t)(h->cfg.n_ghost_capacity > 0 ? h->cfg.n_ghost_capacity : 0);
+	if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; } // the graph holds the old pointers
 	switch (field) {
 	case SPH_F_FLUID_POS:
 		if (n < ncap) return sph_fail(h, SPH_EINVAL, "sph_bind: fluid pos needs %zu float4, got %zu", ncap, n);
@@ -492,6 +495,69 @@ extern "C" int sph_phase(SphHandle *h, int phase, void *stream) {
 	return check_launch(h, "sph_phase");
 }
 
+// one solver step on `st`: prologue (SB:136-143) + the solver's phases
+static void enqueue_step(SphHandle *h, cudaStream_t st, bool strict) {
+	base_step(h, st);
+	if (h->c.solver == SPH_SOLVER_PBF) sph_finish_deferred_vel(h, st); // its first phase integrates the velocities
+	switch (h->c.solver) {
+	case SPH_SOLVER_DFSPH:
+		if (strict) sph_strict::df_step(h, st); else sph_fast::df_step(h, st);
+		break;
+	case SPH_SOLVER_WCSPH:
+		for (int p = SPH_PH_WC_PRESSURE; p <= SPH_PH_WC_KINEMATIC; ++p)
+			if (strict) sph_strict::wc_phase(h, p, st); else sph_fast::wc_phase(h, p, st);
+		break;
+	case SPH_SOLVER_PCISPH:
+		for (int p = SPH_PH_PC_EXT_FORCE; p <= SPH_PH_PC_INTEGRATION; ++p)
+			if (strict) sph_strict::pc_phase(h, p, st); else sph_fast::pc_phase(h, p, st);
+		break;
+	case SPH_SOLVER_IISPH:
+		for (int p = SPH_PH_II_PREDICT_ADVECTION; p <= SPH_PH_II_INTEGRATION; ++p)
+			if (strict) sph_strict::ii_phase(h, p, st); else sph_fast::ii_phase(h, p, st);
+		break;
+	case SPH_SOLVER_PBF:
+		for (int p = SPH_PH_PBF_PREDICT; p <= SPH_PH_PBF_UPDATE_POS; ++p)
+			if (strict) sph_strict::pbf_phase(h, p, st); else sph_fast::pbf_phase(h, p, st);
+		break;
+	default: break;
+	}
+}
+
+// CUDA graph of a whole step for the solvers whose step never looks at the host (WCSPH, PBF: no convergence loop).
+// Their step is ~13 launches of a few microseconds each on the small scenes the reference ships (BASELINE configs[0]:
+// 29 k particles), i.e. launch-bound; the graph is captured once on an internal stream (the caller's may be the
+// legacy default stream, which cannot be captured) and replayed into the caller's stream.  Not used on slabs (the
+// exchange epochs are launch arguments), while per-launch profiling is on, or while a deferred upload is pending.
+static bool step_graphable(const SphHandle *h) {
+	static const bool off = getenv("SPH_NO_GRAPH") != nullptr;
+	if (off || h->comm || (h->prof && h->prof->on) || h->vel_in_flight || h->vel_gather_pending) return false;
+	return h->c.solver == SPH_SOLVER_WCSPH || h->c.solver == SPH_SOLVER_PBF;
+}
+static int step_graph_launch(SphHandle *h, cudaStream_t st, bool strict) {
+	if (!h->step_graph) {
+		if (!h->graph_stream) SPH_CUDA_CHECK(h, cudaStreamCreateWithFlags(&h->graph_stream, cudaStreamNonBlocking));
+		SPH_CUDA_CHECK(h, cudaStreamSynchronize(st)); // the capture stream is not ordered behind the caller's stream
+		int launches0 = h->launches, sim0 = h->simulate_cnt;
+		cudaGraph_t g = nullptr;
+		SPH_CUDA_CHECK(h, cudaStreamBeginCapture(h->graph_stream, cudaStreamCaptureModeThreadLocal));
+		enqueue_step(h, h->graph_stream, strict);
+		cudaError_t e = cudaStreamEndCapture(h->graph_stream, &g);
+		h->step_graph_launches = h->launches - launches0;
+		h->launches = launches0;
+		h->simulate_cnt = sim0;
+		if (e != cudaSuccess || !g) return sph_fail(h, SPH_ECUDA, "sph_step: graph capture failed: %s", cudaGetErrorString(e));
+		e = cudaGraphInstantiate(&h->step_graph, g, 0);
+		cudaGraphDestroy(g);
+		if (e != cudaSuccess) { h->step_graph = nullptr; return sph_fail(h, SPH_ECUDA, "sph_step: cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+	}
+	SPH_CUDA_CHECK(h, cudaGraphLaunch(h->step_graph, st));
+	h->launches += h->step_graph_launches;
+	h->simulate_cnt += 1;
+	h->grid_valid = true; // what enqueue_step leaves behind on the host side
+	h->lists_fresh = false;
+	return SPH_OK;
+}
+
 extern "C" int sph_step(SphHandle *h, int n_substeps, void *stream) {
 	int rc = require_state(h);
 	if (rc != SPH_OK) return rc;
@@ -508,29 +574,11 @@ extern "C" int sph_step(SphHandle *h, int n_substeps, void *stream) {
 			rc = mg_begin_step(h, st);
 			if (rc != SPH_OK) return rc;
 		}
-		base_step(h, st);
-		if (h->c.solver == SPH_SOLVER_PBF) sph_finish_deferred_vel(h, st); // its first phase integrates the velocities
-		switch (h->c.solver) {
-		case SPH_SOLVER_DFSPH:
-			if (strict) sph_strict::df_step(h, st); else sph_fast::df_step(h, st);
-			break;
-		case SPH_SOLVER_WCSPH:
-			for (int p = SPH_PH_WC_PRESSURE; p <= SPH_PH_WC_KINEMATIC; ++p)
-				if (strict) sph_strict::wc_phase(h, p, st); else sph_fast::wc_phase(h, p, st);
-			break;
-		case SPH_SOLVER_PCISPH:
-			for (int p = SPH_PH_PC_EXT_FORCE; p <= SPH_PH_PC_INTEGRATION; ++p)
-				if (strict) sph_strict::pc_phase(h, p, st); else sph_fast::pc_phase(h, p, st);
-			break;
-		case SPH_SOLVER_IISPH:
-			for (int p = SPH_PH_II_PREDICT_ADVECTION; p <= SPH_PH_II_INTEGRATION; ++p)
-				if (strict) sph_strict::ii_phase(h, p, st); else sph_fast::ii_phase(h, p, st);
-			break;
-		case SPH_SOLVER_PBF:
-			for (int p = SPH_PH_PBF_PREDICT; p <= SPH_PH_PBF_UPDATE_POS; ++p)
-				if (strict) sph_strict::pbf_phase(h, p, st); else sph_fast::pbf_phase(h, p, st);
-			break;
-		default: break;
+		if (step_graphable(h)) {
+			rc = step_graph_launch(h, st, strict);
+			if (rc != SPH_OK) return rc;
+		} else {
+			enqueue_step(h, st, strict);
 		}
 		h->grid_valid = false; // positions moved: sorted buffers describe the previous state
 		h->lists_valid = false;

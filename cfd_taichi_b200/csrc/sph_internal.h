@@ -79,6 +79,9 @@ struct SphHandle {
 	int n_partials;
 	double *red; // device: {sum, cnt, max} of the last reduction (all ranks)
 	bool grid_valid, boundary_ready, lists_valid;
+	cudaGraphExec_t step_graph;   // whole-step CUDA graph of the loop-free solvers (sph_api.cu: step_graph_launch)
+	cudaStream_t graph_stream;
+	int step_graph_launches;
 	cudaStream_t copy_stream;  // deferred velocity upload (sph_upload_state_xyz)
 	cudaEvent_t ev_vel_ready, ev_mark;
 	bool vel_in_flight;        // a velocity upload is on the copy stream: h->vel is not complete yet
