@@ -69,8 +69,9 @@ typedef struct SphConfig {
 	                             neighbour sets, results within 1e-5) */
 	int32_t n_ghost_capacity; /* multi-GPU: room for ghost fluid particles after the owned ones */
 	double rigid_rho;         /* solid.rho_0 */
-	int32_t use_graph;        /* reserved, must be 0: the solver loops are stream-ordered launches gated by device
-	                             flags (one host look per step); CUDA-graph capture is not implemented */
+	int32_t use_graph;        /* reserved, must be 0.  The solver loops are stream-ordered launches gated by device
+	                             flags; the loop-free solvers (WCSPH, PBF) replay a whole step as one CUDA graph on
+	                             their own (one GPU, captured at the first sph_step; SPH_NO_GRAPH=1 disables it) */
 	int32_t reserved;
 } SphConfig;
 
