@@ -143,3 +143,39 @@ def test_ply_and_obj_writers(tmp_path):
     assert np.allclose(np.loadtxt(lines[11:]), np.concatenate([pos, rgba], axis=1), atol=1e-6)
     app.write_obj(str(tmp_path / "a.obj"), pos, np.array([[0, 1, 0]]))
     assert (tmp_path / "a.obj").read_text().splitlines() == ["v 0.100000 0.200000 0.300000", "v 1.000000 2.000000 3.000000", "f 1 2 1"]
+
+
+def test_selfcheck_relinf_and_error_bits():
+    """The comparison helper of the parity harness and the decoding of the device error flags (no GPU needed)."""
+    import numpy as np
+    import torch
+    from cfd_taichi_b200 import _lib, selfcheck
+    assert selfcheck.relinf([], []) == 0.0
+    assert selfcheck.relinf([1.0, np.nan, 2.0], [1.0, np.nan, 2.0]) == 0.0            # equal garbage is no difference
+    assert abs(selfcheck.relinf([1.0, 2.00002], [1.0, 2.0]) - 1e-5) < 1e-9
+    assert selfcheck.relinf([np.nan], [1.0]) == float("inf")                          # a NaN where the reference has a number
+    assert selfcheck.relinf(torch.tensor([1.0, 2.0]), np.array([1.0, 2.5])) == 0.2    # tensors and arrays mix
+    assert selfcheck.relinf([1.0], [1.1], scale=10.0) == pytest.approx(0.01)
+    err = {"a": {"x": 1e-7, "~info": {"x (vs current max)": 3e-3}}, "b": {"y": 2e-6}}
+    assert selfcheck.worst(err) == (2e-6, "b / y")                                    # informational entries do not count
+    assert _lib.decode_error_flags(0) == []
+    msgs = _lib.decode_error_flags(2 | 32 | 64)
+    assert len(msgs) == 3 and "max_neighbors" in msgs[0] and "peer" in msgs[1] and "bounds" in msgs[2]
+
+
+def test_reference_golden_script_names_existing_scene_files():
+    """tests/golden/make_reference_golden.py cannot run here (no taichi); at least its scene list must be real."""
+    import importlib.util
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not present")
+    spec = importlib.util.spec_from_file_location("mrg", os.path.join(ROOT, "tests", "golden", "make_reference_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for name, rel, solver in mod.CASES:
+        assert os.path.exists(os.path.join(ref, rel)), rel
+        assert solver in (None, "wcsph", "pcisph", "iisph", "dfsph")
+    for solver, fields in mod.SOLVER_FIELDS.items():
+        src = open(os.path.join(ref, solver + "_solver.py")).read() + open(os.path.join(ref, "solver_base.py")).read()
+        for f in fields:
+            assert "self.%s" % f in src, "%s_solver has no field %s" % (solver, f)
