@@ -56,3 +56,80 @@ def test_native_sources_use_the_references_loop_constants():
     assert "self.omega = 0.5" in ii
     for lit in ("0.9999", "15", "80", "180"):
         assert lit in orc
+
+
+# ---- the reference's own HOST code, executed ------------------------------------------------------------------
+# ParticleSystem.__init__ derives the particle count, the boundary particle count and the grid size in Python scope
+# (PS:78-102, 129-137) before any Taichi kernel runs.  Those statements are extracted from the reference's source with
+# `ast`, executed unmodified against a minimal stand-in for the Python-scope `ti.Vector` (a list of Python floats with
+# .x/.y/.z, -, / and to_numpy) and compared with scene.derive_sizes -- the numbers every array of the CUDA path is
+# sized with -- for every shipped scene and every synthetic BASELINE block.  This IS reference output, for the sizes.
+class _Vec:
+    def __init__(self, v):
+        self.v = list(v)
+    x = property(lambda s: s.v[0]); y = property(lambda s: s.v[1]); z = property(lambda s: s.v[2])
+    def __sub__(self, o): return _Vec([a - b for a, b in zip(self.v, o.v)])
+    def __truediv__(self, k): return _Vec([a / k for a in self.v])
+    def __mul__(self, k): return _Vec([a * k for a in self.v])
+    def __getitem__(self, i): return self.v[i]
+    def to_numpy(self):
+        import numpy as np
+        return np.array(self.v)
+
+
+def _reference_sizes(config):
+    import ast
+    import math
+    import types
+    import numpy as np
+    tree = ast.parse(open(os.path.join(REF, "ParticleSystem.py")).read())
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "ParticleSystem"][0]
+    init = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "__init__"][0]
+    count = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "compute_boundary_particles_count"][0]
+    want = {"water_size", "start_pos", "particle_radius", "particle_diameter", "support_radius", "particle_m", "particle_num",
+            "box_max", "box_min", "boundary_particles_num", "grid_num"}
+    keep = []
+    for st in init.body:
+        if isinstance(st, ast.Assign) and len(st.targets) == 1:
+            t = st.targets[0]
+            if isinstance(t, ast.Attribute) and isinstance(t.value, ast.Name) and t.value.id == "self" and t.attr in want:
+                keep.append(st)
+            elif isinstance(t, ast.Name) and t.id in ("scene_config", "solver_config", "fluid_config", "solid_config", "grid_num_np"):
+                keep.append(st)
+    assert {s.targets[0].attr for s in keep if isinstance(s.targets[0], ast.Attribute)} == want
+    fn = ast.FunctionDef(name="derive", args=init.args, body=keep, decorator_list=[], returns=None, type_comment=None, type_params=[])
+    count.decorator_list = []
+    mod = ast.Module(body=[count, fn], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ti = types.SimpleNamespace(Vector=_Vec, ceil=math.ceil, math=types.SimpleNamespace(pi=math.pi))
+    ns = {"ti": ti, "np": np}
+    exec(compile(mod, "<reference ParticleSystem.__init__ (sizes)>", "exec"), ns)
+    self = types.SimpleNamespace()
+    self.compute_boundary_particles_count = lambda: ns["compute_boundary_particles_count"](self)
+    ns["derive"](self, config)
+    return self.particle_num, self.boundary_particles_num, tuple(int(g) for g in self.grid_num.v), self.particle_m
+
+
+def test_derived_sizes_are_the_references_own_host_code():
+    import json
+    from cfd_taichi_b200 import scene, scenes
+    cases = []
+    for dirpath in (REF, os.path.join(REF, "config")):
+        for f in sorted(os.listdir(dirpath)):
+            if f.endswith(".json"):
+                with open(os.path.join(dirpath, f)) as fh:
+                    cases.append((f, json.load(fh)))             # the reference's own scene files
+    for n_side, gx in ((100, 1), (160, 1), (200, 1), (200, 8)):      # BASELINE.json's synthetic blocks
+        cases.append(("synthetic %d^3 x %d" % (n_side, gx), scenes.breaking_dam(n_side, gpus_x=gx)))
+    assert len(cases) >= 12
+    for name, cfg in cases:
+        pn, bn, grid, m = _reference_sizes(cfg)
+        assert scene.derive_sizes(cfg) == (pn, bn, grid), name
+        assert m == 1000 * (cfg["scene"]["particle_radius"] ** 3) * 8
+    # and the shipped copies of those scene files describe the same scenes
+    for f in ("default.json",) + tuple("config/" + x for x in sorted(os.listdir(os.path.join(REF, "config"))) if x.endswith(".json")):
+        mine = os.path.join(ROOT, f)
+        if os.path.exists(mine):
+            a, b = json.load(open(mine)), json.load(open(os.path.join(REF, f)))
+            assert scene.derive_sizes(a) == scene.derive_sizes(b), f
+            assert a["solver"]["name"] == b["solver"]["name"] and a["solver"]["delta_time"] == b["solver"]["delta_time"], f
