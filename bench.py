@@ -184,7 +184,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -196,6 +196,15 @@ ALG_BYTES = {"grid": 84, "lists": 20, "df_warm_start": 48, "df_drho": 28, "df_di
 STEP_BYTES = {"dfsph": lambda st: 268 + 84 * st.div_iters + 80 * st.den_iters, "wcsph": lambda st: 200,
               "pcisph": lambda st: 300 + 128 * st.pc_iters, "iisph": lambda st: 304 + 92 * st.ii_iters}
 STEP_FORMULA = {"dfsph": "268 + 84 D + 80 C", "wcsph": "200", "pcisph": "300 + 128 I", "iisph": "304 + 92 I"}
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def quiet(f, *a, **k):
@@ -612,14 +621,20 @@ def run_ours(args):
                 line["parity"] = parity
         if also:
             line["also"] = also
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    global _JSON_OUT
     args = parse()
+    # the contract is ONE JSON line on stdout: whatever a library writes to file descriptor 1 meanwhile (NCCL's version banner
+    # at N > 1, constructor prints) is sent to stderr, and the line itself goes to the saved descriptor
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

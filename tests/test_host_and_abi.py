@@ -179,3 +179,24 @@ def test_reference_golden_script_names_existing_scene_files():
         src = open(os.path.join(ref, solver + "_solver.py")).read() + open(os.path.join(ref, "solver_base.py")).read()
         for f in fields:
             assert "self.%s" % f in src, "%s_solver has no field %s" % (solver, f)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """The bench contract, on the arm that runs without a GPU: stdout is ONE JSON line (anything a library writes to file
+    descriptor 1 goes to stderr), carrying the base keys plus `impl`, `cpu_baseline` and a zero-copy `e2e`."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--cpu-n-side", "12"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "dfsph_particle_steps_per_sec" and d["unit"] == "particle-steps/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # rank != 0 under torchrun: exits 0 without work and without output
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                       text=True, timeout=120, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert r.returncode == 0 and r.stdout == ""
