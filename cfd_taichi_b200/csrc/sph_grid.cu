@@ -481,7 +481,7 @@ extern "C" int sph_init_fluid_lattice(const SphLattice *lat, long long particle_
 	double d = lat->particle_radius * 2;
 	double x_num_d = lat->water_size[0] / d, z_num_d = lat->water_size[2] / d;
 	k_init_fluid_lattice<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-	    particle_num_total, dev_ids, (long long)n, (float)x_num_d, (float)z_num_d, (float)(x_num_d * z_num_d),
+	    particle_num_total, dev_ids, (long long)n, (float)x_num_d, (float)z_num_d, (float)x_num_d * (float)z_num_d, // PS:145: f32 locals
 	    (int)llround(x_num_d), (int)llround(z_num_d), (float)lat->particle_radius, (float)lat->start_pos[0],
 	    (float)lat->start_pos[1], (float)lat->start_pos[2], (float4 *)dev_pos4);
 	return cudaGetLastError() == cudaSuccess ? SPH_OK : SPH_ECUDA;
@@ -493,8 +493,12 @@ extern "C" int sph_init_boundary_shell(const SphLattice *lat, size_t nb, void *d
 	if (!dev_bpos4) return SPH_EINVAL;
 	if (cudaSetDevice(device) != cudaSuccess) return SPH_ECUDA;
 	double dd = lat->particle_radius * 2;
-	long long x_cnt = (long long)((lat->box_max[0] - lat->box_min[0]) / dd + 1); // PS:157-158
-	long long z_cnt = (long long)((lat->box_max[2] - lat->box_min[2]) / dd + 1);
+	// PS:155-158: `box` is bound to a kernel local, i.e. an f32 vector, so the two counts are f32 arithmetic in the kernel
+	// although compute_boundary_particles_count (PS:129-137, host, fp64) sized the array; they disagree for some boxes
+	// (5.2 / 0.05: 105 on the host, 104 here) and the reference lays its shell out with THESE counts (quirk B-18)
+	const float df = (float)dd;
+	long long x_cnt = (long long)((float)(lat->box_max[0] - lat->box_min[0]) / df + 1.0f);
+	long long z_cnt = (long long)((float)(lat->box_max[2] - lat->box_min[2]) / df + 1.0f);
 	long long bottom = x_cnt * z_cnt, one_round = x_cnt * z_cnt - (x_cnt - 2) * (z_cnt - 2);
 	k_init_boundary_shell<<<(unsigned)((nb + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
 	    (long long)nb, x_cnt, z_cnt, bottom, one_round, (float)dd, (float)lat->box_max[1], (float4 *)dev_bpos4);

@@ -42,11 +42,11 @@ def init_fluid_positions(config, particle_num, ids=None):
     ws, sp = fluid["water_size"], fluid["start_pos"]
     x_num_d = ws[0] / d
     z_num_d = ws[2] / d
-    xz_num_d = x_num_d * z_num_d
     n = particle_num
     if n < (1 << 24):
         fi = (np.arange(n, dtype=np.int32) if ids is None else np.asarray(ids, dtype=np.int32)).astype(F32)
-        x_num, z_num, xz_num = F32(x_num_d), F32(z_num_d), F32(xz_num_d)
+        x_num, z_num = F32(x_num_d), F32(z_num_d)
+        xz_num = x_num * z_num                                     # PS:145: a product of two f32 kernel locals
         x = fi - x_num * np.floor(fi / x_num)                      # PS:147  i % x_num (float mod)
         t = np.floor(fi / x_num)
         z = t - z_num * np.floor(t / z_num)                        # PS:148
@@ -73,8 +73,9 @@ def init_boundary_positions(config, boundary_num):
     dd = r * 2
     box_x = scene["box_max"][0] - scene["box_min"][0]
     box_z = scene["box_max"][2] - scene["box_min"][2]
-    x_cnt = int(box_x / dd + 1)
-    z_cnt = int(box_z / dd + 1)
+    # PS:155-158: `box` is a kernel local (f32), so these two counts are f32 arithmetic, unlike derive_sizes (host, fp64)
+    x_cnt = int(F32(box_x) / F32(dd) + F32(1))
+    z_cnt = int(F32(box_z) / F32(dd) + F32(1))
     xr, zr = x_cnt - 1, z_cnt - 1
     bottom = x_cnt * z_cnt
     one_round = x_cnt * z_cnt - (x_cnt - 2) * (z_cnt - 2)

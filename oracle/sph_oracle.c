@@ -457,8 +457,7 @@ static void init_particle_pos(OrcSim *s) {
 	/* PS:143-145: Python-scope fp64, cast to f32 when meeting the i32->f32 loop index */
 	double x_num_d = c->water_size[0] / s->d_d;
 	double z_num_d = c->water_size[2] / s->d_d;
-	double xz_num_d = x_num_d * z_num_d;
-	float x_num = (float)x_num_d, z_num = (float)z_num_d, xz_num = (float)xz_num_d;
+	float x_num = (float)x_num_d, z_num = (float)z_num_d, xz_num = x_num * z_num; /* PS:145: product of two f32 locals */
 	float sx = (float)c->start_pos[0], sy = (float)c->start_pos[1], sz = (float)c->start_pos[2];
 	float rad = (float)s->r_d;
 	long long xi_num = llround(x_num_d), zi_num = llround(z_num_d);
@@ -483,10 +482,14 @@ static void init_particle_pos(OrcSim *s) {
 		s->pos[3 * i + 2] = ((z * rad) * 2.0f) + sz;
 	}
 	/* PS:155-195 boundary shell */
-	double bx = c->box_max[0] - c->box_min[0];
-	double bz = c->box_max[2] - c->box_min[2];
-	int x_cnt = (int)(bx / s->d_d + 1);
-	int z_cnt = (int)(bz / s->d_d + 1);
+	/* PS:155-158: `box = (box_max - box_min)` is a Python-scope (fp64) subtraction, but binding it to a kernel local makes
+	 * it an f32 vector, so x_cnt / z_cnt are f32 arithmetic HERE while compute_boundary_particles_count (PS:129-137, host,
+	 * fp64) sized the array: the two disagree for some boxes (5.2 / 0.05: 105 on the host, 104 in the kernel), and the
+	 * reference then lays its shell out with the kernel's counts over the host's particle count (quirk B-18). */
+	float bxf = (float)(c->box_max[0] - c->box_min[0]);
+	float bzf = (float)(c->box_max[2] - c->box_min[2]);
+	int x_cnt = (int)(bxf / s->d + 1.0f);
+	int z_cnt = (int)(bzf / s->d + 1.0f);
 	int x_cnt_round = x_cnt - 1;
 	int z_cnt_round = z_cnt - 1;
 	int bottom = x_cnt * z_cnt;

@@ -7,9 +7,15 @@
  * canonical neighbour order = ti.cpu with cpu_max_num_threads=1 (27 cells in (dx,dy,dz)
  * lexicographic order with dz fastest, ascending global particle index inside a cell).
  *
- * PARITY UNPINNED: the reference has no tests or golden vectors and taichi==1.6.0 cannot be
- * imported in this image, so this oracle is pinned only by hand-derived known-answer checks
- * (tests/test_oracle_*.py), not by outputs of the reference itself.
+ * PARITY UNPINNED for the compiled reference: it has no tests or golden vectors and taichi==1.6.0
+ * cannot be imported in this image.  What IS pinned: the reference's own solver sources, imported
+ * unmodified from /root/reference and EXECUTED under a stand-in for the Taichi front end
+ * (tests/golden/ti_shim, Taichi's scalar rules as read in SURVEY.md appendix A), give the
+ * fixtures tests/golden/refshim_*.npz, which this oracle reproduces bit for bit -- every solver
+ * array after every step, iteration counts and printed residuals (tests/test_reference_shim.py).
+ * That pins the transcription (statements, operand order, loop structure, constants, quirks);
+ * Taichi's own code generation stays this repository's reading, hence the first two words.
+ * Hand-derived known-answer checks: tests/test_oracle_*.py.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  The product (cfd_taichi_b200/) never does.

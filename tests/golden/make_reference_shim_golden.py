@@ -1,0 +1,153 @@
+"""Golden vectors from the reference's OWN solver sources, executed here.
+
+Taichi cannot be installed in this container (no wheel, no network), so the reference cannot run as it is.  Its
+solver sources, however, are plain Python once `import taichi` resolves: tests/golden/ti_shim/taichi is a stand-in that
+rewrites every `@ti.kernel` / `@ti.func` the way Taichi's front end does and runs it with Taichi's scalar rules
+(binary32 / int32 runtime values, compile-time Python constants, declared local types, by-reference template arguments,
+array-of-structures fields, dynamic cell lists; see its docstring).  This script imports the UNMODIFIED files from
+/root/reference (ParticleSystem.py, solver_base.py, <name>_solver.py), builds small scenes through the reference's own
+constructors, sets a seeded perturbed state through the reference's own `from_numpy`, calls the reference's own `step()`
+and writes the state after every step to tests/golden/refshim_<case>.npz.
+
+    python tests/golden/make_reference_shim_golden.py            # every case (minutes: pure Python)
+    python tests/golden/make_reference_shim_golden.py wcsph_block --out /tmp/x.npz
+
+tests/test_reference_shim.py holds the oracle (and, with -m gpu, the strict CUDA path) to these files bit for bit.  What the files
+pin: the oracle's transcription of the reference's statements, operand order, loop structure, constants and quirks.
+What they cannot pin: Taichi's own code generation (SURVEY.md appendix A is still this repository's reading of it), which
+is why the oracle's header keeps the words "parity unpinned" for the compiled reference.
+"""
+import contextlib
+import io
+import json
+import os
+import re
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("SPH_REFERENCE_DIR", "/root/reference")
+
+
+def block_scene(solver, dt, water=(0.35, 0.4, 0.35), box=(0.7, 0.8, 0.7), boundary_handle=True):
+    return {"scene": {"box_min": [0.0, 0.0, 0.0], "box_max": list(box), "particle_radius": 0.025, "gravity": 9.8},
+            "fluid": {"start_pos": [0.15, 0.1, 0.15], "water_size": list(water)},
+            "solver": {"name": solver, "delta_time": dt, "iter_cnt": 1, "boundary_handle": boundary_handle}}
+
+
+# name -> (config, steps, perturbation or None); perturbation = (seed, position jitter in particle diameters, velocity scale,
+# compression of the block about its centre: the rest lattice has density 682 < rho_0 (quirk B-3), so without compression no
+# pressure solver would iterate)
+CASES = {
+    "wcsph_block": (block_scene("wcsph", 2.5e-4), 3, (11, 0.18, 1.5, 0.85)),
+    "dfsph_block": (block_scene("dfsph", 1e-3), 2, (12, 0.18, 0.3, 0.85)),
+    "dfsph_lattice": (block_scene("dfsph", 1e-3, water=(0.3, 0.3, 0.3)), 2, None),
+    "dfsph_clamp": (block_scene("dfsph", 1e-3, water=(0.3, 0.3, 0.3), boundary_handle=False), 2, (13, 0.18, 2.5, 1.0)),
+    "pcisph_block": (block_scene("pcisph", 1.5e-4, water=(0.3, 0.3, 0.3)), 2, (14, 0.1, 0.5, 0.86)),
+    "iisph_block": (block_scene("iisph", 2.5e-4, water=(0.3, 0.3, 0.3)), 2, (15, 0.1, 0.5, 0.86)),
+    "wcsph_clamp": (block_scene("wcsph", 2.5e-4, water=(0.3, 0.3, 0.3), boundary_handle=False), 2, (16, 0.18, 2.5, 1.0)),
+    # seconds, not minutes: the case tests/test_reference_shim.py re-runs from /root/reference on every CPU test run
+    "wcsph_tiny": (block_scene("wcsph", 2.5e-4, water=(0.2, 0.25, 0.2), box=(0.5, 0.5, 0.5)), 2, (17, 0.18, 1.5, 0.85)),
+}
+
+FIELDS = {
+    "wcsph": ["rho", "pressure", "pressure_gradient", "boundary_acc", "viscosity", "tension"],
+    "dfsph": ["rho", "alpha", "rho_adv", "rho_derivative", "vel_adv", "vel_adv_delta", "force_ext", "warm_start_k", "viscosity",
+              "tension"],
+    "pcisph": ["rho", "pos_predict", "vel_predict", "ext_force", "press_force", "rho_predict", "rho_err", "press_iter",
+               "viscosity", "tension"],
+    "iisph": ["rho", "v_adv", "f_adv", "d_ii", "a_ii", "d_ij", "rho_adv", "p_iter", "p_past", "r_sum", "f_press", "viscosity",
+              "tension"],
+}
+
+LOG_PATTERNS = {
+    "df_div": re.compile(r"\[divergence iteration\] count: (\S+), first error (\S+), error (\S+)"),
+    "df_den": re.compile(r"\[density iteration\] count: (\S+), error (\S+)"),
+    "pc": re.compile(r"\t\tIter cnt: (\S+), error: (\S+)"),
+    "ii": re.compile(r"Iter cnt:  (\S+) (\S+)"),
+}
+
+
+def perturbed_state(lattice, seed, jitter, vscale, compress, diameter=0.05):
+    rng = np.random.default_rng(seed)
+    n = lattice.shape[0]
+    centre = lattice.astype(np.float64).mean(axis=0)
+    pos = centre + (lattice.astype(np.float64) - centre) * compress + rng.uniform(-jitter, jitter, size=(n, 3)) * diameter
+    vel = rng.standard_normal(size=(n, 3)) * vscale
+    return pos.astype(np.float32), vel.astype(np.float32)
+
+
+def run_case(name):
+    cfg, steps, pert = CASES[name]
+    solver = cfg["solver"]["name"]
+    for m in ("taichi", "trimesh", "ParticleSystem", "solver_base", solver + "_solver"):
+        sys.modules.pop(m, None)
+    sys.path[:0] = [os.path.join(HERE, "ti_shim"), REF]
+    try:
+        import importlib
+        ps_mod = importlib.import_module("ParticleSystem")
+        assert os.path.dirname(os.path.abspath(ps_mod.__file__)) == os.path.abspath(REF), ps_mod.__file__
+        sol_mod = importlib.import_module(solver + "_solver")
+        assert os.path.dirname(os.path.abspath(sol_mod.__file__)) == os.path.abspath(REF), sol_mod.__file__
+    finally:
+        del sys.path[:2]
+    out = {"config_json": np.array(json.dumps(cfg)), "solver": np.array(solver), "steps": np.array(steps)}
+    log = io.StringIO()
+    t0 = time.time()
+    with contextlib.redirect_stdout(log):
+        ps = ps_mod.ParticleSystem(cfg)
+        sol = getattr(sol_mod, solver + "_solver")(ps, cfg)
+    n = ps.particle_num
+    out["particle_num"] = np.array(n)
+    out["boundary_particles_num"] = np.array(ps.boundary_particles_num)
+    out["grid_num"] = np.array(ps.grid_num.to_list(), dtype=np.int32)
+    out["boundary_pos"] = ps.boundary_particles.pos.to_numpy()
+    out["boundary_volume"] = ps.boundary_particles.volume.to_numpy()
+    out["lattice_pos"] = ps.fluid_particles.pos.to_numpy()
+    if solver == "pcisph":
+        out["pc_delta"] = np.array(sol.delta[None], dtype=np.float32)
+        out["pc_beta"] = np.array(sol.beta, dtype=np.float64)
+    if pert is not None:
+        pos0, vel = perturbed_state(out["lattice_pos"], *pert)
+        ps.fluid_particles.pos.from_numpy(pos0)
+        ps.fluid_particles.vel.from_numpy(vel)
+    out["pos0"] = ps.fluid_particles.pos.to_numpy()
+    out["vel0"] = ps.fluid_particles.vel.to_numpy()
+    for s in range(1, steps + 1):
+        log.seek(0)
+        log.truncate()
+        with contextlib.redirect_stdout(log):
+            sol.step()
+        text = log.getvalue()
+        out["pos_%d" % s] = ps.fluid_particles.pos.to_numpy()
+        out["vel_%d" % s] = ps.fluid_particles.vel.to_numpy()
+        out["cell3_%d" % s] = ps.fluid_particles.belong_grid.to_numpy()
+        for f in FIELDS[solver]:
+            out["%s_%d" % (f, s)] = getattr(sol, f).to_numpy()
+        out["delta_time_%d" % s] = np.array(sol.delta_time[None], dtype=np.float32)
+        for key, pat in LOG_PATTERNS.items():
+            m = pat.findall(text)
+            if m:
+                out["log_%s_%d" % (key, s)] = np.array([float(x) for x in m[-1]], dtype=np.float64)
+        sys.stderr.write("%s step %d: %.0f s  %s\n" % (name, s, time.time() - t0, " | ".join(
+            l.strip() for l in text.splitlines() if "iteration" in l or "Iter cnt" in l)))
+    return out
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    out_path = None
+    if "--out" in sys.argv:
+        out_path = sys.argv[sys.argv.index("--out") + 1]
+        args = [a for a in args if a != out_path]
+    for name in args or list(CASES):
+        res = run_case(name)
+        path = out_path or os.path.join(HERE, "refshim_%s.npz" % name)
+        np.savez_compressed(path, **res)
+        sys.stderr.write("wrote %s (%d bytes)\n" % (path, os.path.getsize(path)))
+
+
+if __name__ == "__main__":
+    main()

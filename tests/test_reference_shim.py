@@ -1,0 +1,150 @@
+"""The oracle (and, with -m gpu, the strict CUDA path) against the reference's OWN solver sources, executed.
+
+tests/golden/refshim_<case>.npz were written by tests/golden/make_reference_shim_golden.py: the unmodified
+ParticleSystem.py / solver_base.py / <name>_solver.py of the reference, imported from /root/reference and run under
+tests/golden/ti_shim/taichi (a stand-in for the Taichi front end with Taichi's scalar rules; its docstring lists them).
+Every array the reference's solver holds after each step() is compared BIT FOR BIT, together with the iteration counts and
+residuals the reference prints.  What this pins: the transcription (statements, operand order, loop structure, constants,
+quirks B-1 ... B-13).  What it cannot pin: Taichi's own code generation -- the stand-in follows SURVEY.md appendix A, the
+same reading the oracle follows -- so oracle/sph_oracle.h keeps the words "parity unpinned" for the compiled reference."""
+import importlib
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+CASES = sorted(f[len("refshim_"):-len(".npz")] for f in os.listdir(GOLD) if f.startswith("refshim_") and f.endswith(".npz"))
+
+sys.path.insert(0, GOLD)
+import make_reference_shim_golden as gen  # noqa: E402  (case table and field lists; importing it runs nothing)
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(bits(a), bits(b))
+
+
+def describe(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        return "shapes %s / %s" % (a.shape, b.shape)
+    d = np.abs(a - b)
+    k = int(np.argmax(d))
+    return "max |diff| %.3e at flat index %d (%r vs %r), %d of %d differ" % (d.max(), k, a.reshape(-1)[k], b.reshape(-1)[k],
+                                                                           int((d > 0).sum()), d.size)
+
+
+def load(case):
+    d = np.load(os.path.join(GOLD, "refshim_%s.npz" % case))
+    cfg = json.loads(str(d["config_json"]))
+    return d, cfg, str(d["solver"]), int(d["steps"])
+
+
+def test_the_committed_cases_are_the_generators_cases():
+    assert CASES == sorted(gen.CASES), "run tests/golden/make_reference_shim_golden.py (it needs /root/reference)"
+    for case in CASES:
+        d, cfg, solver, steps = load(case)
+        assert (cfg, steps) == (gen.CASES[case][0], gen.CASES[case][1]), case
+        # and the runs are not trivial: hundreds of particles, the pressure loops iterate
+        assert int(d["particle_num"]) >= 200 or case.endswith("_tiny"), case
+    d = load("dfsph_block")[0]
+    assert d["log_df_div_1"][0] >= 2 and d["log_df_den_1"][0] >= 2
+    assert load("pcisph_block")[0]["log_pc_1"][0] >= 2 and load("iisph_block")[0]["log_ii_1"][0] >= 2
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_reproduces_the_executed_reference_source(case):
+    from oracle import oracle as O
+    d, cfg, solver, steps = load(case)
+    o = O.Oracle(cfg, solver=solver, threads=1)
+    # construction: ParticleSystem.__init__ (sizes, lattice, boundary shell, Akinci volumes), solver __init__
+    assert int(o.scalar("particle_num")) == int(d["particle_num"])
+    assert int(o.scalar("boundary_particles_num")) == int(d["boundary_particles_num"])
+    assert [int(o.scalar("grid_" + a)) for a in "xyz"] == list(d["grid_num"])
+    assert same(o.field("pos"), d["lattice_pos"]), describe(o.field("pos"), d["lattice_pos"])
+    assert same(o.field("bpos"), d["boundary_pos"]), describe(o.field("bpos"), d["boundary_pos"])
+    assert same(o.field("bvol"), d["boundary_volume"]), describe(o.field("bvol"), d["boundary_volume"])
+    if solver == "pcisph":
+        assert np.float32(o.scalar("pc_delta")) == d["pc_delta"], (o.scalar("pc_delta"), d["pc_delta"])
+        assert o.scalar("pc_beta") == float(d["pc_beta"])
+    o.field("pos")[:] = d["pos0"]
+    o.field("vel")[:] = d["vel0"]
+    for s in range(1, steps + 1):
+        o.step(1, rigid=False)
+        for name in ["pos", "vel", "cell3"] + gen.FIELDS[solver]:
+            ref = d["%s_%d" % (name, s)]
+            got = o.field(name)
+            assert same(got, ref), "%s, step %d, %s: %s" % (case, s, name, describe(got, ref))
+        assert np.float32(o.scalar("delta_time")) == d["delta_time_%d" % s]
+        if solver == "dfsph":
+            cnt, first, err = d["log_df_div_%d" % s]
+            assert (int(o.scalar("df_div_iters")), np.float32(o.scalar("df_div_first_err")), np.float32(o.scalar("df_div_err"))) == (
+                int(cnt), np.float32(first), np.float32(err))
+            cnt, err = d["log_df_den_%d" % s]
+            assert int(o.scalar("df_den_iters")) == int(cnt)
+            assert np.float32(o.scalar("df_den_err")) == np.float32(err), (o.scalar("df_den_err"), err)
+        if solver == "pcisph":
+            cnt, err = d["log_pc_%d" % s]
+            assert (int(o.scalar("pc_iters")), np.float32(o.scalar("pc_err"))) == (int(cnt), np.float32(err))
+        if solver == "iisph":
+            cnt, res = d["log_ii_%d" % s]
+            assert (int(o.scalar("ii_iters")), np.float32(o.scalar("ii_residual"))) == (int(cnt), np.float32(res))
+    o.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES)
+def test_cuda_strict_reproduces_the_executed_reference_source(built, case):
+    """The same files against the product: strict kernels through the reference-named Python classes."""
+    import torch
+    from conftest import quiet_ps, quiet_solver
+    d, cfg, solver, steps = load(case)
+    ps = quiet_ps(cfg, strict=True, solver_name=solver)
+    cls = getattr(importlib.import_module("cfd_taichi_b200.%s_solver" % solver), "%s_solver" % solver)
+    sol = quiet_solver(cls, ps, cfg)
+    n = ps.particle_num
+    assert n == int(d["particle_num"]) and ps.boundary_particles_num == int(d["boundary_particles_num"])
+    assert same(ps.fluid_particles.pos.to_numpy(), d["lattice_pos"])
+    ps._pos4[:n, :3] = torch.from_numpy(d["pos0"]).to(ps._device)
+    ps._vel4[:n, :3] = torch.from_numpy(d["vel0"]).to(ps._device)
+    for s in range(1, steps + 1):
+        sol.step()
+        got = {"pos": ps.fluid_particles.pos.to_numpy(), "vel": ps.fluid_particles.vel.to_numpy(), "rho": sol.rho.to_numpy()}
+        for name, a in got.items():
+            ref = d["%s_%d" % (name, s)]
+            assert same(a, ref), "%s, step %d, %s: %s" % (case, s, name, describe(a, ref))
+        st = sol.stats()
+        assert np.float32(st.delta_time) == d["delta_time_%d" % s]
+        if solver == "dfsph":
+            assert (st.div_iters, st.den_iters) == (int(d["log_df_div_%d" % s][0]), int(d["log_df_den_%d" % s][0]))
+        if solver == "pcisph":
+            assert st.pc_iters == int(d["log_pc_%d" % s][0])
+        if solver == "iisph":
+            assert st.ii_iters == int(d["log_ii_%d" % s][0])
+        assert st.error_flags == 0
+    ps.close()
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference sources are not on this machine")
+def test_fixture_regenerates_from_the_reference_source(tmp_path):
+    """Re-run the smallest case from /root/reference now (a subprocess with a clean module table) and require the committed
+    file byte-equal array by array: the fixtures are what the generator produces from the reference as it lies there."""
+    out = tmp_path / "again.npz"
+    r = subprocess.run([sys.executable, os.path.join(GOLD, "make_reference_shim_golden.py"), "wcsph_tiny", "--out", str(out)],
+                       capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-3000:]
+    a, b = np.load(out), np.load(os.path.join(GOLD, "refshim_wcsph_tiny.npz"))
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert same(a[k], b[k]) or (a[k].dtype.kind == "U" and str(a[k]) == str(b[k])), k
