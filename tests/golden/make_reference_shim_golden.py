@@ -49,6 +49,10 @@ CASES = {
     "iisph_block": (block_scene("iisph", 2.5e-4, water=(0.3, 0.3, 0.3)), 2, (15, 0.1, 0.5, 0.86)),
     "wcsph_clamp": (block_scene("wcsph", 2.5e-4, water=(0.3, 0.3, 0.3), boundary_handle=False), 2, (16, 0.18, 2.5, 1.0)),
     # seconds, not minutes: the case tests/test_reference_shim.py re-runs from /root/reference on every CPU test run
+    # the reference's own shipped scene files, as they are, from the lattice start (5 879 fluid + 9 002 boundary particles:
+    # tens of minutes of pure Python per DFSPH step)
+    "shipped_wcsph": ("ref:config/wcsph_config_backup.json", 2, None),
+    "shipped_dfsph": ("ref:config/dfsph_config_backup.json", 1, None),
     "wcsph_tiny": (block_scene("wcsph", 2.5e-4, water=(0.2, 0.25, 0.2), box=(0.5, 0.5, 0.5)), 2, (17, 0.18, 1.5, 0.85)),
 }
 
@@ -81,6 +85,9 @@ def perturbed_state(lattice, seed, jitter, vscale, compress, diameter=0.05):
 
 def run_case(name):
     cfg, steps, pert = CASES[name]
+    if isinstance(cfg, str):
+        with open(os.path.join(REF, cfg[len("ref:"):])) as fh:
+            cfg = json.load(fh)
     solver = cfg["solver"]["name"]
     for m in ("taichi", "trimesh", "ParticleSystem", "solver_base", solver + "_solver"):
         sys.modules.pop(m, None)
