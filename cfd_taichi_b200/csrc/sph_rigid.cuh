@@ -22,12 +22,21 @@ __device__ inline void mat_mul(const float *A, const float *B, float *C) {
 		for (int j = 0; j < 3; ++j) T[3 * i + j] = (A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j]) + A[3 * i + 2] * B[6 + j];
 	for (int k = 0; k < 9; ++k) C[k] = T[k];
 }
+// Taichi's Matrix.inverse() for n = 3 (as restated in the oracle): 1 / determinant first, then the cofactor products
 __device__ inline void mat_inverse(const float *m, float *inv) {
-	float a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
-	float A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
-	float det = (a * A + b * B) + c * C;
-	float t[9] = {A, -(b * i - c * h), b * f - c * e, B, a * i - c * g, -(a * f - c * d), C, -(a * h - b * g), a * e - b * d};
-	for (int k = 0; k < 9; ++k) inv[k] = t[k] / det;
+#define MI_E(x, y) m[3 * ((x) % 3) + ((y) % 3)]
+	float det = (MI_E(0, 0) * (MI_E(1, 1) * MI_E(2, 2) - MI_E(2, 1) * MI_E(1, 2)) -
+	             MI_E(1, 0) * (MI_E(0, 1) * MI_E(2, 2) - MI_E(2, 1) * MI_E(0, 2))) +
+	            MI_E(2, 0) * (MI_E(0, 1) * MI_E(1, 2) - MI_E(1, 1) * MI_E(0, 2));
+	float inv_det = 1.0f / det;
+	float t[9];
+#pragma unroll
+	for (int i = 0; i < 3; ++i)
+#pragma unroll
+		for (int j = 0; j < 3; ++j)
+			t[3 * j + i] = inv_det * (MI_E(i + 1, j + 1) * MI_E(i + 2, j + 2) - MI_E(i + 2, j + 1) * MI_E(i + 1, j + 2));
+#undef MI_E
+	for (int k = 0; k < 9; ++k) inv[k] = t[k];
 }
 // ti.math.rotation3d as restated in the oracle.  sin / cos are evaluated in fp64
 // and rounded once so that they agree with a correctly rounded libm sinf / cosf.
@@ -324,7 +333,7 @@ k_rigid_step(SphConsts c, float4 *__restrict__ rpos, float4 *__restrict__ rvel, 
 		mat_mul(T, Rt, st->inertia_inv); // RS:141
 		// RS:40-46
 		f3 acc = force / st->mass + F3(c.gravity * 0.0f, c.gravity * -1.0f, c.gravity * 0.0f);
-		f3 vel = acc * dt + ld3(st->vel); // RS:43 (vel[0] == the uniform body velocity)
+		f3 vel = acc * dt + xyz(rvel[0]); // RS:43: the body velocity IS rigid_particles.vel[0] (a caller's vel.fill() sets it)
 		f3 disp = vel * dt;
 		st3(st->acc, acc);
 		st3(sv + 0, cen); st3(sv + 3, disp); st3(sv + 6, disp); st3(sv + 9, vel); st3(sv + 12, omega);

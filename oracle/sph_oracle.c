@@ -559,13 +559,20 @@ static void mat3_transpose(const float A[9], float T[9]) {
 	memcpy(T, t, sizeof(t));
 }
 static void mat3_inverse(const float m[9], float inv[9]) {
-	/* closed-form adjugate / determinant (ti.math.inverse for 3x3) */
-	float a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
-	float A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
-	float det = (a * A + b * B) + c * C;
-	float t[9] = {A, -(b * i - c * h), b * f - c * e, B, a * i - c * g, -(a * f - c * d),
-	              C, -(a * h - b * g), a * e - b * d};
-	for (int k = 0; k < 9; ++k) inv[k] = t[k] / det;
+	/* Taichi's Matrix.inverse() for n = 3 as recalled: inv_determinant = 1.0 / determinant() first,
+	 * then entries[j][i] = inv_determinant * (E(i+1,j+1) E(i+2,j+2) - E(i+2,j+1) E(i+1,j+2)) with E(x,y) = a(x % 3, y % 3);
+	 * determinant() = a00 (a11 a22 - a21 a12) - a10 (a01 a22 - a21 a02) + a20 (a01 a12 - a11 a02) */
+#define MI_E(x, y) m[3 * ((x) % 3) + ((y) % 3)]
+	float det = (MI_E(0, 0) * (MI_E(1, 1) * MI_E(2, 2) - MI_E(2, 1) * MI_E(1, 2)) -
+	             MI_E(1, 0) * (MI_E(0, 1) * MI_E(2, 2) - MI_E(2, 1) * MI_E(0, 2))) +
+	            MI_E(2, 0) * (MI_E(0, 1) * MI_E(1, 2) - MI_E(1, 1) * MI_E(0, 2));
+	float inv_det = 1.0f / det;
+	float t[9];
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j)
+			t[3 * j + i] = inv_det * (MI_E(i + 1, j + 1) * MI_E(i + 2, j + 2) - MI_E(i + 2, j + 1) * MI_E(i + 1, j + 2));
+#undef MI_E
+	memcpy(inv, t, sizeof(t));
 }
 
 /* PS:198-223 */

@@ -37,7 +37,15 @@ def block_scene(solver, dt, water=(0.35, 0.4, 0.35), box=(0.7, 0.8, 0.7), bounda
             "solver": {"name": solver, "delta_time": dt, "iter_cnt": 1, "boundary_handle": boundary_handle}}
 
 
-# name -> (config, steps, perturbation or None); perturbation = (seed, position jitter in particle diameters, velocity scale,
+def rigid_scene(solver, dt, pos_offset, attitude_deg, scale=0.4):
+    cfg = block_scene(solver, dt, water=(0.3, 0.3, 0.3), box=(0.8, 0.8, 0.8))
+    cfg["fluid"]["start_pos"] = [0.1, 0.1, 0.1]
+    cfg["solid"] = {"active": True, "attitude_offset": list(attitude_deg), "fill": True, "mesh": "./obj/cube1.STL",
+                    "pos_offset": list(pos_offset), "rho_0": 2000, "scale": scale, "voxel_radius": 0.025}
+    return cfg
+
+
+# name -> (config, steps, perturbation or None[, initial velocity of the rigid body]); perturbation = (seed, position jitter in particle diameters, velocity scale,
 # compression of the block about its centre: the rest lattice has density 682 < rho_0 (quirk B-3), so without compression no
 # pressure solver would iterate)
 CASES = {
@@ -48,6 +56,13 @@ CASES = {
     "pcisph_block": (block_scene("pcisph", 1.5e-4, water=(0.3, 0.3, 0.3)), 2, (14, 0.1, 0.5, 0.86)),
     "iisph_block": (block_scene("iisph", 2.5e-4, water=(0.3, 0.3, 0.3)), 2, (15, 0.1, 0.5, 0.86)),
     "wcsph_clamp": (block_scene("wcsph", 2.5e-4, water=(0.3, 0.3, 0.3), boundary_handle=False), 2, (16, 0.18, 2.5, 1.0)),
+    # fluid-rigid coupling (ParticleSystem.py:198-307, rigid_solver.py, the material_solid branches of every sweep): a
+    # 0.32 x 0.2 x 0.4 box of 315 rigid particles 0.07 above the block, pushed sideways and down so that it meets the fluid
+    # and, in the second case, the floor (rigid_solver.kinematic's contact impulse)
+    # (140 rigid particles here: get_neighbour_count reads fluid_particles.pos[rigid-local index], quirk B-7, which is
+    # only defined while there are fewer rigid than fluid particles)
+    "dfsph_rigid": (rigid_scene("dfsph", 1e-3, [0.12, 0.36, 0.1], [0.0, 0.0, 0.0], scale=0.3), 3, (18, 0.1, 0.5, 0.82), [0.3, -2.0, 0.1]),
+    "wcsph_rigid_floor": (rigid_scene("wcsph", 2.5e-4, [0.42, 0.0512, 0.2], [0.0, 15.0, 0.0]), 4, (19, 0.1, 0.5, 0.9), [-0.5, -3.0, 0.2]),
     # seconds, not minutes: the case tests/test_reference_shim.py re-runs from /root/reference on every CPU test run
     # the reference's own shipped scene files, as they are, from the lattice start (5 879 fluid + 9 002 boundary particles:
     # tens of minutes of pure Python per DFSPH step)
@@ -84,12 +99,13 @@ def perturbed_state(lattice, seed, jitter, vscale, compress, diameter=0.05):
 
 
 def run_case(name):
-    cfg, steps, pert = CASES[name]
+    cfg, steps, pert = CASES[name][:3]
+    rigid_vel = CASES[name][3] if len(CASES[name]) > 3 else None
     if isinstance(cfg, str):
         with open(os.path.join(REF, cfg[len("ref:"):])) as fh:
             cfg = json.load(fh)
     solver = cfg["solver"]["name"]
-    for m in ("taichi", "trimesh", "ParticleSystem", "solver_base", solver + "_solver"):
+    for m in ("taichi", "trimesh", "ParticleSystem", "solver_base", "rigid_solver", solver + "_solver"):
         sys.modules.pop(m, None)
     sys.path[:0] = [os.path.join(HERE, "ti_shim"), REF]
     try:
@@ -98,14 +114,22 @@ def run_case(name):
         assert os.path.dirname(os.path.abspath(ps_mod.__file__)) == os.path.abspath(REF), ps_mod.__file__
         sol_mod = importlib.import_module(solver + "_solver")
         assert os.path.dirname(os.path.abspath(sol_mod.__file__)) == os.path.abspath(REF), sol_mod.__file__
+        rig_mod = importlib.import_module("rigid_solver") if "solid" in cfg else None
+        ti = importlib.import_module("taichi")
     finally:
         del sys.path[:2]
     out = {"config_json": np.array(json.dumps(cfg)), "solver": np.array(solver), "steps": np.array(steps)}
     log = io.StringIO()
     t0 = time.time()
-    with contextlib.redirect_stdout(log):
-        ps = ps_mod.ParticleSystem(cfg)
-        sol = getattr(sol_mod, solver + "_solver")(ps, cfg)
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(os.path.dirname(HERE)))          # "./obj/cube1.STL" (ParticleSystem.py:42 loads it relative to cwd)
+    try:
+        with contextlib.redirect_stdout(log):
+            ps = ps_mod.ParticleSystem(cfg)
+            sol = getattr(sol_mod, solver + "_solver")(ps, cfg)
+            rig = rig_mod.rigid_solver(ps, cfg) if rig_mod else None
+    finally:
+        os.chdir(cwd)
     n = ps.particle_num
     out["particle_num"] = np.array(n)
     out["boundary_particles_num"] = np.array(ps.boundary_particles_num)
@@ -122,11 +146,31 @@ def run_case(name):
         ps.fluid_particles.vel.from_numpy(vel)
     out["pos0"] = ps.fluid_particles.pos.to_numpy()
     out["vel0"] = ps.fluid_particles.vel.to_numpy()
+
+    def rigid_state(tag):
+        rp = ps.rigid_particles
+        for f in ("pos", "vel", "acc", "force", "omega", "alpha", "volume", "mass"):
+            out["rigid_%s_%s" % (f, tag)] = getattr(rp, f).to_numpy()
+        out["rigid_centroid_%s" % tag] = ps.rigid_centriod.to_numpy().reshape(3)
+        out["rigid_inertia_inv_%s" % tag] = ps.rigid_inertia_tensor_inv.to_numpy().reshape(9)
+        out["rigid_vertices_%s" % tag] = ps.rigid_vertices.to_numpy()
+    if rig is not None:
+        out["rigid_inertia"] = ps.rigid_inertia_tensor.to_numpy().reshape(9)
+        if rigid_vel is not None:
+            ps.rigid_particles.vel.fill(ti.Vector(rigid_vel))
+        rigid_state("0")
     for s in range(1, steps + 1):
         log.seek(0)
         log.truncate()
         with contextlib.redirect_stdout(log):
             sol.step()
+            if rig is not None:                       # main.py:166-171: the fluid sub-steps, then the rigid ones
+                out["rigid_force_fluid_%d" % s] = ps.rigid_particles.force.to_numpy()
+                rig.step()
+                rigid_state(str(s))
+                out["rs_omega_%d" % s] = rig.omega.to_numpy().reshape(3)
+                out["rs_attitude_%d" % s] = rig.attitude.to_numpy().reshape(3)
+                out["rs_dt_%d" % s] = np.array(rig.delta_time[None], dtype=np.float32)
         text = log.getvalue()
         out["pos_%d" % s] = ps.fluid_particles.pos.to_numpy()
         out["vel_%d" % s] = ps.fluid_particles.vel.to_numpy()

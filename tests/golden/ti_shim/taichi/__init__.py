@@ -1,5 +1,5 @@
 """A stand-in for the `taichi` package, just large enough to EXECUTE the reference's own solver sources
-(ParticleSystem.py, solver_base.py, dfsph/wcsph/pcisph/iisph_solver.py) on the CPU, unmodified, where Taichi itself
+(ParticleSystem.py, solver_base.py, dfsph/wcsph/pcisph/iisph_solver.py, rigid_solver.py) on the CPU, unmodified, where Taichi itself
 cannot be installed (no wheel for this interpreter, no network).  TEST INFRASTRUCTURE: used only by
 tests/golden/make_reference_shim_golden.py (which writes the committed fixtures) and by the CPU test that re-runs a
 small case when /root/reference is present.  Nothing in the product imports it.
@@ -22,6 +22,8 @@ value classes that carry Taichi's arithmetic:
   * top-level loops run in ascending order on one thread (the reference's own cpu_max_num_threads=1 order), `+=` on a
     kernel local from inside a loop is the sequential sum, ti.atomic_max / atomic_min return the OLD value (A-8).
   * dynamic SNodes are per-cell Python lists: append order = arrival order, deactivate() empties the cell (A-9).
+  * matrices (rigid body): products accumulate left to right; inverse / determinant / ti.math.rotation3d are Taichi's
+    closed forms as recalled (A-6, A-11: the two items of the appendix that cannot be checked offline).
 
 What it is NOT: Taichi.  Every rule above is this repository's reading of Taichi 1.6; the
 reference's own statements, loop structure, operand order, constants and quirks, however, are executed as written,
@@ -60,7 +62,7 @@ def _dt(x):
         return f32
     if x is int or x is i32:
         return i32
-    if isinstance(x, (_VecType, _DType)):
+    if isinstance(x, (_VecType, _MatType, _DType)):
         return x
     raise TypeError("shim: unsupported dtype %r" % (x,))
 
@@ -420,7 +422,7 @@ class Vector:
         else:
             entries = [_plain(a) if isinstance(a, np.generic) else a for a in arr]
         if any(isinstance(a, (list, tuple, Vector)) for a in entries):
-            raise NotImplementedError("shim: matrices are not supported (rigid-body scenes)")
+            raise TypeError("shim: nested lists make a ti.Matrix, not a ti.Vector")
         if _in_kernel():
             entries = _coerce_entries(entries)
         self.e = entries
@@ -436,10 +438,10 @@ class Vector:
         return _Field(_VecType(n, _dt(dtype)), shape)
 
     # element access
-    x = property(lambda s: s.e[0])
-    y = property(lambda s: s.e[1])
-    z = property(lambda s: s.e[2])
-    w = property(lambda s: s.e[3])
+    x = property(lambda s: s.e[0], lambda s, v: s.__setitem__(0, v))
+    y = property(lambda s: s.e[1], lambda s, v: s.__setitem__(1, v))
+    z = property(lambda s: s.e[2], lambda s, v: s.__setitem__(2, v))
+    w = property(lambda s: s.e[3], lambda s, v: s.__setitem__(3, v))
 
     def __len__(self):
         return len(self.e)
@@ -586,9 +588,146 @@ class _VecType:
 
 
 class Matrix:
+    """Small dense matrices (rigid_solver.py, ParticleSystem.py:198-295).  Products accumulate left to right:
+    c_ij = (a_i0 b_0j + a_i1 b_1j) + a_i2 b_2j; inverse / determinant are the closed forms of Taichi's matrix.py as recalled
+    (1 / det first, then cofactor products) -- like rotation3d below, unverifiable here."""
+    __slots__ = ("r",)
+
+    def __init__(self, rows):
+        rows = [list(r.e) if isinstance(r, Vector) else list(r) for r in rows]
+        if _in_kernel():
+            flat = _coerce_entries([x for r in rows for x in r])
+            m = len(rows[0])
+            rows = [flat[k * m:(k + 1) * m] for k in range(len(rows))]
+        self.r = rows
+
+    @staticmethod
+    def _mk(rows):
+        a = Matrix.__new__(Matrix)
+        a.r = rows
+        return a
+
     @staticmethod
     def identity(dt, n):
-        raise NotImplementedError("shim: matrices are not supported (rigid-body scenes)")
+        one, zero = (F32(1.0), F32(0.0)) if _in_kernel() else (1.0, 0.0)
+        return Matrix._mk([[one if a == b else zero for b in range(n)] for a in range(n)])
+
+    n = property(lambda s: len(s.r))
+    m = property(lambda s: len(s.r[0]))
+
+    def __getitem__(self, ij):
+        return self.r[int(ij[0])][int(ij[1])]
+
+    def __setitem__(self, ij, v):
+        old = self.r[int(ij[0])][int(ij[1])]
+        self.r[int(ij[0])][int(ij[1])] = _cast_like(old, v) if _is_rt(old) else v
+
+    def _zip(self, o, f, swap=False):
+        if isinstance(o, Matrix):
+            return Matrix._mk([[f(b, a) if swap else f(a, b) for a, b in zip(ra, rb)] for ra, rb in zip(self.r, o.r)])
+        if isinstance(o, Vector):
+            raise TypeError("shim: matrix (op) vector")
+        return Matrix._mk([[f(o, a) if swap else f(a, o) for a in ra] for ra in self.r])
+
+    def __add__(self, o):
+        return self._zip(o, lambda a, b: a + b)
+
+    def __radd__(self, o):
+        return self._zip(o, lambda a, b: a + b, swap=True)
+
+    def __sub__(self, o):
+        return self._zip(o, lambda a, b: a - b)
+
+    def __rsub__(self, o):
+        return self._zip(o, lambda a, b: a - b, swap=True)
+
+    def __mul__(self, o):
+        return self._zip(o, lambda a, b: a * b)
+
+    def __rmul__(self, o):
+        return self._zip(o, lambda a, b: a * b, swap=True)
+
+    def __truediv__(self, o):
+        return self._zip(o, lambda a, b: a / b)
+
+    def __neg__(self):
+        return Matrix._mk([[-a for a in ra] for ra in self.r])
+
+    def __matmul__(self, o):
+        if isinstance(o, Vector):
+            out = []
+            for ra in self.r:
+                acc = ra[0] * o.e[0]
+                for k_ in range(1, len(ra)):
+                    acc = acc + ra[k_] * o.e[k_]
+                out.append(acc)
+            return Vector._mk(out)
+        rows = []
+        for ra in self.r:
+            row = []
+            for c in range(o.m):
+                acc = ra[0] * o.r[0][c]
+                for k_ in range(1, len(ra)):
+                    acc = acc + ra[k_] * o.r[k_][c]
+                row.append(acc)
+            rows.append(row)
+        return Matrix._mk(rows)
+
+    def transpose(self):
+        return Matrix._mk([[self.r[a][b] for a in range(self.n)] for b in range(self.m)])
+
+    def determinant(self):
+        a = self.r
+        if self.n != 3 or self.m != 3:
+            raise NotImplementedError("shim: determinant of a %dx%d matrix" % (self.n, self.m))
+        return (a[0][0] * (a[1][1] * a[2][2] - a[2][1] * a[1][2]) - a[1][0] * (a[0][1] * a[2][2] - a[2][1] * a[0][2])
+                + a[2][0] * (a[0][1] * a[1][2] - a[1][1] * a[0][2]))
+
+    def inverse(self):
+        if self.n != 3 or self.m != 3:
+            raise NotImplementedError("shim: inverse of a %dx%d matrix" % (self.n, self.m))
+        inv_det = _init(1.0 / self.determinant())
+        a = self.r
+
+        def E(x, y):
+            return a[x % 3][y % 3]
+        out = [[None] * 3 for _ in range(3)]
+        for i_ in range(3):
+            for j_ in range(3):
+                out[j_][i_] = inv_det * (E(i_ + 1, j_ + 1) * E(i_ + 2, j_ + 2) - E(i_ + 2, j_ + 1) * E(i_ + 1, j_ + 2))
+        return Matrix._mk(out)
+
+    def to_numpy(self):
+        return np.array([[_plain(x) for x in ra] for ra in self.r])
+
+    def __repr__(self):
+        return "Matrix(%r)" % (self.r,)
+
+    def __format__(self, spec):
+        return repr(self)
+
+
+class _MatType:
+    def __init__(self, n, m, dt):
+        self.n, self.m, self.dt = n, m, dt
+
+    def __call__(self, *rows):
+        if len(rows) == 1:
+            rows = rows[0]
+        return Matrix(list(rows))
+
+
+def _rotation3d(ang_x, ang_y, ang_z):
+    """ti.math.rotation3d = rot_yaw_pitch_roll(yaw = ang_z, pitch = ang_x, roll = ang_y) as recalled (appendix A-11)"""
+    yaw, pitch, roll = _init(ang_z), _init(ang_x), _init(ang_y)
+    ch, sh = cos(yaw), sin(yaw)
+    cp, sp = cos(pitch), sin(pitch)
+    cb, sb = cos(roll), sin(roll)
+    z, o = F32(0.0), F32(1.0)
+    return Matrix._mk([[ch * cb + sh * sp * sb, sb * cp, -sh * cb + ch * sp * sb, z],
+                       [-ch * sb + sh * sp * cb, cb * cp, sb * sh + ch * sp * cb, z],
+                       [sh * cp, -sp, ch * cp, z],
+                       [z, z, z, o]])
 
 
 def _cross(a, b):
@@ -615,6 +754,14 @@ def sqrt(x):
         with np.errstate(all="ignore"):
             return F32(np.sqrt(_tof(a)))
     return _unary(x, rt, _pm.sqrt)
+
+
+def cos(x):
+    return _unary(x, lambda a: F32(np.cos(_tof(a))), _pm.cos)
+
+
+def sin(x):
+    return _unary(x, lambda a: F32(np.sin(_tof(a))), _pm.sin)
 
 
 def floor(x, dtype=None):
@@ -762,6 +909,8 @@ def _init(v):
         return v._copy()
     if isinstance(v, Vector):
         return Vector._mk(_coerce_entries(list(v.e)))
+    if isinstance(v, Matrix):
+        return Matrix._mk([_coerce_entries(list(ra)) for ra in v.r])
     if isinstance(v, (bool, np.bool_, int, float, np.integer, np.floating)):
         return _rt_scalar(v)
     return v           # bound methods, fields, None ...
@@ -786,6 +935,8 @@ def _store(old, new):
         if not isinstance(new, Vector) or len(new.e) != len(old.e):
             raise TypeError("shim: vector store of %r into %r" % (new, old))
         return Vector._mk([_cast_like(o, n) for o, n in zip(old.e, new.e)])
+    if isinstance(old, Matrix):
+        return Matrix._mk([[_cast_like(o, n) for o, n in zip(ro, rn)] for ro, rn in zip(old.r, new.r)])
     if _is_rt(old):
         if isinstance(new, Vector):
             raise TypeError("shim: vector stored into a scalar local")
@@ -1112,7 +1263,9 @@ class _Field:
         if len(self.shape) > 1:
             raise NotImplementedError("shim: multi-dimensional fields")
         n = self.shape[0] if self.shape else 1
-        if isinstance(self.dtype, _VecType):
+        if isinstance(self.dtype, _MatType):
+            self.a = np.zeros((n, self.dtype.n, self.dtype.m), dtype=_np_dt(self.dtype.dt))
+        elif isinstance(self.dtype, _VecType):
             self.a = np.zeros((n, self.dtype.n), dtype=_np_dt(self.dtype.dt))
         else:
             self.a = np.zeros((n,), dtype=_np_dt(self.dtype))
@@ -1128,6 +1281,9 @@ class _Field:
                 return I32(v) if _in_kernel() else v
             return _DynCell(self.lists[int(i)])
         i = self._ix(i)
+        if isinstance(self.dtype, _MatType):
+            mk = (F32 if self.dtype.dt is f32 else I32) if _in_kernel() else (float if self.dtype.dt is f32 else int)
+            return Matrix._mk([[mk(x) for x in ra] for ra in self.a[i]])
         if isinstance(self.dtype, _VecType):
             row = self.a[i]
             dt = self.dtype.dt
@@ -1141,6 +1297,11 @@ class _Field:
 
     def __setitem__(self, i, v):
         i = self._ix(i)
+        if isinstance(self.dtype, _MatType):
+            for a_, ra in enumerate(v.r):
+                for b_, e in enumerate(ra):
+                    self.a[i, a_, b_] = _store_scalar(self.dtype.dt, e)
+            return
         if isinstance(self.dtype, _VecType):
             if not isinstance(v, Vector) or len(v.e) != self.dtype.n:
                 raise TypeError("shim: vector field store of %r" % (v,))
@@ -1165,7 +1326,7 @@ class _Field:
 
     def to_numpy(self):
         out = self.a.copy()
-        return out.reshape(()) if self.shape == () and not isinstance(self.dtype, _VecType) else out
+        return out.reshape(()) if self.shape == () and not isinstance(self.dtype, (_VecType, _MatType)) else out
 
 
 def field(dtype, shape=None):
@@ -1344,12 +1505,6 @@ class _StructField:
 # ---------------------------------------------------------------------------------------------------------------
 # ti.types / ti.math namespaces
 # ---------------------------------------------------------------------------------------------------------------
-def _not_supported(what):
-    def f(*a, **k):
-        raise NotImplementedError("shim: %s is not supported (rigid-body scenes)" % what)
-    return f
-
-
 def _isnan(x):
     return _unary(x, lambda a: I32(int(np.isnan(_tof(a)))), _pm.isnan)
 
@@ -1360,6 +1515,6 @@ def _isinf(x):
 
 types = _pt.SimpleNamespace(struct=lambda **m: _StructType(**m), vector=lambda n=3, dt=f32: _VecType(n, _dt(dt)))
 math = _pt.SimpleNamespace(pi=_pm.pi, inf=_pm.inf, vec3=_VecType(3, f32), vec4=_VecType(4, f32), vec2=_VecType(2, f32),
-                           ivec3=_VecType(3, i32), mat3=_not_supported("ti.math.mat3"), cross=_cross,
-                           rotation3d=_not_supported("ti.math.rotation3d"), inverse=_not_supported("ti.math.inverse"),
+                           ivec3=_VecType(3, i32), mat3=_MatType(3, 3, f32), mat4=_MatType(4, 4, f32), cross=_cross,
+                           rotation3d=_rotation3d, inverse=lambda a: a.inverse(), cos=cos, sin=sin,
                            isnan=_isnan, isinf=_isinf, sqrt=sqrt, floor=floor, pow=pow, max=max, min=min)

@@ -45,6 +45,20 @@ def describe(a, b):
                                                                            int((d > 0).sum()), d.size)
 
 
+RIGID_FIELDS = {"pos": "rpos", "vel": "rvel", "acc": "racc", "force": "rforce", "omega": "romega", "alpha": "ralpha",
+                "volume": "rvol", "mass": "rmass"}
+
+
+def rigid_equal(o, d, tag, case):
+    for ref_name, name in RIGID_FIELDS.items():
+        ref = d["rigid_%s_%s" % (ref_name, tag)]
+        assert same(o.field(name), ref), "%s, state %s, rigid %s: %s" % (case, tag, ref_name, describe(o.field(name), ref))
+    for ref_name, name in (("centroid", "centroid"), ("inertia_inv", "inertia_inv"), ("vertices", "rverts")):
+        ref = d["rigid_%s_%s" % (ref_name, tag)]
+        got = o.field(name).reshape(ref.shape)
+        assert same(got, ref), "%s, state %s, %s: %s" % (case, tag, ref_name, describe(got, ref))
+
+
 def load(case):
     d = np.load(os.path.join(GOLD, "refshim_%s.npz" % case))
     cfg = json.loads(str(d["config_json"]))
@@ -74,7 +88,11 @@ def test_the_committed_cases_are_the_generators_cases():
 def test_oracle_reproduces_the_executed_reference_source(case):
     from oracle import oracle as O
     d, cfg, solver, steps = load(case)
-    o = O.Oracle(cfg, solver=solver, threads=1)
+    pts = verts = None
+    if "solid" in cfg:        # the voxel points are this repository's restatement of trimesh (B-R1), the same on both sides
+        from cfd_taichi_b200 import scene
+        pts, verts, _ = scene.rigid_points_from_config(cfg["solid"], ROOT)
+    o = O.Oracle(cfg, solver=solver, rigid_points=pts, rigid_vertices=verts, threads=1)
     # construction: ParticleSystem.__init__ (sizes, lattice, boundary shell, Akinci volumes), solver __init__
     assert int(o.scalar("particle_num")) == int(d["particle_num"])
     assert int(o.scalar("boundary_particles_num")) == int(d["boundary_particles_num"])
@@ -85,10 +103,23 @@ def test_oracle_reproduces_the_executed_reference_source(case):
     if solver == "pcisph":
         assert np.float32(o.scalar("pc_delta")) == d["pc_delta"], (o.scalar("pc_delta"), d["pc_delta"])
         assert o.scalar("pc_beta") == float(d["pc_beta"])
+    if pts is not None:       # ParticleSystem.py:198-295: rotation, offset, Akinci volumes, mass, centroid, inertia and inverse
+        assert same(o.field("inertia").reshape(9), d["rigid_inertia"]), describe(o.field("inertia").reshape(9), d["rigid_inertia"])
+        o.field("rvel")[:] = d["rigid_vel_0"]
+        rigid_equal(o, d, "0", case)
     o.field("pos")[:] = d["pos0"]
     o.field("vel")[:] = d["vel0"]
     for s in range(1, steps + 1):
         o.step(1, rigid=False)
+        if pts is not None:   # main.py:166-171: the fluid step leaves the gathered fluid->rigid forces, then the rigid step
+            ref = d["rigid_force_fluid_%d" % s]
+            assert same(o.field("rforce"), ref), "%s, step %d, fluid->rigid force: %s" % (case, s, describe(o.field("rforce"), ref))
+            assert np.abs(ref).max() > 1.0, "the case must couple"
+            O.lib().orc_rigid_step(o._h)
+            rigid_equal(o, d, str(s), case)
+            for name, key in (("rs_omega", "rs_omega"), ("rs_attitude", "rs_attitude")):
+                assert same(o.field(name).reshape(3), d["%s_%d" % (key, s)]), "%s, step %d, %s" % (case, s, name)
+            assert np.float32(o.scalar("rs_dt")) == d["rs_dt_%d" % s]
         for name in ["pos", "vel", "cell3"] + gen.FIELDS[solver]:
             ref = d["%s_%d" % (name, s)]
             got = o.field(name)
@@ -123,10 +154,40 @@ def test_cuda_strict_reproduces_the_executed_reference_source(built, case):
     n = ps.particle_num
     assert n == int(d["particle_num"]) and ps.boundary_particles_num == int(d["boundary_particles_num"])
     assert same(ps.fluid_particles.pos.to_numpy(), d["lattice_pos"])
+    assert same(ps.boundary_particles.pos.to_numpy(), d["boundary_pos"])
+    assert same(ps.boundary_particles.volume.to_numpy(), d["boundary_volume"])
+    rs = None
+    if "solid" in cfg:
+        import ctypes
+        from cfd_taichi_b200 import _lib
+        from cfd_taichi_b200.rigid_solver import rigid_solver
+        rs = rigid_solver(ps, cfg)
+        nr = ps.rigid_particles_num
+        assert same(ps.rigid_particles.pos.to_numpy(), d["rigid_pos_0"])
+        assert same(ps.rigid_particles.volume.to_numpy(), d["rigid_volume_0"])
+        info = ps.rigid_state()
+        assert same(np.array(list(info.inertia_inv), dtype=np.float32), d["rigid_inertia_inv_0"])
+        # the body's initial velocity: the reference holds it in rigid_particles.vel (rigid_solver.py:43 reads element 0),
+        # the library in its device-side body state as well
+        v0 = d["rigid_vel_0"][0]
+        ps._rvel4[:nr, :3] = torch.from_numpy(v0).to(ps._device)
+        for k in range(3):
+            info.vel[k] = float(v0[k])
+        _lib.check(ps._lib.sph_rigid_set_state(ps._h, ctypes.byref(info)), ps._h)
     ps._pos4[:n, :3] = torch.from_numpy(d["pos0"]).to(ps._device)
     ps._vel4[:n, :3] = torch.from_numpy(d["vel0"]).to(ps._device)
     for s in range(1, steps + 1):
         sol.step()
+        if rs is not None:
+            assert same(ps.rigid_particles.force.to_numpy(), d["rigid_force_fluid_%d" % s]), "%s, step %d, fluid->rigid force" % (case, s)
+            rs.step()
+            for name in ("pos", "vel"):
+                ref = d["rigid_%s_%d" % (name, s)]
+                got = getattr(ps.rigid_particles, name).to_numpy()
+                assert same(got, ref), "%s, step %d, rigid %s: %s" % (case, s, name, describe(got, ref))
+            info = ps.rigid_state()
+            assert same(np.array(list(info.omega), dtype=np.float32), d["rs_omega_%d" % s])
+            assert same(np.array(list(info.centroid), dtype=np.float32), d["rigid_centroid_%d" % s])
         got = {"pos": ps.fluid_particles.pos.to_numpy(), "vel": ps.fluid_particles.vel.to_numpy(), "rho": sol.rho.to_numpy()}
         for name, a in got.items():
             ref = d["%s_%d" % (name, s)]

@@ -257,3 +257,37 @@ def test_python_scope_sees_plain_numbers():
     assert v.x == 0.7 and isinstance(v.x, float)      # Python scope: binary64 (compute_boundary_particles_count)
     assert int(v.x / 0.05 + 1) == 14                  # ... 14 on the host,
     assert int(F(0.7) / F(0.05) + F(1)) == 15         # ... 15 where the same expression runs on f32 locals (quirk B-18)
+
+
+def test_matrices_products_inverse_and_rotation():
+    rng = np.random.default_rng(5)
+    A = (rng.standard_normal((3, 3)) + 3 * np.eye(3)).astype(F)
+    v = rng.standard_normal(3).astype(F)
+
+    class K:
+        a = ti.field(ti.math.mat3, shape=())
+        out = ti.field(ti.math.mat3, shape=2)
+        w = ti.Vector.field(3, ti.f32, shape=2)
+
+        @ti.kernel
+        def run(self):
+            m = self.a[None]
+            self.w[0] = m @ self.w[1]
+            self.out[0] = ti.math.inverse(m)
+            r = ti.math.rotation3d(0.0, 0.0, 0.0)
+            k_ = ti.Matrix.identity(ti.f32, 3) / 4 - m @ ti.math.mat3([[r[0, 0], r[0, 1], r[0, 2]], [r[1, 0], r[1, 1], r[1, 2]],
+                                                                        [r[2, 0], r[2, 1], r[2, 2]]]).transpose()
+            self.out[1] = k_
+
+    k = K()
+    k.a[None] = ti.Matrix(A.tolist())
+    k.w[1] = ti.Vector(v.tolist())
+    k.run()
+    want = [(A[i, 0] * v[0] + A[i, 1] * v[1]) + A[i, 2] * v[2] for i in range(3)]     # left to right
+    assert k.w.to_numpy()[0].tolist() == [float(x) for x in want]
+    inv = k.out.to_numpy()[0]
+    assert np.abs(inv.astype(np.float64) @ A.astype(np.float64) - np.eye(3)).max() < 1e-5
+    det = (A[0, 0] * (A[1, 1] * A[2, 2] - A[2, 1] * A[1, 2]) - A[1, 0] * (A[0, 1] * A[2, 2] - A[2, 1] * A[0, 2])) \
+        + A[2, 0] * (A[0, 1] * A[1, 2] - A[1, 1] * A[0, 2])
+    assert inv[0, 0] == (F(1.0) / det) * (A[1, 1] * A[2, 2] - A[2, 1] * A[1, 2])      # 1 / det first, then the cofactor
+    assert np.array_equal(k.out.to_numpy()[1], (np.eye(3, dtype=F) / F(4)) - A)        # rotation3d(0, 0, 0) is the identity
