@@ -173,6 +173,9 @@ def test_cuda_strict_reproduces_the_executed_reference_source(built, case):
         ps._rvel4[:nr, :3] = torch.from_numpy(v0).to(ps._device)
         for k in range(3):
             info.vel[k] = float(v0[k])
+        # ... together with the largest surface speed of the body, which the library caches at the end of every rigid step
+        # for the next step's adaptive time step (dfsph_solver.py:104-111 recomputes it from rigid_particles every step)
+        info.max_surface_vel = float(np.sqrt((v0[0] * v0[0] + v0[1] * v0[1]) + v0[2] * v0[2]))
         _lib.check(ps._lib.sph_rigid_set_state(ps._h, ctypes.byref(info)), ps._h)
     ps._pos4[:n, :3] = torch.from_numpy(d["pos0"]).to(ps._device)
     ps._vel4[:n, :3] = torch.from_numpy(d["vel0"]).to(ps._device)
