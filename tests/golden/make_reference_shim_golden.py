@@ -54,6 +54,7 @@ CASES = {
     "dfsph_lattice": (block_scene("dfsph", 1e-3, water=(0.3, 0.3, 0.3)), 2, None),
     "dfsph_clamp": (block_scene("dfsph", 1e-3, water=(0.3, 0.3, 0.3), boundary_handle=False), 2, (13, 0.18, 2.5, 1.0)),
     "pcisph_block": (block_scene("pcisph", 1.5e-4, water=(0.3, 0.3, 0.3)), 2, (14, 0.1, 0.5, 0.86)),
+    "pcisph_converging": (block_scene("pcisph", 1.5e-4, water=(0.3, 0.3, 0.3)), 2, (21, 0.1, 0.5, 0.93)),   # 25 iterations, then below 0.1 %
     "iisph_block": (block_scene("iisph", 2.5e-4, water=(0.3, 0.3, 0.3)), 2, (15, 0.1, 0.5, 0.86)),
     "wcsph_clamp": (block_scene("wcsph", 2.5e-4, water=(0.3, 0.3, 0.3), boundary_handle=False), 2, (16, 0.18, 2.5, 1.0)),
     # fluid-rigid coupling (ParticleSystem.py:198-307, rigid_solver.py, the material_solid branches of every sweep): a
