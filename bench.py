@@ -345,6 +345,9 @@ def cpu_baseline_and_parity(args):
         rel = selfcheck.relinf
         parity = {
             "block": "%d^3 = %d particles (the timed block), from the oracle's state after %d steps" % (n_side, n, warm),
+            "oracle": "C restatement; reproduces, bit for bit, the reference's own solver sources executed under a stand-in for "
+                      "the Taichi front end (tests/golden/refshim_*.npz, tests/test_reference_shim.py); unpinned for Taichi's "
+                      "own code generation",
             "strict_vs_oracle": {"bit_exact": exact, "iterations": {"oracle": list(o_iters), "strict": list(info["iters"]["strict"])}},
             "fast_vs_strict_every_sweep": {"max_rel_err": w, "at": where, "tolerance": 1e-5, "sweeps": len(err),
                                            "loop_decisions_identical": info["loop_flags_equal"],

@@ -37,6 +37,14 @@ def block_scene(solver, dt, water=(0.35, 0.4, 0.35), box=(0.7, 0.8, 0.7), bounda
             "solver": {"name": solver, "delta_time": dt, "iter_cnt": 1, "boundary_handle": boundary_handle}}
 
 
+def other_radius_scene():
+    cfg = block_scene("dfsph", 5e-4, water=(0.24, 0.24, 0.2), box=(0.56, 0.6, 0.5))
+    cfg["scene"]["particle_radius"] = 0.02
+    cfg["scene"]["gravity"] = 3.7
+    cfg["fluid"]["start_pos"] = [0.12, 0.08, 0.12]
+    return cfg
+
+
 def rigid_scene(solver, dt, pos_offset, attitude_deg, scale=0.4):
     cfg = block_scene(solver, dt, water=(0.3, 0.3, 0.3), box=(0.8, 0.8, 0.8))
     cfg["fluid"]["start_pos"] = [0.1, 0.1, 0.1]
@@ -64,6 +72,9 @@ CASES = {
     # only defined while there are fewer rigid than fluid particles)
     "dfsph_rigid": (rigid_scene("dfsph", 1e-3, [0.12, 0.36, 0.1], [0.0, 0.0, 0.0], scale=0.3), 3, (18, 0.1, 0.5, 0.82), [0.3, -2.0, 0.1]),
     "wcsph_rigid_floor": (rigid_scene("wcsph", 2.5e-4, [0.42, 0.0512, 0.2], [0.0, 15.0, 0.0]), 4, (19, 0.1, 0.5, 0.9), [-0.5, -3.0, 0.2]),
+    # another particle radius and gravity than every shipped scene has (h = 0.08: the cull threshold, the kernel constants
+    # and the boundary spacing all move)
+    "dfsph_radius_002": (other_radius_scene(), 2, (22, 0.15, 0.8, 0.86)),
     # seconds, not minutes: the case tests/test_reference_shim.py re-runs from /root/reference on every CPU test run
     # the reference's own shipped scene files, as they are, from the lattice start (5 879 fluid + 9 002 boundary particles:
     # tens of minutes of pure Python per DFSPH step)
@@ -142,7 +153,7 @@ def run_case(name):
         out["pc_delta"] = np.array(sol.delta[None], dtype=np.float32)
         out["pc_beta"] = np.array(sol.beta, dtype=np.float64)
     if pert is not None:
-        pos0, vel = perturbed_state(out["lattice_pos"], *pert)
+        pos0, vel = perturbed_state(out["lattice_pos"], *pert, diameter=2 * cfg["scene"]["particle_radius"])
         ps.fluid_particles.pos.from_numpy(pos0)
         ps.fluid_particles.vel.from_numpy(vel)
     out["pos0"] = ps.fluid_particles.pos.to_numpy()
