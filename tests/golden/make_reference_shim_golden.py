@@ -72,6 +72,11 @@ CASES = {
     # only defined while there are fewer rigid than fluid particles)
     "dfsph_rigid": (rigid_scene("dfsph", 1e-3, [0.12, 0.36, 0.1], [0.0, 0.0, 0.0], scale=0.3), 3, (18, 0.1, 0.5, 0.82), [0.3, -2.0, 0.1]),
     "wcsph_rigid_floor": (rigid_scene("wcsph", 2.5e-4, [0.42, 0.0512, 0.2], [0.0, 15.0, 0.0]), 4, (19, 0.1, 0.5, 0.9), [-0.5, -3.0, 0.2]),
+    # PBF: pbf_solver.py cannot compile at the reference's HEAD (its tasks take integer (i, j), for_all_neighbor passes
+    # structs: quirk B-14).  The ONE line that makes it run is the reference's own commented-out alternative at
+    # ParticleSystem.py:468, `ret += task(i, neighbor_index)`, substituted in the function's source at import time
+    # (index_based_for_all_neighbor below); everything else is executed as it is written
+    "pbf_block": (block_scene("pbf", 2.5e-4, water=(0.3, 0.3, 0.3)), 2, (23, 0.12, 0.8, 0.86)),
     # another particle radius and gravity than every shipped scene has (h = 0.08: the cull threshold, the kernel constants
     # and the boundary spacing all move)
     "dfsph_radius_002": (other_radius_scene(), 2, (22, 0.15, 0.8, 0.86)),
@@ -83,12 +88,31 @@ CASES = {
     "wcsph_tiny": (block_scene("wcsph", 2.5e-4, water=(0.2, 0.25, 0.2), box=(0.5, 0.5, 0.5)), 2, (17, 0.18, 1.5, 0.85)),
 }
 
+def index_based_for_all_neighbor(ps_mod, ti):
+    """SURVEY.md 8(f) rank 4, "PBF with index-based semantics": activate the reference's own commented-out line PS:468."""
+    import inspect
+    import linecache
+    import textwrap
+    orig = ps_mod.ParticleSystem.for_all_neighbor.__ti_original__
+    src = textwrap.dedent(inspect.getsource(orig))
+    struct_call, index_call = "ret += task(particle, particle_j)", "ret += task(i, neighbor_index)"
+    assert src.count(struct_call) == 1 and src.count("# " + index_call) == 1
+    src = src.replace("# " + index_call, "#").replace(struct_call, index_call)
+    src = "\n".join(l for l in src.splitlines() if not l.startswith("@")) + "\n"
+    fname = "<%s: for_all_neighbor with line 468 active>" % os.path.join(REF, "ParticleSystem.py")
+    linecache.cache[fname] = (len(src), None, src.splitlines(True), fname)
+    ns = {}
+    exec(compile(src, fname, "exec"), ps_mod.__dict__, ns)
+    ps_mod.ParticleSystem.for_all_neighbor = ti.func(ns["for_all_neighbor"])
+
+
 FIELDS = {
     "wcsph": ["rho", "pressure", "pressure_gradient", "boundary_acc", "viscosity", "tension"],
     "dfsph": ["rho", "alpha", "rho_adv", "rho_derivative", "vel_adv", "vel_adv_delta", "force_ext", "warm_start_k", "viscosity",
               "tension"],
     "pcisph": ["rho", "pos_predict", "vel_predict", "ext_force", "press_force", "rho_predict", "rho_err", "press_iter",
                "viscosity", "tension"],
+    "pbf": ["rho", "constrain", "pos_predict", "delta_pos", "constrain_derivative", "pbf_lambda"],
     "iisph": ["rho", "v_adv", "f_adv", "d_ii", "a_ii", "d_ij", "rho_adv", "p_iter", "p_past", "r_sum", "f_press", "viscosity",
               "tension"],
 }
@@ -128,6 +152,8 @@ def run_case(name):
         assert os.path.dirname(os.path.abspath(sol_mod.__file__)) == os.path.abspath(REF), sol_mod.__file__
         rig_mod = importlib.import_module("rigid_solver") if "solid" in cfg else None
         ti = importlib.import_module("taichi")
+        if solver == "pbf":
+            index_based_for_all_neighbor(ps_mod, ti)
     finally:
         del sys.path[:2]
     out = {"config_json": np.array(json.dumps(cfg)), "solver": np.array(solver), "steps": np.array(steps)}

