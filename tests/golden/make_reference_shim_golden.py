@@ -71,12 +71,16 @@ CASES = {
     # (140 rigid particles here: get_neighbour_count reads fluid_particles.pos[rigid-local index], quirk B-7, which is
     # only defined while there are fewer rigid than fluid particles)
     "dfsph_rigid": (rigid_scene("dfsph", 1e-3, [0.12, 0.36, 0.1], [0.0, 0.0, 0.0], scale=0.3), 3, (18, 0.1, 0.5, 0.82), [0.3, -2.0, 0.1]),
+    "pcisph_rigid": (rigid_scene("pcisph", 1.5e-4, [0.12, 0.375, 0.1], [0.0, 0.0, 0.0], scale=0.3), 2, (25, 0.1, 0.5, 0.93), [0.2, -1.0, 0.1]),
+    "iisph_rigid": (rigid_scene("iisph", 2.5e-4, [0.12, 0.36, 0.1], [5.0, 0.0, 10.0], scale=0.3), 3, (26, 0.1, 0.5, 0.84), [0.2, -1.0, 0.1]),
     "wcsph_rigid_floor": (rigid_scene("wcsph", 2.5e-4, [0.42, 0.0512, 0.2], [0.0, 15.0, 0.0]), 4, (19, 0.1, 0.5, 0.9), [-0.5, -3.0, 0.2]),
     # PBF: pbf_solver.py cannot compile at the reference's HEAD (its tasks take integer (i, j), for_all_neighbor passes
     # structs: quirk B-14).  The ONE line that makes it run is the reference's own commented-out alternative at
     # ParticleSystem.py:468, `ret += task(i, neighbor_index)`, substituted in the function's source at import time
     # (index_based_for_all_neighbor below); everything else is executed as it is written
     "pbf_block": (block_scene("pbf", 2.5e-4, water=(0.3, 0.3, 0.3)), 2, (23, 0.12, 0.8, 0.86)),
+    # the colour maps of solver_base.visualize_rho / visualize_neighbour (SB:219-245) after one step and a grid rebuild
+    "wcsph_visualize": (block_scene("wcsph", 2.5e-4, water=(0.3, 0.3, 0.3)), 1, (24, 0.15, 1.0, 0.9)),
     # another particle radius and gravity than every shipped scene has (h = 0.08: the cull threshold, the kernel constants
     # and the boundary spacing all move)
     "dfsph_radius_002": (other_radius_scene(), 2, (22, 0.15, 0.8, 0.86)),
@@ -220,6 +224,13 @@ def run_case(name):
             m = pat.findall(text)
             if m:
                 out["log_%s_%d" % (key, s)] = np.array([float(x) for x in m[-1]], dtype=np.float64)
+        if name.endswith("_visualize") and s == steps:
+            ps.reset_grid()
+            ps.update_grid()
+            sol.visualize_rho()
+            out["rgb_rho"] = ps.rgb.to_numpy()
+            sol.visualize_neighbour()
+            out["rgb_neighbour"] = ps.rgb.to_numpy()
         sys.stderr.write("%s step %d: %.0f s  %s\n" % (name, s, time.time() - t0, " | ".join(
             l.strip() for l in text.splitlines() if "iteration" in l or "Iter cnt" in l)))
     return out

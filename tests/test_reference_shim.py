@@ -225,3 +225,25 @@ def test_fixture_regenerates_from_the_reference_source(tmp_path):
     assert sorted(a.files) == sorted(b.files)
     for k in a.files:
         assert same(a[k], b[k]) or (a[k].dtype.kind == "U" and str(a[k]) == str(b[k])), k
+
+
+def test_colour_maps_of_the_executed_reference():
+    """solver_base.visualize_rho / visualize_neighbour (SB:219-245) as the reference computes them, against the statement of
+    them that tests/test_gpu_dfsph.py holds the CUDA colour maps to: b = (x - min) / (max - min) in f32, rgb = (0, 0.28, b);
+    the neighbour count is get_neighbour_count's (quirk B-7), i.e. the oracle's."""
+    from oracle import oracle as O
+    d, cfg, solver, steps = load("wcsph_visualize")
+    o = O.Oracle(cfg, solver=solver, threads=1)
+    o.field("pos")[:] = d["pos0"]
+    o.field("vel")[:] = d["vel0"]
+    o.step(steps, rigid=False)
+    assert same(o.field("pos"), d["pos_%d" % steps])
+    o.phase("reset_grid_update_grid")
+    o.phase("neighbour_counts")
+    for key, x in (("rgb_rho", o.field("rho").copy()), ("rgb_neighbour", o.field("nbr_count").astype(np.float32))):
+        rgb = d[key]
+        b = (x - x.min()) / (x.max() - x.min())
+        assert b.dtype == np.float32 and 0.0 == b.min() and b.max() == 1.0
+        assert same(rgb[:, 2], b), "%s: %s" % (key, describe(rgb[:, 2], b))
+        assert same(rgb[:, 0], np.zeros_like(b)) and same(rgb[:, 1], np.full_like(b, np.float32(0.28)))
+    o.close()
