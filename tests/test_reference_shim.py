@@ -112,12 +112,13 @@ def test_oracle_reproduces_the_executed_reference_source(case):
         rigid_equal(o, d, "0", case)
     o.field("pos")[:] = d["pos0"]
     o.field("vel")[:] = d["vel0"]
+    coupled = 0.0
     for s in range(1, steps + 1):
         o.step(1, rigid=False)
         if pts is not None:   # main.py:166-171: the fluid step leaves the gathered fluid->rigid forces, then the rigid step
             ref = d["rigid_force_fluid_%d" % s]
             assert same(o.field("rforce"), ref), "%s, step %d, fluid->rigid force: %s" % (case, s, describe(o.field("rforce"), ref))
-            assert np.abs(ref).max() > 1.0, "the case must couple"
+            coupled = max(coupled, float(np.abs(ref).max()))
             O.lib().orc_rigid_step(o._h)
             rigid_equal(o, d, str(s), case)
             for name, key in (("rs_omega", "rs_omega"), ("rs_attitude", "rs_attitude")):
@@ -141,6 +142,7 @@ def test_oracle_reproduces_the_executed_reference_source(case):
         if solver == "iisph":
             cnt, res = d["log_ii_%d" % s]
             assert (int(o.scalar("ii_iters")), np.float32(o.scalar("ii_residual"))) == (int(cnt), np.float32(res))
+    assert pts is None or coupled > 1.0, "the case must couple"
     o.close()
 
 
