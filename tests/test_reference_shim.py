@@ -249,3 +249,17 @@ def test_colour_maps_of_the_executed_reference():
         assert same(rgb[:, 2], b), "%s: %s" % (key, describe(rgb[:, 2], b))
         assert same(rgb[:, 0], np.zeros_like(b)) and same(rgb[:, 1], np.full_like(b, np.float32(0.28)))
     o.close()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_product_host_formulas_against_the_executed_reference(case):
+    """The product's own host statement of ParticleSystem.__init__ / init_particle_pos (cfd_taichi_b200/scene.py: the sizes
+    every device array is allocated with, the lattice and the boundary shell the CUDA initialisers are tested against) on the
+    executed reference's output -- no oracle involved."""
+    from cfd_taichi_b200 import scene
+    d, cfg, solver, steps = load(case)
+    pn, bn, grid = scene.derive_sizes(cfg)
+    assert (pn, bn, list(grid)) == (int(d["particle_num"]), int(d["boundary_particles_num"]), list(d["grid_num"]))
+    assert same(scene.init_fluid_positions(cfg, pn), d["lattice_pos"])
+    got = scene.init_boundary_positions(cfg, bn)
+    assert same(got, d["boundary_pos"]), describe(got, d["boundary_pos"])
