@@ -91,7 +91,7 @@ CASES = {
     # the reference's own shipped scene files, as they are, from the lattice start (5 879 fluid + 9 002 boundary particles:
     # tens of minutes of pure Python per DFSPH step)
     "shipped_wcsph": ("ref:config/wcsph_config_backup.json", 2, None),
-    "shipped_dfsph": ("ref:config/dfsph_config_backup.json", 1, None),
+    "shipped_dfsph": ("ref:config/dfsph_config_backup.json", 3, None),
     "shipped_pcisph": ("ref:config/pcisph_config_backup.json", 1, None),       # pre_compute's delta on the reference's own scene
     "shipped_iisph": ("ref:config/iisph_config_backup.json", 1, None),
     "wcsph_tiny": (block_scene("wcsph", 2.5e-4, water=(0.2, 0.25, 0.2), box=(0.5, 0.5, 0.5)), 2, (17, 0.18, 1.5, 0.85)),
