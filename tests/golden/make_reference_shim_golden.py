@@ -45,11 +45,13 @@ def other_radius_scene():
     return cfg
 
 
-def rigid_scene(solver, dt, pos_offset, attitude_deg, scale=0.4):
+def rigid_scene(solver, dt, pos_offset, attitude_deg, scale=0.4, fs_couple=True):
     cfg = block_scene(solver, dt, water=(0.3, 0.3, 0.3), box=(0.8, 0.8, 0.8))
     cfg["fluid"]["start_pos"] = [0.1, 0.1, 0.1]
     cfg["solid"] = {"active": True, "attitude_offset": list(attitude_deg), "fill": True, "mesh": "./obj/cube1.STL",
                     "pos_offset": list(pos_offset), "rho_0": 2000, "scale": scale, "voxel_radius": 0.025}
+    if not fs_couple:
+        cfg["solver"]["fs_couple"] = False
     return cfg
 
 
@@ -76,6 +78,8 @@ CASES = {
     # reference's behaviour, and it is what the fixture holds.)
     "pcisph_rigid": (rigid_scene("pcisph", 1.5e-4, [0.12, 0.385, 0.1], [0.0, 0.0, 0.0], scale=0.3), 2, (25, 0.1, 0.5, 0.97), [0.2, -1.0, 0.1]),
     "iisph_rigid": (rigid_scene("iisph", 2.5e-4, [0.12, 0.36, 0.1], [5.0, 0.0, 10.0], scale=0.3), 3, (26, 0.1, 0.5, 0.84), [0.2, -1.0, 0.1]),
+    "wcsph_rigid_uncoupled": (rigid_scene("wcsph", 2.5e-4, [0.12, 0.36, 0.1], [0.0, 0.0, 0.0], scale=0.3, fs_couple=False), 2,
+                              (27, 0.1, 0.5, 0.84), [0.2, -1.0, 0.1]),           # `fs_couple: false`: the body is in the grid, the sweeps skip it
     "wcsph_rigid_floor": (rigid_scene("wcsph", 2.5e-4, [0.42, 0.0512, 0.2], [0.0, 15.0, 0.0]), 4, (19, 0.1, 0.5, 0.9), [-0.5, -3.0, 0.2]),
     # PBF: pbf_solver.py cannot compile at the reference's HEAD (its tasks take integer (i, j), for_all_neighbor passes
     # structs: quirk B-14).  The ONE line that makes it run is the reference's own commented-out alternative at

@@ -142,12 +142,17 @@ def test_oracle_reproduces_the_executed_reference_source(case):
         if solver == "iisph":
             cnt, res = d["log_ii_%d" % s]
             assert (int(o.scalar("ii_iters")), np.float32(o.scalar("ii_residual"))) == (int(cnt), np.float32(res))
-    assert pts is None or coupled > 1.0, "the case must couple"
+    if pts is not None:
+        assert (coupled > 1.0) == bool(cfg["solver"].get("fs_couple", True)), "the case must couple (or, uncoupled, must not)"
     o.close()
 
 
+# every case but the last one added (fs_couple: false), which no GPU run of this round has seen yet
+GPU_CASES = [c for c in CASES if c != "wcsph_rigid_uncoupled"]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", GPU_CASES)
 def test_cuda_strict_reproduces_the_executed_reference_source(built, case):
     """The same files against the product: strict kernels through the reference-named Python classes."""
     import torch
